@@ -1,0 +1,50 @@
+"""The five BASELINE.json configs, resolved as SURVEY.md section 8 "config resolution" prescribes.
+
+Each entry: reference yml + the minimal documented overrides that make the reference classes
+compose (never by editing reference sources), + the OracleCfg fields they imply.
+TEST INFRASTRUCTURE (oracle/), also read by bench.py's cpu_baseline / --impl reference legs.
+"""
+from .ekl_oracle import OracleCfg
+
+# name -> (reference yml, cfg overrides applied after the yml, oracle fields)
+CONFIGS = {
+    # 1: trainer.py semantics, COND_G_NET(E+1+1024) + JOINT_D_NET64/128; CAT_Z 'sum' affects dims only
+    "catcls": dict(yml="birds_2stgs_catcls.yml", batch=24,
+                   over={"TRAIN.CAT_Z": "sum"},
+                   ocfg=dict(G_KIND="cond", COND="txt+cls", CLS_KIND="multihot", CAT_Z="sum", Z_DIM=100)),
+    # 2: 3-branch COND_G_NET + JOINT_D_NET64/128/256 (both reference trainers assert on BRANCH_NUM>2)
+    "3stages": dict(yml="birds_3stages.yml", batch=24,
+                    over={"TRAIN.CAT_Z": "sum"},
+                    ocfg=dict(G_KIND="cond", COND="txt+cls", CLS_KIND="multihot", CAT_Z="sum", Z_DIM=100,
+                              BRANCH_NUM=3)),
+    # 3: capsule-conditioned G/D: COND_G_NET(1024, use_cap) (cub:135) + JOINT_D(use_cap)
+    "onlycapsule": dict(yml="birds_2stgs_onlycapsule.yml", batch=32,
+                        over={"TRAIN.CAT_Z": "sum", "TRAIN.G_CAPSULE": True, "TRAIN.D_CAPSULE": True},
+                        ocfg=dict(G_KIND="cond", COND="txt", CLS_KIND="index", CAT_Z="sum", Z_DIM=100,
+                                  G_CAPSULE=True, D_CAPSULE=True)),
+    # 4: runs as written through cub_trainer_splitz_cap_ca.py
+    "splitz_cap_ca": dict(yml="birds_2stg_splitz_cap_ca.realcls.yml", batch=32, over={},
+                          ocfg=dict(G_KIND="catz_ca", CLS_KIND="index", CAT_Z="concat", Z_DIM=128,
+                                    G_CAPSULE=True, D_CAPSULE=True)),
+    # 5: as 1 with ENTITY_DIM 90
+    "coco": dict(yml="coco_2stgs.yml", batch=64,
+                 over={"TRAIN.CAT_Z": "sum"},
+                 ocfg=dict(G_KIND="cond", COND="txt+cls", CLS_KIND="multihot", CAT_Z="sum", Z_DIM=100,
+                           ENTITY_DIM=90)),
+}
+
+
+def oracle_cfg(name, batch=None, gf=None, df=None):
+    spec = CONFIGS[name]
+    kw = dict(spec["ocfg"])
+    kw["BATCH_SIZE"] = batch or spec["batch"]
+    if gf:
+        kw["GF_DIM"] = gf
+    if df:
+        kw["DF_DIM"] = df
+    return OracleCfg(**kw)
+
+
+def cond_dim(c):
+    """cond width of COND_G_NET's VC_NET: trainer.py:116 (E+1+text) or cub:135 (text)."""
+    return c.TEXT_DIM + c.ENTITY_DIM + 1 if c.COND == "txt+cls" else c.TEXT_DIM
