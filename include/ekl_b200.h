@@ -1,0 +1,97 @@
+/* ekl_b200 -- C ABI of the B200-native (sm_100a) kernels behind the StackGAN++-style G+D training step of
+ * Multimodal-Group/Text2img_EKL.
+ *
+ * The reference has NO native / FFI layer: its hot path is Python nn.Modules calling torch (cuDNN/cuBLAS).
+ * This header is therefore the interface a maintainer binds *below* the reference's Python modules; each entry
+ * point names the reference operation it replaces (file:line under /root/reference).  INTEGRATION.md shows the
+ * ctypes stub.
+ *
+ * Conventions
+ *  - plain C: device pointers + sizes, no torch types.  The library never allocates or frees caller tensors;
+ *    scratch is passed in (sizes from the *_rows / *_elems queries).
+ *  - activations: NHWC bf16 (row = pixel, channels contiguous).  Parameters / gradients / statistics: fp32.
+ *    Conv filters: fp32 [Cout][KH][KW][Cin] == torch channels_last storage of the reference's [Cout,Cin,KH,KW].
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, and returns
+ *    0 = ok, <0 = invalid argument, >0 = cudaError_t / 1000+CUresult.  ekl_last_error() = thread-local text.
+ *  - no CPU fallback: ekl_require_sm100() fails on anything but compute capability 10.x.
+ */
+#ifndef EKL_B200_H_
+#define EKL_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EKL_B200_VERSION 100
+
+const char* ekl_last_error(void);
+int ekl_version(void);
+int ekl_require_sm100(void);
+
+/* ---------------------------------------------------------------- convolutions ----------------------------
+ * mode EKL_S1    conv3x3 s1 p1 no bias                      model.py:79-82  (conv3x3; ResBlock :107-123,
+ *                                                           Block3x3_relu :98-104, Block3x3_leakRelu :812-818)
+ * mode EKL_UP2   nn.Upsample(x2, nearest) + conv3x3         model.py:87-94  (upBlock; the 4x tensor is never
+ *                                                           materialised: 4 sub-pixel 2x2 convs, 2.25x fewer MACs)
+ * mode EKL_DOWN2 conv4x4 s2 p1 no bias                      model.py:822-850 (downBlock, encode_image_by_16times)
+ * forward / backward-data / backward-weight replace the cuDNN fprop / dgrad / wgrad calls autograd makes. */
+enum { EKL_S1 = 0, EKL_UP2 = 1, EKL_DOWN2 = 2 };
+enum { EKL_IMPL_TC = 0, EKL_IMPL_SIMT = 1 };              /* tcgen05 product path | SIMT small-channel / cross-check */
+enum { EKL_FMT_NHWC_BF16 = 0, EKL_FMT_NCHW_F32 = 1 };     /* NCHW fp32 = the loader's images (datasets.py:346) */
+enum { EKL_ACT_NONE = 0, EKL_ACT_GLU = 1, EKL_ACT_LRELU = 2, EKL_ACT_RELU = 3, EKL_ACT_TANH = 4 };
+
+typedef struct ekl_conv {
+  int mode;          /* EKL_S1 | EKL_UP2 | EKL_DOWN2 */
+  int B, H, W;       /* extents of the conv INPUT x */
+  int Cin, Cout;
+  int group_b;       /* batch extent of one BatchNorm-statistics group (0 = B) */
+  int impl;          /* EKL_IMPL_TC | EKL_IMPL_SIMT */
+  int x_fmt, y_fmt;  /* SIMT only: EKL_FMT_* of x and y */
+  int act;           /* SIMT only: fused epilogue EKL_ACT_NONE | EKL_ACT_LRELU | EKL_ACT_TANH */
+} ekl_conv;
+
+/* bf16 elements of the packed forward (dgrad=0) / data-gradient (dgrad=1) filter operand */
+int64_t ekl_conv_packed_elems(const ekl_conv* c, int dgrad);
+/* fp32 master filter -> packed bf16 operands (either output may be NULL) */
+int ekl_conv_pack(const ekl_conv* c, const float* w_master, void* w_fwd, void* w_dgrad, void* stream);
+/* rows of the per-tile BatchNorm partial-statistics buffer [rows][2][Cout] ekl_conv_fwd writes (TC impl) */
+int ekl_conv_stats_rows(const ekl_conv* c);
+/* y = conv(x); stats (may be NULL): per-tile per-channel sum / sum-of-squares of y */
+int ekl_conv_fwd(const ekl_conv* c, const void* x, const void* w_fwd, void* y, float* stats, void* stream);
+/* dx = conv^T(dy) */
+int ekl_conv_bwd_data(const ekl_conv* c, const void* dy, const void* w_dgrad, void* dx, void* stream);
+/* dw[Cout][KH][KW][Cin] += x (*) dy   (fp32, accumulated: zero it first for a fresh gradient) */
+int ekl_conv_bwd_weight(const ekl_conv* c, const void* x, const void* dy, float* dw, void* stream);
+
+/* test hook: integer structure of the gather plan (taps, parity views, master-filter taps summed per packed tap) */
+int ekl_conv_plan_dump(const ekl_conv* c, int dgrad, int* out, int cap);
+
+/* ---------------------------------------------------------------- BatchNorm (train mode) + activation -----
+ * replaces nn.BatchNorm2d/1d + GLU (model.py:68-76,91-93) | LeakyReLU(0.2) (:816,826) | ReLU (:177-178) and the
+ * ResBlock skip add (:119-123).  y: conv output bf16 [M][C]; rows form `groups` contiguous equal groups with
+ * independent batch statistics (the reference's separate real / wrong / fake forwards, cub_trainer...:418-420). */
+int ekl_col_stats_rows(int64_t M, int C, int groups);
+int ekl_col_stats(const void* y, int64_t M, int C, int groups, float* partial /*[rows][2][C]*/, void* stream);
+/* partial [groups*rows_per_group][2][C] -> mean/rstd [groups][C]; running stats (may be NULL) get one momentum
+ * update per group, in group order, with the unbiased variance -- exactly one update per reference forward. */
+int ekl_bn_finalize(const float* partial, int rows_per_group, int C, int groups, float count, float eps, float momentum,
+                    float* mean, float* rstd, float* running_mean, float* running_var, void* stream);
+int ekl_bn_act_fwd(const void* y, int64_t M, int Cy, int groups, const float* mean, const float* rstd,
+                   const float* gamma, const float* beta, int act, const void* residual, void* out, void* stream);
+int ekl_bn_act_bwd_rows(int64_t M, int Cy, int groups, int act);
+/* dy from dout; dgamma/dbeta are accumulated (+=). partial: [ekl_bn_act_bwd_rows][2][Cy], sums: [groups][2][Cy] */
+int ekl_bn_act_bwd(const void* y, const void* dout, int64_t M, int Cy, int groups, const float* mean, const float* rstd,
+                   const float* gamma, const float* beta, int act, float* partial, float* sums, float* dgamma,
+                   float* dbeta, void* dy, void* stream);
+/* LeakyReLU(0.2) backward from the OUTPUT (first discriminator conv has no BN, model.py:835-836) */
+int ekl_lrelu_bwd(const void* out, const void* dout, void* dx, int64_t n, void* stream);
+/* cat(tile(c_code), h) along channels (model.py:411-414, 956-959) and its backward (dcode accumulated) */
+int ekl_cat_code(const float* code, int Cc, const void* x, int Cx, int B, int HW, void* out, void* stream);
+int ekl_cat_code_bwd(const void* dcat, int Cc, int Cx, int B, int HW, float* dcode, void* dx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EKL_B200_H_ */

@@ -1,0 +1,120 @@
+"""Host logic of the conv family, no GPU: the gather plans (tap tables, parity views, packed-filter sums) that
+the tcgen05 / SIMT kernels execute are emulated in torch on the CPU from ekl_conv_plan_dump() and compared with
+F.conv2d / autograd for forward and data-gradient, and the weight-gradient scatter is checked the same way."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from text2img_ekl_b200 import _lib as L
+
+
+def dump(conv, dgrad):
+    buf = (C.c_int * 1024)()
+    L.check(L.lib().ekl_conv_plan_dump(conv, dgrad, buf, 1024))
+    h = list(buf[:11])
+    nvar, ntaps = h[0], h[1]
+    taps = [[tuple(buf[11 + (v * ntaps + t) * 8: 11 + (v * ntaps + t) * 8 + 8]) for t in range(ntaps)] for v in range(nvar)]
+    return dict(nvar=nvar, ntaps=ntaps, n_a=h[2], m=(h[3], h[4], h[5]), Cin=h[6], N=h[7], transposed=h[8], KK=h[9] * h[10]), taps
+
+
+def parity_views(t, n):
+    """t [B,H,W,C] -> list of n views (n=1: [t]; n=4: (ph,pw) parity classes)."""
+    if n == 1:
+        return [t]
+    return [t[:, ph::2, pw::2, :] for ph in range(2) for pw in range(2)]
+
+
+def shifted(v, dh, dw):
+    """out[b,h,w] = v[b,h+dh,w+dw] with zeros outside."""
+    B, H, W, Cc = v.shape
+    out = torch.zeros_like(v)
+    hs, he = max(0, -dh), min(H, H - dh)
+    ws, we = max(0, -dw), min(W, W - dw)
+    if hs < he and ws < we:
+        out[:, hs:he, ws:we] = v[:, hs + dh:he + dh, ws + dw:we + dw]
+    return out
+
+
+def pack(wm, info, taps):
+    """master [Cout,KK,Cin] -> packed [nvar][N][ntaps][K]."""
+    Cout, KK, Cin = wm.shape
+    out = torch.zeros(info["nvar"], info["N"], info["ntaps"], info["Cin"], dtype=wm.dtype)
+    for v in range(info["nvar"]):
+        for t in range(info["ntaps"]):
+            tp = taps[v][t]
+            acc = sum(wm[:, tp[4 + i], :] for i in range(tp[3]))          # [Cout, Cin]
+            out[v, :, t, :] = acc.t() if info["transposed"] else acc
+    return out
+
+
+def run_gather(A, out_shape, info, taps, wp):
+    """emulate out_v[p,n] = sum_t sum_k A_map[p+(dh,dw),k] * Wp[v][n][t][k]; returns full-resolution output."""
+    views = parity_views(A, info["n_a"])
+    out = torch.zeros(out_shape, dtype=A.dtype)
+    outs = parity_views(out, info["nvar"])
+    for v in range(info["nvar"]):
+        acc = 0
+        for t in range(info["ntaps"]):
+            m, dh, dw = taps[v][t][:3]
+            acc = acc + torch.einsum("bhwk,nk->bhwn", shifted(views[m], dh, dw), wp[v, :, t, :])
+        outs[v].copy_(acc)
+    return out
+
+
+CASES = [(0, 2, 6, 5, 4, 6), (1, 2, 3, 4, 5, 3), (2, 2, 8, 6, 3, 5), (0, 1, 4, 4, 8, 8), (1, 1, 4, 4, 2, 2), (2, 3, 4, 4, 4, 2)]
+
+
+@pytest.mark.parametrize("mode,B,H,W,Cin,Cout", CASES)
+def test_plan_forward_and_dgrad_and_wgrad(mode, B, H, W, Cin, Cout):
+    torch.manual_seed(mode * 7 + B)
+    K = 4 if mode == 2 else 3
+    Ho, Wo = (2 * H, 2 * W) if mode == 1 else ((H // 2, W // 2) if mode == 2 else (H, W))
+    conv = L.EklConv(mode, B, H, W, Cin, Cout, 0, 1, 0, 0, 0)
+    x = torch.randn(B, H, W, Cin, dtype=torch.float64)
+    wm = torch.randn(Cout, K * K, Cin, dtype=torch.float64)
+    xr = x.permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    wr = wm.view(Cout, K, K, Cin).permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    xin = F.interpolate(xr, scale_factor=2, mode="nearest") if mode == 1 else xr
+    yr = F.conv2d(xin, wr, stride=2 if mode == 2 else 1, padding=1)
+    dy = torch.randn(B, Ho, Wo, Cout, dtype=torch.float64)
+    yr.backward(dy.permute(0, 3, 1, 2))
+    # forward
+    info, taps = dump(conv, 0)
+    y = run_gather(x, (B, Ho, Wo, Cout), info, taps, pack(wm, info, taps).double())
+    assert torch.allclose(y.permute(0, 3, 1, 2), yr, atol=1e-9)
+    # weight gradient through the forward plan: dW[co][src][ci] += sum_p dY_v[p,co] * A_map[p+(dh,dw),ci]
+    views = parity_views(x, info["n_a"])
+    dys = parity_views(dy, info["nvar"])
+    dw = torch.zeros(Cout, K * K, Cin, dtype=torch.float64)
+    for v in range(info["nvar"]):
+        for t in range(info["ntaps"]):
+            m, dh, dw_, nsrc = taps[v][t][:4]
+            contrib = torch.einsum("bhwn,bhwk->nk", dys[v], shifted(views[m], dh, dw_))
+            for i in range(nsrc):
+                dw[:, taps[v][t][4 + i], :] += contrib
+    assert torch.allclose(dw.view(Cout, K, K, Cin).permute(0, 3, 1, 2), wr.grad, atol=1e-9)
+    # data gradient
+    info, taps = dump(conv, 1)
+    assert info["transposed"] == 1 and info["N"] == Cin and info["Cin"] == Cout
+    dx = run_gather(dy, (B, H, W, Cin), info, taps, pack(wm, info, taps).double())
+    assert torch.allclose(dx.permute(0, 3, 1, 2), xr.grad, atol=1e-9)
+
+
+def test_library_exports_every_declared_symbol():
+    import re, os
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "ekl_b200.h")).read()
+    names = set(re.findall(r"\b(ekl_[a-z0-9_]+)\s*\(", hdr))
+    lib = L.lib()
+    for n in sorted(names):
+        assert hasattr(lib, n), n
+        assert n in L.SIGNATURES, "binding missing for " + n
+    assert lib.ekl_version() == 100
+
+
+def test_no_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert L.lib().ekl_require_sm100() != 0
+    assert L.lib().ekl_last_error()

@@ -1,0 +1,82 @@
+"""ctypes binding of libekl_b200.so (the C ABI declared in include/ekl_b200.h).
+
+The product path has no fallback: if the shared library is missing or the device is not sm_100a the ops layer
+fails loudly.  `python -m text2img_ekl_b200.build` (or __graft_entry__.build()) compiles it in-tree.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libekl_b200.so")
+
+S1, UP2, DOWN2 = 0, 1, 2
+IMPL_TC, IMPL_SIMT = 0, 1
+FMT_NHWC_BF16, FMT_NCHW_F32 = 0, 1
+ACT_NONE, ACT_GLU, ACT_LRELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3, 4
+
+
+class EklConv(C.Structure):
+    _fields_ = [("mode", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
+                ("group_b", C.c_int), ("impl", C.c_int), ("x_fmt", C.c_int), ("y_fmt", C.c_int), ("act", C.c_int)]
+
+
+class EklError(RuntimeError):
+    pass
+
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_cp = C.POINTER(EklConv)
+
+# name -> (restype, argtypes); every symbol include/ekl_b200.h declares
+SIGNATURES = {
+    "ekl_last_error": (C.c_char_p, []),
+    "ekl_version": (_i, []),
+    "ekl_require_sm100": (_i, []),
+    "ekl_conv_packed_elems": (_i64, [_cp, _i]),
+    "ekl_conv_pack": (_i, [_cp, _vp, _vp, _vp, _vp]),
+    "ekl_conv_stats_rows": (_i, [_cp]),
+    "ekl_conv_fwd": (_i, [_cp, _vp, _vp, _vp, _vp, _vp]),
+    "ekl_conv_bwd_data": (_i, [_cp, _vp, _vp, _vp, _vp]),
+    "ekl_conv_bwd_weight": (_i, [_cp, _vp, _vp, _vp, _vp]),
+    "ekl_conv_plan_dump": (_i, [_cp, _i, C.POINTER(C.c_int), _i]),
+    "ekl_col_stats_rows": (_i, [_i64, _i, _i]),
+    "ekl_col_stats": (_i, [_vp, _i64, _i, _i, _vp, _vp]),
+    "ekl_bn_finalize": (_i, [_vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "ekl_bn_act_fwd": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "ekl_bn_act_bwd_rows": (_i, [_i64, _i, _i, _i]),
+    "ekl_bn_act_bwd": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ekl_lrelu_bwd": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "ekl_cat_code": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "ekl_cat_code_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EklError("libekl_b200.so not built (%s). Run `python -m text2img_ekl_b200.build`; there is no "
+                           "fallback path." % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise EklError("ekl_b200 error %d: %s" % (rc, lib().ekl_last_error().decode()))
+
+
+def ptr(t):
+    """device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

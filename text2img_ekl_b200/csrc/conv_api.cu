@@ -1,0 +1,130 @@
+// C-ABI entry points of the convolution family: ekl_conv descriptor -> gather-GEMM plans -> kernels.
+#include "../../include/ekl_b200.h"
+#include "conv_plan.h"
+#include "ekl_common.cuh"
+
+int ekl_tc_supported(const EklGather* g);
+void ekl_tc_geometry(const EklGather* g, int group_b, int* tb, int* th, int* tw);
+int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, int group_b, int* mtiles_out, cudaStream_t st);
+int ekl_gather_simt(const EklGather* g, const void* w_packed, int act, cudaStream_t st);
+int ekl_wgrad_simt(const EklGather* fwd_plan, float* dw_master, cudaStream_t st);
+int ekl_wgrad_tc_supported(const EklGather* g);
+int ekl_wgrad_tc(const EklGather* g, float* dw, cudaStream_t st);
+int ekl_pack_weights(const EklGather* g, const float* w_master, void* out, int Cout, int Cin, cudaStream_t st);
+
+namespace {
+
+void out_extent(const ekl_conv* c, int* Ho, int* Wo) {
+  if (c->mode == EKL_UP2) { *Ho = 2 * c->H; *Wo = 2 * c->W; }
+  else if (c->mode == EKL_DOWN2) { *Ho = c->H / 2; *Wo = c->W / 2; }
+  else { *Ho = c->H; *Wo = c->W; }
+}
+
+EklView make_view(const void* p, int B, int H, int W, int C, int fmt) {
+  if (fmt == EKL_FMT_NCHW_F32) {
+    EklView v;
+    v.base = const_cast<void*>(p); v.sC = (int64_t)H * W; v.sW = 1; v.sH = W; v.sB = (int64_t)C * H * W;
+    v.dB = B; v.dH = H; v.dW = W; v.C = C; v.f32 = 1;
+    return v;
+  }
+  return ekl_view_nhwc(const_cast<void*>(p), B, H, W, C, 0);
+}
+
+int check(const ekl_conv* c) {
+  EKL_REQUIRE(c != nullptr, "null ekl_conv");
+  EKL_REQUIRE(c->mode >= EKL_S1 && c->mode <= EKL_DOWN2, "bad conv mode %d", c->mode);
+  EKL_REQUIRE(c->B > 0 && c->H > 0 && c->W > 0 && c->Cin > 0 && c->Cout > 0, "bad conv extents");
+  EKL_REQUIRE(c->mode != EKL_DOWN2 || (c->H % 2 == 0 && c->W % 2 == 0), "DOWN2 needs even H, W");
+  return 0;
+}
+
+int plan(const ekl_conv* c, int dgrad, const void* x, const void* y, EklGather* g) {
+  int Ho, Wo;
+  out_extent(c, &Ho, &Wo);
+  EklView xv = make_view(x, c->B, c->H, c->W, c->Cin, c->x_fmt);
+  EklView yv = make_view(y, c->B, Ho, Wo, c->Cout, c->y_fmt);
+  return ekl_build_gather(g, c->mode, dgrad, xv, yv, c->Cin, c->Cout);
+}
+
+}  // namespace
+
+extern "C" int64_t ekl_conv_packed_elems(const ekl_conv* c, int dgrad) {
+  if (check(c)) return -1;
+  EklGather g;
+  plan(c, dgrad, nullptr, nullptr, &g);
+  return ekl_packed_elems(&g);
+}
+
+extern "C" int ekl_conv_pack(const ekl_conv* c, const float* w_master, void* w_fwd, void* w_dgrad, void* stream) {
+  if (int rc = check(c)) return rc;
+  EklGather g;
+  if (w_fwd) {
+    plan(c, 0, nullptr, nullptr, &g);
+    if (int rc = ekl_pack_weights(&g, w_master, w_fwd, c->Cout, c->Cin, (cudaStream_t)stream)) return rc;
+  }
+  if (w_dgrad) {
+    plan(c, 1, nullptr, nullptr, &g);
+    if (int rc = ekl_pack_weights(&g, w_master, w_dgrad, c->Cout, c->Cin, (cudaStream_t)stream)) return rc;
+  }
+  return 0;
+}
+
+extern "C" int ekl_conv_stats_rows(const ekl_conv* c) {
+  if (check(c)) return -1;
+  EklGather g;
+  plan(c, 0, nullptr, nullptr, &g);
+  int tb, th, tw;
+  ekl_tc_geometry(&g, c->group_b, &tb, &th, &tw);
+  return ekl_cdiv(g.mW, tw) * ekl_cdiv(g.mH, th) * ekl_cdiv(g.mB, tb) * g.nvar;
+}
+
+extern "C" int ekl_conv_fwd(const ekl_conv* c, const void* x, const void* w_fwd, void* y, float* stats, void* stream) {
+  if (int rc = check(c)) return rc;
+  EklGather g;
+  plan(c, 0, x, y, &g);
+  if (c->impl == EKL_IMPL_SIMT) {
+    EKL_REQUIRE(stats == nullptr, "SIMT conv does not produce BatchNorm partials (use ekl_col_stats)");
+    const int act = c->act == EKL_ACT_LRELU ? 1 : (c->act == EKL_ACT_TANH ? 2 : 0);
+    return ekl_gather_simt(&g, w_fwd, act, (cudaStream_t)stream);
+  }
+  EKL_REQUIRE(c->act == EKL_ACT_NONE && c->x_fmt == 0 && c->y_fmt == 0, "TC conv: NHWC bf16, no fused activation");
+  return ekl_gather_gemm_tc(&g, w_fwd, stats, c->group_b, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int ekl_conv_bwd_data(const ekl_conv* c, const void* dy, const void* w_dgrad, void* dx, void* stream) {
+  if (int rc = check(c)) return rc;
+  EklGather g;
+  plan(c, 1, dx, dy, &g);
+  if (c->impl == EKL_IMPL_SIMT) return ekl_gather_simt(&g, w_dgrad, 0, (cudaStream_t)stream);
+  EKL_REQUIRE(c->x_fmt == 0 && c->y_fmt == 0, "TC conv: NHWC bf16 only");
+  return ekl_gather_gemm_tc(&g, w_dgrad, nullptr, 0, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int ekl_conv_bwd_weight(const ekl_conv* c, const void* x, const void* dy, float* dw, void* stream) {
+  if (int rc = check(c)) return rc;
+  EklGather g;
+  plan(c, 0, x, dy, &g);
+  if (c->impl == EKL_IMPL_SIMT) return ekl_wgrad_simt(&g, dw, (cudaStream_t)stream);
+  EKL_REQUIRE(c->x_fmt == 0 && c->y_fmt == 0, "TC conv: NHWC bf16 only");
+  return ekl_wgrad_tc(&g, dw, (cudaStream_t)stream);
+}
+
+// Debug / test hook: dump a plan's integer structure so the host logic can be verified without a GPU.
+// out: [nvar, ntaps, n_a, mB, mH, mW, Cin, N, transposed, KH, KW] then per (v,t): map, dh, dw, nsrc, src[0..3]
+extern "C" int ekl_conv_plan_dump(const ekl_conv* c, int dgrad, int* out, int cap) {
+  if (int rc = check(c)) return rc;
+  EklGather g;
+  plan(c, dgrad, nullptr, nullptr, &g);
+  const int need = 11 + g.nvar * g.ntaps * 8;
+  EKL_REQUIRE(cap >= need, "plan_dump: need %d ints", need);
+  int* o = out;
+  *o++ = g.nvar; *o++ = g.ntaps; *o++ = g.n_a; *o++ = g.mB; *o++ = g.mH; *o++ = g.mW; *o++ = g.Cin; *o++ = g.N;
+  *o++ = g.transposed; *o++ = g.KH; *o++ = g.KW;
+  for (int v = 0; v < g.nvar; ++v)
+    for (int t = 0; t < g.ntaps; ++t) {
+      const EklTap& tp = g.taps[v][t];
+      *o++ = tp.map; *o++ = tp.dh; *o++ = tp.dw; *o++ = tp.nsrc;
+      for (int i = 0; i < 4; ++i) *o++ = tp.src[i];
+    }
+  return 0;
+}

@@ -1,0 +1,74 @@
+// Weight packing: fp32 master filters [Cout][KH][KW][Cin] (the channels_last storage of the reference's
+// [Cout,Cin,KH,KW] parameters) -> bf16 K-major operands of the gather-GEMM plans (conv_plan.h):
+//   forward        Wp[v][co][t][ci] = sum_{s in src(v,t)} W[co][s][ci]
+//   data-gradient  Wp[v][ci][t][co] = sum_{s in src(v,t)} W[co][s][ci]      (transposed through a smem tile)
+// HBM-bound: 4 B read + 2 B written per (variant, tap) element.
+#include "conv_plan.h"
+#include "ekl_common.cuh"
+
+namespace {
+
+struct PackParams {
+  EklTap taps[EKL_MAX_VAR][EKL_MAX_TAPS];
+  const float* w;
+  bf16* out;
+  int nvar, ntaps, Cout, Cin, KK;
+};
+
+// non-transposed: one thread per output element, ci fastest (coalesced both sides)
+__global__ void pack_fwd_kernel(const __grid_constant__ PackParams p) {
+  const int64_t total = (int64_t)p.nvar * p.Cout * p.ntaps * p.Cin;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % p.Cin);
+    int64_t r = i / p.Cin;
+    const int t = (int)(r % p.ntaps); r /= p.ntaps;
+    const int co = (int)(r % p.Cout);
+    const int v = (int)(r / p.Cout);
+    const EklTap tap = p.taps[v][t];
+    float acc = 0.f;
+    for (int s = 0; s < tap.nsrc; ++s) acc += p.w[((int64_t)co * p.KK + tap.src[s]) * p.Cin + ci];
+    p.out[i] = __float2bfloat16(acc);
+  }
+}
+
+// transposed: block (32x8) moves a 32(co) x 32(ci) tile for one (v, t)
+__global__ void pack_dgrad_kernel(const __grid_constant__ PackParams p) {
+  __shared__ float tile[32][33];
+  const int v = blockIdx.z / p.ntaps, t = blockIdx.z % p.ntaps;
+  const EklTap tap = p.taps[v][t];
+  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int co = co0 + r, ci = ci0 + threadIdx.x;
+    float acc = 0.f;
+    if (co < p.Cout && ci < p.Cin)
+      for (int s = 0; s < tap.nsrc; ++s) acc += p.w[((int64_t)co * p.KK + tap.src[s]) * p.Cin + ci];
+    tile[r][threadIdx.x] = acc;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;
+    if (ci < p.Cin && co < p.Cout)
+      p.out[(((int64_t)v * p.Cin + ci) * p.ntaps + t) * p.Cout + co] = __float2bfloat16(tile[threadIdx.x][r]);
+  }
+}
+
+}  // namespace
+
+// g: forward or data-gradient plan of a conv with master filter [Cout][KH*KW][Cin]
+int ekl_pack_weights(const EklGather* g, const float* w_master, void* out, int Cout, int Cin, cudaStream_t st) {
+  PackParams p;
+  memcpy(p.taps, g->taps, sizeof(p.taps));
+  p.w = w_master; p.out = (bf16*)out; p.nvar = g->nvar; p.ntaps = g->ntaps; p.Cout = Cout; p.Cin = Cin;
+  p.KK = g->KH * g->KW;
+  if (!g->transposed) {
+    const int64_t total = (int64_t)p.nvar * Cout * p.ntaps * Cin;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    pack_fwd_kernel<<<blocks, 256, 0, st>>>(p);
+  } else {
+    dim3 grid(ekl_cdiv(Cin, 32), ekl_cdiv(Cout, 32), p.nvar * p.ntaps);
+    pack_dgrad_kernel<<<grid, dim3(32, 8), 0, st>>>(p);
+  }
+  EKL_LAUNCH_CHECK();
+  return 0;
+}

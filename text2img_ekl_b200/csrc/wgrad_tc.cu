@@ -1,0 +1,241 @@
+// tcgen05 weight-gradient kernel.
+//
+//   dW[co][src(v,t)][ci] += sum_{p in M grid} dY_v[p, co] * A_{map(v,t)}[p + (dh,dw), ci]
+//
+// GEMM view: D[(t,ci) 128 rows][co BNW cols] accumulated over PIXELS (the GEMM K dimension).  Both operands are
+// pixel-major in memory (NHWC), i.e. "MN-major" UMMA operands: a TMA box [64 pixels][CW channels] is a K x MN
+// tile whose 128/64/32-byte rows are exactly the canonical SWIZZLE_{128,64,32}B MN-major atoms
+// (cute/atom/mma_traits_sm100.hpp make_umma_desc<Major::MN>): SBO = 8 pixel rows, LBO = one box.
+// The 128 accumulator rows are 128/CW boxes = consecutive (tap, channel-block) pairs sharing one dY operand.
+// Split-K over pixel tiles across CTAs; epilogue = tcgen05.ld + red.global.add.f32 straight into the fp32
+// gradient buffer in master layout [Cout][KH*KW][Cin] (coalesced along ci).
+#include "conv_plan.h"
+#include "ekl_common.cuh"
+
+namespace {
+
+constexpr int KP = 64;   // pixels per pipeline stage
+
+struct WgParams {
+  CUtensorMap a_maps[4];
+  CUtensorMap y_maps[EKL_MAX_VAR];
+  EklTap taps[EKL_MAX_VAR][EKL_MAX_TAPS];
+  float* dw;
+  int ntaps, ncb, Cin, Cout, KK;
+  int tiles_per_var;       // M tiles per variant
+  int tb, th, tw, nTh, nTw, ptiles;   // pixel tiling
+  int rows_valid;          // tb*th*tw (<= KP)
+};
+
+template <int BNW, int CW>
+struct WgCfg {
+  static constexpr int BPT = 128 / CW;                 // A boxes per M tile
+  static constexpr int A_BOX = KP * CW * 2;
+  static constexpr int A_BYTES = 128 * KP * 2;
+  static constexpr int YW = BNW < 64 ? BNW : 64;       // channels per dY box
+  static constexpr int Y_BOX = KP * YW * 2;
+  static constexpr int B_BYTES = BNW * KP * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (96 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = BNW < 32 ? 32 : BNW;
+  static constexpr uint32_t A_LAYOUT = CW == 64 ? 2u : (CW == 32 ? 4u : 6u);
+  static constexpr uint32_t Y_LAYOUT = YW == 64 ? 2u : (YW == 32 ? 4u : 6u);
+};
+
+template <int BNW, int CW>
+__global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+  using C = WgCfg<BNW, CW>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tmem_full = empty + C::STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v = blockIdx.x / p.tiles_per_var;
+  const int mt = blockIdx.x - v * p.tiles_per_var;
+  const int n0 = blockIdx.y * BNW;
+  const int npairs = p.ntaps * p.ncb;                  // (tap, channel block) pairs of this variant
+  const int pair0 = mt * C::BPT;
+  const int nbox = (npairs - pair0) < C::BPT ? (npairs - pair0) : C::BPT;
+  // pixel tiles of this split
+  const int per = (p.ptiles + gridDim.z - 1) / gridDim.z;
+  const int pt0 = blockIdx.z * per;
+  const int pt1 = (pt0 + per) < p.ptiles ? (pt0 + per) : p.ptiles;
+  const int n_iters = pt1 - pt0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (n_iters > 0) {
+    if (warp == 0) {
+      if (elect_one()) {
+        const uint32_t tx = (uint32_t)(nbox * p.rows_valid * CW * 2 + (BNW / C::YW) * p.rows_valid * C::YW * 2);
+        for (int it = 0; it < n_iters; ++it) {
+          const int s = it % C::STAGES;
+          const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          int pt = pt0 + it;
+          const int twi = pt % p.nTw; pt /= p.nTw;
+          const int thi = pt % p.nTh; pt /= p.nTh;
+          const int w0 = twi * p.tw, h0 = thi * p.th, b0 = pt * p.tb;
+          uint8_t* sa = smem + s * C::STAGE_BYTES;
+          mbar_expect_tx(&full[s], tx);
+          for (int j = 0; j < nbox; ++j) {
+            const int pair = pair0 + j;
+            const int t = pair / p.ncb, cb = pair - t * p.ncb;
+            const EklTap tap = p.taps[v][t];
+            tma_load_4d(&p.a_maps[tap.map], &full[s], sa + j * C::A_BOX, cb * CW, w0 + tap.dw, h0 + tap.dh, b0);
+          }
+#pragma unroll
+          for (int j = 0; j < BNW / C::YW; ++j)
+            tma_load_4d(&p.y_maps[v], &full[s], sa + C::A_BYTES + j * C::Y_BOX, n0 + j * C::YW, w0, h0, b0);
+        }
+      }
+    } else if (warp == 1) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BNW, 1, 1);
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % C::STAGES;
+        const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+          const int ksteps = (p.rows_valid + 15) / 16;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t da = umma_desc(sa + k * 16 * CW * 2, C::A_BOX, 8 * CW * 2, C::A_LAYOUT);
+            const uint64_t db = umma_desc(sb + k * 16 * C::YW * 2, C::Y_BOX, 8 * C::YW * 2, C::Y_LAYOUT);
+            tc_mma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty[s]);
+          if (it == n_iters - 1) tc_commit(tmem_full);
+        }
+        __syncwarp();
+      }
+    } else {
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      const int j = row / CW;                       // box index -> (tap, channel block)
+      const bool valid = j < nbox;
+      const int pair = pair0 + (valid ? j : 0);
+      const int t = pair / p.ncb, cb = pair - t * p.ncb;
+      const EklTap tap = p.taps[v][t];
+      const int ci = cb * CW + (row % CW);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BNW; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int co = n0 + c0 + i;
+            const float val = __uint_as_float(r[i]);
+            for (int s = 0; s < tap.nsrc; ++s)
+              atomicAdd(p.dw + ((size_t)co * p.KK + tap.src[s]) * p.Cin + ci, val);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+int make_map(CUtensorMap* m, const EklView& v, int boxC, int tw, int th, int tb, int swz) {
+  uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)v.dW, (uint64_t)v.dH, (uint64_t)v.dB};
+  uint64_t strides[3] = {(uint64_t)v.sW * 2, (uint64_t)v.sH * 2, (uint64_t)v.sB * 2};
+  uint32_t box[4] = {(uint32_t)boxC, (uint32_t)tw, (uint32_t)th, (uint32_t)tb};
+  return ekl_make_tmap(m, v.base, 4, dims, strides, box, swz, 2);
+}
+
+template <int BNW, int CW>
+int launch_wg(const EklGather* g, WgParams& p, int splits, cudaStream_t st) {
+  using C = WgCfg<BNW, CW>;
+  auto kern = conv_wgrad_tc_kernel<BNW, CW>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EKL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  dim3 grid(p.tiles_per_var * g->nvar, g->N / BNW, splits);
+  kern<<<grid, 192, C::SMEM_BYTES, st>>>(p);
+  EKL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+int ekl_wgrad_tc_supported(const EklGather* g) {
+  auto pow2 = [](int x) { return x > 0 && (x & (x - 1)) == 0; };
+  if (g->transposed) return 0;
+  if (g->Cin % 16 != 0 || g->N % 32 != 0) return 0;
+  if (g->Cin < 64 && !pow2(g->Cin)) return 0;
+  if (g->Cin >= 64 && g->Cin % 64 != 0) return 0;
+  if (!pow2(g->mW) || !pow2(g->mH)) return 0;
+  for (int i = 0; i < g->n_a; ++i)
+    if (g->a[i].f32 || g->a[i].sC != 1) return 0;
+  for (int i = 0; i < g->nvar; ++i)
+    if (g->o[i].f32 || g->o[i].sC != 1) return 0;
+  return 1;
+}
+
+// fwd_plan: forward plan whose `o` views hold dY.  dw: master-layout fp32 gradient, ACCUMULATED into.
+int ekl_wgrad_tc(const EklGather* g, float* dw, cudaStream_t st) {
+  EKL_REQUIRE(ekl_wgrad_tc_supported(g), "wgrad_tc: unsupported shape Cin=%d Cout=%d", g->Cin, g->N);
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  memcpy(p.taps, g->taps, sizeof(p.taps));
+  p.dw = dw; p.ntaps = g->ntaps; p.Cin = g->Cin; p.Cout = g->N; p.KK = g->KH * g->KW;
+  const int CW = g->Cin >= 64 ? 64 : g->Cin;          // 64 / 32 / 16
+  p.ncb = g->Cin / CW;
+  const int BPT = 128 / CW;
+  p.tiles_per_var = ekl_cdiv(g->ntaps * p.ncb, BPT);
+  // pixel tiling: KP = tb*th*tw
+  int tw = g->mW < KP ? g->mW : KP;
+  int rest = KP / tw;
+  int th = g->mH < rest ? g->mH : rest;
+  int tb = rest / th;
+  p.tw = tw; p.th = th; p.tb = tb;
+  p.nTw = ekl_cdiv(g->mW, tw); p.nTh = ekl_cdiv(g->mH, th);
+  p.ptiles = p.nTw * p.nTh * ekl_cdiv(g->mB, tb);
+  p.rows_valid = tb * th * tw;
+  const int BNW = g->N % 256 == 0 ? 256 : (g->N % 128 == 0 ? 128 : (g->N % 64 == 0 ? 64 : 32));
+  const int YW = BNW < 64 ? BNW : 64;
+  const int a_swz = CW == 64 ? 3 : (CW == 32 ? 2 : 1);
+  const int y_swz = YW == 64 ? 3 : 2;
+  for (int i = 0; i < g->n_a; ++i) {
+    int rc = make_map(&p.a_maps[i], g->a[i], CW, tw, th, tb, a_swz);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < g->nvar; ++i) {
+    int rc = make_map(&p.y_maps[i], g->o[i], YW, tw, th, tb, y_swz);
+    if (rc) return rc;
+  }
+  // split-K so the grid covers the machine ~2x, keeping >= 4 pixel tiles per CTA
+  const int base_ctas = p.tiles_per_var * g->nvar * (g->N / BNW);
+  int splits = ekl_cdiv(296, base_ctas);
+  if (splits > p.ptiles / 4) splits = p.ptiles / 4;
+  if (splits < 1) splits = 1;
+#define EKL_WG_CASE(bn, cw) if (BNW == bn && CW == cw) return launch_wg<bn, cw>(g, p, splits, st);
+  EKL_WG_CASE(256, 64) EKL_WG_CASE(128, 64) EKL_WG_CASE(64, 64) EKL_WG_CASE(32, 64)
+  EKL_WG_CASE(256, 32) EKL_WG_CASE(128, 32) EKL_WG_CASE(64, 32) EKL_WG_CASE(32, 32)
+  EKL_WG_CASE(256, 16) EKL_WG_CASE(128, 16) EKL_WG_CASE(64, 16) EKL_WG_CASE(32, 16)
+#undef EKL_WG_CASE
+  return ekl_fail(-1, "wgrad_tc: no kernel for BNW=%d CW=%d", BNW, CW);
+}

@@ -1,0 +1,177 @@
+"""On-GPU numerical check of the conv kernel family through the C ABI; prints one line per case and keeps going
+after failures (each group runs in its own subprocess so a trapped kernel cannot poison the others).
+
+    python tools/kernel_check.py            # all groups
+    python tools/kernel_check.py --group tc_fwd
+"""
+import argparse
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+SHAPES = {  # mode -> list of (B, H, W, Cin, Cout)
+    0: [(4, 8, 8, 64, 128), (2, 16, 16, 128, 64), (3, 4, 4, 64, 256), (2, 32, 32, 32, 64), (2, 64, 64, 16, 32),
+        (8, 4, 4, 192, 512), (2, 8, 8, 320, 128)],
+    1: [(4, 4, 4, 128, 128), (2, 8, 8, 64, 64), (3, 16, 16, 64, 128), (2, 32, 32, 32, 32), (2, 4, 4, 256, 512)],
+    2: [(4, 16, 16, 64, 128), (2, 8, 8, 128, 256), (3, 32, 32, 64, 64), (2, 8, 8, 512, 1024), (2, 64, 64, 32, 64)],
+}
+GROUPS = ["tc_fwd", "tc_dgrad", "tc_wgrad", "simt_fwd", "simt_dgrad", "simt_wgrad", "bn"]
+
+
+def run_group(group):
+    import torch
+    import torch.nn.functional as F
+    from text2img_ekl_b200 import _lib as L
+    lib = L.lib()
+    L.check(lib.ekl_require_sm100())
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    nfail = 0
+
+    def rel(a, b):
+        return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-20))
+
+    if group == "bn":
+        return run_bn(torch, L, lib, dev, rel)
+    impl = L.IMPL_TC if group.startswith("tc") else L.IMPL_SIMT
+    what = group.split("_")[1]
+    for mode, shapes in SHAPES.items():
+        for (B, H, W, Cin, Cout) in shapes:
+            K = 4 if mode == 2 else 3
+            Ho, Wo = (2 * H, 2 * W) if mode == 1 else ((H // 2, W // 2) if mode == 2 else (H, W))
+            x = torch.randn(B, H, W, Cin, device=dev).bfloat16()
+            wm = (torch.randn(Cout, K, K, Cin, device=dev) / (K * K * Cin) ** 0.5).bfloat16().float()  # master, bf16-exact
+            conv = L.EklConv(mode, B, H, W, Cin, Cout, 0, impl, 0, 0, 0)
+            nf = lib.ekl_conv_packed_elems(conv, 0)
+            nd = lib.ekl_conv_packed_elems(conv, 1)
+            wf = torch.empty(nf, device=dev, dtype=torch.bfloat16)
+            wd = torch.empty(nd, device=dev, dtype=torch.bfloat16)
+            L.check(lib.ekl_conv_pack(conv, L.ptr(wm), L.ptr(wf), L.ptr(wd), L.stream()))
+            # torch reference (fp32, NCHW)
+            xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+            wr = wm.permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+            xin = F.interpolate(xr, scale_factor=2, mode="nearest") if mode == 1 else xr
+            yr = F.conv2d(xin, wr, stride=2 if mode == 2 else 1, padding=1)
+            dyn = torch.randn(B, Ho, Wo, Cout, device=dev).bfloat16()
+            yr.backward(dyn.float().permute(0, 3, 1, 2))
+            tag = "%-10s mode%d B%d %dx%d Cin%d Cout%d" % (group, mode, B, H, W, Cin, Cout)
+            try:
+                if what == "fwd":
+                    y = torch.full((B, Ho, Wo, Cout), float("nan"), device=dev, dtype=torch.bfloat16)
+                    stats = None
+                    if impl == L.IMPL_TC:
+                        rows = lib.ekl_conv_stats_rows(conv)
+                        stats = torch.full((rows, 2, Cout), float("nan"), device=dev)
+                    L.check(lib.ekl_conv_fwd(conv, L.ptr(x), L.ptr(wf), L.ptr(y), L.ptr(stats), L.stream()))
+                    torch.cuda.synchronize()
+                    e = rel(y.permute(0, 3, 1, 2), yr)
+                    msg = "rel %.2e" % e
+                    ok = e < 6e-3
+                    if stats is not None:
+                        s = stats.sum(0)
+                        yf = y.float().reshape(-1, Cout)
+                        e1, e2 = rel(s[0], yf.sum(0)), rel(s[1], (yf * yf).sum(0))
+                        msg += " stats %.1e %.1e" % (e1, e2)
+                        ok = ok and e2 < 1e-3 and (e1 < 1e-2 or float((s[0] - yf.sum(0)).abs().max()) < 0.5)
+                elif what == "dgrad":
+                    dx = torch.full((B, H, W, Cin), float("nan"), device=dev, dtype=torch.bfloat16)
+                    L.check(lib.ekl_conv_bwd_data(conv, L.ptr(dyn), L.ptr(wd), L.ptr(dx), L.stream()))
+                    torch.cuda.synchronize()
+                    e = rel(dx.permute(0, 3, 1, 2), xr.grad)
+                    msg, ok = "rel %.2e" % e, e < 6e-3
+                else:
+                    dw = torch.zeros(Cout, K, K, Cin, device=dev)
+                    L.check(lib.ekl_conv_bwd_weight(conv, L.ptr(x), L.ptr(dyn), L.ptr(dw), L.stream()))
+                    torch.cuda.synchronize()
+                    e = rel(dw.permute(0, 3, 1, 2), wr.grad)
+                    msg, ok = "rel %.2e" % e, e < 6e-3
+            except Exception as ex:  # noqa: BLE001
+                msg, ok = "EXC %s" % str(ex)[:200], False
+            print("%s %s %s" % ("PASS" if ok else "FAIL", tag, msg), flush=True)
+            nfail += 0 if ok else 1
+    return nfail
+
+
+def run_bn(torch, L, lib, dev, rel):
+    nfail = 0
+    for (M, Cy, groups, act) in [(3 * 512, 128, 3, L.ACT_GLU), (2048, 64, 1, L.ACT_LRELU), (96, 32768, 1, L.ACT_GLU),
+                                 (1536, 512, 3, L.ACT_LRELU), (4096, 64, 1, L.ACT_NONE), (640, 320, 1, L.ACT_GLU),
+                                 (64, 512, 1, L.ACT_RELU)]:
+        y = (torch.randn(M, Cy, device=dev) * 1.5 + 0.3).bfloat16()
+        gamma = 1 + 0.1 * torch.randn(Cy, device=dev)
+        beta = 0.1 * torch.randn(Cy, device=dev)
+        Co = Cy // 2 if act == L.ACT_GLU else Cy
+        res = torch.randn(M, Co, device=dev).bfloat16() if act == L.ACT_NONE else None
+        dout = torch.randn(M, Co, device=dev).bfloat16()
+        rows = lib.ekl_col_stats_rows(M, Cy, groups)
+        part = torch.empty(rows, 2, Cy, device=dev)
+        mean = torch.empty(groups, Cy, device=dev)
+        rstd = torch.empty(groups, Cy, device=dev)
+        rm, rv = torch.zeros(Cy, device=dev), torch.ones(Cy, device=dev)
+        out = torch.empty(M, Co, device=dev, dtype=torch.bfloat16)
+        L.check(lib.ekl_col_stats(L.ptr(y), M, Cy, groups, L.ptr(part), L.stream()))
+        L.check(lib.ekl_bn_finalize(L.ptr(part), rows // groups, Cy, groups, float(M // groups), 1e-5, 0.1, L.ptr(mean),
+                                    L.ptr(rstd), L.ptr(rm), L.ptr(rv), L.stream()))
+        L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, Cy, groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), act,
+                                   L.ptr(res), L.ptr(out), L.stream()))
+        prow = lib.ekl_bn_act_bwd_rows(M, Cy, groups, act)
+        part2 = torch.empty(prow, 2, Cy, device=dev)
+        sums = torch.empty(groups, 2, Cy, device=dev)
+        dg, db = torch.zeros(Cy, device=dev), torch.zeros(Cy, device=dev)
+        dy = torch.empty(M, Cy, device=dev, dtype=torch.bfloat16)
+        L.check(lib.ekl_bn_act_bwd(L.ptr(y), L.ptr(dout), M, Cy, groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta),
+                                   act, L.ptr(part2), L.ptr(sums), L.ptr(dg), L.ptr(db), L.ptr(dy), L.stream()))
+        torch.cuda.synchronize()
+        # reference
+        yr = y.float().requires_grad_(True)
+        g_, b_ = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        rm2, rv2 = torch.zeros(Cy, device=dev), torch.ones(Cy, device=dev)
+        outs = []
+        for g in range(groups):
+            sl = slice(g * M // groups, (g + 1) * M // groups)
+            z = torch.nn.functional.batch_norm(yr[sl], rm2, rv2, g_, b_, True, 0.1, 1e-5)
+            if act == L.ACT_GLU:
+                o = z[:, :Co] * torch.sigmoid(z[:, Co:])
+            elif act == L.ACT_LRELU:
+                o = torch.nn.functional.leaky_relu(z, 0.2)
+            elif act == L.ACT_RELU:
+                o = torch.relu(z)
+            else:
+                o = z + res[sl].float()
+            outs.append(o)
+        o = torch.cat(outs)
+        o.backward(dout.float())
+        errs = dict(out=rel(out, o), dy=rel(dy, yr.grad), dgamma=rel(dg, g_.grad), dbeta=rel(db, b_.grad),
+                    rmean=rel(rm, rm2), rvar=rel(rv, rv2))
+        ok = all(v < 1e-2 for v in errs.values())
+        print("%s bn M%d C%d g%d act%d %s" % ("PASS" if ok else "FAIL", M, Cy, groups, act,
+                                               " ".join("%s %.1e" % kv for kv in errs.items())), flush=True)
+        nfail += 0 if ok else 1
+    return nfail
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--group", default=None)
+    ap.add_argument("--child", action="store_true")
+    a = ap.parse_args()
+    if a.child:
+        sys.exit(1 if run_group(a.group) else 0)
+    bad = 0
+    for g in ([a.group] if a.group else GROUPS):
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "--group", g], timeout=300)
+            rc = r.returncode
+        except subprocess.TimeoutExpired:
+            rc = -9
+            print("TIMEOUT group %s" % g, flush=True)
+        print("== group %s exit %d" % (g, rc), flush=True)
+        bad += rc != 0
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
