@@ -10,7 +10,8 @@
  *  - plain C: device pointers + sizes, no torch types.  The library never allocates or frees caller tensors;
  *    scratch is passed in (sizes from the *_rows / *_elems queries).
  *  - activations: NHWC bf16 (row = pixel, channels contiguous).  Parameters / gradients / statistics: fp32.
- *    Conv filters: fp32 [Cout][KH][KW][Cin] == torch channels_last storage of the reference's [Cout,Cin,KH,KW].
+ *    Conv filters: fp32, either [Cout][KH][KW][Cin] (torch channels_last storage of the reference's
+ *    [Cout,Cin,KH,KW] parameters; coalesced for the kernels) or torch-default [Cout][Cin][KH][KW] (ekl_conv.w_layout).
  *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, and returns
  *    0 = ok, <0 = invalid argument, >0 = cudaError_t / 1000+CUresult.  ekl_last_error() = thread-local text.
  *  - no CPU fallback: ekl_require_sm100() fails on anything but compute capability 10.x.
@@ -40,6 +41,7 @@ int ekl_require_sm100(void);
 enum { EKL_S1 = 0, EKL_UP2 = 1, EKL_DOWN2 = 2 };
 enum { EKL_IMPL_TC = 0, EKL_IMPL_SIMT = 1 };              /* tcgen05 product path | SIMT small-channel / cross-check */
 enum { EKL_FMT_NHWC_BF16 = 0, EKL_FMT_NCHW_F32 = 1 };     /* NCHW fp32 = the loader's images (datasets.py:346) */
+enum { EKL_W_KRSC = 0, EKL_W_KCRS = 1 };                  /* KRSC = torch channels_last storage, KCRS = torch default */
 enum { EKL_ACT_NONE = 0, EKL_ACT_GLU = 1, EKL_ACT_LRELU = 2, EKL_ACT_RELU = 3, EKL_ACT_TANH = 4 };
 
 typedef struct ekl_conv {
@@ -50,6 +52,7 @@ typedef struct ekl_conv {
   int impl;          /* EKL_IMPL_TC | EKL_IMPL_SIMT */
   int x_fmt, y_fmt;  /* SIMT only: EKL_FMT_* of x and y */
   int act;           /* SIMT only: fused epilogue EKL_ACT_NONE | EKL_ACT_LRELU | EKL_ACT_TANH */
+  int w_layout;      /* master filter / gradient memory: EKL_W_KRSC [Cout][KH][KW][Cin] | EKL_W_KCRS [Cout][Cin][KH][KW] */
 } ekl_conv;
 
 /* bf16 elements of the packed forward (dgrad=0) / data-gradient (dgrad=1) filter operand */

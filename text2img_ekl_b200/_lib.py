@@ -13,11 +13,12 @@ S1, UP2, DOWN2 = 0, 1, 2
 IMPL_TC, IMPL_SIMT = 0, 1
 FMT_NHWC_BF16, FMT_NCHW_F32 = 0, 1
 ACT_NONE, ACT_GLU, ACT_LRELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3, 4
+W_KRSC, W_KCRS = 0, 1
 
 
 class EklConv(C.Structure):
     _fields_ = [("mode", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
-                ("group_b", C.c_int), ("impl", C.c_int), ("x_fmt", C.c_int), ("y_fmt", C.c_int), ("act", C.c_int)]
+                ("group_b", C.c_int), ("impl", C.c_int), ("x_fmt", C.c_int), ("y_fmt", C.c_int), ("act", C.c_int), ("w_layout", C.c_int)]
 
 
 class EklError(RuntimeError):

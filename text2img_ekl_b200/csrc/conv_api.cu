@@ -43,7 +43,9 @@ int plan(const ekl_conv* c, int dgrad, const void* x, const void* y, EklGather* 
   out_extent(c, &Ho, &Wo);
   EklView xv = make_view(x, c->B, c->H, c->W, c->Cin, c->x_fmt);
   EklView yv = make_view(y, c->B, Ho, Wo, c->Cout, c->y_fmt);
-  return ekl_build_gather(g, c->mode, dgrad, xv, yv, c->Cin, c->Cout);
+  int rc = ekl_build_gather(g, c->mode, dgrad, xv, yv, c->Cin, c->Cout);
+  g->w_kcrs = c->w_layout == EKL_W_KCRS;
+  return rc;
 }
 
 }  // namespace

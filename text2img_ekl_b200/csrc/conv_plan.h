@@ -33,7 +33,12 @@ struct EklGather {
   EklTap taps[EKL_MAX_VAR][EKL_MAX_TAPS];
   int transposed;             // packed weights are [.][Cin_master][t][Cout_master] (data-gradient) instead of [Cout][t][Cin]
   int KH, KW;                 // master filter taps
+  int w_kcrs;                 // master filter / gradient memory is [Cout][Cin][KH][KW] instead of [Cout][KH][KW][Cin]
 };
+
+// element offset of master-filter entry (co, tap, ci)
+#define EKL_WIDX(kcrs, co, tap, ci, KK, Cin) \
+  ((kcrs) ? (((int64_t)(co) * (Cin) + (ci)) * (KK) + (tap)) : (((int64_t)(co) * (KK) + (tap)) * (Cin) + (ci)))
 
 enum { EKL_CONV_S1 = 0, EKL_CONV_UP2 = 1, EKL_CONV_DOWN2 = 2 };
 

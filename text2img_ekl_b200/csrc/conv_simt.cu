@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(const __grid_const
       const float dy = load_elem(yv, b_, h_, w_, co);
       if (dy != 0.f) acc += dy * load_elem(av, b_, h_ + tap.dh, w_ + tap.dw, ci);
     }
-    for (int s = 0; s < tap.nsrc; ++s) atomicAdd(p.dw + ((int64_t)co * KK + tap.src[s]) * g.Cin + ci, acc);
+    for (int s = 0; s < tap.nsrc; ++s) atomicAdd(p.dw + EKL_WIDX(g.w_kcrs, co, tap.src[s], ci, KK, g.Cin), acc);
   }
 }
 

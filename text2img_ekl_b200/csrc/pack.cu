@@ -12,7 +12,7 @@ struct PackParams {
   EklTap taps[EKL_MAX_VAR][EKL_MAX_TAPS];
   const float* w;
   bf16* out;
-  int nvar, ntaps, Cout, Cin, KK;
+  int nvar, ntaps, Cout, Cin, KK, kcrs;
 };
 
 // non-transposed: one thread per output element, ci fastest (coalesced both sides)
@@ -26,7 +26,7 @@ __global__ void pack_fwd_kernel(const __grid_constant__ PackParams p) {
     const int v = (int)(r / p.Cout);
     const EklTap tap = p.taps[v][t];
     float acc = 0.f;
-    for (int s = 0; s < tap.nsrc; ++s) acc += p.w[((int64_t)co * p.KK + tap.src[s]) * p.Cin + ci];
+    for (int s = 0; s < tap.nsrc; ++s) acc += p.w[EKL_WIDX(p.kcrs, co, tap.src[s], ci, p.KK, p.Cin)];
     p.out[i] = __float2bfloat16(acc);
   }
 }
@@ -41,7 +41,7 @@ __global__ void pack_dgrad_kernel(const __grid_constant__ PackParams p) {
     const int co = co0 + r, ci = ci0 + threadIdx.x;
     float acc = 0.f;
     if (co < p.Cout && ci < p.Cin)
-      for (int s = 0; s < tap.nsrc; ++s) acc += p.w[((int64_t)co * p.KK + tap.src[s]) * p.Cin + ci];
+      for (int s = 0; s < tap.nsrc; ++s) acc += p.w[EKL_WIDX(p.kcrs, co, tap.src[s], ci, p.KK, p.Cin)];
     tile[r][threadIdx.x] = acc;
   }
   __syncthreads();
@@ -59,7 +59,7 @@ int ekl_pack_weights(const EklGather* g, const float* w_master, void* out, int C
   PackParams p;
   memcpy(p.taps, g->taps, sizeof(p.taps));
   p.w = w_master; p.out = (bf16*)out; p.nvar = g->nvar; p.ntaps = g->ntaps; p.Cout = Cout; p.Cin = Cin;
-  p.KK = g->KH * g->KW;
+  p.KK = g->KH * g->KW; p.kcrs = g->w_kcrs;
   if (!g->transposed) {
     const int64_t total = (int64_t)p.nvar * Cout * p.ntaps * Cin;
     int blocks = (int)((total + 255) / 256);

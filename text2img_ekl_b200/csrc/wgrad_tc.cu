@@ -21,7 +21,7 @@ struct WgParams {
   CUtensorMap y_maps[EKL_MAX_VAR];
   EklTap taps[EKL_MAX_VAR][EKL_MAX_TAPS];
   float* dw;
-  int ntaps, ncb, Cin, Cout, KK;
+  int ntaps, ncb, Cin, Cout, KK, kcrs;
   int tiles_per_var;       // M tiles per variant
   int tb, th, tw, nTh, nTw, ptiles;   // pixel tiling
   int rows_valid;          // tb*th*tw (<= KP)
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
             const int co = n0 + c0 + i;
             const float val = __uint_as_float(r[i]);
             for (int s = 0; s < tap.nsrc; ++s)
-              atomicAdd(p.dw + ((size_t)co * p.KK + tap.src[s]) * p.Cin + ci, val);
+              atomicAdd(p.dw + EKL_WIDX(p.kcrs, co, tap.src[s], ci, p.KK, p.Cin), val);
           }
         }
       }
@@ -185,8 +185,6 @@ int ekl_wgrad_tc_supported(const EklGather* g) {
   auto pow2 = [](int x) { return x > 0 && (x & (x - 1)) == 0; };
   if (g->transposed) return 0;
   if (g->Cin % 16 != 0 || g->N % 32 != 0) return 0;
-  if (g->Cin < 64 && !pow2(g->Cin)) return 0;
-  if (g->Cin >= 64 && g->Cin % 64 != 0) return 0;
   if (!pow2(g->mW) || !pow2(g->mH)) return 0;
   for (int i = 0; i < g->n_a; ++i)
     if (g->a[i].f32 || g->a[i].sC != 1) return 0;
@@ -201,8 +199,8 @@ int ekl_wgrad_tc(const EklGather* g, float* dw, cudaStream_t st) {
   WgParams p;
   memset(&p, 0, sizeof(p));
   memcpy(p.taps, g->taps, sizeof(p.taps));
-  p.dw = dw; p.ntaps = g->ntaps; p.Cin = g->Cin; p.Cout = g->N; p.KK = g->KH * g->KW;
-  const int CW = g->Cin >= 64 ? 64 : g->Cin;          // 64 / 32 / 16
+  p.dw = dw; p.ntaps = g->ntaps; p.Cin = g->Cin; p.Cout = g->N; p.KK = g->KH * g->KW; p.kcrs = g->w_kcrs;
+  const int CW = g->Cin % 64 == 0 ? 64 : (g->Cin % 32 == 0 ? 32 : 16);
   p.ncb = g->Cin / CW;
   const int BPT = 128 / CW;
   p.tiles_per_var = ekl_cdiv(g->ntaps * p.ncb, BPT);

@@ -1,0 +1,167 @@
+"""The G+D training step (hot loop of cub_trainer_splitz_cap_ca.py:547-608 / trainer.py:509-545), B200-native.
+
+What changes against the reference, with semantics preserved:
+  * the three discriminator forwards of a D update (real / wrong / fake, cub:418-420) run as ONE pass over the
+    stacked batch with per-group BatchNorm statistics (weights are read once instead of three times);
+  * gradients accumulate in place into one flat fp32 buffer per network (zeroed with a single memset; this is
+    also the NCCL all-reduce bucket when WORLD_SIZE > 1, replacing nn.DataParallel's reduce-to-GPU0);
+  * the discriminator weight gradients that `errGs.backward()` produces in the reference and the next
+    `netD.zero_grad()` throws away (cub:414,607) are not computed;
+  * label tensors (one-hot / multi-hot normalisation) are built on the device.
+RNG draws (noise, CA eps, VC seed) can be injected for parity tests; otherwise they are drawn on the device.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .miscc.config import cfg
+
+
+def KL_loss(mu, logvar):
+    """cub:54-58: -0.5 * mean(1 + logvar - mu^2 - exp(logvar))."""
+    return -0.5 * torch.mean(1 + logvar - mu.pow(2) - logvar.exp())
+
+
+def ce_loss(logq, p, average=True):
+    """cub:60-65: -sum(p * logq) / B."""
+    n = p.shape[0] if average else 1
+    return -torch.sum(p * logq) / n
+
+
+def compute_mean_covariance(img):
+    """cub:33-52: per-image channel mean [B,C,1,1] and channel covariance [B,C,C] (colour-consistency statistics)."""
+    b, c, h, w = img.shape
+    mu = img.mean(2, keepdim=True).mean(3, keepdim=True)
+    d = (img - mu).reshape(b, c, h * w)
+    return mu, torch.bmm(d, d.transpose(1, 2)) / (h * w)
+
+
+def onehot(cls_vec, n):
+    """cub:322-331 on the device: [B] int64 class index -> [B,n] float one-hot."""
+    out = torch.zeros(cls_vec.shape[0], n, device=cls_vec.device)
+    out.scatter_(1, cls_vec.view(-1, 1).long(), 1.0)
+    return out
+
+
+def _bce_const(p, target):
+    """nn.BCELoss() against a constant 0/1 label vector (cub:423-431); log clamped at -100 like torch."""
+    if target:
+        return -torch.clamp(torch.log(p), min=-100.0).mean()
+    return -torch.clamp(torch.log1p(-p), min=-100.0).mean()
+
+
+class FlatGrads:
+    """All gradients of a network as views into one flat fp32 buffer (same memory layout as each parameter)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        off = 0
+        for p in self.params:
+            g = self.flat[off:off + p.numel()]
+            if p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last) and not p.is_contiguous():
+                g = g.view(p.shape[0], p.shape[2], p.shape[3], p.shape[1]).permute(0, 3, 1, 2)
+            else:
+                g = g.view(p.shape)
+            p.grad = g
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+
+class StepEngine:
+    """kind 'catz_ca': COND_G_NET_CATZ_CA flavour (cub trainer); 'cond': COND_G_NET flavour (trainer.py)."""
+
+    def __init__(self, netG, netsD, optimizerG, optimizersD, kind, cond="txt+cls", allreduce=None):
+        self.netG, self.netsD = netG, netsD
+        self.optG, self.optsD = optimizerG, optimizersD
+        self.kind, self.cond = kind, cond
+        self.gradsG = FlatGrads(netG.parameters())
+        self.gradsD = [FlatGrads(d.parameters()) for d in netsD]
+        self.allreduce = allreduce           # callable(flat_tensor) or None
+        self.uncond = float(cfg.TRAIN.COEFF.UNCOND_LOSS)
+        self.kl_coeff = float(cfg.TRAIN.COEFF.KL)
+        self.cat_z = cfg.TRAIN.CAT_Z
+
+    # ---- (1) generate: cub:567-587 / trainer.py:524-528
+    def generate(self, noise, txt, cls_cond, eps=None, seed=None):
+        if self.kind == "catz_ca":
+            (self.hcodes, self.mu1, self.mu2, self.logvar1, self.logvar2, self.std1, self.std2) = \
+                self.netG(noise, txt, cls_cond, eps=eps, seed=seed)
+            if self.cat_z == "concat":
+                self.mu = torch.cat((self.mu1, self.mu2), 1)
+            elif self.cat_z == "product":
+                self.mu = self.mu1 * self.mu2
+            else:
+                self.mu = self.mu1 + self.mu2
+            self.kls = [(self.mu1, self.logvar1), (self.mu2, self.logvar2)]
+        else:
+            cond_info = torch.cat((txt, cls_cond), 1) if self.cond == "txt+cls" else txt
+            self.hcodes, self.mu, self.logvar, self.std = self.netG(noise, cond_info, seed=seed)
+            self.kls = [(self.mu, self.logvar)]
+        self.fake_imgs = self.netG.image(self.hcodes)
+        return self.fake_imgs
+
+    # ---- (2) one discriminator update: cub:404-461
+    def d_step(self, idx, real_imgs, wrong_imgs, real_cp, fake_cp):
+        netD, opt, grads = self.netsD[idx], self.optsD[idx], self.gradsD[idx]
+        B = real_imgs.shape[0]
+        grads.zero()
+        x = torch.cat((real_imgs, wrong_imgs, self.fake_imgs[idx].detach()), 0)
+        out = netD(x, self.mu.detach(), groups=3)
+        real, wrong, fake = [[o[i * B:(i + 1) * B] for o in out] for i in range(3)]
+        errD_match = _bce_const(real[0], 1) + _bce_const(wrong[0], 0) + _bce_const(fake[0], 0)
+        if len(out) > 1 and self.uncond > 0:
+            u = self.uncond
+            errD_uncond = u * _bce_const(real[1], 1) + u * _bce_const(wrong[1], 1) + u * _bce_const(fake[1], 0)
+            errD_cls = ce_loss(real[2], real_cp) + ce_loss(fake[2], fake_cp)
+            errD = errD_match + errD_uncond + errD_cls
+        else:
+            errD_uncond = errD_cls = torch.zeros((), device=x.device)
+            errD = _bce_const(real[0], 1) + 0.5 * (_bce_const(wrong[0], 0) + _bce_const(fake[0], 0))
+        errD.backward()
+        if self.allreduce is not None:
+            self.allreduce(grads.flat)
+        opt.step()
+        self.last_d_logits = (real, wrong, fake)
+        return errD, errD_match, errD_uncond, errD_cls
+
+    # ---- (3) generator loss through the UPDATED discriminators: cub:463-490
+    def g_loss(self, real_cp):
+        errGs_match = errGs_uncond = errGs_cls = 0
+        self.last_g_logits = []
+        for i, netD in enumerate(self.netsD):
+            outputs = netD(self.fake_imgs[i], self.mu)
+            errGs_match = errGs_match + _bce_const(outputs[0], 1)
+            if len(outputs) > 1 and self.uncond > 0:
+                errGs_uncond = errGs_uncond + self.uncond * _bce_const(outputs[1], 1)
+                errGs_cls = errGs_cls + ce_loss(outputs[2], real_cp)
+            self.last_g_logits.append(outputs)
+        kl = [KL_loss(m, lv) for m, lv in self.kls]
+        errG_total = errGs_match + errGs_uncond + errGs_cls + sum(kl) * self.kl_coeff
+        return (errG_total, errGs_match, errGs_uncond, errGs_cls) + tuple(kl)
+
+    def g_step(self, real_cp):
+        self.gradsG.zero()
+        for d in self.netsD:
+            d.requires_grad_(False)          # the reference computes and discards these
+        try:
+            res = self.g_loss(real_cp)
+            res[0].backward()
+        finally:
+            for d in self.netsD:
+                d.requires_grad_(True)
+        if self.allreduce is not None:
+            self.allreduce(self.gradsG.flat)
+        self.optG.step()
+        return res
+
+    # ---- whole step on device-resident inputs
+    def step(self, real_imgs, wrong_imgs, txt, cls_cond, real_cp, fake_cp, noise, eps=None, seed=None):
+        self.generate(noise, txt, cls_cond, eps, seed)
+        errDs = [self.d_step(i, real_imgs[i], wrong_imgs[i], real_cp, fake_cp) for i in range(len(self.netsD))]
+        errG = self.g_step(real_cp)
+        return errDs, errG

@@ -1,0 +1,240 @@
+"""torch.autograd glue over the C ABI (include/ekl_b200.h).
+
+Internal activation layout is NHWC bf16 ([B,H,W,C] contiguous).  Parameters stay fp32 in the reference's
+shapes; conv filters are stored channels_last so that their memory is the [Cout][KH][KW][Cin] master layout
+the kernels read and the weight-gradient kernel accumulates into (`.grad` is written in place, no autograd
+accumulation pass).  No op here has a non-CUDA fallback.
+"""
+import torch
+
+from . import _lib as L
+
+S1, UP2, DOWN2 = L.S1, L.UP2, L.DOWN2
+ACT_NONE, ACT_GLU, ACT_LRELU, ACT_RELU, ACT_TANH = L.ACT_NONE, L.ACT_GLU, L.ACT_LRELU, L.ACT_RELU, L.ACT_TANH
+BN_EPS, BN_MOM = 1e-5, 0.1          # nn.BatchNorm defaults (model.py:91)
+
+# counts launches of this library's kernels (bench.py reports it as gpu_launches)
+LAUNCHES = [0]
+
+
+def _count(n=1):
+    LAUNCHES[0] += n
+
+
+def _grad_buffer(p):
+    """fp32 gradient tensor of parameter p with p's memory layout, created zeroed on first use."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.preserve_format)
+    return p.grad
+
+
+class ConvSpec:
+    """One convolution layer's kernel-side state: packed bf16 filter operands, refreshed when the fp32 master
+    parameter changes (optimizer step / load_state_dict)."""
+
+    def __init__(self, mode, cin, cout, impl=L.IMPL_TC, x_fmt=0, y_fmt=0, act=ACT_NONE):
+        self.mode, self.cin, self.cout, self.impl = mode, cin, cout, impl
+        self.x_fmt, self.y_fmt, self.act = x_fmt, y_fmt, act
+        self._ver = None
+        self.w_layout = L.W_KCRS
+        self.w_fwd = self.w_dgrad = None
+
+    def conv(self, B, H, W, group_b=0):
+        return L.EklConv(self.mode, B, H, W, self.cin, self.cout, group_b, self.impl, self.x_fmt, self.y_fmt, self.act,
+                         self.w_layout)
+
+    def out_hw(self, H, W):
+        return (2 * H, 2 * W) if self.mode == UP2 else ((H // 2, W // 2) if self.mode == DOWN2 else (H, W))
+
+    def bind(self, weight):
+        """Detect the master filter's memory layout (channels_last storage is the fast, coalesced one)."""
+        if weight.is_contiguous(memory_format=torch.channels_last):
+            self.w_layout = L.W_KRSC
+        elif weight.is_contiguous():
+            self.w_layout = L.W_KCRS
+        else:
+            raise L.EklError("conv filter must be contiguous or channels_last")
+
+    def packed(self, weight):
+        key = (weight._version, weight.data_ptr())
+        if key != self._ver:
+            self.bind(weight)
+            lib = L.lib()
+            c = self.conv(1, 4, 4)
+            if self.w_fwd is None:
+                self.w_fwd = torch.empty(lib.ekl_conv_packed_elems(c, 0), device=weight.device, dtype=torch.bfloat16)
+                self.w_dgrad = torch.empty(lib.ekl_conv_packed_elems(c, 1), device=weight.device, dtype=torch.bfloat16)
+            L.check(lib.ekl_conv_pack(c, L.ptr(weight), L.ptr(self.w_fwd), L.ptr(self.w_dgrad), L.stream()))
+            _count(2)
+            self._ver = key
+        return self.w_fwd, self.w_dgrad
+
+
+class _Conv(torch.autograd.Function):
+    """y = conv(x) (+ per-tile BatchNorm partial statistics).  Backward: tcgen05 dgrad + wgrad."""
+
+    @staticmethod
+    def forward(ctx, x, weight, spec, group_b, want_stats, skip_wgrad):
+        lib = L.lib()
+        if spec.x_fmt == L.FMT_NCHW_F32:
+            B, _, H, W = x.shape
+            assert x.dtype == torch.float32 and x.is_contiguous()
+        else:
+            B, H, W, _ = x.shape
+            assert x.dtype == torch.bfloat16 and x.is_contiguous()
+        Ho, Wo = spec.out_hw(H, W)
+        w_fwd, _ = spec.packed(weight)
+        c = spec.conv(B, H, W, group_b)
+        if spec.y_fmt == L.FMT_NCHW_F32:
+            y = torch.empty(B, spec.cout, Ho, Wo, device=x.device, dtype=torch.float32)
+        else:
+            y = torch.empty(B, Ho, Wo, spec.cout, device=x.device, dtype=torch.bfloat16)
+        stats = None
+        if want_stats and spec.impl == L.IMPL_TC:
+            stats = torch.empty(lib.ekl_conv_stats_rows(c), 2, spec.cout, device=x.device, dtype=torch.float32)
+        L.check(lib.ekl_conv_fwd(c, L.ptr(x), L.ptr(w_fwd), L.ptr(y), L.ptr(stats), L.stream()))
+        _count()
+        ctx.save_for_backward(x, weight)
+        ctx.spec, ctx.c, ctx.skip_wgrad = spec, c, skip_wgrad
+        ctx.mark_non_differentiable(*([stats] if stats is not None else []))
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, _dstats):
+        lib = L.lib()
+        x, weight = ctx.saved_tensors
+        spec, c = ctx.spec, ctx.c
+        dy = dy.contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            _, w_dgrad = spec.packed(weight)
+            dx = torch.empty_like(x)
+            L.check(lib.ekl_conv_bwd_data(c, L.ptr(dy), L.ptr(w_dgrad), L.ptr(dx), L.stream()))
+            _count()
+        if weight.requires_grad and not ctx.skip_wgrad:
+            L.check(lib.ekl_conv_bwd_weight(c, L.ptr(x), L.ptr(dy), L.ptr(_grad_buffer(weight)), L.stream()))
+            _count()
+        return dx, None, None, None, None, None
+
+
+def conv(x, weight, spec, group_b=0, want_stats=False, skip_wgrad=False):
+    return _Conv.apply(x, weight, spec, group_b, want_stats, skip_wgrad)
+
+
+class _BnAct(torch.autograd.Function):
+    """Train-mode BatchNorm (per-group batch statistics) + GLU / LeakyReLU / ReLU / identity (+ residual)."""
+
+    @staticmethod
+    def forward(ctx, y, stats, gamma, beta, running_mean, running_var, groups, act, residual, skip_pgrad):
+        lib = L.lib()
+        C = y.shape[-1]
+        M = y.numel() // C
+        dev = y.device
+        if stats is None:
+            rows = lib.ekl_col_stats_rows(M, C, groups)
+            stats = torch.empty(rows, 2, C, device=dev, dtype=torch.float32)
+            L.check(lib.ekl_col_stats(L.ptr(y), M, C, groups, L.ptr(stats), L.stream()))
+            _count()
+        rows_per_group = stats.shape[0] // groups
+        mean = torch.empty(groups, C, device=dev, dtype=torch.float32)
+        rstd = torch.empty(groups, C, device=dev, dtype=torch.float32)
+        L.check(lib.ekl_bn_finalize(L.ptr(stats), rows_per_group, C, groups, float(M // groups), BN_EPS, BN_MOM,
+                                    L.ptr(mean), L.ptr(rstd), L.ptr(running_mean), L.ptr(running_var), L.stream()))
+        Co = C // 2 if act == ACT_GLU else C
+        out = torch.empty(*y.shape[:-1], Co, device=dev, dtype=torch.bfloat16)
+        L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, C, groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), act,
+                                   L.ptr(residual), L.ptr(out), L.stream()))
+        _count(2)
+        ctx.save_for_backward(y, mean, rstd, gamma, beta)
+        ctx.groups, ctx.act, ctx.has_res, ctx.skip_pgrad = groups, act, residual is not None, skip_pgrad
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = L.lib()
+        y, mean, rstd, gamma, beta = ctx.saved_tensors
+        C = y.shape[-1]
+        M = y.numel() // C
+        dout = dout.contiguous()
+        prow = lib.ekl_bn_act_bwd_rows(M, C, ctx.groups, ctx.act)
+        partial = torch.empty(prow, 2, C, device=y.device, dtype=torch.float32)
+        sums = torch.empty(ctx.groups, 2, C, device=y.device, dtype=torch.float32)
+        dy = torch.empty_like(y)
+        pg = gamma.requires_grad and not ctx.skip_pgrad
+        L.check(lib.ekl_bn_act_bwd(L.ptr(y), L.ptr(dout), M, C, ctx.groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma),
+                                   L.ptr(beta), ctx.act, L.ptr(partial), L.ptr(sums),
+                                   L.ptr(_grad_buffer(gamma)) if pg else None, L.ptr(_grad_buffer(beta)) if pg else None,
+                                   L.ptr(dy), L.stream()))
+        _count(3)
+        return dy, None, None, None, None, None, None, None, (dout if ctx.has_res else None), None
+
+
+def bn_act(y, stats, bn, groups, act, residual=None, skip_pgrad=False):
+    """bn: an nn.BatchNorm{1,2}d module holding weight/bias/running stats (state_dict-compatible)."""
+    if not bn.training:
+        # inference: normalise with the running statistics (no autograd; the evaluate() path)
+        lib = L.lib()
+        C = y.shape[-1]
+        M = y.numel() // C
+        mean = bn.running_mean.detach().view(1, C).contiguous()
+        rstd = torch.rsqrt(bn.running_var.detach() + bn.eps).view(1, C).contiguous()
+        Co = C // 2 if act == ACT_GLU else C
+        out = torch.empty(*y.shape[:-1], Co, device=y.device, dtype=torch.bfloat16)
+        L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, C, 1, L.ptr(mean), L.ptr(rstd), L.ptr(bn.weight), L.ptr(bn.bias), act,
+                                   L.ptr(residual), L.ptr(out), L.stream()))
+        _count()
+        return out
+    if bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(groups)
+    return _BnAct.apply(y, stats, bn.weight, bn.bias, bn.running_mean, bn.running_var, groups, act, residual, skip_pgrad)
+
+
+class _LReluFromOut(torch.autograd.Function):
+    """identity forward on an already-activated tensor; backward = LeakyReLU'(0.2) evaluated from the output."""
+
+    @staticmethod
+    def forward(ctx, out):
+        ctx.save_for_backward(out)
+        return out.view_as(out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (out,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        dx = torch.empty_like(out)
+        L.check(L.lib().ekl_lrelu_bwd(L.ptr(out), L.ptr(dout), L.ptr(dx), out.numel(), L.stream()))
+        _count()
+        return dx
+
+
+def lrelu_from_out(out):
+    return _LReluFromOut.apply(out)
+
+
+class _CatCode(torch.autograd.Function):
+    """cat(tile(c_code over HxW), x) along channels (model.py:411-414 / 956-959), NHWC bf16."""
+
+    @staticmethod
+    def forward(ctx, code, x):
+        B, H, W, Cx = x.shape
+        Cc = code.shape[1]
+        code = code.float().contiguous()
+        out = torch.empty(B, H, W, Cc + Cx, device=x.device, dtype=torch.bfloat16)
+        L.check(L.lib().ekl_cat_code(L.ptr(code), Cc, L.ptr(x), Cx, B, H * W, L.ptr(out), L.stream()))
+        _count()
+        ctx.dims = (B, H, W, Cc, Cx)
+        return out
+
+    @staticmethod
+    def backward(ctx, dcat):
+        B, H, W, Cc, Cx = ctx.dims
+        dcat = dcat.contiguous()
+        dcode = torch.zeros(B, Cc, device=dcat.device, dtype=torch.float32)
+        dx = torch.empty(B, H, W, Cx, device=dcat.device, dtype=torch.bfloat16)
+        L.check(L.lib().ekl_cat_code_bwd(L.ptr(dcat), Cc, Cx, B, H * W, L.ptr(dcode), L.ptr(dx), L.stream()))
+        _count()
+        return (dcode if ctx.needs_input_grad[0] else None), (dx if ctx.needs_input_grad[1] else None)
+
+
+def cat_code(code, x):
+    return _CatCode.apply(code, x)
