@@ -13,6 +13,7 @@ import torch.nn as nn
 import torch.optim as optim
 
 from . import model
+from . import ops
 from .engine import (KL_loss, StepEngine, ce_loss, compute_mean_covariance, onehot)  # noqa: F401  (reference names)
 from .miscc.config import cfg
 from .miscc.utils import mkdir_p
@@ -101,6 +102,10 @@ def define_optimizers(netG, netsD=()):
         kw.update(fused=True, capturable=True)
     optimizersD = [optim.Adam(d.parameters(), lr=cfg.TRAIN.DISCRIMINATOR_LR, **kw) for d in netsD]
     optimizerG = optim.Adam(netG.parameters(), lr=cfg.TRAIN.GENERATOR_LR, **kw)
+    for opt, net in [(optimizerG, netG)] + list(zip(optimizersD, netsD)):
+        params = list(net.parameters())
+        # fused Adam does not bump parameter version counters: tell the kernels their packed bf16 filters are stale
+        opt.register_step_post_hook(lambda o, a, k, params=params: ops.mark_dirty(params))
     return optimizerG, optimizersD
 
 

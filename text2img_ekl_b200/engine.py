@@ -165,3 +165,69 @@ class StepEngine:
         errDs = [self.d_step(i, real_imgs[i], wrong_imgs[i], real_cp, fake_cp) for i in range(len(self.netsD))]
         errG = self.g_step(real_cp)
         return errDs, errG
+
+
+class GraphedStep:
+    """The whole training step captured once into a CUDA graph (generate -> D updates -> G update, Adam and the
+    gradient all-reduce included) and replayed per batch: ~10^3 kernel launches per step become one graph launch.
+
+    step(data): copies the loader's host batch into static device buffers (async from pinned memory), replays, and
+    returns the static loss tensors (errDs [num_Ds,4], errG [4+]).  RNG (noise, CA eps, VC seed) is drawn on the
+    device inside the graph."""
+
+    def __init__(self, trainer, example_data, warmup=3):
+        self.tr = trainer
+        dev = trainer.device
+        imgs, wrong, emb, cls, _ = example_data
+        n = trainer.num_Ds
+        self.s_imgs = [torch.empty_like(imgs[i], device=dev) for i in range(n)]
+        self.s_wrong = [torch.empty_like(wrong[i], device=dev) for i in range(n)]
+        self.s_emb = torch.empty_like(emb, device=dev)
+        self.s_cls = torch.empty_like(cls, device=dev)
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.s_imgs + self.s_wrong + [self.s_emb, self.s_cls])
+        self.load(example_data)
+        B, dv = emb.shape[0], dev
+        self.eps = torch.zeros(B, cfg.GAN.EMBEDDING_DIM, device=dv)
+        self.seed = torch.zeros(B, cfg.GAN.MANIFD_DIM, device=dv)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = ops.LAUNCHES[0]
+        with torch.cuda.graph(self.graph):
+            self.out = self._body()
+        self.launches_per_step = ops.LAUNCHES[0] - n0
+        torch.cuda.synchronize()
+
+    def _body(self):
+        tr = self.tr
+        tr.real_imgs, tr.wrong_imgs, tr.txt_embedding = self.s_imgs, self.s_wrong, self.s_emb
+        tr.cls_label = (self.s_cls.long() - 1) if getattr(tr, "CLS_KIND", "index") == "index" else self.s_cls
+        tr.noise.normal_(0, 1)
+        self.eps.normal_(0, 1)
+        self.seed.normal_(0, 1)
+        tr.generate(self.eps, self.seed)
+        errDs = [tr.train_joint_Dnet(i, 1) for i in range(tr.num_Ds)]
+        errG = tr.engine.g_step(tr.real_cp)
+        return torch.stack([torch.stack([x.detach().float() for x in e]) for e in errDs]), \
+            torch.stack([x.detach().float() for x in errG])
+
+    def load(self, data):
+        imgs, wrong, emb, cls, _ = data
+        for i in range(self.tr.num_Ds):
+            self.s_imgs[i].copy_(imgs[i], non_blocking=True)
+            self.s_wrong[i].copy_(wrong[i], non_blocking=True)
+        self.s_emb.copy_(emb, non_blocking=True)
+        self.s_cls.copy_(cls, non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+    def step(self, data):
+        self.load(data)
+        return self.replay()

@@ -21,11 +21,52 @@ def _count(n=1):
     LAUNCHES[0] += n
 
 
+# bench.py's kernel_roofline(): when a list, every library call appends (family, algorithmic flops, algorithmic bytes,
+# start event, end event) recorded on the launching stream
+PROFILE = None
+
+
+class _prof:
+    def __init__(self, name, flops=0.0, nbytes=0.0):
+        self.a = (name, float(flops), float(nbytes))
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append(self.a + (self.e0, e1))
+        return False
+
+
+def _conv_flops(spec, B, H, W):
+    Ho, Wo = spec.out_hw(H, W)
+    k = 16 if spec.mode == DOWN2 else 9
+    return 2.0 * B * Ho * Wo * spec.cout * spec.cin * k       # reference dense-conv count (upsampled grid for UP2)
+
+
 def _grad_buffer(p):
     """fp32 gradient tensor of parameter p with p's memory layout, created zeroed on first use."""
     if p.grad is None:
         p.grad = torch.zeros_like(p, memory_format=torch.preserve_format)
     return p.grad
+
+
+# id(parameter) -> ConvSpecs packed from it.  Fused optimisers update parameters WITHOUT bumping their autograd
+# version counter, so optimiser steps must invalidate the packed operands explicitly (mark_dirty; installed as an
+# optimizer post-step hook by define_optimizers).
+_SPECS_OF = {}
+
+
+def mark_dirty(params):
+    for p in params:
+        for spec in _SPECS_OF.get(id(p), ()):
+            spec._ver = None
 
 
 class ConvSpec:
@@ -59,12 +100,16 @@ class ConvSpec:
         key = (weight._version, weight.data_ptr())
         if key != self._ver:
             self.bind(weight)
+            lst = _SPECS_OF.setdefault(id(weight), [])
+            if self not in lst:
+                lst.append(self)
             lib = L.lib()
             c = self.conv(1, 4, 4)
             if self.w_fwd is None:
                 self.w_fwd = torch.empty(lib.ekl_conv_packed_elems(c, 0), device=weight.device, dtype=torch.bfloat16)
                 self.w_dgrad = torch.empty(lib.ekl_conv_packed_elems(c, 1), device=weight.device, dtype=torch.bfloat16)
-            L.check(lib.ekl_conv_pack(c, L.ptr(weight), L.ptr(self.w_fwd), L.ptr(self.w_dgrad), L.stream()))
+            with _prof("pack_weights", 0, weight.numel() * 4 + (self.w_fwd.numel() + self.w_dgrad.numel()) * 2):
+                L.check(lib.ekl_conv_pack(c, L.ptr(weight), L.ptr(self.w_fwd), L.ptr(self.w_dgrad), L.stream()))
             _count(2)
             self._ver = key
         return self.w_fwd, self.w_dgrad
@@ -92,8 +137,11 @@ class _Conv(torch.autograd.Function):
         stats = None
         if want_stats and spec.impl == L.IMPL_TC:
             stats = torch.empty(lib.ekl_conv_stats_rows(c), 2, spec.cout, device=x.device, dtype=torch.float32)
-        L.check(lib.ekl_conv_fwd(c, L.ptr(x), L.ptr(w_fwd), L.ptr(y), L.ptr(stats), L.stream()))
+        fam = "conv_tc" if spec.impl == L.IMPL_TC else "conv_simt"
+        with _prof(fam + "_fwd", _conv_flops(spec, B, H, W), x.numel() * x.element_size() + y.numel() * y.element_size()):
+            L.check(lib.ekl_conv_fwd(c, L.ptr(x), L.ptr(w_fwd), L.ptr(y), L.ptr(stats), L.stream()))
         _count()
+        ctx.dims = (B, H, W)
         ctx.save_for_backward(x, weight)
         ctx.spec, ctx.c, ctx.skip_wgrad = spec, c, skip_wgrad
         ctx.mark_non_differentiable(*([stats] if stats is not None else []))
@@ -104,15 +152,18 @@ class _Conv(torch.autograd.Function):
         lib = L.lib()
         x, weight = ctx.saved_tensors
         spec, c = ctx.spec, ctx.c
+        fam = "conv_tc" if spec.impl == L.IMPL_TC else "conv_simt"
         dy = dy.contiguous()
         dx = None
         if ctx.needs_input_grad[0]:
             _, w_dgrad = spec.packed(weight)
             dx = torch.empty_like(x)
-            L.check(lib.ekl_conv_bwd_data(c, L.ptr(dy), L.ptr(w_dgrad), L.ptr(dx), L.stream()))
+            with _prof(fam + "_dgrad", _conv_flops(spec, *ctx.dims), dx.numel() * dx.element_size() + dy.numel() * dy.element_size()):
+                L.check(lib.ekl_conv_bwd_data(c, L.ptr(dy), L.ptr(w_dgrad), L.ptr(dx), L.stream()))
             _count()
         if weight.requires_grad and not ctx.skip_wgrad:
-            L.check(lib.ekl_conv_bwd_weight(c, L.ptr(x), L.ptr(dy), L.ptr(_grad_buffer(weight)), L.stream()))
+            with _prof(fam + "_wgrad", _conv_flops(spec, *ctx.dims), x.numel() * x.element_size() + dy.numel() * dy.element_size()):
+                L.check(lib.ekl_conv_bwd_weight(c, L.ptr(x), L.ptr(dy), L.ptr(_grad_buffer(weight)), L.stream()))
             _count()
         return dx, None, None, None, None, None
 
@@ -133,17 +184,20 @@ class _BnAct(torch.autograd.Function):
         if stats is None:
             rows = lib.ekl_col_stats_rows(M, C, groups)
             stats = torch.empty(rows, 2, C, device=dev, dtype=torch.float32)
-            L.check(lib.ekl_col_stats(L.ptr(y), M, C, groups, L.ptr(stats), L.stream()))
+            with _prof("bn_col_stats", 0, M * C * 2):
+                L.check(lib.ekl_col_stats(L.ptr(y), M, C, groups, L.ptr(stats), L.stream()))
             _count()
         rows_per_group = stats.shape[0] // groups
         mean = torch.empty(groups, C, device=dev, dtype=torch.float32)
         rstd = torch.empty(groups, C, device=dev, dtype=torch.float32)
-        L.check(lib.ekl_bn_finalize(L.ptr(stats), rows_per_group, C, groups, float(M // groups), BN_EPS, BN_MOM,
-                                    L.ptr(mean), L.ptr(rstd), L.ptr(running_mean), L.ptr(running_var), L.stream()))
+        with _prof("bn_finalize", 0, stats.numel() * 4):
+            L.check(lib.ekl_bn_finalize(L.ptr(stats), rows_per_group, C, groups, float(M // groups), BN_EPS, BN_MOM,
+                                        L.ptr(mean), L.ptr(rstd), L.ptr(running_mean), L.ptr(running_var), L.stream()))
         Co = C // 2 if act == ACT_GLU else C
         out = torch.empty(*y.shape[:-1], Co, device=dev, dtype=torch.bfloat16)
-        L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, C, groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), act,
-                                   L.ptr(residual), L.ptr(out), L.stream()))
+        with _prof("bn_act_fwd", 0, M * (C + Co + (Co if residual is not None else 0)) * 2):
+            L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, C, groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), act,
+                                       L.ptr(residual), L.ptr(out), L.stream()))
         _count(2)
         ctx.save_for_backward(y, mean, rstd, gamma, beta)
         ctx.groups, ctx.act, ctx.has_res, ctx.skip_pgrad = groups, act, residual is not None, skip_pgrad
@@ -161,10 +215,12 @@ class _BnAct(torch.autograd.Function):
         sums = torch.empty(ctx.groups, 2, C, device=y.device, dtype=torch.float32)
         dy = torch.empty_like(y)
         pg = gamma.requires_grad and not ctx.skip_pgrad
-        L.check(lib.ekl_bn_act_bwd(L.ptr(y), L.ptr(dout), M, C, ctx.groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma),
-                                   L.ptr(beta), ctx.act, L.ptr(partial), L.ptr(sums),
-                                   L.ptr(_grad_buffer(gamma)) if pg else None, L.ptr(_grad_buffer(beta)) if pg else None,
-                                   L.ptr(dy), L.stream()))
+        Co = C // 2 if ctx.act == ACT_GLU else C
+        with _prof("bn_act_bwd", 0, M * (2 * C + 2 * Co + C) * 2):     # two passes over y and dout, one write of dy
+            L.check(lib.ekl_bn_act_bwd(L.ptr(y), L.ptr(dout), M, C, ctx.groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma),
+                                       L.ptr(beta), ctx.act, L.ptr(partial), L.ptr(sums),
+                                       L.ptr(_grad_buffer(gamma)) if pg else None, L.ptr(_grad_buffer(beta)) if pg else None,
+                                       L.ptr(dy), L.stream()))
         _count(3)
         return dy, None, None, None, None, None, None, None, (dout if ctx.has_res else None), None
 
