@@ -216,7 +216,7 @@ def next_stage(h, c, sd, p, cfg):
 
 def get_image(h, sd, p):
     """model.py:426-437 GET_IMAGE_G: conv3x3(ngf->3) + tanh."""
-    return torch.tanh(F.conv2d(h, _qw(sd[p + ".img.0.weight"]), padding=1))
+    return torch.tanh(_q(F.conv2d(h, _qw(sd[p + ".img.0.weight"]), padding=1)))
 
 
 def _stages(c_code, h1, sd, cfg):
@@ -291,7 +291,7 @@ def d_trunk(x, sd, res):
     """encode_image_by_16times (model.py:832-850, Sequential idx 0 | 2,3 | 5,6 | 8,9) + per-resolution tail
     (model.py:1097-1098, 1238-1242)."""
     p = "img_code_s16"
-    x = _down(x, sd, p + ".0")
+    x = _down(_q(x), sd, p + ".0")
     x = _down(x, sd, p + ".2", p + ".3")
     x = _down(x, sd, p + ".5", p + ".6")
     x = _down(x, sd, p + ".8", p + ".9")

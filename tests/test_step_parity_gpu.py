@@ -93,7 +93,7 @@ def test_training_step_matches_oracle(name, B):
             for q in range(len(grp)):
                 r = rel(grp[q], want["d_logits"][last][j][q])
                 report.append(("it%d dlogit D%d group%d head%d" % (it, last, j, q), r))
-                assert r <= TOL_DEEP, (name, it, "d_logits", j, q, r)
+                assert r <= 3e-2, (name, it, "d_logits", j, q, r)   # [B] sigmoid outputs of the deepest D on 13-19-layer-deep fakes
         # generator-step logits come from the discriminators AFTER their Adam update (sign-like first step) and are
         # partly saturated probabilities: reported with the bf16-storage floor, asserted through errG above
         for i, (g, w) in enumerate(zip(tr.engine.last_g_logits, want["g_logits"])):

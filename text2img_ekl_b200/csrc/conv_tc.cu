@@ -120,6 +120,18 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     uint8_t* stage = smem;             // pipeline smem is idle now (all TMA loads consumed, all MMAs retired)
+    if constexpr (BN == 16) {
+      // one box of [128][16] bf16, 32-byte rows, no swizzle (a warp's 32 rows are 1 KB contiguous: conflict-free)
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16), r);
+      tmem_ld_wait();
+      uint32_t pk[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+      uint8_t* box = stage + row * 32;
+      *reinterpret_cast<uint4*>(box) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(box + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    } else {
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
@@ -147,6 +159,7 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
         }
       }
     }
+    }
     tc_fence_before();
     fence_proxy_async_smem();
     asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -168,7 +181,8 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
         for (int rr = 0; rr < p.rows_valid; ++rr) {
           const uint8_t* ptr;
           if constexpr (BN >= 64) ptr = base + rr * 128 + ((chunk ^ (rr & 7)) << 4) + sub;
-          else ptr = base + rr * 64 + ((chunk ^ ((rr >> 1) & 3)) << 4) + sub;
+          else if constexpr (BN == 32) ptr = base + rr * 64 + ((chunk ^ ((rr >> 1) & 3)) << 4) + sub;
+          else ptr = base + rr * 32 + (chunk << 4) + sub;
           const float x = __bfloat162float(*reinterpret_cast<const bf16*>(ptr));
           s1 += x; s2 += x * x;
         }
@@ -224,7 +238,7 @@ void ekl_tc_geometry(const EklGather* g, int group_b, int* tb, int* th, int* tw)
 
 int ekl_tc_supported(const EklGather* g) {
   auto pow2 = [](int x) { return x > 0 && (x & (x - 1)) == 0; };
-  if (g->Cin % 16 != 0 || g->N % 32 != 0) return 0;
+  if (g->Cin % 16 != 0 || g->N % 16 != 0) return 0;
   if (!pow2(g->mW) || !pow2(g->mH)) return 0;
   for (int i = 0; i < g->n_a; ++i)
     if (g->a[i].f32 || g->a[i].sC != 1) return 0;
@@ -252,7 +266,7 @@ int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, i
   const int KC = g->Cin % 64 == 0 ? 64 : (g->Cin % 32 == 0 ? 32 : 16);
   p.ncb = g->Cin / KC;
   const int swz = KC == 64 ? 3 : (KC == 32 ? 2 : 1);
-  int BN = g->N % 256 == 0 ? 256 : (g->N % 128 == 0 ? 128 : (g->N % 64 == 0 ? 64 : 32));
+  int BN = g->N % 256 == 0 ? 256 : (g->N % 128 == 0 ? 128 : (g->N % 64 == 0 ? 64 : (g->N % 32 == 0 ? 32 : 16)));
   // prefer more CTAs when the grid would not fill the machine
   while (BN > 64 && (int64_t)mtiles * (g->N / BN) * g->nvar < 148) BN /= 2;
   for (int i = 0; i < g->n_a; ++i) {
@@ -261,7 +275,7 @@ int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, i
   }
   const int obox = BN < 64 ? BN : 64;
   for (int i = 0; i < g->nvar; ++i) {
-    int rc = make_view_map(&p.o_maps[i], g->o[i], obox, tw, th, tb, BN < 64 ? 2 : 3);
+    int rc = make_view_map(&p.o_maps[i], g->o[i], obox, tw, th, tb, BN >= 64 ? 3 : (BN == 32 ? 2 : 0));
     if (rc) return rc;
   }
   {
@@ -272,9 +286,9 @@ int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, i
     if (rc) return rc;
   }
 #define EKL_TC_CASE(bn, kc) if (BN == bn && KC == kc) return launch_tc<bn, kc>(g, p, mtiles, st);
-  EKL_TC_CASE(256, 64) EKL_TC_CASE(128, 64) EKL_TC_CASE(64, 64) EKL_TC_CASE(32, 64)
-  EKL_TC_CASE(256, 32) EKL_TC_CASE(128, 32) EKL_TC_CASE(64, 32) EKL_TC_CASE(32, 32)
-  EKL_TC_CASE(256, 16) EKL_TC_CASE(128, 16) EKL_TC_CASE(64, 16) EKL_TC_CASE(32, 16)
+  EKL_TC_CASE(256, 64) EKL_TC_CASE(128, 64) EKL_TC_CASE(64, 64) EKL_TC_CASE(32, 64) EKL_TC_CASE(16, 64)
+  EKL_TC_CASE(256, 32) EKL_TC_CASE(128, 32) EKL_TC_CASE(64, 32) EKL_TC_CASE(32, 32) EKL_TC_CASE(16, 32)
+  EKL_TC_CASE(256, 16) EKL_TC_CASE(128, 16) EKL_TC_CASE(64, 16) EKL_TC_CASE(32, 16) EKL_TC_CASE(16, 16)
 #undef EKL_TC_CASE
   return ekl_fail(-1, "gather_gemm_tc: no kernel for BN=%d KC=%d", BN, KC);
 }

@@ -325,18 +325,28 @@ class _TanhFromOut(torch.autograd.Function):
 
 
 class GET_IMAGE_G(nn.Module):
-    """model.py:426-437: conv3x3(ngf -> 3) + tanh.  Cout = 3 is HBM-bound: one SIMT kernel reads the NHWC bf16
-    h_code once and writes the NCHW fp32 image with tanh fused."""
+    """model.py:426-437: conv3x3(ngf -> 3) + tanh.  Runs on the tcgen05 conv kernels with the 3 output channels
+    zero-padded to one 32-wide tile (the layer is HBM-bound: it reads h_code once); tanh is applied to the 3 real
+    channels while converting to the reference's NCHW fp32 image."""
+    PAD = 32
 
     def __init__(self, ngf):
         super().__init__()
         self.gf_dim = ngf
         self.img = nn.Sequential(conv3x3(ngf, 3), nn.Tanh())
-        self._spec = ops.ConvSpec(ops.S1, ngf, 3, impl=L.IMPL_SIMT, y_fmt=L.FMT_NCHW_F32, act=ops.ACT_TANH)
+        if ngf % 16 == 0:
+            self._spec = ops.ConvSpec(ops.S1, ngf, self.PAD, impl=L.IMPL_TC)
+        else:
+            self._spec = ops.ConvSpec(ops.S1, ngf, 3, impl=L.IMPL_SIMT, y_fmt=L.FMT_NCHW_F32, act=ops.ACT_TANH)
 
     def forward(self, h_code):
-        y, _ = ops.conv(to_nhwc(h_code), self.img[0].weight, self._spec)
-        return _TanhFromOut.apply(y)
+        w = self.img[0].weight
+        if self._spec.impl == L.IMPL_SIMT:
+            y, _ = ops.conv(to_nhwc(h_code), w, self._spec)
+            return _TanhFromOut.apply(y)
+        w_pad = F.pad(w, (0, 0, 0, 0, 0, 0, 0, self.PAD - 3))
+        y, _ = ops.conv(to_nhwc(h_code), w_pad, self._spec)                   # [B,H,W,32] bf16
+        return torch.tanh(y[..., :3].permute(0, 3, 1, 2).float())
 
 
 def get_shareGs(gf_dim):            # model.py:439-451
@@ -510,7 +520,8 @@ def downBlock(in_planes, out_planes):
 
 class _Encode16(nn.Sequential):
     """model.py:832-850 encode_image_by_16times; children keep indices 0..10.  The first conv (Cin = 3) is HBM-bound:
-    one SIMT kernel reads the NCHW fp32 image and writes NHWC bf16 with LeakyReLU fused."""
+    the NCHW fp32 image is converted once to NHWC bf16 with channels zero-padded to 16 and runs on the tcgen05
+    kernels like every other layer (widths that are not multiples of 32 fall back to the SIMT conv)."""
 
     def __init__(self, ndf):
         super().__init__(
@@ -518,14 +529,25 @@ class _Encode16(nn.Sequential):
             nn.Conv2d(ndf, ndf * 2, 4, 2, 1, bias=False), nn.BatchNorm2d(ndf * 2), nn.LeakyReLU(0.2, inplace=True),
             nn.Conv2d(ndf * 2, ndf * 4, 4, 2, 1, bias=False), nn.BatchNorm2d(ndf * 4), nn.LeakyReLU(0.2, inplace=True),
             nn.Conv2d(ndf * 4, ndf * 8, 4, 2, 1, bias=False), nn.BatchNorm2d(ndf * 8), nn.LeakyReLU(0.2, inplace=True))
-        self._s0 = ops.ConvSpec(ops.DOWN2, 3, ndf, impl=L.IMPL_SIMT, x_fmt=L.FMT_NCHW_F32, act=ops.ACT_LRELU)
+        self._tc0 = ndf % 32 == 0
+        if self._tc0:      # Cin 3 zero-padded to one 16-channel K block of the tcgen05 kernel
+            self._s0 = ops.ConvSpec(ops.DOWN2, 16, ndf, impl=L.IMPL_TC)
+        else:
+            self._s0 = ops.ConvSpec(ops.DOWN2, 3, ndf, impl=L.IMPL_SIMT, x_fmt=L.FMT_NCHW_F32, act=ops.ACT_LRELU)
         self._s = [_spec(ops.DOWN2, ndf, ndf * 2), _spec(ops.DOWN2, ndf * 2, ndf * 4), _spec(ops.DOWN2, ndf * 4, ndf * 8)]
 
     def forward(self, x, groups=1):
-        if x.dtype != torch.float32 or not x.is_contiguous():
-            x = x.float().contiguous()
-        y, _ = ops.conv(x, self[0].weight, self._s0)
-        h = ops.lrelu_from_out(y)
+        if self._tc0:
+            # NCHW fp32 image -> NHWC bf16 with channels padded 3 -> 16 (one fused cast/copy), filter padded alike
+            xp = F.pad(x.permute(0, 2, 3, 1), (0, 13)).to(torch.bfloat16).contiguous()
+            wp = F.pad(self[0].weight, (0, 0, 0, 0, 0, 13))
+            y, _ = ops.conv(xp, wp, self._s0)
+            h = F.leaky_relu(y, 0.2)
+        else:
+            if x.dtype != torch.float32 or not x.is_contiguous():
+                x = x.float().contiguous()
+            y, _ = ops.conv(x, self[0].weight, self._s0)
+            h = ops.lrelu_from_out(y)
         for i, (ci, bi) in enumerate(((2, 3), (5, 6), (8, 9))):
             h = _conv_bn_act(h, self[ci], self[bi], self._s[i], ops.ACT_LRELU, groups)
         return to_public(h)

@@ -98,7 +98,7 @@ class ConvSpec:
 
     def packed(self, weight):
         key = (weight._version, weight.data_ptr())
-        if key != self._ver:
+        if key != self._ver or not weight.is_leaf:      # derived (e.g. zero-padded) filters are rebuilt every step
             self.bind(weight)
             lst = _SPECS_OF.setdefault(id(weight), [])
             if self not in lst:
@@ -143,7 +143,7 @@ class _Conv(torch.autograd.Function):
         _count()
         ctx.dims = (B, H, W)
         ctx.save_for_backward(x, weight)
-        ctx.spec, ctx.c, ctx.skip_wgrad = spec, c, skip_wgrad
+        ctx.spec, ctx.c, ctx.skip_wgrad, ctx.w_leaf = spec, c, skip_wgrad, weight.is_leaf
         ctx.mark_non_differentiable(*([stats] if stats is not None else []))
         return y, stats
 
@@ -161,11 +161,16 @@ class _Conv(torch.autograd.Function):
             with _prof(fam + "_dgrad", _conv_flops(spec, *ctx.dims), dx.numel() * dx.element_size() + dy.numel() * dy.element_size()):
                 L.check(lib.ekl_conv_bwd_data(c, L.ptr(dy), L.ptr(w_dgrad), L.ptr(dx), L.stream()))
             _count()
-        if weight.requires_grad and not ctx.skip_wgrad:
+        dw = None
+        if ctx.needs_input_grad[1] and not ctx.skip_wgrad:
+            if ctx.w_leaf:
+                buf = _grad_buffer(weight)          # parameters: accumulate in place, autograd sees no gradient
+            else:
+                buf = dw = torch.zeros_like(weight, memory_format=torch.preserve_format)
             with _prof(fam + "_wgrad", _conv_flops(spec, *ctx.dims), x.numel() * x.element_size() + dy.numel() * dy.element_size()):
-                L.check(lib.ekl_conv_bwd_weight(c, L.ptr(x), L.ptr(dy), L.ptr(_grad_buffer(weight)), L.stream()))
+                L.check(lib.ekl_conv_bwd_weight(c, L.ptr(x), L.ptr(dy), L.ptr(buf), L.stream()))
             _count()
-        return dx, None, None, None, None, None
+        return dx, dw, None, None, None, None
 
 
 def conv(x, weight, spec, group_b=0, want_stats=False, skip_wgrad=False):
