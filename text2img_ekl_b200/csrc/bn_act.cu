@@ -133,28 +133,44 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const bf16* __restrict_
       sc2[i] = s_; sh2[i] = beta[c] - mean[t.g * Cy + c] * s_;
     }
   }
-  for (int64_t r = t.r0 + t.rt; r < t.r1; r += t.RT) {
-    float a[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(y + r * Cy + c0), a);
-    if (ACT == ACT_GLU) {
-      float b[8];
-      unpack8(*reinterpret_cast<const uint4*>(y + r * Cy + Co + c0), b);
+  constexpr int U = 4;                      // rows in flight per thread (memory-level parallelism)
+  for (int64_t rb = t.r0 + t.rt; rb < t.r1; rb += (int64_t)U * t.RT) {
+    uint4 ua[U], ub[U], uq[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = (a[i] * sc[i] + sh[i]) * sigmoidf_(b[i] * sc2[i] + sh2[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float z = a[i] * sc[i] + sh[i];
-        o[i] = ACT == ACT_LRELU ? (z > 0.f ? z : 0.2f * z) : (ACT == ACT_RELU ? fmaxf(z, 0.f) : z);
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = rb + (int64_t)u * t.RT;
+      if (r < t.r1) {
+        ua[u] = *reinterpret_cast<const uint4*>(y + r * Cy + c0);
+        if (ACT == ACT_GLU) ub[u] = *reinterpret_cast<const uint4*>(y + r * Cy + Co + c0);
+        if (residual != nullptr) uq[u] = *reinterpret_cast<const uint4*>(residual + r * Co + c0);
       }
     }
-    if (residual != nullptr) {
-      float q[8];
-      unpack8(*reinterpret_cast<const uint4*>(residual + r * Co + c0), q);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] += q[i];
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = rb + (int64_t)u * t.RT;
+      if (r >= t.r1) break;
+      float a[8], o[8];
+      unpack8(ua[u], a);
+      if (ACT == ACT_GLU) {
+        float b[8];
+        unpack8(ub[u], b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (a[i] * sc[i] + sh[i]) * sigmoidf_(b[i] * sc2[i] + sh2[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float z = a[i] * sc[i] + sh[i];
+          o[i] = ACT == ACT_LRELU ? (z > 0.f ? z : 0.2f * z) : (ACT == ACT_RELU ? fmaxf(z, 0.f) : z);
+        }
+      }
+      if (residual != nullptr) {
+        float q[8];
+        unpack8(uq[u], q);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += q[i];
+      }
+      *reinterpret_cast<uint4*>(out + r * Co + c0) = pack8(o);
     }
-    *reinterpret_cast<uint4*>(out + r * Co + c0) = pack8(o);
   }
 }
 
@@ -208,16 +224,32 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const bf16* __re
         sc2[i] = gamma[c] * rs2[i]; sh2[i] = beta[c] - mu2[i] * sc2[i];
       }
     }
-    for (int64_t r = t.r0 + t.rt; r < t.r1; r += t.RT) {
-      float ya[8], yb[8], d[8], dza[8], dzb[8];
-      unpack8(*reinterpret_cast<const uint4*>(y + r * Cy + c0), ya);
-      if (ACT == ACT_GLU) unpack8(*reinterpret_cast<const uint4*>(y + r * Cy + Co + c0), yb);
-      unpack8(*reinterpret_cast<const uint4*>(dout + r * Co + c0), d);
-      act_bwd8<ACT>(ya, yb, d, sc, sh, sc2, sh2, dza, dzb);
+    constexpr int U = 4;
+    for (int64_t rb = t.r0 + t.rt; rb < t.r1; rb += (int64_t)U * t.RT) {
+      uint4 ua[U], ub[U], ud[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        s1[0][i] += dza[i]; s2[0][i] += dza[i] * (ya[i] - mu[i]) * rs[i];
-        if (ACT == ACT_GLU) { s1[NH - 1][i] += dzb[i]; s2[NH - 1][i] += dzb[i] * (yb[i] - mu2[i]) * rs2[i]; }
+      for (int u = 0; u < U; ++u) {
+        const int64_t r = rb + (int64_t)u * t.RT;
+        if (r < t.r1) {
+          ua[u] = *reinterpret_cast<const uint4*>(y + r * Cy + c0);
+          if (ACT == ACT_GLU) ub[u] = *reinterpret_cast<const uint4*>(y + r * Cy + Co + c0);
+          ud[u] = *reinterpret_cast<const uint4*>(dout + r * Co + c0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t r = rb + (int64_t)u * t.RT;
+        if (r >= t.r1) break;
+        float ya[8], yb[8], d[8], dza[8], dzb[8];
+        unpack8(ua[u], ya);
+        if (ACT == ACT_GLU) unpack8(ub[u], yb);
+        unpack8(ud[u], d);
+        act_bwd8<ACT>(ya, yb, d, sc, sh, sc2, sh2, dza, dzb);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s1[0][i] += dza[i]; s2[0][i] += dza[i] * (ya[i] - mu[i]) * rs[i];
+          if (ACT == ACT_GLU) { s1[NH - 1][i] += dzb[i]; s2[NH - 1][i] += dzb[i] * (yb[i] - mu2[i]) * rs2[i]; }
+        }
       }
     }
   }
@@ -298,19 +330,35 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const bf16* __res
       m1b[i] = sums[(t.g * 2 + 0) * Cy + c] * inv_n; m2b[i] = sums[(t.g * 2 + 1) * Cy + c] * inv_n;
     }
   }
-  for (int64_t r = t.r0 + t.rt; r < t.r1; r += t.RT) {
-    float ya[8], yb[8], d[8], dza[8], dzb[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(y + r * Cy + c0), ya);
-    if (ACT == ACT_GLU) unpack8(*reinterpret_cast<const uint4*>(y + r * Cy + Co + c0), yb);
-    unpack8(*reinterpret_cast<const uint4*>(dout + r * Co + c0), d);
-    act_bwd8<ACT>(ya, yb, d, sc, sh, sc2, sh2, dza, dzb);
+  constexpr int U = 4;
+  for (int64_t rb = t.r0 + t.rt; rb < t.r1; rb += (int64_t)U * t.RT) {
+    uint4 ua[U], ub[U], ud[U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = sc[i] * (dza[i] - m1[i] - (ya[i] - mu[i]) * rs[i] * m2[i]);
-    *reinterpret_cast<uint4*>(dy + r * Cy + c0) = pack8(o);
-    if (ACT == ACT_GLU) {
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = rb + (int64_t)u * t.RT;
+      if (r < t.r1) {
+        ua[u] = *reinterpret_cast<const uint4*>(y + r * Cy + c0);
+        if (ACT == ACT_GLU) ub[u] = *reinterpret_cast<const uint4*>(y + r * Cy + Co + c0);
+        ud[u] = *reinterpret_cast<const uint4*>(dout + r * Co + c0);
+      }
+    }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = sc2[i] * (dzb[i] - m1b[i] - (yb[i] - mu2[i]) * rs2[i] * m2b[i]);
-      *reinterpret_cast<uint4*>(dy + r * Cy + Co + c0) = pack8(o);
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = rb + (int64_t)u * t.RT;
+      if (r >= t.r1) break;
+      float ya[8], yb[8], d[8], dza[8], dzb[8], o[8];
+      unpack8(ua[u], ya);
+      if (ACT == ACT_GLU) unpack8(ub[u], yb);
+      unpack8(ud[u], d);
+      act_bwd8<ACT>(ya, yb, d, sc, sh, sc2, sh2, dza, dzb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = sc[i] * (dza[i] - m1[i] - (ya[i] - mu[i]) * rs[i] * m2[i]);
+      *reinterpret_cast<uint4*>(dy + r * Cy + c0) = pack8(o);
+      if (ACT == ACT_GLU) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = sc2[i] * (dzb[i] - m1b[i] - (yb[i] - mu2[i]) * rs2[i] * m2b[i]);
+        *reinterpret_cast<uint4*>(dy + r * Cy + Co + c0) = pack8(o);
+      }
     }
   }
 }
@@ -376,8 +424,8 @@ int grid_rows(int64_t M, int noct, int groups, dim3* grid) {
   const int xs = ekl_cdiv(noct, CT);
   const int64_t Mg = M / groups;
   // enough chunks to fill the machine ~4x, at least 4*RT rows per chunk
-  int64_t chunks = (148 * 4 + xs * groups - 1) / (xs * groups);
-  const int64_t maxc = (Mg + 4 * RT - 1) / (4 * RT);
+  int64_t chunks = (148 * 8 + xs * groups - 1) / (xs * groups);
+  const int64_t maxc = (Mg + 8 * RT - 1) / (8 * RT);
   if (chunks > maxc) chunks = maxc;
   if (chunks < 1) chunks = 1;
   *grid = dim3(xs, (unsigned)(chunks * groups));

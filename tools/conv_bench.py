@@ -6,6 +6,8 @@ import torch
 from text2img_ekl_b200 import _lib as L
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+ONLY = set(sys.argv[2].split(",")) if len(sys.argv) > 2 else None
+ITERS = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 # (name, mode, B, H, W, Cin, Cout)
 LAYERS = [("up1", 1, B, 4, 4, 1024, 1024), ("up2", 1, B, 8, 8, 512, 512), ("up3", 1, B, 16, 16, 256, 256),
           ("up4", 1, B, 32, 32, 128, 128), ("joint2", 0, B, 64, 64, 320, 128), ("res2a", 0, B, 64, 64, 64, 128),
@@ -22,6 +24,8 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     print("%-8s %5s %14s | %8s %8s %8s (us) | %7s %7s %7s (TF/s exec) | ref-count TF/s fwd" % ("layer", "mode", "shape", "fwd", "dgrad", "wgrad", "fwd", "dgrad", "wgrad"))
     for name, mode, b, H, W, Cin, Cout in LAYERS:
+        if ONLY and name not in ONLY:
+            continue
         K = 4 if mode == 2 else 3
         Ho, Wo = (2 * H, 2 * W) if mode == 1 else ((H // 2, W // 2) if mode == 2 else (H, W))
         conv = L.EklConv(mode, b, H, W, Cin, Cout, 0, 0, 0, 0, 0, 0)
@@ -43,7 +47,7 @@ def main():
             for _ in range(3):
                 L.check(fn())
             ts = []
-            for _ in range(8):
+            for _ in range(ITERS):
                 flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(); L.check(fn()); e1.record(); torch.cuda.synchronize()
