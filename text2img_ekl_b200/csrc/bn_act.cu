@@ -79,24 +79,33 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const bf16* __restrict__
 
 // ---------------------------------------------------------------- finalize
 // partial [rows][2][C]; rows = groups * rows_per_group (group-contiguous). One block (256 thr) per 32 channels.
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int rows_per_group, int C,
-                                                          int groups, float count, float eps, float momentum,
-                                                          float* __restrict__ mean, float* __restrict__ rstd,
-                                                          float* running_mean, float* running_var) {
-  __shared__ double sh[2][8][32];
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partial, int rows_per_group, int C,
+                                                           int groups, float count, float eps, float momentum,
+                                                           float* __restrict__ mean, float* __restrict__ rstd,
+                                                           float* running_mean, float* running_var) {
+  __shared__ double sh[2][32][33];
   const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   for (int g = 0; g < groups; ++g) {
-    double a = 0.0, b = 0.0;
-    if (c < C)
-      for (int r = sl; r < rows_per_group; r += 8) {
-        const float* p = partial + ((size_t)(g * rows_per_group + r)) * 2 * C;
-        a += (double)p[c]; b += (double)p[C + c];
+    float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f, a2 = 0.f, b2 = 0.f, a3 = 0.f, b3 = 0.f;
+    if (c < C) {
+      const float* base = partial + (size_t)g * rows_per_group * 2 * C + c;
+      int r = sl;
+      for (; r + 96 < rows_per_group; r += 128) {       // 4 independent row loads in flight
+        const float* p0 = base + (size_t)r * 2 * C;
+        const float* p1 = p0 + (size_t)64 * C;
+        const float* p2 = p1 + (size_t)64 * C;
+        const float* p3 = p2 + (size_t)64 * C;
+        a0 += p0[0]; b0 += p0[C]; a1 += p1[0]; b1 += p1[C]; a2 += p2[0]; b2 += p2[C]; a3 += p3[0]; b3 += p3[C];
       }
-    sh[0][sl][cl] = a; sh[1][sl][cl] = b;
+      for (; r < rows_per_group; r += 32) { const float* p0 = base + (size_t)r * 2 * C; a0 += p0[0]; b0 += p0[C]; }
+    }
+    sh[0][sl][cl] = (double)a0 + (double)a1 + (double)a2 + (double)a3;
+    sh[1][sl][cl] = (double)b0 + (double)b1 + (double)b2 + (double)b3;
     __syncthreads();
     if (sl == 0 && c < C) {
-      for (int k = 1; k < 8; ++k) { a += sh[0][k][cl]; b += sh[1][k][cl]; }
+      double a = 0.0, b = 0.0;
+      for (int k = 0; k < 32; ++k) { a += sh[0][k][cl]; b += sh[1][k][cl]; }
       const double m = a / count;
       double var = b / count - m * m;
       if (var < 0.0) var = 0.0;
@@ -424,8 +433,9 @@ int grid_rows(int64_t M, int noct, int groups, dim3* grid) {
   const int xs = ekl_cdiv(noct, CT);
   const int64_t Mg = M / groups;
   // enough chunks to fill the machine ~4x, at least 4*RT rows per chunk
-  int64_t chunks = (148 * 8 + xs * groups - 1) / (xs * groups);
-  const int64_t maxc = (Mg + 8 * RT - 1) / (8 * RT);
+  // ~3 fat blocks per SM: per-block prologue (per-channel parameter loads) is amortised over >= 16 rows per thread
+  int64_t chunks = (148 * 3 + xs * groups - 1) / (xs * groups);
+  const int64_t maxc = (Mg + 16 * RT - 1) / (16 * RT);
   if (chunks > maxc) chunks = maxc;
   if (chunks < 1) chunks = 1;
   *grid = dim3(xs, (unsigned)(chunks * groups));
@@ -453,7 +463,7 @@ extern "C" int ekl_col_stats(const void* y, int64_t M, int C, int groups, float*
 extern "C" int ekl_bn_finalize(const float* partial, int rows_per_group, int C, int groups, float count, float eps,
                                float momentum, float* mean, float* rstd, float* running_mean, float* running_var,
                                void* stream) {
-  bn_finalize_kernel<<<ekl_cdiv(C, 32), 256, 0, (cudaStream_t)stream>>>(partial, rows_per_group, C, groups, count, eps,
+  bn_finalize_kernel<<<ekl_cdiv(C, 32), 1024, 0, (cudaStream_t)stream>>>(partial, rows_per_group, C, groups, count, eps,
                                                                         momentum, mean, rstd, running_mean, running_var);
   EKL_LAUNCH_CHECK();
   return 0;

@@ -31,13 +31,35 @@ __global__ void pack_fwd_kernel(const __grid_constant__ PackParams p) {
   }
 }
 
-// transposed: block (32x8) moves a 32(co) x 32(ci) tile for one (v, t)
+// non-transposed, KRSC master, Cin % 8 == 0: one thread per 8 consecutive ci (2 x float4 in, 1 x uint4 out)
+__global__ void pack_fwd_vec8_kernel(const __grid_constant__ PackParams p) {
+  const int c8 = p.Cin / 8;
+  const int64_t total = (int64_t)p.nvar * p.Cout * p.ntaps * c8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % c8) * 8;
+    int64_t r = i / c8;
+    const int t = (int)(r % p.ntaps); r /= p.ntaps;
+    const int co = (int)(r % p.Cout);
+    const int v = (int)(r / p.Cout);
+    const EklTap tap = p.taps[v][t];
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < tap.nsrc; ++s) {
+      const float4* src = reinterpret_cast<const float4*>(p.w + ((int64_t)co * p.KK + tap.src[s]) * p.Cin + ci);
+      const float4 a = src[0], b = src[1];
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    uint4 o = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+    *reinterpret_cast<uint4*>(p.out + i * 8) = o;
+  }
+}
+
+// transposed: block (32x8) moves a 64(co) x 32(ci) tile for one (v, t): 128-byte reads and 128-byte writes
 __global__ void pack_dgrad_kernel(const __grid_constant__ PackParams p) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[64][33];
   const int v = blockIdx.z / p.ntaps, t = blockIdx.z % p.ntaps;
   const EklTap tap = p.taps[v][t];
-  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
-  for (int r = threadIdx.y; r < 32; r += 8) {
+  const int co0 = blockIdx.y * 64, ci0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 64; r += 8) {
     const int co = co0 + r, ci = ci0 + threadIdx.x;
     float acc = 0.f;
     if (co < p.Cout && ci < p.Cin)
@@ -46,9 +68,13 @@ __global__ void pack_dgrad_kernel(const __grid_constant__ PackParams p) {
   }
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += 8) {
-    const int ci = ci0 + r, co = co0 + threadIdx.x;
-    if (ci < p.Cin && co < p.Cout)
-      p.out[(((int64_t)v * p.Cin + ci) * p.ntaps + t) * p.Cout + co] = __float2bfloat16(tile[threadIdx.x][r]);
+    const int ci = ci0 + r, co = co0 + 2 * threadIdx.x;
+    if (ci < p.Cin && co + 1 < p.Cout) {
+      const uint32_t pk = pack_bf16x2(tile[2 * threadIdx.x][r], tile[2 * threadIdx.x + 1][r]);
+      *reinterpret_cast<uint32_t*>(p.out + (((int64_t)v * p.Cin + ci) * p.ntaps + t) * p.Cout + co) = pk;
+    } else if (ci < p.Cin && co < p.Cout) {
+      p.out[(((int64_t)v * p.Cin + ci) * p.ntaps + t) * p.Cout + co] = __float2bfloat16(tile[2 * threadIdx.x][r]);
+    }
   }
 }
 
@@ -62,11 +88,17 @@ int ekl_pack_weights(const EklGather* g, const float* w_master, void* out, int C
   p.KK = g->KH * g->KW; p.kcrs = g->w_kcrs;
   if (!g->transposed) {
     const int64_t total = (int64_t)p.nvar * Cout * p.ntaps * Cin;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    pack_fwd_kernel<<<blocks, 256, 0, st>>>(p);
+    if (!p.kcrs && Cin % 8 == 0) {
+      int blocks = (int)((total / 8 + 255) / 256);
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      pack_fwd_vec8_kernel<<<blocks, 256, 0, st>>>(p);
+    } else {
+      int blocks = (int)((total + 255) / 256);
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      pack_fwd_kernel<<<blocks, 256, 0, st>>>(p);
+    }
   } else {
-    dim3 grid(ekl_cdiv(Cin, 32), ekl_cdiv(Cout, 32), p.nvar * p.ntaps);
+    dim3 grid(ekl_cdiv(Cin, 32), ekl_cdiv(Cout, 64), p.nvar * p.ntaps);
     pack_dgrad_kernel<<<grid, dim3(32, 8), 0, st>>>(p);
   }
   EKL_LAUNCH_CHECK();
