@@ -4,6 +4,7 @@
 #include "ekl_common.cuh"
 
 int ekl_tc_supported(const EklGather* g);
+int ekl_tc_stats_rows(const EklGather* g, int group_b);
 void ekl_tc_geometry(const EklGather* g, int group_b, int* tb, int* th, int* tw);
 int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, int group_b, int* mtiles_out, cudaStream_t st);
 int ekl_gather_simt(const EklGather* g, const void* w_packed, int act, cudaStream_t st);
@@ -75,9 +76,7 @@ extern "C" int ekl_conv_stats_rows(const ekl_conv* c) {
   if (check(c)) return -1;
   EklGather g;
   plan(c, 0, nullptr, nullptr, &g);
-  int tb, th, tw;
-  ekl_tc_geometry(&g, c->group_b, &tb, &th, &tw);
-  return ekl_cdiv(g.mW, tw) * ekl_cdiv(g.mH, th) * ekl_cdiv(g.mB, tb) * g.nvar;
+  return ekl_tc_stats_rows(&g, c->group_b);
 }
 
 extern "C" int ekl_conv_fwd(const ekl_conv* c, const void* x, const void* w_fwd, void* y, float* stats, void* stream) {

@@ -20,11 +20,13 @@ struct TcParams {
   CUtensorMap o_maps[EKL_MAX_VAR];
   CUtensorMap w_map;
   EklTap taps[EKL_MAX_VAR][EKL_MAX_TAPS];
-  float* stats;       // [(mtile*nvar + v)][2][N] or null
+  float* stats;       // [((g*grid + cta)*nvar + v)][2][N] or null
   int ntaps, ncb;     // taps, Cin/KC
   int Cin, N;
   int tb, th, tw, nTh, nTw;
   int rows_valid;     // tb*th*tw
+  int nvar, ntn;      // variants, N tiles
+  int groups, mtg;    // BatchNorm statistic groups, M tiles per group
 };
 
 template <int BN, int KC>
@@ -33,40 +35,55 @@ struct TcCfg {
   static constexpr int B_BYTES = BN * KC * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OUT_BYTES = 128 * BN * 2;
-  // two CTAs per SM: <= ~100 KB of stages each
-  static constexpr int STAGES_RAW = (96 * 1024) / STAGE_BYTES;
+  // one persistent CTA per SM: pipeline stages + a dedicated epilogue staging tile within ~220 KB
+  static constexpr int STAGES_RAW = (220 * 1024 - OUT_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int SMEM_MAIN = PIPE_BYTES > OUT_BYTES ? PIPE_BYTES : OUT_BYTES;
-  static constexpr int SMEM_BYTES = SMEM_MAIN + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM_BYTES = PIPE_BYTES + OUT_BYTES + 1024 /*align slack*/ + 512 /*barriers + reduction scratch*/ +
+                                    2 * 2 * BN * 4 * (BN <= 128 ? 256 / BN : 1);
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;               // double-buffered accumulator
   static constexpr uint32_t LAYOUT = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);   // SW128 / SW64 / SW32
   static constexpr uint32_t SBO = 8 * KC * 2;
   static constexpr int OBOX = BN < 64 ? BN : 64;   // channels per output TMA box
+  // statistics: each epilogue thread owns one channel PAIR over a slice of the rows
+  static constexpr int PAIRS = BN / 2;
+  static constexpr int SLICES = PAIRS >= 128 ? 1 : 128 / PAIRS;
 };
 
+// byte offset of channel c (even) of row r inside the swizzled staging tile
+template <int BN>
+__device__ __forceinline__ uint32_t stage_off(int r, int c) {
+  if constexpr (BN >= 64) return (uint32_t)((c >> 6) * (128 * 128) + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2);
+  else if constexpr (BN == 32) return (uint32_t)(r * 64 + (((c >> 3) ^ ((r >> 1) & 3)) << 4) + (c & 7) * 2);
+  else return (uint32_t)(r * 32 + c * 2);
+}
+
+// Persistent kernel: grid = #SMs; every CTA walks the same static schedule
+//   for round (v, n, g):  M tiles of group g with index (cta + rotation) + i*grid
+// so that one CTA's tiles of a round share the output-channel range (their BatchNorm partial sums accumulate in
+// registers and are flushed once per round) and consecutive rounds land on different CTAs when a round has fewer
+// tiles than CTAs.  TMEM holds two accumulators: the epilogue of tile i overlaps the main loop of tile i+1.
 template <int BN, int KC>
-__global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
   using C = TcCfg<BN, KC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = (uint64_t*)(smem + C::SMEM_MAIN);
+  uint8_t* stage_out = smem + C::PIPE_BYTES;
+  uint64_t* full = (uint64_t*)(stage_out + C::OUT_BYTES);
   uint64_t* empty = full + C::STAGES;
-  uint64_t* tmem_full = empty + C::STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  uint64_t* tmem_full = empty + C::STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  float* red = (float*)(stage_out + C::OUT_BYTES + 512);   // [SLICES][2][BN] cross-slice reduction scratch
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int v = blockIdx.z;
-  const int n0 = blockIdx.y * BN;
-  int mt = blockIdx.x;
-  const int twi = mt % p.nTw; mt /= p.nTw;
-  const int thi = mt % p.nTh; mt /= p.nTh;
-  const int w0 = twi * p.tw, h0 = thi * p.th, b0 = mt * p.tb;
+  const int grid = gridDim.x, cta = blockIdx.x;
   const int n_iters = p.ntaps * p.ncb;
+  const int rounds = p.nvar * p.ntn * p.groups;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -75,122 +92,159 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // schedule helpers (identical in every role)
+  auto round_vng = [&](int r, int& v, int& n, int& g) { g = r % p.groups; int q = r / p.groups; n = q % p.ntn; v = q / p.ntn; };
+  auto first_tile = [&](int r) { int rot = (int)(((long long)r * p.mtg) % grid); int c = cta - rot; if (c < 0) c += grid; return c; };
+  auto tile_origin = [&](int g, int mloc, int& w0, int& h0, int& b0) {
+    int mt = g * p.mtg + mloc;
+    const int twi = mt % p.nTw; mt /= p.nTw;
+    const int thi = mt % p.nTh; mt /= p.nTh;
+    w0 = twi * p.tw; h0 = thi * p.th; b0 = mt * p.tb;
+  };
+
   if (warp == 0) {
     if (elect_one()) {
       tma_prefetch_desc(&p.w_map);
       const uint32_t tx = (uint32_t)(p.rows_valid * KC * 2 + C::B_BYTES);
-      for (int it = 0; it < n_iters; ++it) {
-        const int s = it % C::STAGES;
-        const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
-        mbar_wait(&empty[s], ph ^ 1u);
-        const int t = it / p.ncb, cb = it - t * p.ncb;
-        const EklTap tap = p.taps[v][t];
-        uint8_t* sa = smem + s * C::STAGE_BYTES;
-        mbar_expect_tx(&full[s], tx);
-        tma_load_4d(&p.a_maps[tap.map], &full[s], sa, cb * KC, w0 + tap.dw, h0 + tap.dh, b0);
-        tma_load_2d(&p.w_map, &full[s], sa + C::A_BYTES, t * p.Cin + cb * KC, v * p.N + n0);
+      uint32_t kit = 0;                      // global k-iteration counter -> smem ring position
+      for (int r = 0; r < rounds; ++r) {
+        int v, n, g;
+        round_vng(r, v, n, g);
+        for (int mloc = first_tile(r); mloc < p.mtg; mloc += grid) {
+          int w0, h0, b0;
+          tile_origin(g, mloc, w0, h0, b0);
+          for (int it = 0; it < n_iters; ++it, ++kit) {
+            const int s = kit % C::STAGES;
+            const uint32_t ph = (kit / C::STAGES) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            const int t = it / p.ncb, cb = it - t * p.ncb;
+            const EklTap tap = p.taps[v][t];
+            uint8_t* sa = smem + s * C::STAGE_BYTES;
+            mbar_expect_tx(&full[s], tx);
+            tma_load_4d(&p.a_maps[tap.map], &full[s], sa, cb * KC, w0 + tap.dw, h0 + tap.dh, b0);
+            tma_load_2d(&p.w_map, &full[s], sa + C::A_BYTES, t * p.Cin + cb * KC, v * p.N + n * BN);
+          }
+        }
       }
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-    for (int it = 0; it < n_iters; ++it) {
-      const int s = it % C::STAGES;
-      const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
-      mbar_wait(&full[s], ph);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
-        const uint32_t sb = sa + C::A_BYTES;
+    uint32_t kit = 0, tile = 0;
+    for (int r = 0; r < rounds; ++r) {
+      for (int mloc = first_tile(r); mloc < p.mtg; mloc += grid, ++tile) {
+        const uint32_t buf = tile & 1u, use = tile >> 1;
+        mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);        // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * BN;
+        for (int it = 0; it < n_iters; ++it, ++kit) {
+          const int s = kit % C::STAGES;
+          const uint32_t ph = (kit / C::STAGES) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+            const uint32_t sb = sa + C::A_BYTES;
 #pragma unroll
-        for (int k = 0; k < KC / 16; ++k) {
-          const uint64_t da = umma_desc(sa + k * 32, 16, C::SBO, C::LAYOUT);
-          const uint64_t db = umma_desc(sb + k * 32, 16, C::SBO, C::LAYOUT);
-          tc_mma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < KC / 16; ++k) {
+              const uint64_t da = umma_desc(sa + k * 32, 16, C::SBO, C::LAYOUT);
+              const uint64_t db = umma_desc(sb + k * 32, 16, C::SBO, C::LAYOUT);
+              tc_mma_bf16(tacc, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+            }
+            tc_commit(&empty[s]);                              // smem stage reusable once these MMAs retire
+            if (it == n_iters - 1) tc_commit(&tmem_full[buf]); // accumulator complete
+          }
+          __syncwarp();
         }
-        tc_commit(&empty[s]);                         // smem stage reusable once these MMAs retire
-        if (it == n_iters - 1) tc_commit(tmem_full);  // accumulator complete
       }
-      __syncwarp();
     }
   } else {
     // ---------------- epilogue (warps 2..5); TMEM lane quarter = warp % 4
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;   // 0..127
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    uint8_t* stage = smem;             // pipeline smem is idle now (all TMA loads consumed, all MMAs retired)
-    if constexpr (BN == 16) {
-      // one box of [128][16] bf16, 32-byte rows, no swizzle (a warp's 32 rows are 1 KB contiguous: conflict-free)
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16), r);
-      tmem_ld_wait();
-      uint32_t pk[8];
+    const int pair = et % C::PAIRS, slice = et / C::PAIRS;      // statistics ownership (BN=256: 128 pairs, 1 slice)
+    uint32_t tile = 0;
+    bool store_pending = false;
+    for (int r = 0; r < rounds; ++r) {
+      int v, n, g;
+      round_vng(r, v, n, g);
+      float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+      for (int mloc = first_tile(r); mloc < p.mtg; mloc += grid, ++tile) {
+        const uint32_t buf = tile & 1u, use = tile >> 1;
+        int w0, h0, b0;
+        tile_origin(g, mloc, w0, h0, b0);
+        mbar_wait(&tmem_full[buf], use & 1u);
+        tc_fence_after();
+        // staging tile must be free: the previous tile's TMA store has finished READING it
+        if (store_pending && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+        if constexpr (BN == 16) {
+          uint32_t rr[16];
+          tmem_ld16(tacc, rr);
+          tmem_ld_wait();
+          uint32_t pk[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-      uint8_t* box = stage + row * 32;
-      *reinterpret_cast<uint4*>(box) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(box + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-    } else {
+          for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1]));
+          uint8_t* box = stage_out + row * 32;
+          *reinterpret_cast<uint4*>(box) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(box + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else {
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      tmem_ld_wait();
-      uint32_t pk[16];
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t rr[32];
+            tmem_ld32(tacc + (uint32_t)c0, rr);
+            tmem_ld_wait();
+            uint32_t pk[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-      if constexpr (BN >= 64) {
-        // staging = BN/64 boxes of [128 rows][64 ch] bf16, 128-byte rows, SWIZZLE_128B (16-B chunk index ^= row & 7)
-        uint8_t* box = stage + (c0 >> 6) * (128 * 128) + row * 128;
-        const int ch0 = (c0 & 63) >> 3;   // first 16-B chunk of this 32-column group: 0 or 4
+            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1]));
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 val = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          *reinterpret_cast<uint4*>(box + (((ch0 + j) ^ (row & 7)) << 4)) = val;
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(stage_out + stage_off<BN>(row, c0 + 8 * j)) =
+                  make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
         }
-      } else {
-        // BN == 32: one box of [128][32] bf16, 64-byte rows, SWIZZLE_64B (chunk index ^= (row >> 1) & 3)
-        uint8_t* box = stage + row * 64;
+        // accumulator drained -> the MMA warp may start the tile after next in this buffer
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[buf]);
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 val = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          *reinterpret_cast<uint4*>(box + ((j ^ ((row >> 1) & 3)) << 4)) = val;
+          for (int j = 0; j < BN / C::OBOX; ++j)
+            tma_store_4d(&p.o_maps[v], stage_out + j * (128 * 128), n * BN + j * C::OBOX, w0, h0, b0);
+          tma_store_commit();
+        }
+        store_pending = true;
+        if (p.stats != nullptr) {
+          // per-channel-pair partial sums of the bf16 values actually stored, over this thread's row slice
+          constexpr int RPS = 128 / C::SLICES;
+          const int r0 = slice * RPS;
+          const int r1 = (r0 + RPS) < p.rows_valid ? (r0 + RPS) : p.rows_valid;
+          for (int rr = r0; rr < r1; ++rr) {
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(stage_out + stage_off<BN>(rr, 2 * pair));
+            const float x0 = bf16_lo(u), x1 = bf16_hi(u);
+            s1a += x0; s2a += x0 * x0; s1b += x1; s2b += x1 * x1;
+          }
+        }
+      }
+      if (p.stats != nullptr) {
+        // flush this round's partial sums: combine the row slices through smem, one row of the stats array per
+        // (group, cta, variant); channels [n*BN, n*BN+BN)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float* my = red + (size_t)slice * 2 * BN;
+        my[2 * pair] = s1a; my[2 * pair + 1] = s1b; my[BN + 2 * pair] = s2a; my[BN + 2 * pair + 1] = s2b;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float* dst = p.stats + (((size_t)g * grid + cta) * p.nvar + v) * 2 * p.N + n * BN;
+        for (int c = et; c < 2 * BN; c += 128) {
+          float acc = 0.f;
+#pragma unroll
+          for (int sl = 0; sl < C::SLICES; ++sl) acc += red[(size_t)sl * 2 * BN + c];
+          dst[(c < BN) ? c : (p.N + c - BN)] = acc;
         }
       }
     }
-    }
-    tc_fence_before();
-    fence_proxy_async_smem();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (et == 0) {
-#pragma unroll
-      for (int j = 0; j < BN / C::OBOX; ++j)
-        tma_store_4d(&p.o_maps[v], stage + j * (128 * 128), n0 + j * C::OBOX, w0, h0, b0);
-      tma_store_commit();
-    }
-    if (p.stats != nullptr) {
-      // per-channel partial sums over this tile's valid rows, from the bf16 values actually stored
-      float* dst = p.stats + ((size_t)blockIdx.x * gridDim.z + v) * 2 * p.N + n0;
-      for (int c = et; c < BN; c += 128) {
-        float s1 = 0.f, s2 = 0.f;
-        const uint8_t* base;
-        int chunk, sub = (c & 7) * 2;
-        if constexpr (BN >= 64) { base = stage + (c >> 6) * (128 * 128); chunk = (c & 63) >> 3; }
-        else { base = stage; chunk = c >> 3; }
-        for (int rr = 0; rr < p.rows_valid; ++rr) {
-          const uint8_t* ptr;
-          if constexpr (BN >= 64) ptr = base + rr * 128 + ((chunk ^ (rr & 7)) << 4) + sub;
-          else if constexpr (BN == 32) ptr = base + rr * 64 + ((chunk ^ ((rr >> 1) & 3)) << 4) + sub;
-          else ptr = base + rr * 32 + (chunk << 4) + sub;
-          const float x = __bfloat162float(*reinterpret_cast<const bf16*>(ptr));
-          s1 += x; s2 += x * x;
-        }
-        dst[c] = s1;
-        dst[p.N + c] = s2;
-      }
-    }
-    if (et == 0) tma_store_wait_all();
+    if (store_pending && et == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -205,7 +259,7 @@ int make_view_map(CUtensorMap* m, const EklView& v, int boxC, int tw, int th, in
 }
 
 template <int BN, int KC>
-int launch_tc(const EklGather* g, TcParams& p, int mtiles, cudaStream_t st) {
+int launch_tc(const EklGather* g, TcParams& p, int grid, cudaStream_t st) {
   using C = TcCfg<BN, KC>;
   auto kern = conv_gemm_tc_kernel<BN, KC>;
   static bool attr_done = false;
@@ -213,7 +267,6 @@ int launch_tc(const EklGather* g, TcParams& p, int mtiles, cudaStream_t st) {
     EKL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_done = true;
   }
-  dim3 grid(mtiles, g->N / BN, g->nvar);
   kern<<<grid, 192, C::SMEM_BYTES, st>>>(p);
   EKL_LAUNCH_CHECK();
   return 0;
@@ -247,7 +300,25 @@ int ekl_tc_supported(const EklGather* g) {
   return 1;
 }
 
-// stats: [(mtile*nvar+v)][2][N] fp32 partials or null. Returns the number of M tiles through *mtiles_out.
+int ekl_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      n = v;
+    else
+      n = 148;
+  }
+  return n;
+}
+
+// rows of the BatchNorm partial-statistics buffer the kernel writes: groups * grid * nvar
+int ekl_tc_stats_rows(const EklGather* g, int group_b) {
+  const int groups = (group_b > 0 && g->mB % group_b == 0) ? g->mB / group_b : 1;
+  return groups * ekl_num_sms() * g->nvar;
+}
+
+// stats: [((grp*grid + cta)*nvar + v)][2][N] fp32 partials or null.
 int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, int group_b, int* mtiles_out,
                        cudaStream_t st) {
   EKL_REQUIRE(ekl_tc_supported(g), "gather_gemm_tc: unsupported shape Cin=%d N=%d mH=%d mW=%d", g->Cin, g->N, g->mH, g->mW);
@@ -257,18 +328,22 @@ int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, i
   ekl_tc_geometry(g, group_b, &tb, &th, &tw);
   p.tb = tb; p.th = th; p.tw = tw;
   p.nTw = ekl_cdiv(g->mW, tw); p.nTh = ekl_cdiv(g->mH, th);
-  const int nTb = ekl_cdiv(g->mB, tb);
-  const int mtiles = p.nTw * p.nTh * nTb;
+  p.groups = (group_b > 0 && g->mB % group_b == 0) ? g->mB / group_b : 1;
+  const int gb = g->mB / p.groups;
+  p.mtg = p.nTw * p.nTh * ekl_cdiv(gb, tb);
+  const int mtiles = p.mtg * p.groups;
   if (mtiles_out) *mtiles_out = mtiles;
   p.rows_valid = tb * th * tw;
-  p.ntaps = g->ntaps; p.Cin = g->Cin; p.N = g->N; p.stats = stats;
+  p.ntaps = g->ntaps; p.Cin = g->Cin; p.N = g->N; p.stats = stats; p.nvar = g->nvar;
   memcpy(p.taps, g->taps, sizeof(p.taps));
   const int KC = g->Cin % 64 == 0 ? 64 : (g->Cin % 32 == 0 ? 32 : 16);
   p.ncb = g->Cin / KC;
   const int swz = KC == 64 ? 3 : (KC == 32 ? 2 : 1);
   int BN = g->N % 256 == 0 ? 256 : (g->N % 128 == 0 ? 128 : (g->N % 64 == 0 ? 64 : (g->N % 32 == 0 ? 32 : 16)));
-  // prefer more CTAs when the grid would not fill the machine
-  while (BN > 64 && (int64_t)mtiles * (g->N / BN) * g->nvar < 148) BN /= 2;
+  const int sms = ekl_num_sms();
+  // prefer more tiles when the work would not fill the machine
+  while (BN > 64 && (int64_t)mtiles * (g->N / BN) * g->nvar < sms) BN /= 2;
+  p.ntn = g->N / BN;
   for (int i = 0; i < g->n_a; ++i) {
     int rc = make_view_map(&p.a_maps[i], g->a[i], KC, tw, th, tb, swz);
     if (rc) return rc;
@@ -285,7 +360,9 @@ int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, i
     int rc = ekl_make_tmap(&p.w_map, w_packed, 2, dims, strides, box, swz, 2);
     if (rc) return rc;
   }
-#define EKL_TC_CASE(bn, kc) if (BN == bn && KC == kc) return launch_tc<bn, kc>(g, p, mtiles, st);
+  // the statistics layout is indexed by the full-machine grid, so the grid is always #SMs
+  const int grid = sms;
+#define EKL_TC_CASE(bn, kc) if (BN == bn && KC == kc) return launch_tc<bn, kc>(g, p, grid, st);
   EKL_TC_CASE(256, 64) EKL_TC_CASE(128, 64) EKL_TC_CASE(64, 64) EKL_TC_CASE(32, 64) EKL_TC_CASE(16, 64)
   EKL_TC_CASE(256, 32) EKL_TC_CASE(128, 32) EKL_TC_CASE(64, 32) EKL_TC_CASE(32, 32) EKL_TC_CASE(16, 32)
   EKL_TC_CASE(256, 16) EKL_TC_CASE(128, 16) EKL_TC_CASE(64, 16) EKL_TC_CASE(32, 16) EKL_TC_CASE(16, 16)
