@@ -19,7 +19,7 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 // Common thread mapping: block = 256 threads = RT row-threads x CT octet-threads; blockIdx.x = octet strip,
 // blockIdx.y = row chunk (chunks never straddle a statistics group).
@@ -121,19 +121,61 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
   }
 }
 
+// ---------------------------------------------------------------- vector helpers for the streaming passes
+// A thread owns VEC consecutive channels (GLU: VEC channels of EACH half): VEC = 4 (8-byte accesses) for GLU, whose
+// two halves double the per-channel coefficients held in registers, VEC = 8 (16-byte accesses) otherwise.  Register
+// budget <= 85 (3 blocks of 256 threads per SM) keeps >= 70 KB of loads in flight per SM.
+template <int VEC> struct VecIO;
+template <> struct VecIO<8> {
+  typedef uint4 T;
+  static __device__ __forceinline__ void unpack(const T& u, float* f) { unpack8(u, f); }
+  static __device__ __forceinline__ T pack(const float* f) { return pack8(f); }
+};
+template <> struct VecIO<4> {
+  typedef uint2 T;
+  static __device__ __forceinline__ void unpack(const T& u, float* f) {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  }
+  static __device__ __forceinline__ T pack(const float* f) { return make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3])); }
+};
+
+template <int VEC>
+__device__ __forceinline__ Tile make_tile_v(int64_t M, int nvec, int groups) { return make_tile(M, nvec, groups); }
+
+template <int ACT> struct ActVec { static constexpr int V = ACT == ACT_GLU ? 4 : 8; };
+
 // ---------------------------------------------------------------- forward
 template <int ACT>
-__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const bf16* __restrict__ y, int64_t M, int Cy, int groups,
-                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                         const bf16* __restrict__ residual, bf16* __restrict__ out) {
+__global__ void __launch_bounds__(256, 3) bn_act_fwd_kernel(const bf16* __restrict__ y, int64_t M, int Cy, int groups,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const bf16* __restrict__ residual, bf16* __restrict__ out) {
+  constexpr int VEC = ActVec<ACT>::V;
+  using IO = VecIO<VEC>;
   const int Co = ACT == ACT_GLU ? Cy / 2 : Cy;
-  const Tile t = make_tile(M, Co / 8, groups);
+  const Tile t = make_tile(M, Co / VEC, groups);
   if (!t.active) return;
-  float sc[8], sh[8], sc2[8], sh2[8];
-  const int c0 = t.oct * 8;
+  const int c0 = t.oct * VEC;
+  // software pipeline: the loads of the next U rows are in flight while the current U rows are computed; the first
+  // batch is issued before the per-channel coefficient loads so the block prologue overlaps the stream
+  constexpr int U = 2;
+  typename IO::T ca[U], cb[U], cq[U], na[U], nb[U], nq[U];
+  auto load = [&](typename IO::T* a, typename IO::T* b, typename IO::T* q, int64_t rb) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = rb + (int64_t)u * t.RT;
+      if (r < t.r1) {
+        a[u] = *reinterpret_cast<const typename IO::T*>(y + r * Cy + c0);
+        if (ACT == ACT_GLU) b[u] = *reinterpret_cast<const typename IO::T*>(y + r * Cy + Co + c0);
+        if (residual != nullptr) q[u] = *reinterpret_cast<const typename IO::T*>(residual + r * Co + c0);
+      }
+    }
+  };
+  int64_t rb = t.r0 + t.rt;
+  load(ca, cb, cq, rb);
+  float sc[VEC], sh[VEC], sc2[VEC], sh2[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
     const float s = gamma[c0 + i] * rstd[t.g * Cy + c0 + i];
     sc[i] = s; sh[i] = beta[c0 + i] - mean[t.g * Cy + c0 + i] * s;
     if (ACT == ACT_GLU) {
@@ -142,53 +184,45 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const bf16* __restrict_
       sc2[i] = s_; sh2[i] = beta[c] - mean[t.g * Cy + c] * s_;
     }
   }
-  constexpr int U = 4;                      // rows in flight per thread (memory-level parallelism)
-  for (int64_t rb = t.r0 + t.rt; rb < t.r1; rb += (int64_t)U * t.RT) {
-    uint4 ua[U], ub[U], uq[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t r = rb + (int64_t)u * t.RT;
-      if (r < t.r1) {
-        ua[u] = *reinterpret_cast<const uint4*>(y + r * Cy + c0);
-        if (ACT == ACT_GLU) ub[u] = *reinterpret_cast<const uint4*>(y + r * Cy + Co + c0);
-        if (residual != nullptr) uq[u] = *reinterpret_cast<const uint4*>(residual + r * Co + c0);
-      }
-    }
+  for (; rb < t.r1; rb += (int64_t)U * t.RT) {
+    load(na, nb, nq, rb + (int64_t)U * t.RT);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t r = rb + (int64_t)u * t.RT;
       if (r >= t.r1) break;
-      float a[8], o[8];
-      unpack8(ua[u], a);
+      float a[VEC], o[VEC];
+      IO::unpack(ca[u], a);
       if (ACT == ACT_GLU) {
-        float b[8];
-        unpack8(ub[u], b);
+        float b[VEC];
+        IO::unpack(cb[u], b);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = (a[i] * sc[i] + sh[i]) * sigmoidf_(b[i] * sc2[i] + sh2[i]);
+        for (int i = 0; i < VEC; ++i) o[i] = (a[i] * sc[i] + sh[i]) * sigmoidf_(b[i] * sc2[i] + sh2[i]);
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < VEC; ++i) {
           const float z = a[i] * sc[i] + sh[i];
           o[i] = ACT == ACT_LRELU ? (z > 0.f ? z : 0.2f * z) : (ACT == ACT_RELU ? fmaxf(z, 0.f) : z);
         }
       }
       if (residual != nullptr) {
-        float q[8];
-        unpack8(uq[u], q);
+        float q[VEC];
+        IO::unpack(cq[u], q);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] += q[i];
+        for (int i = 0; i < VEC; ++i) o[i] += q[i];
       }
-      *reinterpret_cast<uint4*>(out + r * Co + c0) = pack8(o);
+      *reinterpret_cast<typename IO::T*>(out + r * Co + c0) = IO::pack(o);
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { ca[u] = na[u]; cb[u] = nb[u]; cq[u] = nq[u]; }
   }
 }
 
-// dz for the 8 (GLU: 8+8) pre-activation channels a thread owns; also returns xhat
-template <int ACT>
-__device__ __forceinline__ void act_bwd8(const float* ya, const float* yb, const float* d, const float* sc, const float* sh,
-                                         const float* sc2, const float* sh2, float* dza, float* dzb) {
+// dz (pre-activation gradient) for the VEC (GLU: VEC+VEC) channels a thread owns
+template <int ACT, int VEC>
+__device__ __forceinline__ void act_bwd(const float* ya, const float* yb, const float* d, const float* sc, const float* sh,
+                                        const float* sc2, const float* sh2, float* dza, float* dzb) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < VEC; ++i) {
     const float z = ya[i] * sc[i] + sh[i];
     if (ACT == ACT_GLU) {
       const float s = sigmoidf_(yb[i] * sc2[i] + sh2[i]);
@@ -205,61 +239,73 @@ __device__ __forceinline__ void act_bwd8(const float* ya, const float* yb, const
 }
 
 // ---------------------------------------------------------------- backward, pass 1: partial sums
+// S1 = sum dz, S2 = sum dz * xhat with xhat = y*rstd - mean*rstd (one FMA; coefficients rs / nmr)
 template <int ACT>
-__global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dout,
-                                                                int64_t M, int Cy, int groups,
-                                                                const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                float* __restrict__ partial /*[gridDim.y][2][Cy]*/) {
-  __shared__ float red[256 * 16];
+__global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dout,
+                                                                   int64_t M, int Cy, int groups,
+                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   float* __restrict__ partial /*[gridDim.y][2][Cy]*/) {
+  constexpr int VEC = ActVec<ACT>::V;
+  using IO = VecIO<VEC>;
+  __shared__ float red[256 * 2 * VEC];
   const int Co = ACT == ACT_GLU ? Cy / 2 : Cy;
-  const Tile t = make_tile(M, Co / 8, groups);
-  const int c0 = t.oct * 8;
+  const Tile t = make_tile(M, Co / VEC, groups);
+  const int c0 = t.oct * VEC;
   constexpr int NH = ACT == ACT_GLU ? 2 : 1;
-  float sc[8], sh[8], sc2[8], sh2[8], mu[8], rs[8], mu2[8], rs2[8];
-  float s1[NH][8], s2[NH][8];
+  float sc[VEC], sh[VEC], sc2[VEC], sh2[VEC], rs[VEC], nmr[VEC], rs2[VEC], nmr2[VEC];
+  float s1[NH][VEC], s2[NH][VEC];
 #pragma unroll
   for (int h = 0; h < NH; ++h)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s1[h][i] = s2[h][i] = 0.f;
+    for (int i = 0; i < VEC; ++i) s1[h][i] = s2[h][i] = 0.f;
   if (t.active) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      mu[i] = mean[t.g * Cy + c0 + i]; rs[i] = rstd[t.g * Cy + c0 + i];
-      sc[i] = gamma[c0 + i] * rs[i]; sh[i] = beta[c0 + i] - mu[i] * sc[i];
-      if (ACT == ACT_GLU) {
-        const int c = Co + c0 + i;
-        mu2[i] = mean[t.g * Cy + c]; rs2[i] = rstd[t.g * Cy + c];
-        sc2[i] = gamma[c] * rs2[i]; sh2[i] = beta[c] - mu2[i] * sc2[i];
-      }
-    }
-    constexpr int U = 4;
-    for (int64_t rb = t.r0 + t.rt; rb < t.r1; rb += (int64_t)U * t.RT) {
-      uint4 ua[U], ub[U], ud[U];
+    constexpr int U = 2;                   // software pipeline, see bn_act_fwd_kernel
+    typename IO::T ca[U], cb[U], cd[U], na[U], nb[U], nd[U];
+    auto load = [&](typename IO::T* a, typename IO::T* b, typename IO::T* d, int64_t rb) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t r = rb + (int64_t)u * t.RT;
         if (r < t.r1) {
-          ua[u] = *reinterpret_cast<const uint4*>(y + r * Cy + c0);
-          if (ACT == ACT_GLU) ub[u] = *reinterpret_cast<const uint4*>(y + r * Cy + Co + c0);
-          ud[u] = *reinterpret_cast<const uint4*>(dout + r * Co + c0);
+          a[u] = *reinterpret_cast<const typename IO::T*>(y + r * Cy + c0);
+          if (ACT == ACT_GLU) b[u] = *reinterpret_cast<const typename IO::T*>(y + r * Cy + Co + c0);
+          d[u] = *reinterpret_cast<const typename IO::T*>(dout + r * Co + c0);
         }
       }
+    };
+    int64_t rb = t.r0 + t.rt;
+    load(ca, cb, cd, rb);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float mu = mean[t.g * Cy + c0 + i];
+      rs[i] = rstd[t.g * Cy + c0 + i]; nmr[i] = -mu * rs[i];
+      sc[i] = gamma[c0 + i] * rs[i]; sh[i] = beta[c0 + i] - mu * sc[i];
+      if (ACT == ACT_GLU) {
+        const int c = Co + c0 + i;
+        const float mu_ = mean[t.g * Cy + c];
+        rs2[i] = rstd[t.g * Cy + c]; nmr2[i] = -mu_ * rs2[i];
+        sc2[i] = gamma[c] * rs2[i]; sh2[i] = beta[c] - mu_ * sc2[i];
+      }
+    }
+    for (; rb < t.r1; rb += (int64_t)U * t.RT) {
+      load(na, nb, nd, rb + (int64_t)U * t.RT);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t r = rb + (int64_t)u * t.RT;
         if (r >= t.r1) break;
-        float ya[8], yb[8], d[8], dza[8], dzb[8];
-        unpack8(ua[u], ya);
-        if (ACT == ACT_GLU) unpack8(ub[u], yb);
-        unpack8(ud[u], d);
-        act_bwd8<ACT>(ya, yb, d, sc, sh, sc2, sh2, dza, dzb);
+        float ya[VEC], yb[VEC], d[VEC], dza[VEC], dzb[VEC];
+        IO::unpack(ca[u], ya);
+        if (ACT == ACT_GLU) IO::unpack(cb[u], yb);
+        IO::unpack(cd[u], d);
+        act_bwd<ACT, VEC>(ya, yb, d, sc, sh, sc2, sh2, dza, dzb);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          s1[0][i] += dza[i]; s2[0][i] += dza[i] * (ya[i] - mu[i]) * rs[i];
-          if (ACT == ACT_GLU) { s1[NH - 1][i] += dzb[i]; s2[NH - 1][i] += dzb[i] * (yb[i] - mu2[i]) * rs2[i]; }
+        for (int i = 0; i < VEC; ++i) {
+          s1[0][i] += dza[i]; s2[0][i] += dza[i] * (ya[i] * rs[i] + nmr[i]);
+          if (ACT == ACT_GLU) { s1[NH - 1][i] += dzb[i]; s2[NH - 1][i] += dzb[i] * (yb[i] * rs2[i] + nmr2[i]); }
         }
       }
+#pragma unroll
+      for (int u = 0; u < U; ++u) { ca[u] = na[u]; cb[u] = nb[u]; cd[u] = nd[u]; }
     }
   }
   const int CT = t.CT;
@@ -267,18 +313,21 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const bf16* __re
   for (int h = 0; h < NH; ++h) {
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { red[threadIdx.x * 16 + i] = s1[h][i]; red[threadIdx.x * 16 + 8 + i] = s2[h][i]; }
+    for (int i = 0; i < VEC; ++i) { red[threadIdx.x * 2 * VEC + i] = s1[h][i]; red[threadIdx.x * 2 * VEC + VEC + i] = s2[h][i]; }
     __syncthreads();
     if (t.active && t.rt == 0) {
-      float a[8], b[8];
+      float a[VEC], b[VEC];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { a[i] = s1[h][i]; b[i] = s2[h][i]; }
+      for (int i = 0; i < VEC; ++i) { a[i] = s1[h][i]; b[i] = s2[h][i]; }
       for (int k = 1; k < t.RT; ++k)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { a[i] += red[(threadIdx.x + k * CT) * 16 + i]; b[i] += red[(threadIdx.x + k * CT) * 16 + 8 + i]; }
+        for (int i = 0; i < VEC; ++i) {
+          a[i] += red[(threadIdx.x + k * CT) * 2 * VEC + i];
+          b[i] += red[(threadIdx.x + k * CT) * 2 * VEC + VEC + i];
+        }
       float* dst = partial + (size_t)blockIdx.y * 2 * Cy + h * Co + c0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { dst[i] = a[i]; dst[Cy + i] = b[i]; }
+      for (int i = 0; i < VEC; ++i) { dst[i] = a[i]; dst[Cy + i] = b[i]; }
     }
   }
 }
@@ -291,12 +340,20 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
   const int c = blockIdx.x * 32 + cl;
   float tg = 0.f, tb = 0.f;
   for (int g = 0; g < groups; ++g) {
-    float a = 0.f, b = 0.f;
-    if (c < Cy)
-      for (int r = sl; r < rows_per_group; r += 8) {
+    float a = 0.f, b = 0.f, a1 = 0.f, b1 = 0.f;
+    if (c < Cy) {
+      int r = sl;
+      for (; r + 8 < rows_per_group; r += 16) {            // two independent rows in flight
+        const float* p = partial + ((size_t)(g * rows_per_group + r)) * 2 * Cy;
+        const float* q = p + (size_t)16 * Cy;
+        a += p[c]; b += p[Cy + c]; a1 += q[c]; b1 += q[Cy + c];
+      }
+      for (; r < rows_per_group; r += 8) {
         const float* p = partial + ((size_t)(g * rows_per_group + r)) * 2 * Cy;
         a += p[c]; b += p[Cy + c];
       }
+      a += a1; b += b1;
+    }
     sh[0][sl][cl] = a; sh[1][sl][cl] = b;
     __syncthreads();
     if (sl == 0 && c < Cy) {
@@ -314,61 +371,76 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------- backward, pass 2: dy
+// dy = k*(dz - S1/n - xhat*S2/n), k = gamma*rstd  ==  k*dz + A*y + Bc  with  A = -k*rstd*S2/n,  Bc = -k*S1/n - A*mean
 template <int ACT>
-__global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dout,
-                                                               int64_t M, int Cy, int groups,
-                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                               const float* __restrict__ sums /*[groups][2][Cy]*/,
-                                                               bf16* __restrict__ dy) {
+__global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dout,
+                                                                  int64_t M, int Cy, int groups,
+                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  const float* __restrict__ sums /*[groups][2][Cy]*/,
+                                                                  bf16* __restrict__ dy) {
+  constexpr int VEC = ActVec<ACT>::V;
+  using IO = VecIO<VEC>;
   const int Co = ACT == ACT_GLU ? Cy / 2 : Cy;
-  const Tile t = make_tile(M, Co / 8, groups);
+  const Tile t = make_tile(M, Co / VEC, groups);
   if (!t.active) return;
-  const int c0 = t.oct * 8;
+  const int c0 = t.oct * VEC;
   const float inv_n = 1.f / (float)(M / groups);
-  float sc[8], sh[8], sc2[8], sh2[8], mu[8], rs[8], mu2[8], rs2[8], m1[8], m2[8], m1b[8], m2b[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    mu[i] = mean[t.g * Cy + c0 + i]; rs[i] = rstd[t.g * Cy + c0 + i];
-    sc[i] = gamma[c0 + i] * rs[i]; sh[i] = beta[c0 + i] - mu[i] * sc[i];
-    m1[i] = sums[(t.g * 2 + 0) * Cy + c0 + i] * inv_n; m2[i] = sums[(t.g * 2 + 1) * Cy + c0 + i] * inv_n;
-    if (ACT == ACT_GLU) {
-      const int c = Co + c0 + i;
-      mu2[i] = mean[t.g * Cy + c]; rs2[i] = rstd[t.g * Cy + c];
-      sc2[i] = gamma[c] * rs2[i]; sh2[i] = beta[c] - mu2[i] * sc2[i];
-      m1b[i] = sums[(t.g * 2 + 0) * Cy + c] * inv_n; m2b[i] = sums[(t.g * 2 + 1) * Cy + c] * inv_n;
-    }
-  }
-  constexpr int U = 4;
-  for (int64_t rb = t.r0 + t.rt; rb < t.r1; rb += (int64_t)U * t.RT) {
-    uint4 ua[U], ub[U], ud[U];
+  constexpr int U = 2;                     // software pipeline, see bn_act_fwd_kernel
+  typename IO::T ca[U], cb[U], cd[U], na[U], nb[U], nd[U];
+  auto load = [&](typename IO::T* a, typename IO::T* b, typename IO::T* d, int64_t rb) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t r = rb + (int64_t)u * t.RT;
       if (r < t.r1) {
-        ua[u] = *reinterpret_cast<const uint4*>(y + r * Cy + c0);
-        if (ACT == ACT_GLU) ub[u] = *reinterpret_cast<const uint4*>(y + r * Cy + Co + c0);
-        ud[u] = *reinterpret_cast<const uint4*>(dout + r * Co + c0);
+        a[u] = *reinterpret_cast<const typename IO::T*>(y + r * Cy + c0);
+        if (ACT == ACT_GLU) b[u] = *reinterpret_cast<const typename IO::T*>(y + r * Cy + Co + c0);
+        d[u] = *reinterpret_cast<const typename IO::T*>(dout + r * Co + c0);
       }
     }
+  };
+  int64_t rb = t.r0 + t.rt;
+  load(ca, cb, cd, rb);
+  float sc[VEC], sh[VEC], sc2[VEC], sh2[VEC], A[VEC], Bc[VEC], A2[VEC], Bc2[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    {
+      const int c = c0 + i;
+      const float mu = mean[t.g * Cy + c], r = rstd[t.g * Cy + c];
+      sc[i] = gamma[c] * r; sh[i] = beta[c] - mu * sc[i];
+      A[i] = -sc[i] * r * sums[(t.g * 2 + 1) * Cy + c] * inv_n;
+      Bc[i] = -sc[i] * sums[(t.g * 2 + 0) * Cy + c] * inv_n - A[i] * mu;
+    }
+    if (ACT == ACT_GLU) {
+      const int c = Co + c0 + i;
+      const float mu = mean[t.g * Cy + c], r = rstd[t.g * Cy + c];
+      sc2[i] = gamma[c] * r; sh2[i] = beta[c] - mu * sc2[i];
+      A2[i] = -sc2[i] * r * sums[(t.g * 2 + 1) * Cy + c] * inv_n;
+      Bc2[i] = -sc2[i] * sums[(t.g * 2 + 0) * Cy + c] * inv_n - A2[i] * mu;
+    }
+  }
+  for (; rb < t.r1; rb += (int64_t)U * t.RT) {
+    load(na, nb, nd, rb + (int64_t)U * t.RT);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t r = rb + (int64_t)u * t.RT;
       if (r >= t.r1) break;
-      float ya[8], yb[8], d[8], dza[8], dzb[8], o[8];
-      unpack8(ua[u], ya);
-      if (ACT == ACT_GLU) unpack8(ub[u], yb);
-      unpack8(ud[u], d);
-      act_bwd8<ACT>(ya, yb, d, sc, sh, sc2, sh2, dza, dzb);
+      float ya[VEC], yb[VEC], d[VEC], dza[VEC], dzb[VEC], o[VEC];
+      IO::unpack(ca[u], ya);
+      if (ACT == ACT_GLU) IO::unpack(cb[u], yb);
+      IO::unpack(cd[u], d);
+      act_bwd<ACT, VEC>(ya, yb, d, sc, sh, sc2, sh2, dza, dzb);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = sc[i] * (dza[i] - m1[i] - (ya[i] - mu[i]) * rs[i] * m2[i]);
-      *reinterpret_cast<uint4*>(dy + r * Cy + c0) = pack8(o);
+      for (int i = 0; i < VEC; ++i) o[i] = sc[i] * dza[i] + (A[i] * ya[i] + Bc[i]);
+      *reinterpret_cast<typename IO::T*>(dy + r * Cy + c0) = IO::pack(o);
       if (ACT == ACT_GLU) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = sc2[i] * (dzb[i] - m1b[i] - (yb[i] - mu2[i]) * rs2[i] * m2b[i]);
-        *reinterpret_cast<uint4*>(dy + r * Cy + Co + c0) = pack8(o);
+        for (int i = 0; i < VEC; ++i) o[i] = sc2[i] * dzb[i] + (A2[i] * yb[i] + Bc2[i]);
+        *reinterpret_cast<typename IO::T*>(dy + r * Cy + Co + c0) = IO::pack(o);
       }
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { ca[u] = na[u]; cb[u] = nb[u]; cd[u] = nd[u]; }
   }
 }
 
@@ -406,26 +478,60 @@ __global__ void cat_code_kernel(const float* __restrict__ code, int Cc, const bf
   }
 }
 
-// backward of cat_code: dcode[b,c] = sum_{hw} dcat[b,hw,c] (fp32); dx = dcat[..., Cc:]
+// backward of cat_code: dcode[b,c] += sum_{hw} dcat[b,hw,c] (fp32); dx = dcat[..., Cc:].
+// grid = (row chunks, B); block = RT row-threads x (Ct/8) octet-threads: every thread streams 16-byte octets of its
+// column strip (code octets are accumulated in registers, feature octets are copied), then the row-threads are
+// combined through shared memory and one atomicAdd per (block, code channel) lands in dcode.
 __global__ void __launch_bounds__(256) cat_code_bwd_kernel(const bf16* __restrict__ dcat, int Cc, int Cx, int64_t HW,
-                                                           float* __restrict__ dcode, bf16* __restrict__ dx) {
+                                                           int rows_per_block, float* __restrict__ dcode,
+                                                           bf16* __restrict__ dx) {
+  __shared__ float red[256 * 8];
   const int Ct = Cc + Cx;
-  const int b = blockIdx.x;
+  const int noct = Ct / 8, ncode = Cc / 8;
+  const int RT = blockDim.x / noct;
+  const int oct = threadIdx.x % noct, rt = threadIdx.x / noct;
+  const int b = blockIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = (r0 + rows_per_block) < HW ? (r0 + rows_per_block) : HW;
   const bf16* src = dcat + (int64_t)b * HW * Ct;
-  // dx copy
-  const int nox = Cx / 8;
-  for (int64_t i = threadIdx.x; i < HW * nox; i += 256) {
-    const int64_t r = i / nox;
-    const int c0 = (int)(i % nox) * 8;
-    *reinterpret_cast<uint4*>(dx + ((int64_t)b * HW + r) * Cx + c0) = *reinterpret_cast<const uint4*>(src + r * Ct + Cc + c0);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rt < RT) {
+    constexpr int U = 4;
+    for (int64_t rb = r0 + rt; rb < r1; rb += (int64_t)U * RT) {
+      uint4 u[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int64_t r = rb + (int64_t)k * RT;
+        if (r < r1) u[k] = *reinterpret_cast<const uint4*>(src + r * Ct + oct * 8);
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int64_t r = rb + (int64_t)k * RT;
+        if (r >= r1) break;
+        if (oct < ncode) {
+          float f[8];
+          unpack8(u[k], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += f[i];
+        } else {
+          *reinterpret_cast<uint4*>(dx + ((int64_t)b * HW + r) * Cx + (oct - ncode) * 8) = u[k];
+        }
+      }
+    }
   }
-  // dcode reduction: thread c over rows (coalesced across c)
-  for (int c = threadIdx.x; c < Cc; c += 256) {
-    float acc = 0.f;
-    for (int64_t r = 0; r < HW; ++r) acc += __bfloat162float(src[r * Ct + c]);
-    dcode[(int64_t)b * Cc + c] += acc;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
+  __syncthreads();
+  if (rt == 0 && oct < ncode) {
+    for (int k = 1; k < RT; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += red[(threadIdx.x + k * noct) * 8 + i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(dcode + (int64_t)b * Cc + oct * 8 + i, acc[i]);
   }
 }
+
+int act_vec(int act) { return act == ACT_GLU ? 4 : 8; }
 
 int grid_rows(int64_t M, int noct, int groups, dim3* grid) {
   const int CT = noct < 256 ? noct : 256;
@@ -484,7 +590,7 @@ extern "C" int ekl_bn_act_fwd(const void* y, int64_t M, int Cy, int groups, cons
   const int Co = act == ACT_GLU ? Cy / 2 : Cy;
   EKL_REQUIRE(Co % 8 == 0 && M % groups == 0, "bn_act_fwd: bad shape Cy=%d", Cy);
   dim3 grid;
-  grid_rows(M, Co / 8, groups, &grid);
+  grid_rows(M, Co / act_vec(act), groups, &grid);
   EKL_ACT_SWITCH(act, (bn_act_fwd_kernel<A><<<grid, 256, 0, (cudaStream_t)stream>>>(
                           (const bf16*)y, M, Cy, groups, mean, rstd, gamma, beta, (const bf16*)residual, (bf16*)out)));
   EKL_LAUNCH_CHECK();
@@ -494,7 +600,7 @@ extern "C" int ekl_bn_act_fwd(const void* y, int64_t M, int Cy, int groups, cons
 extern "C" int ekl_bn_act_bwd_rows(int64_t M, int Cy, int groups, int act) {
   const int Co = act == ACT_GLU ? Cy / 2 : Cy;
   dim3 grid;
-  return grid_rows(M, Co / 8, groups, &grid) * groups;
+  return grid_rows(M, Co / act_vec(act), groups, &grid) * groups;
 }
 
 // partial: [ekl_bn_act_bwd_rows][2][Cy] scratch; sums: [groups][2][Cy] scratch; dgamma/dbeta accumulated (+=).
@@ -504,7 +610,7 @@ extern "C" int ekl_bn_act_bwd(const void* y, const void* dout, int64_t M, int Cy
   const int Co = act == ACT_GLU ? Cy / 2 : Cy;
   EKL_REQUIRE(Co % 8 == 0 && M % groups == 0, "bn_act_bwd: bad shape Cy=%d", Cy);
   dim3 grid;
-  const int chunks = grid_rows(M, Co / 8, groups, &grid);
+  const int chunks = grid_rows(M, Co / act_vec(act), groups, &grid);
   cudaStream_t st = (cudaStream_t)stream;
   EKL_ACT_SWITCH(act, (bn_act_bwd_reduce_kernel<A><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M, Cy, groups,
                                                                          mean, rstd, gamma, beta, partial)));
@@ -538,8 +644,16 @@ extern "C" int ekl_cat_code(const float* code, int Cc, const void* x, int Cx, in
 }
 
 extern "C" int ekl_cat_code_bwd(const void* dcat, int Cc, int Cx, int B, int HW, float* dcode, void* dx, void* stream) {
-  EKL_REQUIRE(Cc % 8 == 0 && Cx % 8 == 0, "cat_code_bwd: channels %% 8");
-  cat_code_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const bf16*)dcat, Cc, Cx, HW, dcode, (bf16*)dx);
+  EKL_REQUIRE(Cc % 8 == 0 && Cx % 8 == 0 && (Cc + Cx) / 8 <= 256, "cat_code_bwd: channels %% 8, <= 2048 in total");
+  const int noct = (Cc + Cx) / 8;
+  const int RT = 256 / noct;
+  // ~4 blocks per SM over the whole batch, at least 4*RT rows each
+  int chunks = ekl_cdiv(148 * 4, B);
+  int rows = ekl_cdiv(HW, chunks);
+  if (rows < 4 * RT) rows = 4 * RT;
+  chunks = ekl_cdiv(HW, rows);
+  cat_code_bwd_kernel<<<dim3(chunks, B), RT * noct, 0, (cudaStream_t)stream>>>((const bf16*)dcat, Cc, Cx, HW, rows, dcode,
+                                                                              (bf16*)dx);
   EKL_LAUNCH_CHECK();
   return 0;
 }

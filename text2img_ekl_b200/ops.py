@@ -24,6 +24,13 @@ def _count(n=1):
 # bench.py's kernel_roofline(): when a list, every library call appends (family, algorithmic flops, algorithmic bytes,
 # start event, end event) recorded on the launching stream
 PROFILE = None
+# tools/layer_bench.py: when a list, every conv / BatchNorm call appends its shape key
+SHAPE_LOG = None
+
+
+def _log(*key):
+    if SHAPE_LOG is not None:
+        SHAPE_LOG.append(key)
 
 
 class _prof:
@@ -138,6 +145,7 @@ class _Conv(torch.autograd.Function):
         if want_stats and spec.impl == L.IMPL_TC:
             stats = torch.empty(lib.ekl_conv_stats_rows(c), 2, spec.cout, device=x.device, dtype=torch.float32)
         fam = "conv_tc" if spec.impl == L.IMPL_TC else "conv_simt"
+        _log("fwd", fam, spec.mode, B, H, W, spec.cin, spec.cout, group_b)
         with _prof(fam + "_fwd", _conv_flops(spec, B, H, W), x.numel() * x.element_size() + y.numel() * y.element_size()):
             L.check(lib.ekl_conv_fwd(c, L.ptr(x), L.ptr(w_fwd), L.ptr(y), L.ptr(stats), L.stream()))
         _count()
@@ -158,6 +166,7 @@ class _Conv(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             _, w_dgrad = spec.packed(weight)
             dx = torch.empty_like(x)
+            _log("dgrad", fam, spec.mode, *ctx.dims, spec.cin, spec.cout, 0)
             with _prof(fam + "_dgrad", _conv_flops(spec, *ctx.dims), dx.numel() * dx.element_size() + dy.numel() * dy.element_size()):
                 L.check(lib.ekl_conv_bwd_data(c, L.ptr(dy), L.ptr(w_dgrad), L.ptr(dx), L.stream()))
             _count()
@@ -167,6 +176,7 @@ class _Conv(torch.autograd.Function):
                 buf = _grad_buffer(weight)          # parameters: accumulate in place, autograd sees no gradient
             else:
                 buf = dw = torch.zeros_like(weight, memory_format=torch.preserve_format)
+            _log("wgrad", fam, spec.mode, *ctx.dims, spec.cin, spec.cout, 0)
             with _prof(fam + "_wgrad", _conv_flops(spec, *ctx.dims), x.numel() * x.element_size() + dy.numel() * dy.element_size()):
                 L.check(lib.ekl_conv_bwd_weight(c, L.ptr(x), L.ptr(dy), L.ptr(buf), L.stream()))
             _count()
@@ -193,6 +203,7 @@ class _BnAct(torch.autograd.Function):
                 L.check(lib.ekl_col_stats(L.ptr(y), M, C, groups, L.ptr(stats), L.stream()))
             _count()
         rows_per_group = stats.shape[0] // groups
+        _log("bn_fwd", M, C, groups, act, residual is not None)
         mean = torch.empty(groups, C, device=dev, dtype=torch.float32)
         rstd = torch.empty(groups, C, device=dev, dtype=torch.float32)
         with _prof("bn_finalize", 0, stats.numel() * 4):
@@ -221,6 +232,7 @@ class _BnAct(torch.autograd.Function):
         dy = torch.empty_like(y)
         pg = gamma.requires_grad and not ctx.skip_pgrad
         Co = C // 2 if ctx.act == ACT_GLU else C
+        _log("bn_bwd", M, C, ctx.groups, ctx.act, ctx.has_res)
         with _prof("bn_act_bwd", 0, M * (2 * C + 2 * Co + C) * 2):     # two passes over y and dout, one write of dy
             L.check(lib.ekl_bn_act_bwd(L.ptr(y), L.ptr(dout), M, C, ctx.groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma),
                                        L.ptr(beta), ctx.act, L.ptr(partial), L.ptr(sums),

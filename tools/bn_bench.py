@@ -5,7 +5,8 @@ import torch
 from text2img_ekl_b200 import _lib as L
 
 ITERS = int(sys.argv[1]) if len(sys.argv) > 1 else 6
-SHAPES = [("s3_up", 24 * 256 * 256, 32, 1, L.ACT_GLU), ("s3_res", 24 * 128 * 128, 64, 1, L.ACT_GLU),
+CUSTOM = [tuple(int(v) for v in a.split(",")) for a in sys.argv[2:]]     # M,Cy,groups,act
+SHAPES = [("custom",) + c for c in CUSTOM] or [("s3_up", 24 * 256 * 256, 32, 1, L.ACT_GLU), ("s3_res", 24 * 128 * 128, 64, 1, L.ACT_GLU),
           ("s2_up4", 32 * 64 * 64, 128, 1, L.ACT_GLU), ("d_l2", 3 * 24 * 64 * 64, 128, 3, L.ACT_LRELU),
           ("res_none", 24 * 128 * 128, 32, 1, L.ACT_NONE), ("tail", 3 * 24 * 16, 1024, 3, L.ACT_LRELU)]
 lib = L.lib()

@@ -18,7 +18,7 @@ SHAPES = {  # mode -> list of (B, H, W, Cin, Cout)
     1: [(4, 4, 4, 128, 128), (2, 8, 8, 64, 64), (3, 16, 16, 64, 128), (2, 32, 32, 32, 32), (2, 4, 4, 256, 512)],
     2: [(4, 16, 16, 64, 128), (2, 8, 8, 128, 256), (3, 32, 32, 64, 64), (2, 8, 8, 512, 1024), (2, 64, 64, 32, 64)],
 }
-GROUPS = ["tc_fwd", "tc_dgrad", "tc_wgrad", "simt_fwd", "simt_dgrad", "simt_wgrad", "bn"]
+GROUPS = ["tc_fwd", "tc_dgrad", "tc_wgrad", "simt_fwd", "simt_dgrad", "simt_wgrad", "bn", "misc"]
 
 
 def run_group(group):
@@ -36,6 +36,8 @@ def run_group(group):
 
     if group == "bn":
         return run_bn(torch, L, lib, dev, rel)
+    if group == "misc":
+        return run_misc(torch, L, lib, dev, rel)
     impl = L.IMPL_TC if group.startswith("tc") else L.IMPL_SIMT
     what = group.split("_")[1]
     for mode, shapes in SHAPES.items():
@@ -151,6 +153,38 @@ def run_bn(torch, L, lib, dev, rel):
         ok = all(v < 1e-2 for v in errs.values())
         print("%s bn M%d C%d g%d act%d %s" % ("PASS" if ok else "FAIL", M, Cy, groups, act,
                                                " ".join("%s %.1e" % kv for kv in errs.items())), flush=True)
+        nfail += 0 if ok else 1
+    return nfail
+
+
+def run_misc(torch, L, lib, dev, rel):
+    """cat(tile(code), x) forward / backward and LeakyReLU-from-output backward."""
+    nfail = 0
+    for (B, H, W, Cc, Cx) in [(3, 64, 64, 128, 64), (2, 128, 128, 128, 32), (5, 4, 4, 256, 512), (4, 4, 4, 128, 1024),
+                              (2, 16, 16, 8, 8)]:
+        code = torch.randn(B, Cc, device=dev)
+        x = torch.randn(B, H, W, Cx, device=dev).bfloat16()
+        out = torch.full((B, H, W, Cc + Cx), float("nan"), device=dev, dtype=torch.bfloat16)
+        L.check(lib.ekl_cat_code(L.ptr(code), Cc, L.ptr(x), Cx, B, H * W, L.ptr(out), L.stream()))
+        want = torch.cat((code.bfloat16().view(B, 1, 1, Cc).expand(B, H, W, Cc), x), 3)
+        ok = bool((out == want).all())
+        dcat = torch.randn(B, H, W, Cc + Cx, device=dev).bfloat16()
+        dcode = torch.zeros(B, Cc, device=dev)
+        dx = torch.full((B, H, W, Cx), float("nan"), device=dev, dtype=torch.bfloat16)
+        L.check(lib.ekl_cat_code_bwd(L.ptr(dcat), Cc, Cx, B, H * W, L.ptr(dcode), L.ptr(dx), L.stream()))
+        torch.cuda.synchronize()
+        e = rel(dcode, dcat[..., :Cc].float().sum((1, 2)))
+        ok = ok and bool((dx == dcat[..., Cc:]).all()) and e < 1e-5
+        print("%s cat_code B%d %dx%d Cc%d Cx%d dcode rel %.1e" % ("PASS" if ok else "FAIL", B, H, W, Cc, Cx, e), flush=True)
+        nfail += 0 if ok else 1
+    for n in (8 * 1000, 8 * 123457):
+        o = torch.randn(n, device=dev).bfloat16()
+        d = torch.randn(n, device=dev).bfloat16()
+        dx = torch.empty_like(o)
+        L.check(lib.ekl_lrelu_bwd(L.ptr(o), L.ptr(d), L.ptr(dx), n, L.stream()))
+        want = torch.where(o.float() > 0, d.float(), 0.2 * d.float()).bfloat16()
+        ok = bool((dx == want).all())
+        print("%s lrelu_bwd n%d" % ("PASS" if ok else "FAIL", n), flush=True)
         nfail += 0 if ok else 1
     return nfail
 
