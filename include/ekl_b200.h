@@ -51,7 +51,7 @@ typedef struct ekl_conv {
   int group_b;       /* batch extent of one BatchNorm-statistics group (0 = B) */
   int impl;          /* EKL_IMPL_TC | EKL_IMPL_SIMT */
   int x_fmt, y_fmt;  /* SIMT only: EKL_FMT_* of x and y */
-  int act;           /* SIMT only: fused epilogue EKL_ACT_NONE | EKL_ACT_LRELU | EKL_ACT_TANH */
+  int act;           /* fused epilogue on the conv output: EKL_ACT_NONE | EKL_ACT_LRELU | EKL_ACT_TANH (no BN partials then) */
   int w_layout;      /* master filter / gradient memory: EKL_W_KRSC [Cout][KH][KW][Cin] | EKL_W_KCRS [Cout][Cin][KH][KW] */
 } ekl_conv;
 
@@ -93,6 +93,22 @@ int ekl_lrelu_bwd(const void* out, const void* dout, void* dx, int64_t n, void* 
 /* cat(tile(c_code), h) along channels (model.py:411-414, 956-959) and its backward (dcode accumulated) */
 int ekl_cat_code(const float* code, int Cc, const void* x, int Cx, int B, int HW, void* out, void* stream);
 int ekl_cat_code_bwd(const void* dcat, int Cc, int Cx, int B, int HW, float* dcode, void* dx, void* stream);
+
+/* ---------------------------------------------------------------- discriminator stem: image layout ----------
+ * First discriminator conv = conv4x4 s2 p1 on the loader's 3-channel NCHW fp32 images (model.py:832-836;
+ * datasets.py:346).  Space-to-depth by 2 makes it a 3x3 s1 conv over 12 (padded to 16) channels for the tcgen05
+ * kernel:  out[b,i,j,(c*2+ph)*2+pw] = x[b,c,2i+ph,2j+pw]  (bf16 NHWC, channels 12..15 zero).  `groups` (1..3)
+ * source batches of B images each (real / wrong / fake, cub_trainer_splitz_cap_ca.py:418-420) are gathered into
+ * one [groups*B, H/2, W/2, 16] tensor.  ekl_img_s2d_bwd is the inverse map for the image gradient (fp32 NCHW). */
+int ekl_img_s2d(const float* x0, const float* x1, const float* x2, int groups, int B, int H, int W, void* out, void* stream);
+int ekl_img_s2d_bwd(const void* dxs, int B, int H, int W, float* dx, void* stream);
+
+/* ---------------------------------------------------------------- generator image head ---------------------
+ * GET_IMAGE_G (model.py:426-437) = conv3x3(ngf -> 3) + tanh.  The conv runs on ekl_conv_fwd with the 3 filters
+ * zero-padded to C (>= 8, multiple of 8) output channels; these passes apply tanh to channels 0..2 of the padded
+ * NHWC bf16 conv output and write the NCHW fp32 image, and map the image gradient back (padding channels zero). */
+int ekl_head_tanh_fwd(const void* y, int B, int HW, int C, float* img, void* stream);
+int ekl_head_tanh_bwd(const void* y, const float* dimg, int B, int HW, int C, void* dy, void* stream);
 
 #ifdef __cplusplus
 }

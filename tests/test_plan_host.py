@@ -118,3 +118,23 @@ def test_no_gpu_fails_loudly():
         pytest.skip("GPU present")
     assert L.lib().ekl_require_sm100() != 0
     assert L.lib().ekl_last_error()
+
+
+def test_space_to_depth_filter_equals_conv4x4_stride2():
+    """The discriminator stem identity the tcgen05 path relies on (model._Encode16): conv4x4/s2/p1 over a 3-channel
+    image == conv3x3/s1/p1 over its space-to-depth image with the re-indexed filter (fp32 on the CPU, exact algebra)."""
+    from text2img_ekl_b200 import model
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 16, 12)
+    w = torch.randn(8, 3, 4, 4)
+    idx, mask = model._s2d_filter_index()
+    w2 = (w.reshape(8, 48)[:, idx] * mask).view(8, 3, 3, 16).permute(0, 3, 1, 2)
+    xs = torch.zeros(2, 16, 8, 6)
+    for c in range(3):
+        for ph in range(2):
+            for pw in range(2):
+                xs[:, (c * 2 + ph) * 2 + pw] = x[:, c, ph::2, pw::2]
+    a = F.conv2d(x, w, stride=2, padding=1)
+    b = F.conv2d(xs, w2, stride=1, padding=1)
+    assert torch.allclose(a, b, atol=1e-5)
+    assert int(mask.sum()) == 48           # every master-filter entry appears exactly once

@@ -49,6 +49,10 @@ SIGNATURES = {
     "ekl_lrelu_bwd": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "ekl_cat_code": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "ekl_cat_code_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "ekl_img_s2d": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "ekl_img_s2d_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "ekl_head_tanh_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "ekl_head_tanh_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
 }
 
 _lib = None

@@ -6,7 +6,7 @@
 int ekl_tc_supported(const EklGather* g);
 int ekl_tc_stats_rows(const EklGather* g, int group_b);
 void ekl_tc_geometry(const EklGather* g, int group_b, int* tb, int* th, int* tw);
-int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, int group_b, int* mtiles_out, cudaStream_t st);
+int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, int group_b, int act, int* mtiles_out, cudaStream_t st);
 int ekl_gather_simt(const EklGather* g, const void* w_packed, int act, cudaStream_t st);
 int ekl_wgrad_simt(const EklGather* fwd_plan, float* dw_master, cudaStream_t st);
 int ekl_wgrad_tc_supported(const EklGather* g);
@@ -88,8 +88,11 @@ extern "C" int ekl_conv_fwd(const ekl_conv* c, const void* x, const void* w_fwd,
     const int act = c->act == EKL_ACT_LRELU ? 1 : (c->act == EKL_ACT_TANH ? 2 : 0);
     return ekl_gather_simt(&g, w_fwd, act, (cudaStream_t)stream);
   }
-  EKL_REQUIRE(c->act == EKL_ACT_NONE && c->x_fmt == 0 && c->y_fmt == 0, "TC conv: NHWC bf16, no fused activation");
-  return ekl_gather_gemm_tc(&g, w_fwd, stats, c->group_b, nullptr, (cudaStream_t)stream);
+  EKL_REQUIRE(c->x_fmt == 0 && c->y_fmt == 0, "TC conv: NHWC bf16 only");
+  EKL_REQUIRE(c->act == EKL_ACT_NONE || c->act == EKL_ACT_LRELU || c->act == EKL_ACT_TANH,
+              "TC conv: fused epilogue activation must be none, LeakyReLU or tanh");
+  EKL_REQUIRE(c->act == EKL_ACT_NONE || stats == nullptr, "TC conv: BatchNorm partials are of the raw conv output");
+  return ekl_gather_gemm_tc(&g, w_fwd, stats, c->group_b, c->act, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int ekl_conv_bwd_data(const ekl_conv* c, const void* dy, const void* w_dgrad, void* dx, void* stream) {
@@ -98,7 +101,7 @@ extern "C" int ekl_conv_bwd_data(const ekl_conv* c, const void* dy, const void* 
   plan(c, 1, dx, dy, &g);
   if (c->impl == EKL_IMPL_SIMT) return ekl_gather_simt(&g, w_dgrad, 0, (cudaStream_t)stream);
   EKL_REQUIRE(c->x_fmt == 0 && c->y_fmt == 0, "TC conv: NHWC bf16 only");
-  return ekl_gather_gemm_tc(&g, w_dgrad, nullptr, 0, nullptr, (cudaStream_t)stream);
+  return ekl_gather_gemm_tc(&g, w_dgrad, nullptr, 0, 0, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int ekl_conv_bwd_weight(const ekl_conv* c, const void* x, const void* dy, float* dw, void* stream) {

@@ -27,6 +27,7 @@ struct TcParams {
   int rows_valid;     // tb*th*tw
   int nvar, ntn;      // variants, N tiles
   int groups, mtg;    // BatchNorm statistic groups, M tiles per group
+  int act;            // epilogue activation on the fp32 accumulator: 0 none, 2 LeakyReLU(0.2), 4 tanh
 };
 
 template <int BN, int KC>
@@ -56,6 +57,12 @@ __device__ __forceinline__ uint32_t stage_off(int r, int c) {
   if constexpr (BN >= 64) return (uint32_t)((c >> 6) * (128 * 128) + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2);
   else if constexpr (BN == 32) return (uint32_t)(r * 64 + (((c >> 3) ^ ((r >> 1) & 3)) << 4) + (c & 7) * 2);
   else return (uint32_t)(r * 32 + c * 2);
+}
+
+__device__ __forceinline__ float epi_act(float v, int act) {
+  if (act == 2) return v > 0.f ? v : 0.2f * v;
+  if (act == 4) return tanhf(v);
+  return v;
 }
 
 // Persistent kernel: grid = #SMs; every CTA walks the same static schedule
@@ -184,6 +191,10 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
           tmem_ld16(tacc, rr);
           tmem_ld_wait();
           uint32_t pk[8];
+          if (p.act != 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(epi_act(__uint_as_float(rr[i]), p.act));
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1]));
           uint8_t* box = stage_out + row * 32;
@@ -196,6 +207,10 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
             tmem_ld32(tacc + (uint32_t)c0, rr);
             tmem_ld_wait();
             uint32_t pk[16];
+            if (p.act != 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) rr[i] = __float_as_uint(epi_act(__uint_as_float(rr[i]), p.act));
+            }
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1]));
 #pragma unroll
@@ -319,7 +334,7 @@ int ekl_tc_stats_rows(const EklGather* g, int group_b) {
 }
 
 // stats: [((grp*grid + cta)*nvar + v)][2][N] fp32 partials or null.
-int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, int group_b, int* mtiles_out,
+int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, int group_b, int act, int* mtiles_out,
                        cudaStream_t st) {
   EKL_REQUIRE(ekl_tc_supported(g), "gather_gemm_tc: unsupported shape Cin=%d N=%d mH=%d mW=%d", g->Cin, g->N, g->mH, g->mW);
   TcParams p;
@@ -334,7 +349,7 @@ int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, i
   const int mtiles = p.mtg * p.groups;
   if (mtiles_out) *mtiles_out = mtiles;
   p.rows_valid = tb * th * tw;
-  p.ntaps = g->ntaps; p.Cin = g->Cin; p.N = g->N; p.stats = stats; p.nvar = g->nvar;
+  p.ntaps = g->ntaps; p.Cin = g->Cin; p.N = g->N; p.stats = stats; p.nvar = g->nvar; p.act = act;
   memcpy(p.taps, g->taps, sizeof(p.taps));
   const int KC = g->Cin % 64 == 0 ? 64 : (g->Cin % 32 == 0 ? 32 : 16);
   p.ncb = g->Cin / KC;

@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
         if (valid) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
+            if (c0 + i >= BNW) break;                 // BNW = 16: the TMEM allocation is 32 columns, 16 are live
             const int co = n0 + c0 + i;
             const float val = __uint_as_float(r[i]);
             for (int s = 0; s < tap.nsrc; ++s)
@@ -184,7 +185,7 @@ int launch_wg(const EklGather* g, WgParams& p, int splits, cudaStream_t st) {
 int ekl_wgrad_tc_supported(const EklGather* g) {
   auto pow2 = [](int x) { return x > 0 && (x & (x - 1)) == 0; };
   if (g->transposed) return 0;
-  if (g->Cin % 16 != 0 || g->N % 32 != 0) return 0;
+  if (g->Cin % 16 != 0 || g->N % 16 != 0) return 0;
   if (!pow2(g->mW) || !pow2(g->mH)) return 0;
   for (int i = 0; i < g->n_a; ++i)
     if (g->a[i].f32 || g->a[i].sC != 1) return 0;
@@ -213,10 +214,10 @@ int ekl_wgrad_tc(const EklGather* g, float* dw, cudaStream_t st) {
   p.nTw = ekl_cdiv(g->mW, tw); p.nTh = ekl_cdiv(g->mH, th);
   p.ptiles = p.nTw * p.nTh * ekl_cdiv(g->mB, tb);
   p.rows_valid = tb * th * tw;
-  const int BNW = g->N % 256 == 0 ? 256 : (g->N % 128 == 0 ? 128 : (g->N % 64 == 0 ? 64 : 32));
+  const int BNW = g->N % 256 == 0 ? 256 : (g->N % 128 == 0 ? 128 : (g->N % 64 == 0 ? 64 : (g->N % 32 == 0 ? 32 : 16)));
   const int YW = BNW < 64 ? BNW : 64;
   const int a_swz = CW == 64 ? 3 : (CW == 32 ? 2 : 1);
-  const int y_swz = YW == 64 ? 3 : 2;
+  const int y_swz = YW == 64 ? 3 : (YW == 32 ? 2 : 1);
   for (int i = 0; i < g->n_a; ++i) {
     int rc = make_map(&p.a_maps[i], g->a[i], CW, tw, th, tb, a_swz);
     if (rc) return rc;
@@ -234,6 +235,7 @@ int ekl_wgrad_tc(const EklGather* g, float* dw, cudaStream_t st) {
   EKL_WG_CASE(256, 64) EKL_WG_CASE(128, 64) EKL_WG_CASE(64, 64) EKL_WG_CASE(32, 64)
   EKL_WG_CASE(256, 32) EKL_WG_CASE(128, 32) EKL_WG_CASE(64, 32) EKL_WG_CASE(32, 32)
   EKL_WG_CASE(256, 16) EKL_WG_CASE(128, 16) EKL_WG_CASE(64, 16) EKL_WG_CASE(32, 16)
+  EKL_WG_CASE(16, 64) EKL_WG_CASE(16, 32) EKL_WG_CASE(16, 16)
 #undef EKL_WG_CASE
   return ekl_fail(-1, "wgrad_tc: no kernel for BNW=%d CW=%d", BNW, CW);
 }

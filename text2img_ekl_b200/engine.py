@@ -110,8 +110,8 @@ class StepEngine:
         netD, opt, grads = self.netsD[idx], self.optsD[idx], self.gradsD[idx]
         B = real_imgs.shape[0]
         grads.zero()
-        x = torch.cat((real_imgs, wrong_imgs, self.fake_imgs[idx].detach()), 0)
-        out = netD(x, self.mu.detach(), groups=3)
+        # the three reference forwards (real / wrong / fake) as one pass; the batches are gathered by the stem kernel
+        out = netD((real_imgs, wrong_imgs, self.fake_imgs[idx].detach()), self.mu.detach(), groups=3)
         real, wrong, fake = [[o[i * B:(i + 1) * B] for o in out] for i in range(3)]
         errD_match = _bce_const(real[0], 1) + _bce_const(wrong[0], 0) + _bce_const(fake[0], 0)
         if len(out) > 1 and self.uncond > 0:
@@ -120,7 +120,7 @@ class StepEngine:
             errD_cls = ce_loss(real[2], real_cp) + ce_loss(fake[2], fake_cp)
             errD = errD_match + errD_uncond + errD_cls
         else:
-            errD_uncond = errD_cls = torch.zeros((), device=x.device)
+            errD_uncond = errD_cls = torch.zeros((), device=real_imgs.device)
             errD = _bce_const(real[0], 1) + 0.5 * (_bce_const(wrong[0], 0) + _bce_const(fake[0], 0))
         errD.backward()
         if self.allreduce is not None:

@@ -325,10 +325,11 @@ class _TanhFromOut(torch.autograd.Function):
 
 
 class GET_IMAGE_G(nn.Module):
-    """model.py:426-437: conv3x3(ngf -> 3) + tanh.  Runs on the tcgen05 conv kernels with the 3 output channels
-    zero-padded to one 32-wide tile (the layer is HBM-bound: it reads h_code once); tanh is applied to the 3 real
-    channels while converting to the reference's NCHW fp32 image."""
-    PAD = 32
+    """model.py:426-437: conv3x3(ngf -> 3) + tanh.  Runs on the tcgen05 conv kernel with the 3 output channels
+    zero-padded to one 16-wide N tile (the layer is HBM-bound: it reads h_code once); one fused pass applies tanh in
+    fp32 to the 3 real channels and writes the reference's NCHW fp32 image (tanh' is evaluated from the
+    pre-activation in backward: a bf16 tanh output would lose 1 - y^2 near saturation)."""
+    PAD = 16
 
     def __init__(self, ngf):
         super().__init__()
@@ -345,8 +346,8 @@ class GET_IMAGE_G(nn.Module):
             y, _ = ops.conv(to_nhwc(h_code), w, self._spec)
             return _TanhFromOut.apply(y)
         w_pad = F.pad(w, (0, 0, 0, 0, 0, 0, 0, self.PAD - 3))
-        y, _ = ops.conv(to_nhwc(h_code), w_pad, self._spec)                   # [B,H,W,32] bf16
-        return torch.tanh(y[..., :3].permute(0, 3, 1, 2).float())
+        y, _ = ops.conv(to_nhwc(h_code), w_pad, self._spec)                   # [B,H,W,16] bf16 pre-activation
+        return ops.head_tanh(y)
 
 
 def get_shareGs(gf_dim):            # model.py:439-451
@@ -518,10 +519,29 @@ def downBlock(in_planes, out_planes):
     return _DownBlock(in_planes, out_planes)
 
 
+def _s2d_filter_index():
+    """Index / mask tensors mapping the conv4x4-s2-p1 filter [n, c, kh, kw] (flattened c*16 + kh*4 + kw) onto the
+    3x3 filter over space-to-depth channels ch = (c*2 + ph)*2 + pw (include/ekl_b200.h: ekl_img_s2d):
+    input row 2*ho - 1 + kh is s2d row ho + di with parity ph for (di, ph) = (-1,1), (0,0), (0,1), (1,0) <-> kh 0..3."""
+    k_of = {(-1, 1): 0, (0, 0): 1, (0, 1): 2, (1, 0): 3}
+    idx = torch.zeros(3, 3, 16, dtype=torch.long)
+    mask = torch.zeros(3, 3, 16)
+    for di in (-1, 0, 1):
+        for dj in (-1, 0, 1):
+            for c in range(3):
+                for ph in range(2):
+                    for pw in range(2):
+                        if (di, ph) in k_of and (dj, pw) in k_of:
+                            idx[di + 1, dj + 1, (c * 2 + ph) * 2 + pw] = c * 16 + k_of[(di, ph)] * 4 + k_of[(dj, pw)]
+                            mask[di + 1, dj + 1, (c * 2 + ph) * 2 + pw] = 1.0
+    return idx.reshape(-1), mask.reshape(-1)
+
+
 class _Encode16(nn.Sequential):
-    """model.py:832-850 encode_image_by_16times; children keep indices 0..10.  The first conv (Cin = 3) is HBM-bound:
-    the NCHW fp32 image is converted once to NHWC bf16 with channels zero-padded to 16 and runs on the tcgen05
-    kernels like every other layer (widths that are not multiples of 32 fall back to the SIMT conv)."""
+    """model.py:832-850 encode_image_by_16times; children keep indices 0..10.  The first conv (Cin = 3, HBM-bound)
+    runs on the tcgen05 kernel as a 3x3 conv over the space-to-depth image (12 -> 16 channels, 4x fewer pixels) with
+    LeakyReLU fused into its epilogue; `x` may be a tuple of image batches (real, wrong, fake) which are gathered by
+    the space-to-depth kernel instead of torch.cat.  Widths that are not multiples of 32 use the SIMT conv."""
 
     def __init__(self, ndf):
         super().__init__(
@@ -530,23 +550,28 @@ class _Encode16(nn.Sequential):
             nn.Conv2d(ndf * 2, ndf * 4, 4, 2, 1, bias=False), nn.BatchNorm2d(ndf * 4), nn.LeakyReLU(0.2, inplace=True),
             nn.Conv2d(ndf * 4, ndf * 8, 4, 2, 1, bias=False), nn.BatchNorm2d(ndf * 8), nn.LeakyReLU(0.2, inplace=True))
         self._tc0 = ndf % 32 == 0
-        if self._tc0:      # Cin 3 zero-padded to one 16-channel K block of the tcgen05 kernel
-            self._s0 = ops.ConvSpec(ops.DOWN2, 16, ndf, impl=L.IMPL_TC)
+        if self._tc0:
+            self._s0 = ops.ConvSpec(ops.S1, 16, ndf, impl=L.IMPL_TC, act=ops.ACT_LRELU)
+            self._s2d = None
         else:
             self._s0 = ops.ConvSpec(ops.DOWN2, 3, ndf, impl=L.IMPL_SIMT, x_fmt=L.FMT_NCHW_F32, act=ops.ACT_LRELU)
         self._s = [_spec(ops.DOWN2, ndf, ndf * 2), _spec(ops.DOWN2, ndf * 2, ndf * 4), _spec(ops.DOWN2, ndf * 4, ndf * 8)]
 
     def forward(self, x, groups=1):
+        imgs = list(x) if isinstance(x, (list, tuple)) else [x]
+        w = self[0].weight
         if self._tc0:
-            # NCHW fp32 image -> NHWC bf16 with channels padded 3 -> 16 (one fused cast/copy), filter padded alike
-            xp = F.pad(x.permute(0, 2, 3, 1), (0, 13)).to(torch.bfloat16).contiguous()
-            wp = F.pad(self[0].weight, (0, 0, 0, 0, 0, 13))
-            y, _ = ops.conv(xp, wp, self._s0)
-            h = F.leaky_relu(y, 0.2)
+            if self._s2d is None or self._s2d[0].device != w.device:
+                self._s2d = tuple(t.to(w.device) for t in _s2d_filter_index())
+            idx, mask = self._s2d
+            n = w.shape[0]
+            w2 = (w.reshape(n, 48)[:, idx] * mask).view(n, 3, 3, 16).permute(0, 3, 1, 2)     # [n,16,3,3], KRSC memory
+            h, _ = ops.conv(ops.img_s2d(*imgs), w2, self._s0)                                 # LeakyReLU in the epilogue
         else:
+            x = imgs[0] if len(imgs) == 1 else torch.cat(imgs, 0)
             if x.dtype != torch.float32 or not x.is_contiguous():
                 x = x.float().contiguous()
-            y, _ = ops.conv(x, self[0].weight, self._s0)
+            y, _ = ops.conv(x, w, self._s0)
             h = ops.lrelu_from_out(y)
         for i, (ci, bi) in enumerate(((2, 3), (5, 6), (8, 9))):
             h = _conv_bn_act(h, self[ci], self[bi], self._s[i], ops.ACT_LRELU, groups)

@@ -107,9 +107,10 @@ class ConvSpec:
         key = (weight._version, weight.data_ptr())
         if key != self._ver or not weight.is_leaf:      # derived (e.g. zero-padded) filters are rebuilt every step
             self.bind(weight)
-            lst = _SPECS_OF.setdefault(id(weight), [])
-            if self not in lst:
-                lst.append(self)
+            if weight.is_leaf:
+                lst = _SPECS_OF.setdefault(id(weight), [])
+                if self not in lst:
+                    lst.append(self)
             lib = L.lib()
             c = self.conv(1, 4, 4)
             if self.w_fwd is None:
@@ -150,7 +151,10 @@ class _Conv(torch.autograd.Function):
             L.check(lib.ekl_conv_fwd(c, L.ptr(x), L.ptr(w_fwd), L.ptr(y), L.ptr(stats), L.stream()))
         _count()
         ctx.dims = (B, H, W)
-        ctx.save_for_backward(x, weight)
+        if spec.act != ACT_NONE and spec.impl == L.IMPL_TC:
+            ctx.save_for_backward(x, weight, y)        # fused epilogue activation: its derivative needs the output
+        else:
+            ctx.save_for_backward(x, weight)
         ctx.spec, ctx.c, ctx.skip_wgrad, ctx.w_leaf = spec, c, skip_wgrad, weight.is_leaf
         ctx.mark_non_differentiable(*([stats] if stats is not None else []))
         return y, stats
@@ -158,10 +162,19 @@ class _Conv(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, _dstats):
         lib = L.lib()
-        x, weight = ctx.saved_tensors
+        x, weight = ctx.saved_tensors[:2]
         spec, c = ctx.spec, ctx.c
         fam = "conv_tc" if spec.impl == L.IMPL_TC else "conv_simt"
         dy = dy.contiguous()
+        if len(ctx.saved_tensors) == 3:
+            y = ctx.saved_tensors[2]
+            if spec.act == ACT_LRELU:                   # dpre = dy * LeakyReLU'(0.2), evaluated from the output
+                dpre = torch.empty_like(y)
+                L.check(lib.ekl_lrelu_bwd(L.ptr(y), L.ptr(dy), L.ptr(dpre), y.numel(), L.stream()))
+                _count()
+                dy = dpre
+            elif spec.act == ACT_TANH:
+                dy = dy * (1.0 - y.float() ** 2).to(dy.dtype)
         dx = None
         if ctx.needs_input_grad[0]:
             _, w_dgrad = spec.packed(weight)
@@ -311,3 +324,66 @@ class _CatCode(torch.autograd.Function):
 
 def cat_code(code, x):
     return _CatCode.apply(code, x)
+
+
+class _ImgS2D(torch.autograd.Function):
+    """Space-to-depth of up to three NCHW fp32 image batches into one NHWC bf16 [G*B, H/2, W/2, 16] tensor
+    (include/ekl_b200.h: ekl_img_s2d); backward = inverse map of the (single) image batch that needs a gradient."""
+
+    @staticmethod
+    def forward(ctx, *imgs):
+        B, C, H, W = imgs[0].shape
+        assert C == 3 and len(imgs) <= 3
+        imgs = [t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous() for t in imgs]
+        out = torch.empty(len(imgs) * B, H // 2, W // 2, 16, device=imgs[0].device, dtype=torch.bfloat16)
+        p = [L.ptr(t) for t in imgs] + [None] * (3 - len(imgs))
+        L.check(L.lib().ekl_img_s2d(p[0], p[1], p[2], len(imgs), B, H, W, L.ptr(out), L.stream()))
+        _count()
+        ctx.dims = (B, H, W, len(imgs))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, H, W, n = ctx.dims
+        dout = dout.contiguous()
+        grads = []
+        for g in range(n):
+            if not ctx.needs_input_grad[g]:
+                grads.append(None)
+                continue
+            dx = torch.empty(B, 3, H, W, device=dout.device, dtype=torch.float32)
+            L.check(L.lib().ekl_img_s2d_bwd(L.ptr(dout[g * B:(g + 1) * B]), B, H, W, L.ptr(dx), L.stream()))
+            _count()
+            grads.append(dx)
+        return tuple(grads)
+
+
+def img_s2d(*imgs):
+    return _ImgS2D.apply(*imgs)
+
+
+class _HeadTanh(torch.autograd.Function):
+    """NHWC bf16 [B,H,W,C] conv output (3 real channels) -> tanh -> NCHW fp32 image [B,3,H,W] (model.py:433-436)."""
+
+    @staticmethod
+    def forward(ctx, y):
+        B, H, W, C = y.shape
+        img = torch.empty(B, 3, H, W, device=y.device, dtype=torch.float32)
+        L.check(L.lib().ekl_head_tanh_fwd(L.ptr(y), B, H * W, C, L.ptr(img), L.stream()))
+        _count()
+        ctx.save_for_backward(y)
+        return img
+
+    @staticmethod
+    def backward(ctx, dimg):
+        (y,) = ctx.saved_tensors
+        B, H, W, C = y.shape
+        dimg = dimg.float().contiguous()
+        dy = torch.empty_like(y)
+        L.check(L.lib().ekl_head_tanh_bwd(L.ptr(y), L.ptr(dimg), B, H * W, C, L.ptr(dy), L.stream()))
+        _count()
+        return dy
+
+
+def head_tanh(y):
+    return _HeadTanh.apply(y)

@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 
 SHAPES = {  # mode -> list of (B, H, W, Cin, Cout)
     0: [(4, 8, 8, 64, 128), (2, 16, 16, 128, 64), (3, 4, 4, 64, 256), (2, 32, 32, 32, 64), (2, 64, 64, 16, 32),
-        (8, 4, 4, 192, 512), (2, 8, 8, 320, 128)],
+        (8, 4, 4, 192, 512), (2, 8, 8, 320, 128), (3, 32, 32, 16, 64), (2, 32, 32, 32, 16), (2, 64, 64, 16, 16)],
     1: [(4, 4, 4, 128, 128), (2, 8, 8, 64, 64), (3, 16, 16, 64, 128), (2, 32, 32, 32, 32), (2, 4, 4, 256, 512)],
     2: [(4, 16, 16, 64, 128), (2, 8, 8, 128, 256), (3, 32, 32, 64, 64), (2, 8, 8, 512, 1024), (2, 64, 64, 32, 64)],
 }
@@ -60,8 +60,6 @@ def run_group(group):
             dyn = torch.randn(B, Ho, Wo, Cout, device=dev).bfloat16()
             yr.backward(dyn.float().permute(0, 3, 1, 2))
             tag = "%-10s mode%d B%d %dx%d Cin%d Cout%d" % (group, mode, B, H, W, Cin, Cout)
-            if impl == L.IMPL_TC and what == "dgrad" and Cin % 32 != 0:
-                continue      # data-gradient output channels = Cin: the tcgen05 path needs N % 32 == 0 (16-channel maps use SIMT)
             try:
                 if what == "fwd":
                     y = torch.full((B, Ho, Wo, Cout), float("nan"), device=dev, dtype=torch.bfloat16)
@@ -176,6 +174,50 @@ def run_misc(torch, L, lib, dev, rel):
         e = rel(dcode, dcat[..., :Cc].float().sum((1, 2)))
         ok = ok and bool((dx == dcat[..., Cc:]).all()) and e < 1e-5
         print("%s cat_code B%d %dx%d Cc%d Cx%d dcode rel %.1e" % ("PASS" if ok else "FAIL", B, H, W, Cc, Cx, e), flush=True)
+        nfail += 0 if ok else 1
+    for (G, B, H, W) in [(3, 2, 64, 64), (1, 3, 16, 128), (2, 1, 256, 256)]:
+        xs = [torch.randn(B, 3, H, W, device=dev) for _ in range(G)]
+        out = torch.full((G * B, H // 2, W // 2, 16), float("nan"), device=dev, dtype=torch.bfloat16)
+        p = [L.ptr(t) for t in xs] + [None] * (3 - G)
+        L.check(lib.ekl_img_s2d(p[0], p[1], p[2], G, B, H, W, L.ptr(out), L.stream()))
+        x = torch.cat(xs, 0)
+        want = torch.zeros(G * B, H // 2, W // 2, 16, device=dev)
+        want[..., :12] = torch.nn.functional.pixel_unshuffle(x, 2).permute(0, 2, 3, 1)
+        ok = bool((out == want.bfloat16()).all())
+        d = torch.randn(B, H // 2, W // 2, 16, device=dev).bfloat16()
+        dx = torch.full((B, 3, H, W), float("nan"), device=dev)
+        L.check(lib.ekl_img_s2d_bwd(L.ptr(d), B, H, W, L.ptr(dx), L.stream()))
+        wantd = torch.nn.functional.pixel_shuffle(d[..., :12].float().permute(0, 3, 1, 2), 2)
+        ok = ok and bool((dx == wantd).all())
+        print("%s img_s2d G%d B%d %dx%d" % ("PASS" if ok else "FAIL", G, B, H, W), flush=True)
+        nfail += 0 if ok else 1
+    for (B, H, W, C) in [(2, 64, 64, 16), (3, 16, 32, 8)]:
+        y = torch.randn(B, H, W, C, device=dev).bfloat16()
+        img = torch.full((B, 3, H, W), float("nan"), device=dev)
+        L.check(lib.ekl_head_tanh_fwd(L.ptr(y), B, H * W, C, L.ptr(img), L.stream()))
+        yr = y[..., :3].float().permute(0, 3, 1, 2).requires_grad_(True)
+        want = torch.tanh(yr)
+        dimg = torch.randn(B, 3, H, W, device=dev)
+        want.backward(dimg)
+        dy = torch.full((B, H, W, C), float("nan"), device=dev, dtype=torch.bfloat16)
+        L.check(lib.ekl_head_tanh_bwd(L.ptr(y), L.ptr(dimg), B, H * W, C, L.ptr(dy), L.stream()))
+        e1, e2 = rel(img, want), rel(dy[..., :3].permute(0, 3, 1, 2), yr.grad)
+        ok = e1 < 1e-5 and e2 < 6e-3 and bool((dy[..., 3:] == 0).all())
+        print("%s head_tanh B%d %dx%d C%d img %.1e dy %.1e" % ("PASS" if ok else "FAIL", B, H, W, C, e1, e2), flush=True)
+        nfail += 0 if ok else 1
+    for act, fn in ((L.ACT_LRELU, lambda t: torch.nn.functional.leaky_relu(t, 0.2)), (L.ACT_TANH, torch.tanh)):
+        B, H, W, Cin, Cout = 2, 32, 32, 32, 16 if act == L.ACT_TANH else 64
+        x = torch.randn(B, H, W, Cin, device=dev).bfloat16()
+        wm = (torch.randn(Cout, 3, 3, Cin, device=dev) / (9 * Cin) ** 0.5).bfloat16().float()
+        conv = L.EklConv(0, B, H, W, Cin, Cout, 0, L.IMPL_TC, 0, 0, act, 0)
+        wf = torch.empty(lib.ekl_conv_packed_elems(conv, 0), device=dev, dtype=torch.bfloat16)
+        L.check(lib.ekl_conv_pack(conv, L.ptr(wm), L.ptr(wf), None, L.stream()))
+        y = torch.full((B, H, W, Cout), float("nan"), device=dev, dtype=torch.bfloat16)
+        L.check(lib.ekl_conv_fwd(conv, L.ptr(x), L.ptr(wf), L.ptr(y), None, L.stream()))
+        yr = fn(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wm.permute(0, 3, 1, 2), padding=1))
+        e = rel(y.permute(0, 3, 1, 2), yr)
+        ok = e < 6e-3
+        print("%s tc conv epilogue act%d rel %.2e" % ("PASS" if ok else "FAIL", act, e), flush=True)
         nfail += 0 if ok else 1
     for n in (8 * 1000, 8 * 123457):
         o = torch.randn(n, device=dev).bfloat16()
