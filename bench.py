@@ -270,6 +270,10 @@ def kernel_roofline(tr, batch, pk):
     import torch
     from text2img_ekl_b200 import ops
     ops.PROFILE = []
+    # Park the GPU behind a ~100 ms spin so the host enqueues the whole eager step ahead of it: every event pair then
+    # brackets back-to-back device execution of its kernel(s), not host launch latency.
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(0.1 * 1.9e9))
     tr.train_step(batch)
     torch.cuda.synchronize()
     rec, ops.PROFILE = ops.PROFILE, None

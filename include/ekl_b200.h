@@ -110,6 +110,32 @@ int ekl_img_s2d_bwd(const void* dxs, int B, int H, int W, float* dx, void* strea
 int ekl_head_tanh_fwd(const void* y, int B, int HW, int C, float* img, void* stream);
 int ekl_head_tanh_bwd(const void* y, const float* dimg, int B, int HW, int C, void* dy, void* stream);
 
+/* ---------------------------------------------------------------- discriminator heads + GAN losses -----------
+ * Heads: `logits` / `uncond_logits` = Conv2d(8ndf, 1, 4, stride 4) + Sigmoid on the 4x4 code map (model.py:886-888,
+ * 935-952) == one dot of length K = 16*8ndf per sample.  x_code / h_c: bf16 [GB][K] (NHWC-flattened trunk output /
+ * jointConv output, h_c may be NULL); w_*: fp32 [K] in the same element order (channels_last storage of the
+ * [1,8ndf,4,4] filter); outputs are RAW logits (the sigmoid is applied by the loss kernel / the module forward).
+ * Backward: dx_code / dh_c are written (bf16, either may be NULL), parameter gradients accumulated (+=, may be NULL). */
+int ekl_dhead_dots(const void* x_code, const void* h_c, const float* w_u, const float* b_u, const float* w_m,
+                   const float* b_m, int GB, int K, float* logit_u, float* logit_m, void* stream);
+int ekl_dhead_dots_bwd(const void* x_code, const void* h_c, const float* w_u, const float* w_m, const float* g_u,
+                       const float* g_m, int GB, int K, void* dx_code, void* dh_c, float* dw_u, float* db_u,
+                       float* dw_m, float* db_m, void* stream);
+/* Losses of one discriminator pass over `groups` (1..3) stacked groups of B samples
+ * (cub_trainer_splitz_cap_ca.py:423-448 train_joint_Dnet: groups real/wrong/fake; :470-487 loss_joint_Gnet: one
+ * group): per group a constant 0/1 BCE label for the match and the uncond probability (t_match / t_uncond, host
+ * int[groups]) and a soft class target set (cls_tgt[g]: -1 none, 0 -> cp0, 1 -> cp1; each [B][E1]).
+ * losses[4] = {total, match, uncond_coeff * uncond, class}; p_m / p_u [groups*B] sigmoid probabilities;
+ * logp [groups*B][E1] = log_softmax(cls_logits).  torch semantics: BCE log clamped at -100, means over B,
+ * ce_loss = -sum(p * logq) / B (cub:60-65).  ekl_dloss_bwd: gradients of losses[0] w.r.t. the raw logits,
+ * scaled by the device scalar go[0]. */
+int ekl_dloss_fwd(int groups, int B, int E1, const int* t_match, const int* t_uncond, const int* cls_tgt,
+                  float uncond_coeff, const float* logit_m, const float* logit_u, const float* cls_logits,
+                  const float* cp0, const float* cp1, float* losses, float* p_m, float* p_u, float* logp, void* stream);
+int ekl_dloss_bwd(int groups, int B, int E1, const int* t_match, const int* t_uncond, const int* cls_tgt,
+                  float uncond_coeff, const float* go, const float* p_m, const float* p_u, const float* logp,
+                  const float* cp0, const float* cp1, float* g_m, float* g_u, float* g_cls, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

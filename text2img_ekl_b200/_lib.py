@@ -27,6 +27,7 @@ class EklError(RuntimeError):
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _cp = C.POINTER(EklConv)
+_ip = C.POINTER(C.c_int)
 
 # name -> (restype, argtypes); every symbol include/ekl_b200.h declares
 SIGNATURES = {
@@ -53,6 +54,10 @@ SIGNATURES = {
     "ekl_img_s2d_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "ekl_head_tanh_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "ekl_head_tanh_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "ekl_dhead_dots": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "ekl_dhead_dots_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ekl_dloss_fwd": (_i, [_i, _i, _i, _ip, _ip, _ip, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ekl_dloss_bwd": (_i, [_i, _i, _i, _ip, _ip, _ip, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,241 @@
+// Discriminator logit heads and the multi-branch GAN losses as a handful of fused kernels (HBM / latency bound,
+// warp-shuffle reductions) instead of ~100 elementwise / reduction launches per discriminator pass.
+//
+//   heads   : model.py:886-888, 935-952  `logits` / `uncond_logits` = Conv2d(8ndf, 1, 4, stride 4) + Sigmoid on the 4x4
+//             code map == one dot of length 16*8ndf per sample; computed here as raw (pre-sigmoid) logits.
+//   losses  : cub_trainer_splitz_cap_ca.py:423-448 (train_joint_Dnet) and :470-487 (loss_joint_Gnet):
+//             nn.BCELoss against constant 0/1 labels on the match / uncond probabilities of every group
+//             (real, wrong, fake), + ce_loss(log_softmax(class logits), soft target) (cub:60-65), torch's
+//             log clamp at -100 included.
+#include "../../include/ekl_b200.h"
+#include "ekl_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float block_sum_256(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = l < 8 ? sh[l] : 0.f;
+  return warp_sum(t);      // every warp ends with the full sum
+}
+
+// grid = GB blocks of 256 threads; K % 8 == 0.  feat row (bf16) . w (fp32, same element order) + bias
+__global__ void __launch_bounds__(256) dhead_dots_kernel(const bf16* __restrict__ x, const bf16* __restrict__ h, const float* __restrict__ wu,
+                                                         const float* __restrict__ bu, const float* __restrict__ wm,
+                                                         const float* __restrict__ bm, int K, float* __restrict__ lu,
+                                                         float* __restrict__ lm) {
+  __shared__ float sh[8];
+  const int b = blockIdx.x;
+  float au = 0.f, am = 0.f;
+  for (int k = threadIdx.x * 8; k < K; k += 256 * 8) {
+    const float4 w0 = *reinterpret_cast<const float4*>(wu + k), w1 = *reinterpret_cast<const float4*>(wu + k + 4);
+    const uint4 u = *reinterpret_cast<const uint4*>(x + (int64_t)b * K + k);
+    au += bf16_lo(u.x) * w0.x + bf16_hi(u.x) * w0.y + bf16_lo(u.y) * w0.z + bf16_hi(u.y) * w0.w +
+          bf16_lo(u.z) * w1.x + bf16_hi(u.z) * w1.y + bf16_lo(u.w) * w1.z + bf16_hi(u.w) * w1.w;
+    if (h != nullptr) {
+      const float4 m0 = *reinterpret_cast<const float4*>(wm + k), m1 = *reinterpret_cast<const float4*>(wm + k + 4);
+      const uint4 v = *reinterpret_cast<const uint4*>(h + (int64_t)b * K + k);
+      am += bf16_lo(v.x) * m0.x + bf16_hi(v.x) * m0.y + bf16_lo(v.y) * m0.z + bf16_hi(v.y) * m0.w +
+            bf16_lo(v.z) * m1.x + bf16_hi(v.z) * m1.y + bf16_lo(v.w) * m1.z + bf16_hi(v.w) * m1.w;
+    }
+  }
+  au = block_sum_256(au, sh);
+  if (h != nullptr) am = block_sum_256(am, sh);
+  if (threadIdx.x == 0) {
+    lu[b] = au + bu[0];
+    if (h != nullptr) lm[b] = am + bm[0];
+  }
+}
+
+// one thread per feature index k: dx[b,k] = gu[b]*wu[k] (bf16), dwu[k] += sum_b gu[b]*x[b,k]; likewise (h, wm, gm).
+// block 0 also accumulates the bias gradients.
+__global__ void __launch_bounds__(256) dhead_dots_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ h,
+                                                             const float* __restrict__ wu, const float* __restrict__ wm,
+                                                             const float* __restrict__ gu, const float* __restrict__ gm, int GB,
+                                                             int K, bf16* __restrict__ dx, bf16* __restrict__ dh,
+                                                             float* dwu, float* dbu, float* dwm, float* dbm) {
+  const int k = (blockIdx.x * 256 + threadIdx.x) * 2;
+  if (k < K) {
+    const float2 w_u = *reinterpret_cast<const float2*>(wu + k);
+    float2 w_m = make_float2(0.f, 0.f);
+    if (h != nullptr) w_m = *reinterpret_cast<const float2*>(wm + k);
+    float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
+#pragma unroll 4
+    for (int b = 0; b < GB; ++b) {
+      const float g = gu[b];
+      const uint32_t u = *reinterpret_cast<const uint32_t*>(x + (int64_t)b * K + k);
+      a0 += g * bf16_lo(u); a1 += g * bf16_hi(u);
+      if (dx != nullptr) *reinterpret_cast<uint32_t*>(dx + (int64_t)b * K + k) = pack_bf16x2(g * w_u.x, g * w_u.y);
+      if (h != nullptr) {
+        const float q = gm[b];
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(h + (int64_t)b * K + k);
+        c0 += q * bf16_lo(v); c1 += q * bf16_hi(v);
+        if (dh != nullptr) *reinterpret_cast<uint32_t*>(dh + (int64_t)b * K + k) = pack_bf16x2(q * w_m.x, q * w_m.y);
+      }
+    }
+    if (dwu != nullptr) { dwu[k] += a0; dwu[k + 1] += a1; }
+    if (h != nullptr && dwm != nullptr) { dwm[k] += c0; dwm[k + 1] += c1; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    float su = 0.f, sm = 0.f;
+    for (int b = threadIdx.x; b < GB; b += 32) { su += gu[b]; if (h != nullptr) sm += gm[b]; }
+    su = warp_sum(su); sm = warp_sum(sm);
+    if (threadIdx.x == 0) {
+      if (dbu != nullptr) dbu[0] += su;
+      if (h != nullptr && dbm != nullptr) dbm[0] += sm;
+    }
+  }
+}
+
+struct LossCfg {
+  int groups, B, E1;
+  int t_match[3], t_uncond[3], cls_tgt[3];   // 0/1 labels per group; class-target set per group (-1 none, 0, 1)
+  float uncond_coeff;
+};
+
+// BCE against a constant label with torch's clamp: -max(log(p or 1-p), -100); p = sigmoid(z)
+__device__ __forceinline__ float bce_term(float z, int t, float* p_out) {
+  const float p = 1.f / (1.f + expf(-z));
+  *p_out = p;
+  const float lg = t ? logf(p) : log1pf(-p);
+  return -fmaxf(lg, -100.f);
+}
+// d/dz of the above (through the sigmoid): autograd of -clamp(log p, -100): zero where the clamp is active
+__device__ __forceinline__ float bce_grad(float p, int t) {
+  if (t) return logf(p) >= -100.f ? -(1.f - p) : 0.f;
+  return log1pf(-p) >= -100.f ? p : 0.f;
+}
+
+// grid = ceil(G*B / 8) blocks of 256 threads: one row per warp.  losses[4] must be ZERO on entry; every block adds its
+// share: losses = {total, match, uncond_coeff*uncond, cls}; probs: pm/pu [G*B]; logp [G*B, E1] = log_softmax(cls)
+__global__ void __launch_bounds__(256) dloss_fwd_kernel(LossCfg c, const float* __restrict__ lm, const float* __restrict__ lu,
+                                                        const float* __restrict__ cls, const float* __restrict__ cp0,
+                                                        const float* __restrict__ cp1, float* __restrict__ losses,
+                                                        float* __restrict__ pm, float* __restrict__ pu, float* __restrict__ logp) {
+  __shared__ float sh[8];
+  const int GB = c.groups * c.B;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + w;
+  float lmatch = 0.f, lunc = 0.f, lcls = 0.f;
+  if (r < GB) {
+    const int g = r / c.B;
+    if (l == 0) {
+      float p;
+      lmatch = bce_term(lm[r], c.t_match[g], &p); pm[r] = p;
+      lunc = bce_term(lu[r], c.t_uncond[g], &p); pu[r] = p;
+    }
+    if (cls != nullptr) {
+      const float* row = cls + (int64_t)r * c.E1;
+      float mx = -INFINITY;
+      for (int e = l; e < c.E1; e += 32) mx = fmaxf(mx, row[e]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float se = 0.f;
+      for (int e = l; e < c.E1; e += 32) se += expf(row[e] - mx);
+      se = warp_sum(se);
+      const float lse = mx + logf(se);
+      const int tg = c.cls_tgt[g];
+      const float* tgt = tg < 0 ? nullptr : (tg == 0 ? cp0 : cp1) + (int64_t)(r - g * c.B) * c.E1;
+      for (int e = l; e < c.E1; e += 32) {
+        const float lq = row[e] - lse;
+        logp[(int64_t)r * c.E1 + e] = lq;
+        if (tgt != nullptr) lcls -= tgt[e] * lq;
+      }
+    }
+  }
+  lmatch = block_sum_256(lmatch, sh);
+  lunc = block_sum_256(lunc, sh);
+  lcls = block_sum_256(lcls, sh);
+  if (threadIdx.x == 0) {
+    const float inv = 1.f / (float)c.B;      // every BCE term is a mean over its group of B; ce_loss divides by B
+    const float m = lmatch * inv, u = c.uncond_coeff * lunc * inv, k = lcls * inv;
+    atomicAdd(losses + 0, m + u + k); atomicAdd(losses + 1, m); atomicAdd(losses + 2, u); atomicAdd(losses + 3, k);
+  }
+}
+
+// gradients of losses[0] w.r.t. the raw logits, scaled by the upstream scalar go[0]; same grid as the forward
+__global__ void __launch_bounds__(256) dloss_bwd_kernel(LossCfg c, const float* __restrict__ go, const float* __restrict__ pm,
+                                                        const float* __restrict__ pu, const float* __restrict__ logp,
+                                                        const float* __restrict__ cp0, const float* __restrict__ cp1,
+                                                        float* __restrict__ gm, float* __restrict__ gu, float* __restrict__ gcls) {
+  const int GB = c.groups * c.B;
+  const float s = go[0] / (float)c.B;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + w;
+  if (r >= GB) return;
+  const int g = r / c.B;
+  if (l == 0) {
+    gm[r] = s * bce_grad(pm[r], c.t_match[g]);
+    gu[r] = s * c.uncond_coeff * bce_grad(pu[r], c.t_uncond[g]);
+  }
+  if (gcls == nullptr) return;
+  const int tg = c.cls_tgt[g];
+  const float* tgt = tg < 0 ? nullptr : (tg == 0 ? cp0 : cp1) + (int64_t)(r - g * c.B) * c.E1;
+  float tsum = 0.f;
+  if (tgt != nullptr) {
+    for (int e = l; e < c.E1; e += 32) tsum += tgt[e];
+    tsum = warp_sum(tsum);
+  }
+  for (int e = l; e < c.E1; e += 32) {
+    // d/dlogit of -sum_e t_e * log_softmax_e = softmax_e * sum(t) - t_e
+    const float v = tgt != nullptr ? (expf(logp[(int64_t)r * c.E1 + e]) * tsum - tgt[e]) * s : 0.f;
+    gcls[(int64_t)r * c.E1 + e] = v;
+  }
+}
+
+int make_cfg(LossCfg* c, int groups, int B, int E1, const int* t_match, const int* t_uncond, const int* cls_tgt, float uncond_coeff) {
+  EKL_REQUIRE(groups >= 1 && groups <= 3 && B > 0 && E1 >= 0, "dloss: groups must be 1..3");
+  c->groups = groups; c->B = B; c->E1 = E1; c->uncond_coeff = uncond_coeff;
+  for (int g = 0; g < 3; ++g) {
+    c->t_match[g] = g < groups ? t_match[g] : 0;
+    c->t_uncond[g] = g < groups ? t_uncond[g] : 0;
+    c->cls_tgt[g] = g < groups ? cls_tgt[g] : -1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int ekl_dhead_dots(const void* x_code, const void* h_c, const float* w_u, const float* b_u, const float* w_m,
+                              const float* b_m, int GB, int K, float* logit_u, float* logit_m, void* stream) {
+  EKL_REQUIRE(K % 8 == 0 && GB > 0, "dhead_dots: K %% 8");
+  dhead_dots_kernel<<<GB, 256, 0, (cudaStream_t)stream>>>((const bf16*)x_code, (const bf16*)h_c, w_u, b_u, w_m, b_m, K, logit_u,
+                                                         logit_m);
+  EKL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ekl_dhead_dots_bwd(const void* x_code, const void* h_c, const float* w_u, const float* w_m, const float* g_u,
+                                  const float* g_m, int GB, int K, void* dx_code, void* dh_c, float* dw_u, float* db_u,
+                                  float* dw_m, float* db_m, void* stream) {
+  EKL_REQUIRE(K % 2 == 0 && GB > 0, "dhead_dots_bwd: K %% 2");
+  dhead_dots_bwd_kernel<<<ekl_cdiv(K / 2, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x_code, (const bf16*)h_c, w_u, w_m, g_u, g_m, GB, K, (bf16*)dx_code, (bf16*)dh_c, dw_u, db_u, dw_m, db_m);
+  EKL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ekl_dloss_fwd(int groups, int B, int E1, const int* t_match, const int* t_uncond, const int* cls_tgt,
+                             float uncond_coeff, const float* logit_m, const float* logit_u, const float* cls_logits,
+                             const float* cp0, const float* cp1, float* losses, float* p_m, float* p_u, float* logp,
+                             void* stream) {
+  LossCfg c;
+  if (int rc = make_cfg(&c, groups, B, E1, t_match, t_uncond, cls_tgt, uncond_coeff)) return rc;
+  EKL_CHECK_CUDA(cudaMemsetAsync(losses, 0, 4 * sizeof(float), (cudaStream_t)stream));
+  dloss_fwd_kernel<<<ekl_cdiv(groups * B, 8), 256, 0, (cudaStream_t)stream>>>(c, logit_m, logit_u, cls_logits, cp0, cp1, losses, p_m, p_u, logp);
+  EKL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ekl_dloss_bwd(int groups, int B, int E1, const int* t_match, const int* t_uncond, const int* cls_tgt,
+                             float uncond_coeff, const float* go, const float* p_m, const float* p_u, const float* logp,
+                             const float* cp0, const float* cp1, float* g_m, float* g_u, float* g_cls, void* stream) {
+  LossCfg c;
+  if (int rc = make_cfg(&c, groups, B, E1, t_match, t_uncond, cls_tgt, uncond_coeff)) return rc;
+  dloss_bwd_kernel<<<ekl_cdiv(groups * B, 8), 256, 0, (cudaStream_t)stream>>>(c, go, p_m, p_u, logp, cp0, cp1, g_m, g_u, g_cls);
+  EKL_LAUNCH_CHECK();
+  return 0;
+}

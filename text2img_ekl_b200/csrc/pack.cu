@@ -53,7 +53,48 @@ __global__ void pack_fwd_vec8_kernel(const __grid_constant__ PackParams p) {
   }
 }
 
-// transposed: block (32x8) moves a 64(co) x 32(ci) tile for one (v, t): 128-byte reads and 128-byte writes
+// transposed: a block of 256 threads moves a 64(co) x 64(ci) tile of one (v, t): 16-byte reads along ci (all of a
+// thread's loads issued before use), transpose through shared memory, 16-byte writes along co.
+// Requires KRSC master layout, Cin % 4 == 0 and Cout % 8 == 0 (the generic kernel below covers the rest).
+__global__ void __launch_bounds__(256) pack_dgrad_vec_kernel(const __grid_constant__ PackParams p) {
+  __shared__ float tile[64][65];
+  const int v = blockIdx.z / p.ntaps, t = blockIdx.z % p.ntaps;
+  const EklTap tap = p.taps[v][t];
+  const int co0 = blockIdx.y * 64, ci0 = blockIdx.x * 64;
+  float4 acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int idx = threadIdx.x + k * 256;          // 0..1023 : (row, 16-byte chunk)
+    const int r = idx >> 4, c4 = (idx & 15) * 4;
+    const int co = co0 + r, ci = ci0 + c4;
+    acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (co < p.Cout && ci < p.Cin)
+      for (int s = 0; s < tap.nsrc; ++s) {
+        const float4 a = *reinterpret_cast<const float4*>(p.w + ((int64_t)co * p.KK + tap.src[s]) * p.Cin + ci);
+        acc[k].x += a.x; acc[k].y += a.y; acc[k].z += a.z; acc[k].w += a.w;
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int idx = threadIdx.x + k * 256;
+    const int r = idx >> 4, c4 = (idx & 15) * 4;
+    tile[r][c4] = acc[k].x; tile[r][c4 + 1] = acc[k].y; tile[r][c4 + 2] = acc[k].z; tile[r][c4 + 3] = acc[k].w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int idx = threadIdx.x + k * 256;          // 0..511 : (ci row, 8-co chunk)
+    const int r = idx >> 3, c8 = (idx & 7) * 8;
+    const int ci = ci0 + r, co = co0 + c8;
+    if (ci < p.Cin && co < p.Cout) {
+      const uint4 o = make_uint4(pack_bf16x2(tile[c8][r], tile[c8 + 1][r]), pack_bf16x2(tile[c8 + 2][r], tile[c8 + 3][r]),
+                                 pack_bf16x2(tile[c8 + 4][r], tile[c8 + 5][r]), pack_bf16x2(tile[c8 + 6][r], tile[c8 + 7][r]));
+      *reinterpret_cast<uint4*>(p.out + (((int64_t)v * p.Cin + ci) * p.ntaps + t) * p.Cout + co) = o;
+    }
+  }
+}
+
+// transposed, generic: block (32x8) moves a 64(co) x 32(ci) tile for one (v, t)
 __global__ void pack_dgrad_kernel(const __grid_constant__ PackParams p) {
   __shared__ float tile[64][33];
   const int v = blockIdx.z / p.ntaps, t = blockIdx.z % p.ntaps;
@@ -97,6 +138,9 @@ int ekl_pack_weights(const EklGather* g, const float* w_master, void* out, int C
       if (blocks > 148 * 8) blocks = 148 * 8;
       pack_fwd_kernel<<<blocks, 256, 0, st>>>(p);
     }
+  } else if (!p.kcrs && Cin % 4 == 0 && Cout % 8 == 0) {
+    dim3 grid(ekl_cdiv(Cin, 64), ekl_cdiv(Cout, 64), p.nvar * p.ntaps);
+    pack_dgrad_vec_kernel<<<grid, 256, 0, st>>>(p);
   } else {
     dim3 grid(ekl_cdiv(Cin, 32), ekl_cdiv(Cout, 64), p.nvar * p.ntaps);
     pack_dgrad_kernel<<<grid, dim3(32, 8), 0, st>>>(p);

@@ -50,6 +50,21 @@ def _bce_const(p, target):
     return -torch.clamp(torch.log1p(-p), min=-100.0).mean()
 
 
+class tensor_core_matmul:
+    """The path's few dense Linear layers (CA_NET / VC_NET, the generator stem, the class head fc_ac) are plain library
+    GEMMs on fp32 parameters.  With TF32 off cuBLAS runs them as SIMT sgemm (0.8 ms of an 17 ms step on B200);
+    inside the step they run as TF32 tensor-core GEMMs (fp32 accumulate), which is within the north star's stated
+    BF16/TF32 tolerance.  The caller's global flag is restored on exit."""
+
+    def __enter__(self):
+        self.old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.old
+        return False
+
+
 class FlatGrads:
     """All gradients of a network as views into one flat fp32 buffer (same memory layout as each parameter)."""
 
@@ -88,6 +103,10 @@ class StepEngine:
 
     # ---- (1) generate: cub:567-587 / trainer.py:524-528
     def generate(self, noise, txt, cls_cond, eps=None, seed=None):
+        with tensor_core_matmul():
+            return self._generate(noise, txt, cls_cond, eps, seed)
+
+    def _generate(self, noise, txt, cls_cond, eps=None, seed=None):
         if self.kind == "catz_ca":
             (self.hcodes, self.mu1, self.mu2, self.logvar1, self.logvar2, self.std1, self.std2) = \
                 self.netG(noise, txt, cls_cond, eps=eps, seed=seed)
@@ -107,9 +126,24 @@ class StepEngine:
 
     # ---- (2) one discriminator update: cub:404-461
     def d_step(self, idx, real_imgs, wrong_imgs, real_cp, fake_cp):
+        with tensor_core_matmul():
+            return self._d_step(idx, real_imgs, wrong_imgs, real_cp, fake_cp)
+
+    def _d_step(self, idx, real_imgs, wrong_imgs, real_cp, fake_cp):
         netD, opt, grads = self.netsD[idx], self.optsD[idx], self.gradsD[idx]
         B = real_imgs.shape[0]
         grads.zero()
+        if hasattr(netD, "heads_raw") and self.uncond > 0:
+            # fused path: raw logits of the stacked real / wrong / fake pass -> one loss kernel (cub:423-448)
+            lm, lu, lc = netD.heads_raw((real_imgs, wrong_imgs, self.fake_imgs[idx].detach()), self.mu.detach(), groups=3)
+            losses, pm, pu, logp = ops.d_loss(lm, lu, lc, real_cp, fake_cp, 3, B, (1, 0, 0), (1, 1, 0), (0, -1, 1), self.uncond)
+            losses[0].backward()
+            if self.allreduce is not None:
+                self.allreduce(grads.flat)
+            opt.step()
+            self.last_d_logits = tuple([pm[i * B:(i + 1) * B], pu[i * B:(i + 1) * B], logp[i * B:(i + 1) * B]] for i in range(3))
+            d = losses.detach()
+            return d[0], d[1], d[2], d[3]
         # the three reference forwards (real / wrong / fake) as one pass; the batches are gathered by the stem kernel
         out = netD((real_imgs, wrong_imgs, self.fake_imgs[idx].detach()), self.mu.detach(), groups=3)
         real, wrong, fake = [[o[i * B:(i + 1) * B] for o in out] for i in range(3)]
@@ -131,20 +165,36 @@ class StepEngine:
 
     # ---- (3) generator loss through the UPDATED discriminators: cub:463-490
     def g_loss(self, real_cp):
-        errGs_match = errGs_uncond = errGs_cls = 0
+        errGs_match = errGs_uncond = errGs_cls = errGs_total_fused = 0
         self.last_g_logits = []
         for i, netD in enumerate(self.netsD):
+            if hasattr(netD, "heads_raw") and self.uncond > 0:
+                lm, lu, lc = netD.heads_raw(self.fake_imgs[i], self.mu)
+                B = lm.shape[0]
+                losses, pm, pu, logp = ops.d_loss(lm, lu, lc, real_cp, None, 1, B, (1,), (1,), (0,), self.uncond)
+                d = losses.detach()
+                errGs_match, errGs_uncond, errGs_cls = errGs_match + d[1], errGs_uncond + d[2], errGs_cls + d[3]
+                errGs_total_fused = errGs_total_fused + losses[0]
+                self.last_g_logits.append([pm, pu, logp])
+                continue
             outputs = netD(self.fake_imgs[i], self.mu)
+            errGs_total_fused = errGs_total_fused + _bce_const(outputs[0], 1)
             errGs_match = errGs_match + _bce_const(outputs[0], 1)
             if len(outputs) > 1 and self.uncond > 0:
-                errGs_uncond = errGs_uncond + self.uncond * _bce_const(outputs[1], 1)
-                errGs_cls = errGs_cls + ce_loss(outputs[2], real_cp)
+                u_, c_ = self.uncond * _bce_const(outputs[1], 1), ce_loss(outputs[2], real_cp)
+                errGs_uncond, errGs_cls = errGs_uncond + u_, errGs_cls + c_
+                errGs_total_fused = errGs_total_fused + u_ + c_
             self.last_g_logits.append(outputs)
         kl = [KL_loss(m, lv) for m, lv in self.kls]
-        errG_total = errGs_match + errGs_uncond + errGs_cls + sum(kl) * self.kl_coeff
+        # only losses[0] of the fused kernel carries gradient: the total is assembled from it (components are reported)
+        errG_total = errGs_total_fused + sum(kl) * self.kl_coeff
         return (errG_total, errGs_match, errGs_uncond, errGs_cls) + tuple(kl)
 
     def g_step(self, real_cp):
+        with tensor_core_matmul():
+            return self._g_step(real_cp)
+
+    def _g_step(self, real_cp):
         self.gradsG.zero()
         for d in self.netsD:
             d.requires_grad_(False)          # the reference computes and discards these

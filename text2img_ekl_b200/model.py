@@ -652,18 +652,28 @@ class _JointD(_DBase):
             self.fc_ac = nn.Linear(ndf * 8 * 4 * 4, self.entity_num + 1)
         self.uncond_logits = _logit_head(ndf)
 
-    def forward(self, x_var, c_code, groups=1):
+    def heads_raw(self, x_var, c_code, groups=1):
+        """(match logit [B], uncond logit [B], class logits [B,E+1]) BEFORE sigmoid / log_softmax: what the fused
+        loss kernel consumes (engine.StepEngine); forward() applies the reference's output activations."""
         x_code = self._trunk(x_var, groups)                            # [B,4,4,8ndf] NHWC bf16
-        sen_match = self._cond_logit(x_code, c_code, groups)
-        real = _head_logit(self.uncond_logits, x_code)
+        c = c_code.view(-1, self.ef_dim)
+        if groups > 1:
+            c = c.repeat(groups, 1)
+        h_c = to_nhwc(self.jointConv(to_public(ops.cat_code(c, x_code)), groups))
+        lu, lm = ops.dhead_dots(x_code, h_c, self.uncond_logits[0].weight, self.uncond_logits[0].bias,
+                                self.logits[0].weight, self.logits[0].bias)
         B = x_code.shape[0]
         if self.use_cap:
             out = self.fc_ac_cap(x_code.reshape(B, 16, self.df_dim * 8).float())     # == permute(0,2,3,1).view (:967-968)
-            cp = F.log_softmax(out.norm(dim=-1), dim=1)
+            cls = out.norm(dim=-1)
         else:
             flat = x_code.permute(0, 3, 1, 2).reshape(B, -1).float()                 # NCHW flatten order (:974)
-            cp = F.log_softmax(self.fc_ac(flat), dim=1)
-        return [sen_match.view(-1), real.view(-1), cp]
+            cls = self.fc_ac(flat)
+        return lm, lu, cls
+
+    def forward(self, x_var, c_code, groups=1):
+        lm, lu, cls = self.heads_raw(x_var, c_code, groups)
+        return [torch.sigmoid(lm), torch.sigmoid(lu), F.log_softmax(cls, dim=1)]
 
 
 class JOINT_D_NET64(_JointD):

@@ -387,3 +387,114 @@ class _HeadTanh(torch.autograd.Function):
 
 def head_tanh(y):
     return _HeadTanh.apply(y)
+
+
+def _flat_head_weight(w):
+    """[1,C,4,4] head filter -> ([16*C] fp32 in NHWC (kh,kw,c) order, shares_memory)."""
+    if w.is_contiguous(memory_format=torch.channels_last):
+        return w.permute(0, 2, 3, 1).reshape(-1), True
+    return w.permute(0, 2, 3, 1).reshape(-1).contiguous(), False
+
+
+class _DHeadDots(torch.autograd.Function):
+    """Raw (pre-sigmoid) uncond / match logits of a discriminator: one 16*8ndf-long dot per sample and head
+    (model.py:886-888, 935-952).  x_code / h_c: [GB,4,4,C] NHWC bf16."""
+
+    @staticmethod
+    def forward(ctx, x_code, h_c, w_u, b_u, w_m, b_m):
+        GB = x_code.shape[0]
+        K = x_code.numel() // GB
+        fu, ctx.inplace_u = _flat_head_weight(w_u)
+        fm, ctx.inplace_m = _flat_head_weight(w_m)
+        lu = torch.empty(GB, device=x_code.device, dtype=torch.float32)
+        lm = torch.empty(GB, device=x_code.device, dtype=torch.float32)
+        L.check(L.lib().ekl_dhead_dots(L.ptr(x_code), L.ptr(h_c), L.ptr(fu), L.ptr(b_u), L.ptr(fm), L.ptr(b_m), GB, K,
+                                       L.ptr(lu), L.ptr(lm), L.stream()))
+        _count()
+        ctx.save_for_backward(x_code, h_c, w_u, b_u, w_m, b_m)
+        return lu, lm
+
+    @staticmethod
+    def backward(ctx, g_u, g_m):
+        x_code, h_c, w_u, b_u, w_m, b_m = ctx.saved_tensors
+        GB = x_code.shape[0]
+        K = x_code.numel() // GB
+        fu, _ = _flat_head_weight(w_u)
+        fm, _ = _flat_head_weight(w_m)
+        g_u, g_m = g_u.contiguous(), g_m.contiguous()
+        dx = torch.empty_like(x_code) if ctx.needs_input_grad[0] else None
+        dh = torch.empty_like(h_c) if ctx.needs_input_grad[1] else None
+        outs = [None] * 4
+        bufs = []
+        for i, (p, flat_ok) in enumerate(((w_u, ctx.inplace_u), (b_u, True), (w_m, ctx.inplace_m), (b_m, True))):
+            if not ctx.needs_input_grad[2 + i]:
+                bufs.append(None)
+            elif p.is_leaf and flat_ok:
+                bufs.append(_grad_buffer(p))                    # accumulated in place (same memory order)
+            else:
+                t = torch.zeros(p.numel(), device=p.device, dtype=torch.float32)
+                bufs.append(t)
+                outs[i] = t
+        L.check(L.lib().ekl_dhead_dots_bwd(L.ptr(x_code), L.ptr(h_c), L.ptr(fu), L.ptr(fm), L.ptr(g_u), L.ptr(g_m), GB, K,
+                                           L.ptr(dx), L.ptr(dh), L.ptr(bufs[0]), L.ptr(bufs[1]), L.ptr(bufs[2]),
+                                           L.ptr(bufs[3]), L.stream()))
+        _count()
+        for i, p in enumerate((w_u, b_u, w_m, b_m)):
+            if outs[i] is not None:
+                g = outs[i]
+                outs[i] = g.view(1, 4, 4, -1).permute(0, 3, 1, 2) if p.dim() == 4 else g.view(p.shape)
+        return (dx, dh) + tuple(outs)
+
+
+def dhead_dots(x_code, h_c, w_u, b_u, w_m, b_m):
+    return _DHeadDots.apply(x_code, h_c, w_u, b_u, w_m, b_m)
+
+
+def _int3(vals):
+    import ctypes as C
+    v = list(vals) + [0] * (3 - len(vals))
+    return (C.c_int * 3)(*v)
+
+
+class _DLoss(torch.autograd.Function):
+    """BCE (constant labels per group) + soft-target CE of one discriminator pass, fused (include/ekl_b200.h:
+    ekl_dloss_fwd).  Returns (losses[4], p_match, p_uncond, log_softmax(cls)); only losses[0] is differentiable."""
+
+    @staticmethod
+    def forward(ctx, lm, lu, cls, cp0, cp1, cfg):
+        groups, B, t_match, t_uncond, cls_tgt, coeff = cfg
+        GB, E1 = cls.shape
+        assert GB == groups * B
+        lm, lu, cls = lm.contiguous(), lu.contiguous(), cls.contiguous()
+        dev = cls.device
+        losses = torch.empty(4, device=dev, dtype=torch.float32)
+        pm = torch.empty(GB, device=dev, dtype=torch.float32)
+        pu = torch.empty(GB, device=dev, dtype=torch.float32)
+        logp = torch.empty(GB, E1, device=dev, dtype=torch.float32)
+        cp0 = cp0.float().contiguous()
+        cp1 = cp1.float().contiguous() if cp1 is not None else None
+        L.check(L.lib().ekl_dloss_fwd(groups, B, E1, _int3(t_match), _int3(t_uncond), _int3(cls_tgt), float(coeff),
+                                      L.ptr(lm), L.ptr(lu), L.ptr(cls), L.ptr(cp0), L.ptr(cp1), L.ptr(losses), L.ptr(pm),
+                                      L.ptr(pu), L.ptr(logp), L.stream()))
+        _count()
+        ctx.cfg = cfg
+        ctx.save_for_backward(pm, pu, logp, cp0, cp1)
+        ctx.mark_non_differentiable(pm, pu, logp)
+        return losses, pm, pu, logp
+
+    @staticmethod
+    def backward(ctx, go, *_):
+        groups, B, t_match, t_uncond, cls_tgt, coeff = ctx.cfg
+        pm, pu, logp, cp0, cp1 = ctx.saved_tensors
+        GB, E1 = logp.shape
+        go = go.contiguous()
+        gm, gu, gcls = torch.empty_like(pm), torch.empty_like(pu), torch.empty_like(logp)
+        L.check(L.lib().ekl_dloss_bwd(groups, B, E1, _int3(t_match), _int3(t_uncond), _int3(cls_tgt), float(coeff), L.ptr(go),
+                                      L.ptr(pm), L.ptr(pu), L.ptr(logp), L.ptr(cp0), L.ptr(cp1), L.ptr(gm), L.ptr(gu),
+                                      L.ptr(gcls), L.stream()))
+        _count()
+        return gm, gu, gcls, None, None, None
+
+
+def d_loss(lm, lu, cls, cp0, cp1, groups, B, t_match, t_uncond, cls_tgt, uncond_coeff):
+    return _DLoss.apply(lm, lu, cls, cp0, cp1, (groups, B, tuple(t_match), tuple(t_uncond), tuple(cls_tgt), uncond_coeff))

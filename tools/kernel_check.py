@@ -18,7 +18,7 @@ SHAPES = {  # mode -> list of (B, H, W, Cin, Cout)
     1: [(4, 4, 4, 128, 128), (2, 8, 8, 64, 64), (3, 16, 16, 64, 128), (2, 32, 32, 32, 32), (2, 4, 4, 256, 512)],
     2: [(4, 16, 16, 64, 128), (2, 8, 8, 128, 256), (3, 32, 32, 64, 64), (2, 8, 8, 512, 1024), (2, 64, 64, 32, 64)],
 }
-GROUPS = ["tc_fwd", "tc_dgrad", "tc_wgrad", "simt_fwd", "simt_dgrad", "simt_wgrad", "bn", "misc"]
+GROUPS = ["tc_fwd", "tc_dgrad", "tc_wgrad", "simt_fwd", "simt_dgrad", "simt_wgrad", "bn", "misc", "heads"]
 
 
 def run_group(group):
@@ -38,6 +38,8 @@ def run_group(group):
         return run_bn(torch, L, lib, dev, rel)
     if group == "misc":
         return run_misc(torch, L, lib, dev, rel)
+    if group == "heads":
+        return run_heads(torch, L, lib, dev, rel)
     impl = L.IMPL_TC if group.startswith("tc") else L.IMPL_SIMT
     what = group.split("_")[1]
     for mode, shapes in SHAPES.items():
@@ -151,6 +153,57 @@ def run_bn(torch, L, lib, dev, rel):
         ok = all(v < 1e-2 for v in errs.values())
         print("%s bn M%d C%d g%d act%d %s" % ("PASS" if ok else "FAIL", M, Cy, groups, act,
                                                " ".join("%s %.1e" % kv for kv in errs.items())), flush=True)
+        nfail += 0 if ok else 1
+    return nfail
+
+
+def run_heads(torch, L, lib, dev, rel):
+    """Fused discriminator heads + losses (ops.dhead_dots / ops.d_loss) against the reference formulation in torch:
+    sigmoid(conv4x4/s4) heads, nn.BCELoss on constant labels, ce_loss(log_softmax) (cub:60-65, 423-448)."""
+    import torch.nn.functional as F
+    from text2img_ekl_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False          # the torch reference below must be true fp32
+    nfail = 0
+    for (G, B, C, E1) in [(3, 4, 512, 201), (1, 24, 512, 91), (3, 32, 64, 201)]:
+        GB = G * B
+        x = torch.randn(GB, 4, 4, C, device=dev).bfloat16().requires_grad_(True)
+        h = torch.randn(GB, 4, 4, C, device=dev).bfloat16().requires_grad_(True)
+        ws = [(torch.randn(1, C, 4, 4, device=dev) * 0.02).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+              for _ in range(2)]
+        bs = [torch.randn(1, device=dev).requires_grad_(True) for _ in range(2)]
+        cls = (torch.randn(GB, E1, device=dev) * 3).requires_grad_(True)
+        cp0 = torch.softmax(torch.randn(B, E1, device=dev), 1)
+        cp1 = torch.zeros(B, E1, device=dev); cp1[:, -1] = 1
+        tm, tu, ct = ((1, 0, 0), (1, 1, 0), (0, -1, 1)) if G == 3 else ((1,), (1,), (0,))
+        coeff = 0.7
+        lu, lm = ops.dhead_dots(x, h, ws[0], bs[0], ws[1], bs[1])
+        losses, pm, pu, logp = ops.d_loss(lm, lu, cls, cp0, cp1, G, B, tm, tu, ct, coeff)
+        (losses[0] * 1.5).backward()
+        got = [x.grad, h.grad, ws[0].grad, bs[0].grad, ws[1].grad, bs[1].grad, cls.grad]
+        # reference
+        xr, hr = x.detach().float().requires_grad_(True), h.detach().float().requires_grad_(True)
+        wr = [w.detach().clone().requires_grad_(True) for w in ws]
+        br = [b.detach().clone().requires_grad_(True) for b in bs]
+        cr = cls.detach().clone().requires_grad_(True)
+        pu_r = torch.sigmoid(F.conv2d(xr.permute(0, 3, 1, 2), wr[0], br[0], stride=4)).view(-1)
+        pm_r = torch.sigmoid(F.conv2d(hr.permute(0, 3, 1, 2), wr[1], br[1], stride=4)).view(-1)
+        lq = F.log_softmax(cr, 1)
+        bce = torch.nn.BCELoss()
+        m = u = k = 0
+        for g in range(G):
+            sl = slice(g * B, (g + 1) * B)
+            m = m + bce(pm_r[sl], torch.full((B,), float(tm[g]), device=dev))
+            u = u + coeff * bce(pu_r[sl], torch.full((B,), float(tu[g]), device=dev))
+            if ct[g] >= 0:
+                k = k + (-(cp0 if ct[g] == 0 else cp1) * lq[sl]).sum() / B
+        tot = m + u + k
+        (tot * 1.5).backward()
+        want = [xr.grad, hr.grad, wr[0].grad, br[0].grad, wr[1].grad, br[1].grad, cr.grad]
+        errs = [rel(losses, torch.stack([tot, m, u, k])), rel(pm, pm_r), rel(pu, pu_r), rel(logp, lq)] + \
+               [rel(a, b) for a, b in zip(got, want)]
+        tol = [1e-4, 1e-4, 1e-4, 1e-5, 6e-3, 6e-3, 5e-4, 5e-4, 5e-4, 5e-4, 1e-4]
+        ok = all(e < t for e, t in zip(errs, tol))
+        print("%s heads G%d B%d C%d E%d %s" % ("PASS" if ok else "FAIL", G, B, C, E1, " ".join("%.1e" % e for e in errs)), flush=True)
         nfail += 0 if ok else 1
     return nfail
 
