@@ -63,6 +63,11 @@ int ekl_conv_pack(const ekl_conv* c, const float* w_master, void* w_fwd, void* w
 int ekl_conv_stats_rows(const ekl_conv* c);
 /* y = conv(x); stats (may be NULL): per-tile per-channel sum / sum-of-squares of y */
 int ekl_conv_fwd(const ekl_conv* c, const void* x, const void* w_fwd, void* y, float* stats, void* stream);
+/* y = conv3x3(x) + bias9[b][border class][Cout]: the spatially constant input channels of a jointConv -- the tiled
+ * condition code of NEXT_STAGE_G (model.py:411-414, jointConv :403) -- folded into a per-sample fp32 bias with 9
+ * border variants (class = 3*rc + cc; rc / cc = 0 first row / column, 1 interior, 2 last).  EKL_S1, EKL_IMPL_TC. */
+int ekl_conv_fwd_bias9(const ekl_conv* c, const void* x, const void* w_fwd, const float* bias9, void* y, float* stats,
+                       void* stream);
 /* dx = conv^T(dy) */
 int ekl_conv_bwd_data(const ekl_conv* c, const void* dy, const void* w_dgrad, void* dx, void* stream);
 /* dw[Cout][KH][KW][Cin] += x (*) dy   (fp32, accumulated: zero it first for a fresh gradient) */

@@ -138,3 +138,21 @@ def test_space_to_depth_filter_equals_conv4x4_stride2():
     b = F.conv2d(xs, w2, stride=1, padding=1)
     assert torch.allclose(a, b, atol=1e-5)
     assert int(mask.sum()) == 48           # every master-filter entry appears exactly once
+
+
+def test_joint_conv_fold_identity():
+    """conv3x3(cat(tile(c), h)) == conv3x3(h, Wx) + bias9[b, border class] with bias9 = VALID @ (Wc . c) -- the algebra
+    behind NEXT_STAGE_G._joint / ekl_conv_fwd_bias9, in fp32 on the CPU."""
+    from text2img_ekl_b200 import model
+    torch.manual_seed(0)
+    B, Cc, Cx, N, H, W = 2, 5, 4, 6, 7, 5
+    c, h = torch.randn(B, Cc), torch.randn(B, Cx, H, W)
+    w = torch.randn(N, Cc + Cx, 3, 3)
+    ref = F.conv2d(torch.cat((c.view(B, Cc, 1, 1).expand(B, Cc, H, W), h), 1), w, padding=1)
+    T = torch.einsum("bc,nckl->bkln", c, w[:, :Cc]).reshape(B, 9, N)
+    bias9 = torch.einsum("qt,btn->bqn", model._border_valid(), T)
+    cls_h = torch.tensor([0] + [1] * (H - 2) + [2])
+    cls_w = torch.tensor([0] + [1] * (W - 2) + [2])
+    q = cls_h.view(H, 1) * 3 + cls_w.view(1, W)                      # [H, W]
+    got = F.conv2d(h, w[:, Cc:], padding=1) + bias9[:, q].permute(0, 3, 1, 2)
+    assert torch.allclose(ref, got, atol=1e-4)

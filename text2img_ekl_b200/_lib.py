@@ -38,6 +38,7 @@ SIGNATURES = {
     "ekl_conv_pack": (_i, [_cp, _vp, _vp, _vp, _vp]),
     "ekl_conv_stats_rows": (_i, [_cp]),
     "ekl_conv_fwd": (_i, [_cp, _vp, _vp, _vp, _vp, _vp]),
+    "ekl_conv_fwd_bias9": (_i, [_cp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_conv_bwd_data": (_i, [_cp, _vp, _vp, _vp, _vp]),
     "ekl_conv_bwd_weight": (_i, [_cp, _vp, _vp, _vp, _vp]),
     "ekl_conv_plan_dump": (_i, [_cp, _i, C.POINTER(C.c_int), _i]),

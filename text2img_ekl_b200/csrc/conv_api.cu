@@ -6,14 +6,33 @@
 int ekl_tc_supported(const EklGather* g);
 int ekl_tc_stats_rows(const EklGather* g, int group_b);
 void ekl_tc_geometry(const EklGather* g, int group_b, int* tb, int* th, int* tw);
-int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, int group_b, int act, int* mtiles_out, cudaStream_t st);
+int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, int group_b, int act, const float* bias9,
+                       int* mtiles_out, cudaStream_t st);
+int ekl_rw_supported(const EklGather* g, int group_b);
+int ekl_conv3x3_rw(const EklGather* g, const void* w_packed, float* stats, int act, const float* bias9, cudaStream_t st);
 int ekl_gather_simt(const EklGather* g, const void* w_packed, int act, cudaStream_t st);
 int ekl_wgrad_simt(const EklGather* fwd_plan, float* dw_master, cudaStream_t st);
 int ekl_wgrad_tc_supported(const EklGather* g);
 int ekl_wgrad_tc(const EklGather* g, float* dw, cudaStream_t st);
 int ekl_pack_weights(const EklGather* g, const float* w_master, void* out, int Cout, int Cin, cudaStream_t st);
 
+#include <stdlib.h>
+
 namespace {
+
+// EKL_DISABLE_RW=1 routes the small-channel 3x3 layers through the generic gather-GEMM kernel (A/B measurements)
+bool rw_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("EKL_DISABLE_RW"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
+// stride-1 3x3 plans with one K block per tap run on the resident-filter kernel (conv_rw.cu), everything else on the
+// generic gather-GEMM kernel (conv_tc.cu)
+int run_tc(const EklGather* g, const void* w, float* stats, int group_b, int act, const float* bias9, cudaStream_t st) {
+  if (rw_enabled() && ekl_rw_supported(g, group_b)) return ekl_conv3x3_rw(g, w, stats, act, bias9, st);
+  return ekl_gather_gemm_tc(g, w, stats, group_b, act, bias9, nullptr, st);
+}
 
 void out_extent(const ekl_conv* c, int* Ho, int* Wo) {
   if (c->mode == EKL_UP2) { *Ho = 2 * c->H; *Wo = 2 * c->W; }
@@ -92,7 +111,21 @@ extern "C" int ekl_conv_fwd(const ekl_conv* c, const void* x, const void* w_fwd,
   EKL_REQUIRE(c->act == EKL_ACT_NONE || c->act == EKL_ACT_LRELU || c->act == EKL_ACT_TANH,
               "TC conv: fused epilogue activation must be none, LeakyReLU or tanh");
   EKL_REQUIRE(c->act == EKL_ACT_NONE || stats == nullptr, "TC conv: BatchNorm partials are of the raw conv output");
-  return ekl_gather_gemm_tc(&g, w_fwd, stats, c->group_b, c->act, nullptr, (cudaStream_t)stream);
+  return run_tc(&g, w_fwd, stats, c->group_b, c->act, nullptr, (cudaStream_t)stream);
+}
+
+// y = conv3x3(x) + bias9[b][border class of (h,w)][:]  -- the spatially constant (tiled condition code) input channels
+// of a jointConv (model.py:411-414, 403) folded into a per-sample bias with 9 border variants: class = 3*rc + cc,
+// rc / cc = 0 first row / column, 2 last, 1 interior.  EKL_S1, tcgen05 implementation only.
+extern "C" int ekl_conv_fwd_bias9(const ekl_conv* c, const void* x, const void* w_fwd, const float* bias9, void* y,
+                                  float* stats, void* stream) {
+  if (int rc = check(c)) return rc;
+  EKL_REQUIRE(c->mode == EKL_S1 && c->impl == EKL_IMPL_TC && c->x_fmt == 0 && c->y_fmt == 0 && c->act == EKL_ACT_NONE,
+              "conv_fwd_bias9: stride-1 3x3, tcgen05, NHWC bf16, no activation");
+  EKL_REQUIRE(c->H >= 2 && c->W >= 2, "conv_fwd_bias9: H, W >= 2");
+  EklGather g;
+  plan(c, 0, x, y, &g);
+  return run_tc(&g, w_fwd, stats, c->group_b, 0, bias9, (cudaStream_t)stream);
 }
 
 extern "C" int ekl_conv_bwd_data(const ekl_conv* c, const void* dy, const void* w_dgrad, void* dx, void* stream) {
@@ -101,7 +134,7 @@ extern "C" int ekl_conv_bwd_data(const ekl_conv* c, const void* dy, const void* 
   plan(c, 1, dx, dy, &g);
   if (c->impl == EKL_IMPL_SIMT) return ekl_gather_simt(&g, w_dgrad, 0, (cudaStream_t)stream);
   EKL_REQUIRE(c->x_fmt == 0 && c->y_fmt == 0, "TC conv: NHWC bf16 only");
-  return ekl_gather_gemm_tc(&g, w_dgrad, nullptr, 0, 0, nullptr, (cudaStream_t)stream);
+  return run_tc(&g, w_dgrad, nullptr, 0, 0, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int ekl_conv_bwd_weight(const ekl_conv* c, const void* x, const void* dy, float* dw, void* stream) {

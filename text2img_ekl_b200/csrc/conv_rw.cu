@@ -1,0 +1,319 @@
+// tcgen05 3x3 / stride-1 convolution for SMALL channel counts (Cin in {16, 32, 64}: one K block per tap) with the
+// filter RESIDENT in shared memory and the input fetched once per tile as three column-shifted row-halo boxes.
+//
+// Why: the generic gather-GEMM kernel (conv_tc.cu) re-fetches the 128-pixel A tile and the filter tile for each of the
+// 9 taps; for the generator's high-resolution layers (64..256^2 maps, 16..64 channels, model.py:107-123 ResBlock,
+// :426-437 GET_IMAGE_G, the folded jointConv, the discriminator stem) that makes the kernel L2->SMEM bound at a
+// fraction of the tensor pipe.  Here a CTA tile is 16 image rows x 8 columns of one image:
+//   * per tile, 3 TMA boxes [Cin][8 w][18 h] at column offsets -1, 0, +1 (rows h0-1 .. h0+16; out-of-bounds = the conv
+//     zero padding) -- 432 pixel rows instead of 9 x 128, and no filter traffic at all;
+//   * because a tile row is exactly 8 pixels = one 8-row swizzle atom, the A operand of tap (dh, dw) is the box of
+//     column shift dw advanced by (dh+1) atoms: an atom-aligned descriptor start, no partial-atom addressing;
+//   * the 9 filter taps [BN][Cin] of the current output-channel tile stay in shared memory for all tiles of a round.
+// Pipeline roles / TMEM double buffering / epilogue (bf16 pack, BatchNorm partial sums, TMA store, optional fused
+// activation and border-class bias) follow conv_tc.cu.  Forward and data-gradient of EKL_S1 (taps differ only in sign).
+#include "conv_plan.h"
+#include "ekl_common.cuh"
+
+namespace {
+
+struct RwParams {
+  CUtensorMap a_map, o_map, w_map;
+  EklTap taps[9];
+  float* stats;          // [cta][2][N] or null
+  const float* bias9;    // [B][9][N] or null
+  int N, ntn, H, W, nTh, nTw, tiles, act;
+};
+
+template <int BN, int KC>
+struct RwCfg {
+  static constexpr int ROWB = KC * 2;                                  // bytes per pixel row
+  static constexpr int BOX_BYTES = ((144 * ROWB + 1023) / 1024) * 1024; // 18 x 8 pixel rows, atom aligned
+  static constexpr int STAGE_BYTES = 3 * BOX_BYTES;
+  static constexpr int WT_BYTES = ((BN * ROWB + 1023) / 1024) * 1024;   // one tap's filter tile
+  static constexpr int W_BYTES = 9 * WT_BYTES;
+  static constexpr int OUT_BYTES = 128 * BN * 2;
+  static constexpr int STAGES_RAW = (212 * 1024 - W_BYTES - OUT_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 4 ? 4 : STAGES_RAW;
+  static_assert(STAGES >= 2, "not enough shared memory for two stages");
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + W_BYTES + OUT_BYTES + 1024 + 512 + 2 * 2 * BN * 4 * (256 / BN);
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr uint32_t LAYOUT = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);
+  static constexpr uint32_t SBO = 8 * ROWB;
+  static constexpr int PAIRS = BN / 2;
+  static constexpr int SLICES = 128 / PAIRS;
+};
+
+template <int BN>
+__device__ __forceinline__ uint32_t rw_stage_off(int r, int c) {
+  if constexpr (BN == 64) return (uint32_t)(r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2);
+  else if constexpr (BN == 32) return (uint32_t)(r * 64 + (((c >> 3) ^ ((r >> 1) & 3)) << 4) + (c & 7) * 2);
+  else return (uint32_t)(r * 32 + c * 2);
+}
+
+__device__ __forceinline__ float rw_act(float v, int act) {
+  if (act == 2) return v > 0.f ? v : 0.2f * v;
+  if (act == 4) return tanhf(v);
+  return v;
+}
+
+template <int BN, int KC>
+__global__ void __launch_bounds__(192, 1) conv3x3_rw_kernel(const __grid_constant__ RwParams p) {
+  using C = RwCfg<BN, KC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* wsm = smem + C::STAGES * C::STAGE_BYTES;
+  uint8_t* stage_out = wsm + C::W_BYTES;
+  uint64_t* full = (uint64_t*)(stage_out + C::OUT_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tmem_full = empty + C::STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint64_t* wfull = tmem_empty + 2;
+  uint64_t* wfree = wfull + 1;
+  uint32_t* tmem_slot = (uint32_t*)(wfree + 1);
+  float* red = (float*)(stage_out + C::OUT_BYTES + 512);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grid = gridDim.x, cta = blockIdx.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+    mbar_init(wfull, 1); mbar_init(wfree, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool has_tiles = cta < p.tiles;
+
+  auto tile_origin = [&](int tile, int& w0, int& h0, int& b0) {
+    const int twi = tile % p.nTw; tile /= p.nTw;
+    const int thi = tile % p.nTh; tile /= p.nTh;
+    w0 = twi * 8; h0 = thi * 16; b0 = tile;
+  };
+
+  if (warp == 0) {
+    if (has_tiles && elect_one()) {
+      tma_prefetch_desc(&p.w_map);
+      tma_prefetch_desc(&p.a_map);
+      uint32_t kit = 0;
+      for (int n = 0; n < p.ntn; ++n) {
+        // the filter tile may be overwritten once every MMA of the previous round has retired
+        if (n > 0) mbar_wait(wfree, (uint32_t)(n - 1) & 1u);
+        mbar_expect_tx(wfull, (uint32_t)(9 * BN * C::ROWB));
+        for (int t = 0; t < 9; ++t) tma_load_2d(&p.w_map, wfull, wsm + t * C::WT_BYTES, t * KC, n * BN);
+        for (int tile = cta; tile < p.tiles; tile += grid, ++kit) {
+          const int s = kit % C::STAGES;
+          const uint32_t ph = (kit / C::STAGES) & 1u;
+          int w0, h0, b0;
+          tile_origin(tile, w0, h0, b0);
+          mbar_wait(&empty[s], ph ^ 1u);
+          uint8_t* sa = smem + s * C::STAGE_BYTES;
+          mbar_expect_tx(&full[s], (uint32_t)(3 * 144 * C::ROWB));
+#pragma unroll
+          for (int j = 0; j < 3; ++j) tma_load_4d(&p.a_map, &full[s], sa + j * C::BOX_BYTES, 0, w0 + j - 1, h0 - 1, b0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (has_tiles) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      uint32_t kit = 0;
+      for (int n = 0; n < p.ntn; ++n) {
+        mbar_wait(wfull, (uint32_t)n & 1u);
+        tc_fence_after();
+        for (int tile = cta; tile < p.tiles; tile += grid, ++kit) {
+          const int s = kit % C::STAGES;
+          const uint32_t ph = (kit / C::STAGES) & 1u;
+          const uint32_t buf = kit & 1u, use = kit >> 1;
+          mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+            const uint32_t sw = smem_u32(wsm);
+            const uint32_t tacc = tmem_base + buf * BN;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const EklTap tap = p.taps[t];
+              const uint32_t a0 = sa + (uint32_t)(tap.dw + 1) * C::BOX_BYTES + (uint32_t)(tap.dh + 1) * C::SBO;
+              const uint32_t b0 = sw + (uint32_t)t * C::WT_BYTES;
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k)
+                tc_mma_bf16(tacc, umma_desc(a0 + k * 32, 16, C::SBO, C::LAYOUT), umma_desc(b0 + k * 32, 16, C::SBO, C::LAYOUT),
+                            idesc, (t | k) != 0 ? 1u : 0u);
+            }
+            tc_commit(&empty[s]);
+            tc_commit(&tmem_full[buf]);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) tc_commit(wfree);       // all MMAs of this round retired -> filter tile reusable
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    const int pair = et % C::PAIRS, slice = et / C::PAIRS;
+    uint32_t kit = 0;
+    bool store_pending = false;
+    for (int n = 0; n < p.ntn; ++n) {
+      float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+      if (has_tiles)
+        for (int tile = cta; tile < p.tiles; tile += grid, ++kit) {
+          const uint32_t buf = kit & 1u, use = kit >> 1;
+          int w0, h0, b0;
+          tile_origin(tile, w0, h0, b0);
+          mbar_wait(&tmem_full[buf], use & 1u);
+          tc_fence_after();
+          if (store_pending && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+          const float* brow = nullptr;
+          if (p.bias9 != nullptr) {
+            const int hh = h0 + (row >> 3), ww = w0 + (row & 7);
+            const int cls = (hh == 0 ? 0 : (hh == p.H - 1 ? 2 : 1)) * 3 + (ww == 0 ? 0 : (ww == p.W - 1 ? 2 : 1));
+            brow = p.bias9 + ((size_t)b0 * 9 + cls) * p.N + n * BN;
+          }
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += (BN < 32 ? 16 : 32)) {
+            constexpr int CH = BN < 32 ? 16 : 32;
+            uint32_t rr[CH];
+            if constexpr (CH == 16) tmem_ld16(tacc + (uint32_t)c0, rr); else tmem_ld32(tacc + (uint32_t)c0, rr);
+            tmem_ld_wait();
+            if (brow != nullptr) {
+#pragma unroll
+              for (int i = 0; i < CH; i += 4) {
+                const float4 bv = *reinterpret_cast<const float4*>(brow + c0 + i);
+                rr[i] = __float_as_uint(__uint_as_float(rr[i]) + bv.x); rr[i + 1] = __float_as_uint(__uint_as_float(rr[i + 1]) + bv.y);
+                rr[i + 2] = __float_as_uint(__uint_as_float(rr[i + 2]) + bv.z); rr[i + 3] = __float_as_uint(__uint_as_float(rr[i + 3]) + bv.w);
+              }
+            }
+            if (p.act != 0) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) rr[i] = __float_as_uint(rw_act(__uint_as_float(rr[i]), p.act));
+            }
+#pragma unroll
+            for (int j = 0; j < CH / 8; ++j)
+              *reinterpret_cast<uint4*>(stage_out + rw_stage_off<BN>(row, c0 + 8 * j)) =
+                  make_uint4(pack_bf16x2(__uint_as_float(rr[8 * j]), __uint_as_float(rr[8 * j + 1])),
+                             pack_bf16x2(__uint_as_float(rr[8 * j + 2]), __uint_as_float(rr[8 * j + 3])),
+                             pack_bf16x2(__uint_as_float(rr[8 * j + 4]), __uint_as_float(rr[8 * j + 5])),
+                             pack_bf16x2(__uint_as_float(rr[8 * j + 6]), __uint_as_float(rr[8 * j + 7])));
+          }
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[buf]);
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            tma_store_4d(&p.o_map, stage_out, n * BN, w0, h0, b0);
+            tma_store_commit();
+          }
+          store_pending = true;
+          if (p.stats != nullptr) {
+            constexpr int RPS = 128 / C::SLICES;
+            const int r0 = slice * RPS;
+#pragma unroll 4
+            for (int rr = r0; rr < r0 + RPS; ++rr) {
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(stage_out + rw_stage_off<BN>(rr, 2 * pair));
+              const float x0 = bf16_lo(u), x1 = bf16_hi(u);
+              s1a += x0; s2a += x0 * x0; s1b += x1; s2b += x1 * x1;
+            }
+          }
+        }
+      if (p.stats != nullptr) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float* my = red + (size_t)slice * 2 * BN;
+        my[2 * pair] = s1a; my[2 * pair + 1] = s1b; my[BN + 2 * pair] = s2a; my[BN + 2 * pair + 1] = s2b;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float* dst = p.stats + (size_t)cta * 2 * p.N + n * BN;
+        for (int c = et; c < 2 * BN; c += 128) {
+          float acc = 0.f;
+#pragma unroll
+          for (int sl = 0; sl < C::SLICES; ++sl) acc += red[(size_t)sl * 2 * BN + c];
+          dst[(c < BN) ? c : (p.N + c - BN)] = acc;
+        }
+      }
+    }
+    if (store_pending && et == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+template <int BN, int KC>
+int launch_rw(RwParams& p, int grid, cudaStream_t st) {
+  using C = RwCfg<BN, KC>;
+  auto kern = conv3x3_rw_kernel<BN, KC>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EKL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  kern<<<grid, 192, C::SMEM_BYTES, st>>>(p);
+  EKL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+int ekl_num_sms();
+
+// The resident-filter kernel applies to: stride-1 3x3 plans, one statistics group, Cin in {16,32,64}, N % 16 == 0,
+// H % 16 == 0, W % 8 == 0.
+int ekl_rw_supported(const EklGather* g, int group_b) {
+  if (g->nvar != 1 || g->ntaps != 9 || g->n_a != 1) return 0;
+  if (!(g->Cin == 16 || g->Cin == 32 || g->Cin == 64)) return 0;
+  if (g->N % 16 != 0 || g->mH % 16 != 0 || g->mW % 8 != 0) return 0;
+  if (group_b > 0 && group_b != g->mB) return 0;
+  if (g->a[0].f32 || g->a[0].sC != 1 || g->o[0].f32 || g->o[0].sC != 1) return 0;
+  for (int t = 0; t < 9; ++t)
+    if (g->taps[0][t].dh < -1 || g->taps[0][t].dh > 1 || g->taps[0][t].dw < -1 || g->taps[0][t].dw > 1) return 0;
+  return 1;
+}
+
+int ekl_conv3x3_rw(const EklGather* g, const void* w_packed, float* stats, int act, const float* bias9, cudaStream_t st) {
+  EKL_REQUIRE(ekl_rw_supported(g, 0), "conv3x3_rw: unsupported plan");
+  RwParams p;
+  memset(&p, 0, sizeof(p));
+  memcpy(p.taps, g->taps[0], sizeof(p.taps));
+  p.stats = stats; p.bias9 = bias9; p.N = g->N; p.H = g->mH; p.W = g->mW; p.act = act;
+  p.nTh = g->mH / 16; p.nTw = g->mW / 8; p.tiles = g->mB * p.nTh * p.nTw;
+  const int KC = g->Cin;
+  const int BN = g->N % 64 == 0 ? 64 : (g->N % 32 == 0 ? 32 : 16);
+  p.ntn = g->N / BN;
+  const int swz = KC == 64 ? 3 : (KC == 32 ? 2 : 1);
+  {
+    const EklView& v = g->a[0];
+    uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)v.dW, (uint64_t)v.dH, (uint64_t)v.dB};
+    uint64_t strides[3] = {(uint64_t)v.sW * 2, (uint64_t)v.sH * 2, (uint64_t)v.sB * 2};
+    uint32_t box[4] = {(uint32_t)KC, 8, 18, 1};
+    if (int rc = ekl_make_tmap(&p.a_map, v.base, 4, dims, strides, box, swz, 2)) return rc;
+  }
+  {
+    const EklView& v = g->o[0];
+    uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)v.dW, (uint64_t)v.dH, (uint64_t)v.dB};
+    uint64_t strides[3] = {(uint64_t)v.sW * 2, (uint64_t)v.sH * 2, (uint64_t)v.sB * 2};
+    uint32_t box[4] = {(uint32_t)BN, 8, 16, 1};
+    if (int rc = ekl_make_tmap(&p.o_map, v.base, 4, dims, strides, box, BN == 64 ? 3 : (BN == 32 ? 2 : 0), 2)) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)9 * g->Cin, (uint64_t)g->N};
+    uint64_t strides[1] = {(uint64_t)9 * g->Cin * 2};
+    uint32_t box[2] = {(uint32_t)KC, (uint32_t)BN};
+    if (int rc = ekl_make_tmap(&p.w_map, w_packed, 2, dims, strides, box, swz, 2)) return rc;
+  }
+  const int grid = ekl_num_sms();      // statistics rows are indexed by the full-machine grid (ekl_tc_stats_rows)
+#define EKL_RW_CASE(bn, kc) if (BN == bn && KC == kc) return launch_rw<bn, kc>(p, grid, st);
+  EKL_RW_CASE(64, 64) EKL_RW_CASE(32, 64) EKL_RW_CASE(16, 64)
+  EKL_RW_CASE(64, 32) EKL_RW_CASE(32, 32) EKL_RW_CASE(16, 32)
+  EKL_RW_CASE(64, 16) EKL_RW_CASE(32, 16) EKL_RW_CASE(16, 16)
+#undef EKL_RW_CASE
+  return ekl_fail(-1, "conv3x3_rw: no kernel for BN=%d KC=%d", BN, KC);
+}

@@ -28,6 +28,8 @@ struct TcParams {
   int nvar, ntn;      // variants, N tiles
   int groups, mtg;    // BatchNorm statistic groups, M tiles per group
   int act;            // epilogue activation on the fp32 accumulator: 0 none, 2 LeakyReLU(0.2), 4 tanh
+  const float* bias9; // [B][9][N] per-sample, per-border-class bias added to the accumulator (folded code channels) or null
+  int H, W;           // M-grid extents (border classes of bias9)
 };
 
 template <int BN, int KC>
@@ -186,11 +188,27 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
         if (store_pending && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+        const float* brow = nullptr;
+        if (p.bias9 != nullptr) {
+          // this thread's pixel (b, h, w) -> border class (3 row classes x 3 column classes)
+          const int wi = row % p.tw, hi = (row / p.tw) % p.th, bi = row / (p.tw * p.th);
+          const int hh = h0 + hi, ww = w0 + wi;
+          const int cls = (hh == 0 ? 0 : (hh == p.H - 1 ? 2 : 1)) * 3 + (ww == 0 ? 0 : (ww == p.W - 1 ? 2 : 1));
+          brow = p.bias9 + ((size_t)(b0 + bi) * 9 + cls) * p.N + n * BN;
+        }
         if constexpr (BN == 16) {
           uint32_t rr[16];
           tmem_ld16(tacc, rr);
           tmem_ld_wait();
           uint32_t pk[8];
+          if (brow != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(brow + i);
+              rr[i] = __float_as_uint(__uint_as_float(rr[i]) + bv.x); rr[i + 1] = __float_as_uint(__uint_as_float(rr[i + 1]) + bv.y);
+              rr[i + 2] = __float_as_uint(__uint_as_float(rr[i + 2]) + bv.z); rr[i + 3] = __float_as_uint(__uint_as_float(rr[i + 3]) + bv.w);
+            }
+          }
           if (p.act != 0) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(epi_act(__uint_as_float(rr[i]), p.act));
@@ -207,6 +225,14 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
             tmem_ld32(tacc + (uint32_t)c0, rr);
             tmem_ld_wait();
             uint32_t pk[16];
+            if (brow != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 bv = *reinterpret_cast<const float4*>(brow + c0 + i);
+                rr[i] = __float_as_uint(__uint_as_float(rr[i]) + bv.x); rr[i + 1] = __float_as_uint(__uint_as_float(rr[i + 1]) + bv.y);
+                rr[i + 2] = __float_as_uint(__uint_as_float(rr[i + 2]) + bv.z); rr[i + 3] = __float_as_uint(__uint_as_float(rr[i + 3]) + bv.w);
+              }
+            }
             if (p.act != 0) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) rr[i] = __float_as_uint(epi_act(__uint_as_float(rr[i]), p.act));
@@ -334,8 +360,8 @@ int ekl_tc_stats_rows(const EklGather* g, int group_b) {
 }
 
 // stats: [((grp*grid + cta)*nvar + v)][2][N] fp32 partials or null.
-int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, int group_b, int act, int* mtiles_out,
-                       cudaStream_t st) {
+int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, int group_b, int act, const float* bias9,
+                       int* mtiles_out, cudaStream_t st) {
   EKL_REQUIRE(ekl_tc_supported(g), "gather_gemm_tc: unsupported shape Cin=%d N=%d mH=%d mW=%d", g->Cin, g->N, g->mH, g->mW);
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -350,6 +376,8 @@ int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, i
   if (mtiles_out) *mtiles_out = mtiles;
   p.rows_valid = tb * th * tw;
   p.ntaps = g->ntaps; p.Cin = g->Cin; p.N = g->N; p.stats = stats; p.nvar = g->nvar; p.act = act;
+  p.bias9 = bias9; p.H = g->mH; p.W = g->mW;
+  EKL_REQUIRE(bias9 == nullptr || (g->nvar == 1 && g->ntaps == 9 && g->N % 4 == 0), "bias9: stride-1 3x3 forward only");
   memcpy(p.taps, g->taps, sizeof(p.taps));
   const int KC = g->Cin % 64 == 0 ? 64 : (g->Cin % 32 == 0 ? 32 : 16);
   p.ncb = g->Cin / KC;

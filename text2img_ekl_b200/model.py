@@ -287,8 +287,26 @@ class INIT_STAGE_G(_InitStageBase):
         return self._ups(_stem_bn_glu(self.fc[0](in_code), self.fc[1], self.gf_dim))
 
 
+def _border_valid():
+    """VALID[q, t] = 1 iff tap t = (kh, kw) of a 3x3 / pad-1 conv reads inside the map for a pixel of border class
+    q = 3*rc + cc (rc / cc: 0 first row / column, 1 interior, 2 last)."""
+    v = torch.zeros(9, 9)
+    ok = lambda cls, k: not ((cls == 0 and k == 0) or (cls == 2 and k == 2))
+    for rc in range(3):
+        for cc in range(3):
+            for kh in range(3):
+                for kw in range(3):
+                    v[rc * 3 + cc, kh * 3 + kw] = float(ok(rc, kh) and ok(cc, kw))
+    return v
+
+
 class NEXT_STAGE_G(nn.Module):
-    """model.py:379-423: cat(tile(c_code), h) -> jointConv -> R_NUM ResBlocks -> upBlock (-> upBlock if SCALE 4)."""
+    """model.py:379-423: cat(tile(c_code), h) -> jointConv -> R_NUM ResBlocks -> upBlock (-> upBlock if SCALE 4).
+
+    The tiled code channels are spatially constant, so the jointConv over cat(tile(c), h) is computed as a conv over the
+    h channels only plus a per-sample bias with 9 border variants (bias9[b, q] = sum of the code's tap responses
+    T[b, t] = Wc[:, :, t] c[b] over the taps that fall inside the map for border class q): the [B, ef+ngf, H, W] tensor is
+    never formed and the conv contraction drops from 9*(ef+ngf) to 9*ngf."""
 
     def __init__(self, ngf, num_residual=None):
         super().__init__()
@@ -303,10 +321,28 @@ class NEXT_STAGE_G(nn.Module):
         self.upsample = upBlock(ngf, ngf // 2)
         if cfg.TREE.SCALE == 4:
             self.upsample2 = upBlock(ngf // 2, ngf // 4)
+        self._fold = ngf % 16 == 0 and (2 * ngf) % 32 == 0
+        self._spec_x = ops.ConvSpec(ops.S1, ngf, 2 * ngf, impl=L.IMPL_TC) if self._fold else None
+        self._valid = None
+
+    def _joint(self, h_code, c_code):
+        x = to_nhwc(h_code)
+        c = c_code.view(-1, self.ef_dim)
+        conv_mod, bn_mod = self.jointConv[0], self.jointConv[1]
+        if not (self._fold and x.shape[1] >= 2 and x.shape[2] >= 2):
+            return self.jointConv(to_public(ops.cat_code(c, x)))
+        w = conv_mod.weight                                              # [2ngf, ef+ngf, 3, 3], code channels first
+        if self._valid is None or self._valid.device != w.device:
+            self._valid = _border_valid().to(w.device)
+        B, N = x.shape[0], w.shape[0]
+        T = torch.einsum("bc,nckl->bkln", c.float(), w[:, :self.ef_dim]).reshape(B, 9, N)
+        bias9 = torch.einsum("qt,btn->bqn", self._valid, T)
+        wx = w[:, self.ef_dim:].contiguous(memory_format=torch.channels_last)
+        y, stats = ops.conv_bias9(x, wx, bias9, self._spec_x, want_stats=bn_mod.training)
+        return to_public(ops.bn_act(y, stats, bn_mod, 1, ops.ACT_GLU))
 
     def forward(self, h_code, c_code):
-        h_c = ops.cat_code(c_code.view(-1, self.ef_dim), to_nhwc(h_code))
-        out = self.upsample(self.residual(self.jointConv(to_public(h_c))))
+        out = self.upsample(self.residual(self._joint(h_code, c_code)))
         if cfg.TREE.SCALE == 4:
             out = self.upsample2(out)
         return out

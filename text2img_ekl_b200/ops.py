@@ -200,6 +200,81 @@ def conv(x, weight, spec, group_b=0, want_stats=False, skip_wgrad=False):
     return _Conv.apply(x, weight, spec, group_b, want_stats, skip_wgrad)
 
 
+def border_class_sums(dy):
+    """[B,H,W,N] -> fp32 [B,9,N]: sums of dy over the 9 border classes of ekl_conv_fwd_bias9 (class = 3*rc + cc).
+    The bulk reduction is one pass of the column-statistics kernel with one group per sample; the border rows /
+    columns / corners are small strided slices combined by inclusion-exclusion."""
+    lib = L.lib()
+    B, H, W, N = dy.shape
+    M = B * H * W
+    rows = lib.ekl_col_stats_rows(M, N, B)
+    part = torch.empty(rows, 2, N, device=dy.device, dtype=torch.float32)
+    L.check(lib.ekl_col_stats(L.ptr(dy), M, N, B, L.ptr(part), L.stream()))
+    _count()
+    S = part.view(B, rows // B, 2, N)[:, :, 0].sum(1)
+    f = lambda t: t.float()
+    R0, RL = f(dy[:, 0]).sum(1), f(dy[:, H - 1]).sum(1)
+    C0, CL = f(dy[:, :, 0]).sum(1), f(dy[:, :, W - 1]).sum(1)
+    K00, K0L, KL0, KLL = f(dy[:, 0, 0]), f(dy[:, 0, W - 1]), f(dy[:, H - 1, 0]), f(dy[:, H - 1, W - 1])
+    mid = S - R0 - RL - C0 - CL + K00 + K0L + KL0 + KLL
+    return torch.stack((K00, R0 - K00 - K0L, K0L, C0 - K00 - KL0, mid, CL - K0L - KLL, KL0, RL - KL0 - KLL, KLL), 1)
+
+
+class _ConvBias9(torch.autograd.Function):
+    """y = conv3x3(x, weight) + bias9[b, border class(h, w), :]  (include/ekl_b200.h: ekl_conv_fwd_bias9)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias9, spec, want_stats):
+        lib = L.lib()
+        B, H, W, _ = x.shape
+        assert x.dtype == torch.bfloat16 and x.is_contiguous() and spec.mode == S1 and spec.impl == L.IMPL_TC
+        w_fwd, _ = spec.packed(weight)
+        c = spec.conv(B, H, W, 0)
+        y = torch.empty(B, H, W, spec.cout, device=x.device, dtype=torch.bfloat16)
+        stats = None
+        if want_stats:
+            stats = torch.empty(lib.ekl_conv_stats_rows(c), 2, spec.cout, device=x.device, dtype=torch.float32)
+        bias9 = bias9.float().contiguous()
+        _log("fwd", "conv_tc", spec.mode, B, H, W, spec.cin, spec.cout, 0)
+        with _prof("conv_tc_fwd", _conv_flops(spec, B, H, W), x.numel() * 2 + y.numel() * 2):
+            L.check(lib.ekl_conv_fwd_bias9(c, L.ptr(x), L.ptr(w_fwd), L.ptr(bias9), L.ptr(y), L.ptr(stats), L.stream()))
+        _count()
+        ctx.dims = (B, H, W)
+        ctx.save_for_backward(x, weight)
+        ctx.spec, ctx.c, ctx.w_leaf = spec, c, weight.is_leaf
+        ctx.mark_non_differentiable(*([stats] if stats is not None else []))
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, _dstats):
+        lib = L.lib()
+        x, weight = ctx.saved_tensors
+        spec, c = ctx.spec, ctx.c
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            _, w_dgrad = spec.packed(weight)
+            dx = torch.empty_like(x)
+            _log("dgrad", "conv_tc", spec.mode, *ctx.dims, spec.cin, spec.cout, 0)
+            with _prof("conv_tc_dgrad", _conv_flops(spec, *ctx.dims), dx.numel() * 2 + dy.numel() * 2):
+                L.check(lib.ekl_conv_bwd_data(c, L.ptr(dy), L.ptr(w_dgrad), L.ptr(dx), L.stream()))
+            _count()
+        if ctx.needs_input_grad[1]:
+            buf = _grad_buffer(weight) if ctx.w_leaf else torch.zeros_like(weight, memory_format=torch.preserve_format)
+            dw = None if ctx.w_leaf else buf
+            _log("wgrad", "conv_tc", spec.mode, *ctx.dims, spec.cin, spec.cout, 0)
+            with _prof("conv_tc_wgrad", _conv_flops(spec, *ctx.dims), x.numel() * 2 + dy.numel() * 2):
+                L.check(lib.ekl_conv_bwd_weight(c, L.ptr(x), L.ptr(dy), L.ptr(buf), L.stream()))
+            _count()
+        if ctx.needs_input_grad[2]:
+            db = border_class_sums(dy)
+        return dx, dw, db, None, None
+
+
+def conv_bias9(x, weight, bias9, spec, want_stats=False):
+    return _ConvBias9.apply(x, weight, bias9, spec, want_stats)
+
+
 class _BnAct(torch.autograd.Function):
     """Train-mode BatchNorm (per-group batch statistics) + GLU / LeakyReLU / ReLU / identity (+ residual)."""
 

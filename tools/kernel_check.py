@@ -14,7 +14,9 @@ sys.path.insert(0, ROOT)
 
 SHAPES = {  # mode -> list of (B, H, W, Cin, Cout)
     0: [(4, 8, 8, 64, 128), (2, 16, 16, 128, 64), (3, 4, 4, 64, 256), (2, 32, 32, 32, 64), (2, 64, 64, 16, 32),
-        (8, 4, 4, 192, 512), (2, 8, 8, 320, 128), (3, 32, 32, 16, 64), (2, 32, 32, 32, 16), (2, 64, 64, 16, 16)],
+        (8, 4, 4, 192, 512), (2, 8, 8, 320, 128), (3, 32, 32, 16, 64), (2, 32, 32, 32, 16), (2, 64, 64, 16, 16),
+        # resident-filter kernel (conv_rw.cu): two N tiles, one tile per image, more tiles than SMs
+        (2, 16, 16, 64, 128), (5, 16, 8, 64, 64), (6, 64, 64, 64, 64), (3, 32, 64, 32, 32)],
     1: [(4, 4, 4, 128, 128), (2, 8, 8, 64, 64), (3, 16, 16, 64, 128), (2, 32, 32, 32, 32), (2, 4, 4, 256, 512)],
     2: [(4, 16, 16, 64, 128), (2, 8, 8, 128, 256), (3, 32, 32, 64, 64), (2, 8, 8, 512, 1024), (2, 64, 64, 32, 64)],
 }
@@ -243,6 +245,31 @@ def run_misc(torch, L, lib, dev, rel):
         wantd = torch.nn.functional.pixel_shuffle(d[..., :12].float().permute(0, 3, 1, 2), 2)
         ok = ok and bool((dx == wantd).all())
         print("%s img_s2d G%d B%d %dx%d" % ("PASS" if ok else "FAIL", G, B, H, W), flush=True)
+        nfail += 0 if ok else 1
+    from text2img_ekl_b200 import model as M_, ops as O_
+    for (B, H, W, Cc, Cx, N) in [(3, 64, 64, 128, 64, 128), (2, 128, 128, 128, 32, 64), (2, 8, 16, 256, 64, 128)]:
+        # folded jointConv (ekl_conv_fwd_bias9 + border_class_sums) against conv3x3 over cat(tile(c), h) in fp32
+        c = torch.randn(B, Cc, device=dev).requires_grad_(True)
+        x = torch.randn(B, H, W, Cx, device=dev).bfloat16().requires_grad_(True)
+        w = (torch.randn(N, Cc + Cx, 3, 3, device=dev) / (9 * (Cc + Cx)) ** 0.5).bfloat16().float()
+        w = w.contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        spec = O_.ConvSpec(O_.S1, Cx, N, impl=L.IMPL_TC)
+        valid = M_._border_valid().to(dev)
+        T = torch.einsum("bc,nckl->bkln", c, w[:, :Cc]).reshape(B, 9, N)
+        bias9 = torch.einsum("qt,btn->bqn", valid, T)
+        y, _ = O_.conv_bias9(x, w[:, Cc:].contiguous(memory_format=torch.channels_last), bias9, spec)
+        dy = torch.randn_like(y)
+        y.backward(dy)
+        got = [y.permute(0, 3, 1, 2), x.grad.permute(0, 3, 1, 2), w.grad, c.grad]
+        cr, xr, wr = c.detach().clone().requires_grad_(True), x.detach().float().requires_grad_(True), w.detach().clone().requires_grad_(True)
+        xin = torch.cat((cr.view(B, Cc, 1, 1).expand(B, Cc, H, W), xr.permute(0, 3, 1, 2)), 1)
+        torch.backends.cudnn.allow_tf32 = False
+        yr = torch.nn.functional.conv2d(xin, wr, padding=1)
+        yr.backward(dy.float().permute(0, 3, 1, 2))
+        want = [yr, xr.grad.permute(0, 3, 1, 2), wr.grad, cr.grad]
+        errs = [rel(a, b) for a, b in zip(got, want)]
+        ok = errs[0] < 6e-3 and errs[1] < 6e-3 and errs[2] < 2e-3 and errs[3] < 2e-3
+        print("%s conv_bias9 B%d %dx%d Cc%d Cx%d N%d y %.1e dx %.1e dw %.1e dc %.1e" % (("PASS" if ok else "FAIL", B, H, W, Cc, Cx, N) + tuple(errs)), flush=True)
         nfail += 0 if ok else 1
     for (B, H, W, C) in [(2, 64, 64, 16), (3, 16, 32, 8)]:
         y = torch.randn(B, H, W, C, device=dev).bfloat16()
