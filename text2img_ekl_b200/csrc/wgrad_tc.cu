@@ -9,6 +9,8 @@
 // The 128 accumulator rows are 128/CW boxes = consecutive (tap, channel-block) pairs sharing one dY operand.
 // Split-K over pixel tiles across CTAs; epilogue = tcgen05.ld + red.global.add.f32 straight into the fp32
 // gradient buffer in master layout [Cout][KH*KW][Cin] (coalesced along ci).
+#include <stdlib.h>
+
 #include "conv_plan.h"
 #include "ekl_common.cuh"
 
@@ -158,6 +160,168 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
   if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Big-channel variant (Cin % 64 == 0, Cout % 128 == 0, KRSC master layout): the accumulator is transposed,
+//   D[co 128 rows][(tap, ci) up to 256 columns],
+// so a TMEM lane (= one output channel co) holds runs of 32 CONSECUTIVE ci of one tap: the epilogue moves 16 bytes per
+// lane-instruction (ld/st.global.v4 when this CTA is the only writer of its outputs, red.global.add.v4.f32 otherwise)
+// instead of one scalar red per element.  (Measured on B200: the scalar-red epilogue of a 128x256 tile costs 25-45 us,
+// REDG issues at ~1.3 cycles per lane.)
+struct WgCoParams {
+  CUtensorMap a_maps[4];
+  CUtensorMap y_maps[EKL_MAX_VAR];
+  EklTap taps[EKL_MAX_VAR][EKL_MAX_TAPS];
+  float* dw;
+  int ntaps, ncb, Cin, Cout, KK;
+  int tiles_per_var;
+  int tb, th, tw, nTh, nTw, ptiles;
+  int rows_valid;
+  int exclusive;           // 1: every output element is written by exactly one CTA -> plain read-modify-write
+};
+
+struct WgCoCfg {
+  static constexpr int X_BOX = KP * 64 * 2;          // [64 px][64 ci]
+  static constexpr int Y_BOX = KP * 64 * 2;          // [64 px][64 co]
+  static constexpr int A_BYTES = 2 * Y_BOX;          // M = 128 co
+  static constexpr int B_BYTES = 4 * X_BOX;          // N <= 256 (tap, ci) columns
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 2;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(192) conv_wgrad_co_kernel(const __grid_constant__ WgCoParams p) {
+  using C = WgCoCfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tmem_full = empty + C::STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v = blockIdx.x / p.tiles_per_var;
+  const int nt = blockIdx.x - v * p.tiles_per_var;
+  const int co0 = blockIdx.y * 128;
+  const int npairs = p.ntaps * p.ncb;
+  const int pair0 = nt * 4;
+  const int nbox = (npairs - pair0) < 4 ? (npairs - pair0) : 4;
+  const int per = (p.ptiles + gridDim.z - 1) / gridDim.z;
+  const int pt0 = blockIdx.z * per;
+  const int pt1 = (pt0 + per) < p.ptiles ? (pt0 + per) : p.ptiles;
+  const int n_iters = pt1 - pt0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (n_iters > 0) {
+    if (warp == 0) {
+      if (elect_one()) {
+        const uint32_t tx = (uint32_t)((nbox + 2) * p.rows_valid * 64 * 2);
+        for (int it = 0; it < n_iters; ++it) {
+          const int s = it % C::STAGES;
+          const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          int pt = pt0 + it;
+          const int twi = pt % p.nTw; pt /= p.nTw;
+          const int thi = pt % p.nTh; pt /= p.nTh;
+          const int w0 = twi * p.tw, h0 = thi * p.th, b0 = pt * p.tb;
+          uint8_t* sa = smem + s * C::STAGE_BYTES;
+          mbar_expect_tx(&full[s], tx);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) tma_load_4d(&p.y_maps[v], &full[s], sa + j * C::Y_BOX, co0 + j * 64, w0, h0, b0);
+          for (int j = 0; j < nbox; ++j) {
+            const int pair = pair0 + j;
+            const int t = pair / p.ncb, cb = pair - t * p.ncb;
+            const EklTap tap = p.taps[v][t];
+            tma_load_4d(&p.a_maps[tap.map], &full[s], sa + C::A_BYTES + j * C::X_BOX, cb * 64, w0 + tap.dw, h0 + tap.dh, b0);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      const uint32_t idesc = umma_idesc_bf16(128, nbox * 64, 1, 1);
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % C::STAGES;
+        const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+          const int ksteps = (p.rows_valid + 15) / 16;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t da = umma_desc(sa + k * 16 * 128, C::Y_BOX, 8 * 128, 2u);
+            const uint64_t db = umma_desc(sb + k * 16 * 128, C::X_BOX, 8 * 128, 2u);
+            tc_mma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty[s]);
+          if (it == n_iters - 1) tc_commit(tmem_full);
+        }
+        __syncwarp();
+      }
+    } else {
+      // TMEM lane = output channel; each warp transposes its 32(co) x 32(ci) block through shared memory (the pipeline
+      // stages are free: every MMA has retired) so that 8 consecutive lanes cover one 128-byte run of ci:
+      // every global access below is 4 output-channel rows x 128 contiguous bytes.
+      const int q = warp & 3;
+      float* stg = reinterpret_cast<float*>(smem) + q * (32 * 36);
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      const int rsub = lane >> 3, col = (lane & 7) * 4;
+#pragma unroll 1
+      for (int c0 = 0; c0 < nbox * 64; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(stg + lane * 36 + i) =
+              make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        __syncwarp();
+        const int pair = pair0 + (c0 >> 6);
+        const int t = pair / p.ncb, cb = pair - t * p.ncb;
+        const EklTap tap = p.taps[v][t];
+        const int ci = cb * 64 + (c0 & 63) + col;
+        float4 val[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) val[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * 36 + col);
+        for (int s = 0; s < tap.nsrc; ++s) {
+          float* dst = p.dw + ((int64_t)(co0 + q * 32 + rsub) * p.KK + tap.src[s]) * p.Cin + ci;
+          const int64_t rstride = (int64_t)4 * p.KK * p.Cin;
+          if (p.exclusive) {
+            float4 o[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) o[it] = *reinterpret_cast<const float4*>(dst + it * rstride);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              o[it].x += val[it].x; o[it].y += val[it].y; o[it].z += val[it].z; o[it].w += val[it].w;
+              *reinterpret_cast<float4*>(dst + it * rstride) = o[it];
+            }
+          } else {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) red_add_v4(dst + it * rstride, val[it].x, val[it].y, val[it].z, val[it].w);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem_base);
+}
+
 int make_map(CUtensorMap* m, const EklView& v, int boxC, int tw, int th, int tb, int swz) {
   uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)v.dW, (uint64_t)v.dH, (uint64_t)v.dB};
   uint64_t strides[3] = {(uint64_t)v.sW * 2, (uint64_t)v.sH * 2, (uint64_t)v.sB * 2};
@@ -194,9 +358,60 @@ int ekl_wgrad_tc_supported(const EklGather* g) {
   return 1;
 }
 
+int ekl_num_sms();
+
+// big-channel variant: see conv_wgrad_co_kernel
+static int wgrad_co(const EklGather* g, float* dw, cudaStream_t st) {
+  WgCoParams p;
+  memset(&p, 0, sizeof(p));
+  memcpy(p.taps, g->taps, sizeof(p.taps));
+  p.dw = dw; p.ntaps = g->ntaps; p.Cin = g->Cin; p.Cout = g->N; p.KK = g->KH * g->KW;
+  p.ncb = g->Cin / 64;
+  p.tiles_per_var = ekl_cdiv(g->ntaps * p.ncb, 4);
+  int tw = g->mW < KP ? g->mW : KP;
+  int rest = KP / tw;
+  int th = g->mH < rest ? g->mH : rest;
+  int tb = rest / th;
+  p.tw = tw; p.th = th; p.tb = tb;
+  p.nTw = ekl_cdiv(g->mW, tw); p.nTh = ekl_cdiv(g->mH, th);
+  p.ptiles = p.nTw * p.nTh * ekl_cdiv(g->mB, tb);
+  p.rows_valid = tb * th * tw;
+  for (int i = 0; i < g->n_a; ++i)
+    if (int rc = make_map(&p.a_maps[i], g->a[i], 64, tw, th, tb, 3)) return rc;
+  for (int i = 0; i < g->nvar; ++i)
+    if (int rc = make_map(&p.y_maps[i], g->o[i], 64, tw, th, tb, 3)) return rc;
+  const int base_ctas = p.tiles_per_var * g->nvar * (g->N / 128);
+  int splits = (2 * ekl_num_sms()) / base_ctas;
+  if (splits > p.ptiles / 8) splits = p.ptiles / 8;
+  if (splits < 1) splits = 1;
+  if (const char* e = getenv("EKL_WG_SPLITS")) {
+    const int v = atoi(e);
+    if (v > 0) splits = v < p.ptiles ? v : p.ptiles;
+  }
+  // exclusive ownership: one split, and no master tap receives more than one (variant, tap) product
+  bool multi = false;
+  for (int v = 0; v < g->nvar; ++v)
+    for (int t = 0; t < g->ntaps; ++t) multi = multi || g->taps[v][t].nsrc != 1;
+  p.exclusive = (splits == 1 && g->nvar == 1 && !multi) ? 1 : 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EKL_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_co_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCoCfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  dim3 grid(p.tiles_per_var * g->nvar, g->N / 128, splits);
+  conv_wgrad_co_kernel<<<grid, 192, WgCoCfg::SMEM_BYTES, st>>>(p);
+  EKL_LAUNCH_CHECK();
+  return 0;
+}
+
 // fwd_plan: forward plan whose `o` views hold dY.  dw: master-layout fp32 gradient, ACCUMULATED into.
 int ekl_wgrad_tc(const EklGather* g, float* dw, cudaStream_t st) {
   EKL_REQUIRE(ekl_wgrad_tc_supported(g), "wgrad_tc: unsupported shape Cin=%d Cout=%d", g->Cin, g->N);
+  {
+    static int co_on = -1;
+    if (co_on < 0) { const char* e = getenv("EKL_DISABLE_WGRAD_CO"); co_on = (e && e[0] == '1') ? 0 : 1; }
+    if (co_on && !g->w_kcrs && g->Cin % 64 == 0 && g->N % 128 == 0) return wgrad_co(g, dw, st);
+  }
   WgParams p;
   memset(&p, 0, sizeof(p));
   memcpy(p.taps, g->taps, sizeof(p.taps));
@@ -226,11 +441,16 @@ int ekl_wgrad_tc(const EklGather* g, float* dw, cudaStream_t st) {
     int rc = make_map(&p.y_maps[i], g->o[i], YW, tw, th, tb, y_swz);
     if (rc) return rc;
   }
-  // split-K so the grid covers the machine ~2x, keeping >= 4 pixel tiles per CTA
+  // split-K: fill the resident-CTA slots of the machine (2 CTAs per SM) WITHOUT spilling into a second wave, and keep
+  // >= 8 pixel tiles per CTA (measured: the red.global epilogue and the CTA prologue dominate shorter main loops)
   const int base_ctas = p.tiles_per_var * g->nvar * (g->N / BNW);
-  int splits = ekl_cdiv(296, base_ctas);
-  if (splits > p.ptiles / 4) splits = p.ptiles / 4;
+  int splits = (2 * ekl_num_sms()) / base_ctas;
+  if (splits > p.ptiles / 8) splits = p.ptiles / 8;
   if (splits < 1) splits = 1;
+  if (const char* e = getenv("EKL_WG_SPLITS")) {          // experiment knob
+    const int v = atoi(e);
+    if (v > 0) splits = v < p.ptiles ? v : p.ptiles;
+  }
 #define EKL_WG_CASE(bn, cw) if (BNW == bn && CW == cw) return launch_wg<bn, cw>(g, p, splits, st);
   EKL_WG_CASE(256, 64) EKL_WG_CASE(128, 64) EKL_WG_CASE(64, 64) EKL_WG_CASE(32, 64)
   EKL_WG_CASE(256, 32) EKL_WG_CASE(128, 32) EKL_WG_CASE(64, 32) EKL_WG_CASE(32, 32)
