@@ -260,8 +260,13 @@ def run_ours(a):
     if rank == 0:
         print(json.dumps(line), flush=True)
     if ws > 1:
+        # every rank is past its timed region; leave without tearing the NCCL communicator down under live CUDA
+        # graphs that captured its kernels (destroy_process_group was seen to hang there)
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def kernel_roofline(tr, batch, pk):

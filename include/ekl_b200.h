@@ -141,6 +141,17 @@ int ekl_dloss_bwd(int groups, int B, int E1, const int* t_match, const int* t_un
                   float uncond_coeff, const float* go, const float* p_m, const float* p_u, const float* logp,
                   const float* cp0, const float* cp1, float* g_m, float* g_u, float* g_cls, void* stream);
 
+/* ---------------------------------------------------------------- conditioning augmentation + KL --------------
+ * CA_NET.reparametrize / VC_NET.reparameterize (model.py:145-152, 182-184, 198) fused with KL_loss
+ * (cub_trainer_splitz_cap_ca.py:54-58):  std = exp(0.5*logvar), c = eps*std + mu,
+ * kl[0] = -0.5 * mean(1 + logvar - mu^2 - exp(logvar)).  mu / logvar: fp32 [B][D] with row strides in elements (they
+ * are column halves of one Linear / GLU output); eps, c, std: dense [B][D].  Backward: dc / dstd / dkl may be NULL. */
+int ekl_reparam_kl_fwd(const float* mu, int64_t mu_row_stride, const float* logvar, int64_t lv_row_stride,
+                       const float* eps, int B, int D, float* c, float* stdv, float* kl, void* stream);
+int ekl_reparam_kl_bwd(const float* mu, int64_t mu_row_stride, const float* logvar, int64_t lv_row_stride,
+                       const float* eps, int B, int D, const float* dc, const float* dstd, const float* dkl, float* dmu,
+                       float* dlogvar, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

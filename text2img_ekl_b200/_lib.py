@@ -58,6 +58,8 @@ SIGNATURES = {
     "ekl_dhead_dots": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "ekl_dhead_dots_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_dloss_fwd": (_i, [_i, _i, _i, _ip, _ip, _ip, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ekl_reparam_kl_fwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "ekl_reparam_kl_bwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_dloss_bwd": (_i, [_i, _i, _i, _ip, _ip, _ip, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -239,3 +239,66 @@ extern "C" int ekl_dloss_bwd(int groups, int B, int E1, const int* t_match, cons
   EKL_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------- conditioning augmentation: reparameterisation + KL
+// CA_NET / VC_NET (model.py:145-152, 182-184, 198) + KL_loss (cub_trainer_splitz_cap_ca.py:54-58), one pass:
+//   std = exp(0.5*logvar);  c = eps*std + mu;  kl = -0.5 * mean(1 + logvar - mu^2 - exp(logvar))
+// mu / logvar are [B][D] with row strides (they are column halves of one GLU / Linear output).
+namespace {
+
+__global__ void __launch_bounds__(256) reparam_kl_fwd_kernel(const float* __restrict__ mu, int64_t mu_rs, const float* __restrict__ lv,
+                                                             int64_t lv_rs, const float* __restrict__ eps, int B, int D,
+                                                             float* __restrict__ c, float* __restrict__ stdv, float* __restrict__ kl) {
+  __shared__ float sh[8];
+  const int n = B * D;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int b = i / D, d = i - b * D;
+    const float m = mu[b * mu_rs + d], l = lv[b * lv_rs + d];
+    const float s = expf(0.5f * l);
+    stdv[i] = s;
+    c[i] = eps[i] * s + m;
+    acc += 1.f + l - m * m - expf(l);
+  }
+  acc = block_sum_256(acc, sh);
+  if (threadIdx.x == 0) kl[0] = -0.5f * acc / (float)n;
+}
+
+// dmu = dc + dkl*mu/n ; dlogvar = dc*eps*0.5*std + dstd*0.5*std - dkl*0.5*(1 - exp(logvar))/n   (dc / dstd / dkl may be null)
+__global__ void __launch_bounds__(256) reparam_kl_bwd_kernel(const float* __restrict__ mu, int64_t mu_rs, const float* __restrict__ lv,
+                                                             int64_t lv_rs, const float* __restrict__ eps, int B, int D,
+                                                             const float* __restrict__ dc, const float* __restrict__ dstd,
+                                                             const float* __restrict__ dkl, float* __restrict__ dmu,
+                                                             float* __restrict__ dlv) {
+  const int n = B * D;
+  const float gk = dkl != nullptr ? dkl[0] / (float)n : 0.f;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const int b = i / D, d = i - b * D;
+    const float m = mu[b * mu_rs + d], l = lv[b * lv_rs + d];
+    const float s = expf(0.5f * l);
+    const float g = dc != nullptr ? dc[i] : 0.f;
+    const float gs = dstd != nullptr ? dstd[i] : 0.f;
+    dmu[i] = g + gk * m;
+    dlv[i] = (g * eps[i] + gs) * 0.5f * s - gk * 0.5f * (1.f - expf(l));
+  }
+}
+
+}  // namespace
+
+extern "C" int ekl_reparam_kl_fwd(const float* mu, int64_t mu_row_stride, const float* logvar, int64_t lv_row_stride,
+                                  const float* eps, int B, int D, float* c, float* stdv, float* kl, void* stream) {
+  EKL_REQUIRE(B > 0 && D > 0, "reparam_kl: bad shape");
+  reparam_kl_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(mu, mu_row_stride, logvar, lv_row_stride, eps, B, D, c, stdv, kl);
+  EKL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ekl_reparam_kl_bwd(const float* mu, int64_t mu_row_stride, const float* logvar, int64_t lv_row_stride,
+                                  const float* eps, int B, int D, const float* dc, const float* dstd, const float* dkl,
+                                  float* dmu, float* dlogvar, void* stream) {
+  EKL_REQUIRE(B > 0 && D > 0, "reparam_kl: bad shape");
+  reparam_kl_bwd_kernel<<<ekl_cdiv(B * D, 256), 256, 0, (cudaStream_t)stream>>>(mu, mu_row_stride, logvar, lv_row_stride, eps, B, D,
+                                                                                dc, dstd, dkl, dmu, dlogvar);
+  EKL_LAUNCH_CHECK();
+  return 0;
+}

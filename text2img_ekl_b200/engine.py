@@ -87,6 +87,37 @@ class FlatGrads:
         self.flat.zero_()
 
 
+class BnCounters:
+    """nn.BatchNorm's num_batches_tracked bookkeeping (one += per forward call in the reference) for a whole network
+    as ONE kernel per step: every counter becomes a 0-dim view into one int64 tensor (state_dict keys / values are
+    unchanged), the per-call increments are tallied on the host and added in a single vector add."""
+
+    def __init__(self, nets):
+        self.mods = [m for net in nets for m in net.modules()
+                     if isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and m.num_batches_tracked is not None]
+        if not self.mods:
+            self.flat = None
+            return
+        dev = self.mods[0].num_batches_tracked.device
+        self.flat = torch.stack([m.num_batches_tracked.detach().to(dev).long().reshape(()) for m in self.mods])
+        for i, m in enumerate(self.mods):
+            m._buffers["num_batches_tracked"] = self.flat[i]
+            m._ekl_counted, m._ekl_calls = True, 0
+        self._inc_key, self._inc = None, None
+
+    def flush(self):
+        if self.flat is None:
+            return
+        key = tuple(m._ekl_calls for m in self.mods)
+        if not any(key):
+            return
+        if key != self._inc_key:      # host->device copy: happens on the first step(s), before any graph capture
+            self._inc_key, self._inc = key, torch.tensor(key, dtype=torch.long, device=self.flat.device)
+        self.flat.add_(self._inc)
+        for m in self.mods:
+            m._ekl_calls = 0
+
+
 class StepEngine:
     """kind 'catz_ca': COND_G_NET_CATZ_CA flavour (cub trainer); 'cond': COND_G_NET flavour (trainer.py)."""
 
@@ -97,6 +128,8 @@ class StepEngine:
         self.gradsG = FlatGrads(netG.parameters())
         self.gradsD = [FlatGrads(d.parameters()) for d in netsD]
         self.allreduce = allreduce           # callable(flat_tensor) or None
+        self.bn_counters = BnCounters([netG] + list(netsD))
+        self.comm_stream, self._pending_comm = None, {}
         self.uncond = float(cfg.TRAIN.COEFF.UNCOND_LOSS)
         self.kl_coeff = float(cfg.TRAIN.COEFF.KL)
         self.cat_z = cfg.TRAIN.CAT_Z
@@ -132,15 +165,14 @@ class StepEngine:
     def _d_step(self, idx, real_imgs, wrong_imgs, real_cp, fake_cp):
         netD, opt, grads = self.netsD[idx], self.optsD[idx], self.gradsD[idx]
         B = real_imgs.shape[0]
+        self._join_comm(idx)                 # a still-pending update of this same discriminator must land first
         grads.zero()
         if hasattr(netD, "heads_raw") and self.uncond > 0:
             # fused path: raw logits of the stacked real / wrong / fake pass -> one loss kernel (cub:423-448)
             lm, lu, lc = netD.heads_raw((real_imgs, wrong_imgs, self.fake_imgs[idx].detach()), self.mu.detach(), groups=3)
             losses, pm, pu, logp = ops.d_loss(lm, lu, lc, real_cp, fake_cp, 3, B, (1, 0, 0), (1, 1, 0), (0, -1, 1), self.uncond)
             losses[0].backward()
-            if self.allreduce is not None:
-                self.allreduce(grads.flat)
-            opt.step()
+            self._d_update(idx)
             self.last_d_logits = tuple([pm[i * B:(i + 1) * B], pu[i * B:(i + 1) * B], logp[i * B:(i + 1) * B]] for i in range(3))
             d = losses.detach()
             return d[0], d[1], d[2], d[3]
@@ -157,14 +189,40 @@ class StepEngine:
             errD_uncond = errD_cls = torch.zeros((), device=real_imgs.device)
             errD = _bce_const(real[0], 1) + 0.5 * (_bce_const(wrong[0], 0) + _bce_const(fake[0], 0))
         errD.backward()
-        if self.allreduce is not None:
-            self.allreduce(grads.flat)
-        opt.step()
+        self._d_update(idx)
         self.last_d_logits = (real, wrong, fake)
         return errD, errD_match, errD_uncond, errD_cls
 
+    def _d_update(self, idx):
+        """Gradient all-reduce (N > 1) + Adam step of discriminator idx.  With several ranks it runs on a side stream, so
+        the all-reduce over NVLink and the optimiser pass of D_i overlap the forward / backward of D_{i+1} (their
+        updates are independent: cub:594-596 loops over the discriminators); g_step joins the side stream before the
+        updated discriminators are used."""
+        grads, opt = self.gradsD[idx], self.optsD[idx]
+        if self.allreduce is None:
+            opt.step()
+            return
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        self.comm_stream.wait_stream(main)
+        with torch.cuda.stream(self.comm_stream):
+            self.allreduce(grads.flat)
+            opt.step()
+            ev = torch.cuda.Event()
+            ev.record()
+        self._pending_comm[idx] = ev
+
+    def _join_comm(self, idx=None):
+        """Make the current stream wait for the side-stream update of discriminator idx (all of them if None)."""
+        for k in ([idx] if idx is not None else list(self._pending_comm)):
+            ev = self._pending_comm.pop(k, None)
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+
     # ---- (3) generator loss through the UPDATED discriminators: cub:463-490
     def g_loss(self, real_cp):
+        self._join_comm()
         errGs_match = errGs_uncond = errGs_cls = errGs_total_fused = 0
         self.last_g_logits = []
         for i, netD in enumerate(self.netsD):
@@ -185,16 +243,26 @@ class StepEngine:
                 errGs_uncond, errGs_cls = errGs_uncond + u_, errGs_cls + c_
                 errGs_total_fused = errGs_total_fused + u_ + c_
             self.last_g_logits.append(outputs)
-        kl = [KL_loss(m, lv) for m, lv in self.kls]
+        kl = [self._kl(m, lv) for m, lv in self.kls]
         # only losses[0] of the fused kernel carries gradient: the total is assembled from it (components are reported)
         errG_total = errGs_total_fused + sum(kl) * self.kl_coeff
         return (errG_total, errGs_match, errGs_uncond, errGs_cls) + tuple(kl)
+
+    def _kl(self, mu, logvar):
+        """KL term of one conditioning net: the value its fused reparameterisation kernel already produced for exactly
+        these (mu, logvar) tensors, else cub:54-58 in torch."""
+        for m in self.netG.modules():
+            of = getattr(m, "last_kl_of", None)
+            if of is not None and of[0] is mu and of[1] is logvar:
+                return m.last_kl
+        return KL_loss(mu, logvar)
 
     def g_step(self, real_cp):
         with tensor_core_matmul():
             return self._g_step(real_cp)
 
     def _g_step(self, real_cp):
+        self._join_comm()                    # discriminator updates issued on the side stream must have landed
         self.gradsG.zero()
         for d in self.netsD:
             d.requires_grad_(False)          # the reference computes and discards these (SURVEY app. A #15)
@@ -207,6 +275,7 @@ class StepEngine:
         if self.allreduce is not None:
             self.allreduce(self.gradsG.flat)
         self.optG.step()
+        self.bn_counters.flush()
         return res
 
     # ---- whole step on device-resident inputs

@@ -148,6 +148,13 @@ class CA_NET(nn.Module):
 
     def forward(self, text_embedding, eps=None):
         mu, logvar = self.encode(text_embedding)
+        if mu.is_cuda:
+            if eps is None:
+                eps = torch.randn_like(mu)          # reference draws on the device (model.py:147-150)
+            # one fused kernel: reparameterisation + the KL term the trainer takes of (mu, logvar) (cub:54-58)
+            c_code, std, self.last_kl = ops.reparam_kl(mu, logvar, eps)
+            self.last_kl_of = (mu, logvar)
+            return c_code, mu, logvar, std
         c_code, std = self.reparametrize(mu, logvar, eps)
         return c_code, mu, logvar, std
 
@@ -189,6 +196,10 @@ class VC_NET(nn.Module):
             else:
                 seed = torch.randn(self.bs, self.manifd_dim)     # HOST draw, like the reference (model.py:192)
             seed = seed.to(mu.device)
+        if mu.is_cuda:
+            c, std, self.last_kl = ops.reparam_kl(mu, logvar, seed)
+            self.last_kl_of = (mu, logvar)
+            return c, mu, logvar, std
         c, std = self.reparameterize(mu, logvar, seed)
         return c, mu, logvar, std
 

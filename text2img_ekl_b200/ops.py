@@ -345,7 +345,9 @@ def bn_act(y, stats, bn, groups, act, residual=None, skip_pgrad=False):
                                    L.ptr(residual), L.ptr(out), L.stream()))
         _count()
         return out
-    if bn.num_batches_tracked is not None:
+    if getattr(bn, "_ekl_counted", False):
+        bn._ekl_calls += groups          # flushed once per step for the whole network (engine.BnCounters)
+    elif bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(groups)
     return _BnAct.apply(y, stats, bn.weight, bn.bias, bn.running_mean, bn.running_var, groups, act, residual, skip_pgrad)
 
@@ -573,3 +575,38 @@ class _DLoss(torch.autograd.Function):
 
 def d_loss(lm, lu, cls, cp0, cp1, groups, B, t_match, t_uncond, cls_tgt, uncond_coeff):
     return _DLoss.apply(lm, lu, cls, cp0, cp1, (groups, B, tuple(t_match), tuple(t_uncond), tuple(cls_tgt), uncond_coeff))
+
+
+class _ReparamKL(torch.autograd.Function):
+    """c = eps*exp(0.5*logvar) + mu, std, and KL(mu, logvar) in one kernel (include/ekl_b200.h: ekl_reparam_kl_fwd).
+    mu / logvar: fp32 [B,D] views with unit column stride (e.g. the two halves of a GLU output)."""
+
+    @staticmethod
+    def forward(ctx, mu, logvar, eps):
+        B, D = mu.shape
+        assert mu.dtype == torch.float32 and logvar.dtype == torch.float32 and mu.stride(1) == 1 and logvar.stride(1) == 1
+        eps = eps.float().contiguous()
+        c, std = torch.empty(B, D, device=mu.device), torch.empty(B, D, device=mu.device)
+        kl = torch.empty((), device=mu.device)
+        L.check(L.lib().ekl_reparam_kl_fwd(L.ptr(mu), mu.stride(0), L.ptr(logvar), logvar.stride(0), L.ptr(eps), B, D, L.ptr(c),
+                                           L.ptr(std), L.ptr(kl), L.stream()))
+        _count()
+        ctx.save_for_backward(mu, logvar, eps)
+        return c, std, kl
+
+    @staticmethod
+    def backward(ctx, dc, dstd, dkl):
+        mu, logvar, eps = ctx.saved_tensors
+        B, D = mu.shape
+        dmu, dlv = torch.empty(B, D, device=mu.device), torch.empty(B, D, device=mu.device)
+        dc = dc.contiguous() if dc is not None else None
+        dstd = dstd.contiguous() if dstd is not None else None
+        dkl = dkl.contiguous() if dkl is not None else None
+        L.check(L.lib().ekl_reparam_kl_bwd(L.ptr(mu), mu.stride(0), L.ptr(logvar), logvar.stride(0), L.ptr(eps), B, D, L.ptr(dc),
+                                           L.ptr(dstd), L.ptr(dkl), L.ptr(dmu), L.ptr(dlv), L.stream()))
+        _count()
+        return dmu, dlv, None
+
+
+def reparam_kl(mu, logvar, eps):
+    return _ReparamKL.apply(mu, logvar, eps)

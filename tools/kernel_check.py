@@ -207,6 +207,23 @@ def run_heads(torch, L, lib, dev, rel):
         ok = all(e < t for e, t in zip(errs, tol))
         print("%s heads G%d B%d C%d E%d %s" % ("PASS" if ok else "FAIL", G, B, C, E1, " ".join("%.1e" % e for e in errs)), flush=True)
         nfail += 0 if ok else 1
+    for (B, D) in [(24, 128), (32, 128), (5, 17)]:
+        # fused reparameterisation + KL (model.py:145-152; cub:54-58) on strided halves of one tensor
+        x = torch.randn(B, 2 * D, device=dev).requires_grad_(True)
+        eps = torch.randn(B, D, device=dev)
+        c, std, kl = ops.reparam_kl(x[:, :D], x[:, D:], eps)
+        gc, gs = torch.randn_like(c), torch.randn_like(std)
+        ((c * gc).sum() + (std * gs).sum() + 2.0 * kl).backward()
+        xr = x.detach().clone().requires_grad_(True)
+        mu, lv = xr[:, :D], xr[:, D:]
+        sr = torch.exp(0.5 * lv)
+        cr = eps * sr + mu
+        klr = -0.5 * torch.mean(1 + lv - mu.pow(2) - lv.exp())
+        ((cr * gc).sum() + (sr * gs).sum() + 2.0 * klr).backward()
+        errs = [rel(c, cr), rel(std, sr), abs(float(kl) - float(klr)) / abs(float(klr)), rel(x.grad, xr.grad)]
+        ok = all(e < 1e-5 for e in errs)
+        print("%s reparam_kl B%d D%d %s" % ("PASS" if ok else "FAIL", B, D, " ".join("%.1e" % e for e in errs)), flush=True)
+        nfail += 0 if ok else 1
     return nfail
 
 
