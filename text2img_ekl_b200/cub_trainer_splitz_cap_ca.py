@@ -193,7 +193,9 @@ class condGANTrainer(object):
         else:
             self.noise.copy_(noise)
         self.generate(eps, seed)
-        errDs = [self.train_joint_Dnet(i, count) for i in range(self.num_Ds)]
+        errDs = [None] * self.num_Ds
+        for i in reversed(range(self.num_Ds)):        # independent updates; largest first (engine.StepEngine.step)
+            errDs[i] = self.train_joint_Dnet(i, count)
         errG = self.engine.g_step(self.real_cp)
         return errDs, errG
 

@@ -130,6 +130,7 @@ class StepEngine:
         self.allreduce = allreduce           # callable(flat_tensor) or None
         self.bn_counters = BnCounters([netG] + list(netsD))
         self.comm_stream, self._pending_comm = None, {}
+        self.d_logits = {}                   # idx -> (real, wrong, fake) x [match p, uncond p, class log-probs]
         self.uncond = float(cfg.TRAIN.COEFF.UNCOND_LOSS)
         self.kl_coeff = float(cfg.TRAIN.COEFF.KL)
         self.cat_z = cfg.TRAIN.CAT_Z
@@ -173,7 +174,7 @@ class StepEngine:
             losses, pm, pu, logp = ops.d_loss(lm, lu, lc, real_cp, fake_cp, 3, B, (1, 0, 0), (1, 1, 0), (0, -1, 1), self.uncond)
             losses[0].backward()
             self._d_update(idx)
-            self.last_d_logits = tuple([pm[i * B:(i + 1) * B], pu[i * B:(i + 1) * B], logp[i * B:(i + 1) * B]] for i in range(3))
+            self.d_logits[idx] = tuple([pm[i * B:(i + 1) * B], pu[i * B:(i + 1) * B], logp[i * B:(i + 1) * B]] for i in range(3))
             d = losses.detach()
             return d[0], d[1], d[2], d[3]
         # the three reference forwards (real / wrong / fake) as one pass; the batches are gathered by the stem kernel
@@ -190,8 +191,13 @@ class StepEngine:
             errD = _bce_const(real[0], 1) + 0.5 * (_bce_const(wrong[0], 0) + _bce_const(fake[0], 0))
         errD.backward()
         self._d_update(idx)
-        self.last_d_logits = (real, wrong, fake)
+        self.d_logits[idx] = (real, wrong, fake)
         return errD, errD_match, errD_uncond, errD_cls
+
+    @property
+    def last_d_logits(self):
+        """Logits of the deepest discriminator's latest update (real / wrong / fake groups)."""
+        return self.d_logits[max(self.d_logits)]
 
     def _d_update(self, idx):
         """Gradient all-reduce (N > 1) + Adam step of discriminator idx.  With several ranks it runs on a side stream, so
@@ -281,7 +287,11 @@ class StepEngine:
     # ---- whole step on device-resident inputs
     def step(self, real_imgs, wrong_imgs, txt, cls_cond, real_cp, fake_cp, noise, eps=None, seed=None):
         self.generate(noise, txt, cls_cond, eps, seed)
-        errDs = [self.d_step(i, real_imgs[i], wrong_imgs[i], real_cp, fake_cp) for i in range(len(self.netsD))]
+        # the discriminator updates are independent (cub:594-596); the largest goes first so that its gradient
+        # all-reduce + Adam (side stream, N > 1) hide behind the smaller ones' compute
+        errDs = [None] * len(self.netsD)
+        for i in reversed(range(len(self.netsD))):
+            errDs[i] = self.d_step(i, real_imgs[i], wrong_imgs[i], real_cp, fake_cp)
         errG = self.g_step(real_cp)
         return errDs, errG
 
@@ -330,7 +340,9 @@ class GraphedStep:
         self.eps.normal_(0, 1)
         self.seed.normal_(0, 1)
         tr.generate(self.eps, self.seed)
-        errDs = [tr.train_joint_Dnet(i, 1) for i in range(tr.num_Ds)]
+        errDs = [None] * tr.num_Ds
+        for i in reversed(range(tr.num_Ds)):          # largest discriminator first (see StepEngine.step)
+            errDs[i] = tr.train_joint_Dnet(i, 1)
         errG = tr.engine.g_step(tr.real_cp)
         return torch.stack([torch.stack([x.detach().float() for x in e]) for e in errDs]), \
             torch.stack([x.detach().float() for x in errG])
