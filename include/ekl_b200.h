@@ -152,6 +152,25 @@ int ekl_reparam_kl_bwd(const float* mu, int64_t mu_row_stride, const float* logv
                        const float* eps, int B, int D, const float* dc, const float* dstd, const float* dkl, float* dmu,
                        float* dlogvar, void* stream);
 
+/* ---------------------------------------------------------------- capsule routing (generator stem) -----------
+ * CapsuleLinear of COND_INIT_STAGE_G_withCap (model.py:245-267; third-party `capsule_layer`, un-vendored: parity is
+ * against oracle/capsule_ref.py).  Shared weights W [O][L][K]; x [B][I][K].  Dynamic routing in K space -- the
+ * [B,O,I,L] prior tensor is never formed:
+ *   proj_u   u[b,o,:] = W[o]^T v[b,o,:]                    proj_s   s[b,o,:] = W[o] y[b,o,:] (+ v = squash(s))
+ *   agree    y[b,o,:] = sum_i softmax_o(<x[b,i], u[b,o]>) x[b,i]   (logits / couplings live in registers; M, Z [B][I]
+ *            are the softmax max / normaliser saved for the backward)
+ *   squash_bwd gs = d squash(s)^T gv, gy = W^T gs           outer    gW[o,l,k] += sum_b A[b,o,l] Bm[b,o,k]
+ * Small-K regime only (ekl_caps_supported): K in {4,8}, L <= 64, I % 16 == 0. All tensors fp32, dense. */
+int ekl_caps_supported(int I, int K, int O, int L);
+int ekl_caps_proj_u(const float* W, const float* v, int B, int O, int L, int K, float* u, void* stream);
+int ekl_caps_proj_s(const float* W, const float* y, int B, int O, int L, int K, float* s, float* v_squashed, void* stream);
+int ekl_caps_squash_bwd(const float* W, const float* s, const float* gv, int B, int O, int L, int K, float* gs, float* gy,
+                        void* stream);
+int ekl_caps_outer(const float* A, const float* Bm, int B, int O, int L, int K, float* gW, void* stream);
+int ekl_caps_agree_fwd(const float* x, const float* u, int B, int I, int O, int K, float* y, float* M, float* Z, void* stream);
+int ekl_caps_agree_bwd(const float* x, const float* u, const float* M, const float* Z, const float* gy, int B, int I, int O,
+                       int K, float* gu, float* gx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,13 @@ SIGNATURES = {
     "ekl_dloss_fwd": (_i, [_i, _i, _i, _ip, _ip, _ip, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_reparam_kl_fwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "ekl_reparam_kl_bwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ekl_caps_supported": (_i, [_i, _i, _i, _i]),
+    "ekl_caps_proj_u": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "ekl_caps_proj_s": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "ekl_caps_squash_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "ekl_caps_outer": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "ekl_caps_agree_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "ekl_caps_agree_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "ekl_dloss_bwd": (_i, [_i, _i, _i, _ip, _ip, _ip, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -6,7 +6,10 @@ algorithm as restated (and documented) in oracle/capsule_ref.py; this module is 
 Shared-weight mode only (what the reference uses): weight [out_capsules, out_length, in_length], input
 [B, in_capsules, in_length] -> [B, out_capsules, out_length].
 
-The [B, O, I, L] prior tensor (201 MB at B=32 for the generator stem) is never formed.  Because
+The [B, O, I, L] prior tensor (201 MB at B=32 for the generator stem) is never formed.  On the GPU the
+small-in_length case (the generator stem, in_length 8) runs on the capsule kernels of csrc/capsule.cu (agreement
+logits / softmax over out-capsules kept on chip); the wide case (the discriminator class head, in_length 512) runs the
+same reduced algebra as cuBLAS GEMMs through torch.einsum.  Because
 prior[b,o,i,:] = W[o] x[b,i], every routing quantity lives in in_length space:
     logit[b,o,i] = <x[b,i], u[b,o]>,  u[b,o] = W[o]^T (sum of earlier v[b,o])
     s[b,o]       = W[o] y[b,o],       y[b,o] = sum_i softmax_o(logit)[b,o,i] x[b,i]
@@ -23,9 +26,116 @@ def squash(s):
     return s * (n2 / (1.0 + n2) / torch.sqrt(n2 + EPS))
 
 
+# ------------------------------------------------------------------ CUDA kernels (small in_length: the generator stem)
+def _k():
+    from . import _lib as L
+    return L, L.lib()
+
+
+class _ProjU(torch.autograd.Function):
+    """u[b,o,:] = W[o]^T v[b,o,:]"""
+
+    @staticmethod
+    def forward(ctx, W, v):
+        L, lib = _k()
+        B, O, Lh = v.shape
+        K = W.shape[2]
+        W, v = W.contiguous(), v.contiguous()
+        u = torch.empty(B, O, K, device=v.device)
+        L.check(lib.ekl_caps_proj_u(L.ptr(W), L.ptr(v), B, O, Lh, K, L.ptr(u), L.stream()))
+        ctx.save_for_backward(W, v)
+        return u
+
+    @staticmethod
+    def backward(ctx, gu):
+        L, lib = _k()
+        W, v = ctx.saved_tensors
+        B, O, Lh = v.shape
+        K = W.shape[2]
+        gu = gu.contiguous()
+        gv = torch.empty_like(v)
+        L.check(lib.ekl_caps_proj_s(L.ptr(W), L.ptr(gu), B, O, Lh, K, L.ptr(gv), None, L.stream()))      # gv = W gu
+        gW = torch.zeros_like(W)
+        L.check(lib.ekl_caps_outer(L.ptr(v), L.ptr(gu), B, O, Lh, K, L.ptr(gW), L.stream()))
+        return gW, gv
+
+
+class _SSquash(torch.autograd.Function):
+    """v = squash(W[o] y[b,o,:])"""
+
+    @staticmethod
+    def forward(ctx, W, y):
+        L, lib = _k()
+        B, O, K = y.shape
+        Lh = W.shape[1]
+        W, y = W.contiguous(), y.contiguous()
+        s = torch.empty(B, O, Lh, device=y.device)
+        v = torch.empty(B, O, Lh, device=y.device)
+        L.check(lib.ekl_caps_proj_s(L.ptr(W), L.ptr(y), B, O, Lh, K, L.ptr(s), L.ptr(v), L.stream()))
+        ctx.save_for_backward(W, y, s)
+        return v
+
+    @staticmethod
+    def backward(ctx, gv):
+        L, lib = _k()
+        W, y, s = ctx.saved_tensors
+        B, O, K = y.shape
+        Lh = W.shape[1]
+        gv = gv.contiguous()
+        gs, gy = torch.empty_like(s), torch.empty_like(y)
+        L.check(lib.ekl_caps_squash_bwd(L.ptr(W), L.ptr(s), L.ptr(gv), B, O, Lh, K, L.ptr(gs), L.ptr(gy), L.stream()))
+        gW = torch.zeros_like(W)
+        L.check(lib.ekl_caps_outer(L.ptr(gs), L.ptr(y), B, O, Lh, K, L.ptr(gW), L.stream()))
+        return gW, gy
+
+
+class _Agree(torch.autograd.Function):
+    """y[b,o,:] = sum_i softmax_o(<x[b,i], u[b,o]>) x[b,i]   (routing-by-agreement step; logits stay on chip)"""
+
+    @staticmethod
+    def forward(ctx, x, u):
+        L, lib = _k()
+        B, I, K = x.shape
+        O = u.shape[1]
+        x, u = x.contiguous(), u.contiguous()
+        y = torch.empty(B, O, K, device=x.device)
+        M, Z = torch.empty(B, I, device=x.device), torch.empty(B, I, device=x.device)
+        L.check(lib.ekl_caps_agree_fwd(L.ptr(x), L.ptr(u), B, I, O, K, L.ptr(y), L.ptr(M), L.ptr(Z), L.stream()))
+        ctx.save_for_backward(x, u, M, Z)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        L, lib = _k()
+        x, u, M, Z = ctx.saved_tensors
+        B, I, K = x.shape
+        O = u.shape[1]
+        gy = gy.contiguous()
+        gu, gx = torch.empty_like(u), torch.empty_like(x)
+        L.check(lib.ekl_caps_agree_bwd(L.ptr(x), L.ptr(u), L.ptr(M), L.ptr(Z), L.ptr(gy), B, I, O, K, L.ptr(gu), L.ptr(gx),
+                                       L.stream()))
+        return gx, gu
+
+
+def _dynamic_routing_cuda(x, weight, num_iterations):
+    B, I, K = x.shape
+    O = weight.shape[0]
+    y = (x.sum(dim=1, keepdim=True) / O).expand(B, O, K)          # iteration 0: zero logits -> uniform coupling 1/O
+    v = _SSquash.apply(weight, y)
+    vsum = v
+    for _ in range(1, num_iterations):
+        v = _SSquash.apply(weight, _Agree.apply(x, _ProjU.apply(weight, vsum)))
+        vsum = vsum + v
+    return v
+
+
 def capsule_linear(x, weight, routing_type="dynamic", num_iterations=3):
     x = x.float()
     B, O = x.shape[0], weight.shape[0]
+    if routing_type == "dynamic" and x.is_cuda and weight.dtype == torch.float32:
+        L, lib = _k()
+        if lib.ekl_caps_supported(x.shape[1], x.shape[2], O, weight.shape[1]):
+            return _dynamic_routing_cuda(x, weight, num_iterations)
     if routing_type == "dynamic":
         vsum = x.new_zeros(B, O, weight.shape[1])
         v = None
