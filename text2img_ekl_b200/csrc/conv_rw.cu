@@ -40,8 +40,8 @@ struct RwCfg {
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr uint32_t LAYOUT = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);
   static constexpr uint32_t SBO = 8 * ROWB;
-  static constexpr int PAIRS = BN / 2;
-  static constexpr int SLICES = 128 / PAIRS;
+  static constexpr int QUADS = BN / 4;
+  static constexpr int SLICES = 128 / QUADS;
 };
 
 template <int BN>
@@ -159,11 +159,12 @@ __global__ void __launch_bounds__(192, 1) conv3x3_rw_kernel(const __grid_constan
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;
-    const int pair = et % C::PAIRS, slice = et / C::PAIRS;
+    const int quad = et % C::QUADS, slice = et / C::QUADS;
+    const uint32_t so = smem_u32(stage_out);
     uint32_t kit = 0;
     bool store_pending = false;
     for (int n = 0; n < p.ntn; ++n) {
-      float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
       if (has_tiles)
         for (int tile = cta; tile < p.tiles; tile += grid, ++kit) {
           const uint32_t buf = kit & 1u, use = kit >> 1;
@@ -200,11 +201,11 @@ __global__ void __launch_bounds__(192, 1) conv3x3_rw_kernel(const __grid_constan
             }
 #pragma unroll
             for (int j = 0; j < CH / 8; ++j)
-              *reinterpret_cast<uint4*>(stage_out + rw_stage_off<BN>(row, c0 + 8 * j)) =
-                  make_uint4(pack_bf16x2(__uint_as_float(rr[8 * j]), __uint_as_float(rr[8 * j + 1])),
-                             pack_bf16x2(__uint_as_float(rr[8 * j + 2]), __uint_as_float(rr[8 * j + 3])),
-                             pack_bf16x2(__uint_as_float(rr[8 * j + 4]), __uint_as_float(rr[8 * j + 5])),
-                             pack_bf16x2(__uint_as_float(rr[8 * j + 6]), __uint_as_float(rr[8 * j + 7])));
+              sts128(so + rw_stage_off<BN>(row, c0 + 8 * j),
+                     make_uint4(pack_bf16x2(__uint_as_float(rr[8 * j]), __uint_as_float(rr[8 * j + 1])),
+                                pack_bf16x2(__uint_as_float(rr[8 * j + 2]), __uint_as_float(rr[8 * j + 3])),
+                                pack_bf16x2(__uint_as_float(rr[8 * j + 4]), __uint_as_float(rr[8 * j + 5])),
+                                pack_bf16x2(__uint_as_float(rr[8 * j + 6]), __uint_as_float(rr[8 * j + 7]))));
           }
           tc_fence_before();
           mbar_arrive(&tmem_empty[buf]);
@@ -220,16 +221,18 @@ __global__ void __launch_bounds__(192, 1) conv3x3_rw_kernel(const __grid_constan
             const int r0 = slice * RPS;
 #pragma unroll 4
             for (int rr = r0; rr < r0 + RPS; ++rr) {
-              const uint32_t u = *reinterpret_cast<const uint32_t*>(stage_out + rw_stage_off<BN>(rr, 2 * pair));
-              const float x0 = bf16_lo(u), x1 = bf16_hi(u);
-              s1a += x0; s2a += x0 * x0; s1b += x1; s2b += x1 * x1;
+              const uint2 u = lds64(so + rw_stage_off<BN>(rr, 4 * quad));
+              const float x0 = bf16_lo(u.x), x1 = bf16_hi(u.x), x2 = bf16_lo(u.y), x3 = bf16_hi(u.y);
+              s1[0] += x0; s2[0] += x0 * x0; s1[1] += x1; s2[1] += x1 * x1;
+              s1[2] += x2; s2[2] += x2 * x2; s1[3] += x3; s2[3] += x3 * x3;
             }
           }
         }
       if (p.stats != nullptr) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         float* my = red + (size_t)slice * 2 * BN;
-        my[2 * pair] = s1a; my[2 * pair + 1] = s1b; my[BN + 2 * pair] = s2a; my[BN + 2 * pair + 1] = s2b;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { my[4 * quad + i] = s1[i]; my[BN + 4 * quad + i] = s2[i]; }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         float* dst = p.stats + (size_t)cta * 2 * p.N + n * BN;
         for (int c = et; c < 2 * BN; c += 128) {

@@ -43,14 +43,14 @@ struct TcCfg {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int SMEM_BYTES = PIPE_BYTES + OUT_BYTES + 1024 /*align slack*/ + 512 /*barriers + reduction scratch*/ +
-                                    2 * 2 * BN * 4 * (BN <= 128 ? 256 / BN : 1);
+                                    4096 /* SLICES x 2 x BN floats of cross-slice reduction scratch */;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;               // double-buffered accumulator
   static constexpr uint32_t LAYOUT = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);   // SW128 / SW64 / SW32
   static constexpr uint32_t SBO = 8 * KC * 2;
   static constexpr int OBOX = BN < 64 ? BN : 64;   // channels per output TMA box
-  // statistics: each epilogue thread owns one channel PAIR over a slice of the rows
-  static constexpr int PAIRS = BN / 2;
-  static constexpr int SLICES = PAIRS >= 128 ? 1 : 128 / PAIRS;
+  // statistics: each epilogue thread owns one channel QUAD (8-byte shared loads) over a slice of the rows
+  static constexpr int QUADS = BN / 4;
+  static constexpr int SLICES = 128 / QUADS;
 };
 
 // byte offset of channel c (even) of row r inside the swizzled staging tile
@@ -171,13 +171,14 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;   // 0..127
-    const int pair = et % C::PAIRS, slice = et / C::PAIRS;      // statistics ownership (BN=256: 128 pairs, 1 slice)
+    const int quad = et % C::QUADS, slice = et / C::QUADS;      // statistics ownership (BN=256: 64 quads x 2 slices)
+    const uint32_t so = smem_u32(stage_out);
     uint32_t tile = 0;
     bool store_pending = false;
     for (int r = 0; r < rounds; ++r) {
       int v, n, g;
       round_vng(r, v, n, g);
-      float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
       for (int mloc = first_tile(r); mloc < p.mtg; mloc += grid, ++tile) {
         const uint32_t buf = tile & 1u, use = tile >> 1;
         int w0, h0, b0;
@@ -215,9 +216,8 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1]));
-          uint8_t* box = stage_out + row * 32;
-          *reinterpret_cast<uint4*>(box) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(box + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          sts128(so + row * 32, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+          sts128(so + row * 32 + 16, make_uint4(pk[4], pk[5], pk[6], pk[7]));
         } else {
 #pragma unroll 1
           for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -241,8 +241,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
             for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1]));
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(stage_out + stage_off<BN>(row, c0 + 8 * j)) =
-                  make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              sts128(so + stage_off<BN>(row, c0 + 8 * j), make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
           }
         }
         // accumulator drained -> the MMA warp may start the tile after next in this buffer
@@ -258,14 +257,16 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
         }
         store_pending = true;
         if (p.stats != nullptr) {
-          // per-channel-pair partial sums of the bf16 values actually stored, over this thread's row slice
+          // per-channel partial sums of the bf16 values actually stored, over this thread's row slice
           constexpr int RPS = 128 / C::SLICES;
           const int r0 = slice * RPS;
           const int r1 = (r0 + RPS) < p.rows_valid ? (r0 + RPS) : p.rows_valid;
+#pragma unroll 4
           for (int rr = r0; rr < r1; ++rr) {
-            const uint32_t u = *reinterpret_cast<const uint32_t*>(stage_out + stage_off<BN>(rr, 2 * pair));
-            const float x0 = bf16_lo(u), x1 = bf16_hi(u);
-            s1a += x0; s2a += x0 * x0; s1b += x1; s2b += x1 * x1;
+            const uint2 u = lds64(so + stage_off<BN>(rr, 4 * quad));
+            const float x0 = bf16_lo(u.x), x1 = bf16_hi(u.x), x2 = bf16_lo(u.y), x3 = bf16_hi(u.y);
+            s1[0] += x0; s2[0] += x0 * x0; s1[1] += x1; s2[1] += x1 * x1;
+            s1[2] += x2; s2[2] += x2 * x2; s1[3] += x3; s2[3] += x3 * x3;
           }
         }
       }
@@ -274,7 +275,8 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
         // (group, cta, variant); channels [n*BN, n*BN+BN)
         asm volatile("bar.sync 1, 128;" ::: "memory");
         float* my = red + (size_t)slice * 2 * BN;
-        my[2 * pair] = s1a; my[2 * pair + 1] = s1b; my[BN + 2 * pair] = s2a; my[BN + 2 * pair + 1] = s2b;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { my[4 * quad + i] = s1[i]; my[BN + 4 * quad + i] = s2[i]; }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         float* dst = p.stats + (((size_t)g * grid + cta) * p.nvar + v) * 2 * p.N + n * BN;
         for (int c = et; c < 2 * BN; c += 128) {

@@ -128,6 +128,7 @@ class _Conv(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, spec, group_b, want_stats, skip_wgrad):
+        ctx.set_materialize_grads(False)      # no zero-filled "gradient" of the statistics output
         lib = L.lib()
         if spec.x_fmt == L.FMT_NCHW_F32:
             B, _, H, W = x.shape
@@ -161,6 +162,8 @@ class _Conv(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _dstats):
+        if dy is None:
+            return None, None, None, None, None, None
         lib = L.lib()
         x, weight = ctx.saved_tensors[:2]
         spec, c = ctx.spec, ctx.c
@@ -225,6 +228,7 @@ class _ConvBias9(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias9, spec, want_stats):
+        ctx.set_materialize_grads(False)
         lib = L.lib()
         B, H, W, _ = x.shape
         assert x.dtype == torch.bfloat16 and x.is_contiguous() and spec.mode == S1 and spec.impl == L.IMPL_TC
@@ -247,6 +251,8 @@ class _ConvBias9(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _dstats):
+        if dy is None:
+            return None, None, None, None, None
         lib = L.lib()
         x, weight = ctx.saved_tensors
         spec, c = ctx.spec, ctx.c
@@ -539,6 +545,7 @@ class _DLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, lm, lu, cls, cp0, cp1, cfg):
+        ctx.set_materialize_grads(False)
         groups, B, t_match, t_uncond, cls_tgt, coeff = cfg
         GB, E1 = cls.shape
         assert GB == groups * B
@@ -561,6 +568,8 @@ class _DLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, go, *_):
+        if go is None:
+            return None, None, None, None, None, None
         groups, B, t_match, t_uncond, cls_tgt, coeff = ctx.cfg
         pm, pu, logp, cp0, cp1 = ctx.saved_tensors
         GB, E1 = logp.shape
@@ -583,6 +592,7 @@ class _ReparamKL(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mu, logvar, eps):
+        ctx.set_materialize_grads(False)
         B, D = mu.shape
         assert mu.dtype == torch.float32 and logvar.dtype == torch.float32 and mu.stride(1) == 1 and logvar.stride(1) == 1
         eps = eps.float().contiguous()
@@ -596,6 +606,8 @@ class _ReparamKL(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dc, dstd, dkl):
+        if dc is None and dstd is None and dkl is None:
+            return None, None, None
         mu, logvar, eps = ctx.saved_tensors
         B, D = mu.shape
         dmu, dlv = torch.empty(B, D, device=mu.device), torch.empty(B, D, device=mu.device)
