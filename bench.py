@@ -269,17 +269,42 @@ def run_ours(a):
         os._exit(0)
 
 
+def ncu_traffic(family):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture (profiles/r01_conv_full.json, written by tools/ncu_summary.py); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r01_conv_full.json")
+    if not os.path.exists(p):
+        return None
+    key = "conv_wgrad" if "wgrad" in family else "conv_gemm_tc"
+    rows = [r for r in json.load(open(p)) if key in r.get("kernel", "")]
+    if not rows:
+        return None
+    tot = sum(r.get("dram__bytes_read.sum", 0.0) + r.get("dram__bytes_write.sum", 0.0) for r in rows)
+    return {"bytes_per_launch": tot / len(rows), "launches_captured": len(rows), "source": "profiles/r01_conv_full.json"}
+
+
 def kernel_roofline(tr, batch, pk):
     """One eager step with a CUDA-event pair around every kernel-library call (on the launching stream), aggregated
     per kernel family; `roofline` describes the dominant family (tcgen05 conv forward/dgrad kernel)."""
     import torch
     from text2img_ekl_b200 import ops
     ops.PROFILE = []
-    # Park the GPU behind a ~100 ms spin so the host enqueues the whole eager step ahead of it: every event pair then
-    # brackets back-to-back device execution of its kernel(s), not host launch latency.
+    # Park the GPU behind a ~120 ms spin before every phase of the step (generate, each discriminator update, generator
+    # update) so that the host enqueues the whole phase ahead of the device (each phase stays below the launch-queue
+    # depth): every event pair then brackets back-to-back device execution of its kernel(s), not host launch latency.
+    spin = int(0.12 * 1.9e9)
     torch.cuda.synchronize()
-    torch.cuda._sleep(int(0.1 * 1.9e9))
-    tr.train_step(batch)
+    tr.imgs_tcpu, tr.real_imgs, tr.wrong_imgs, tr.txt_embedding, tr.cls_label = tr.prepare_data(batch)
+    tr.noise.normal_(0, 1)
+    torch.cuda._sleep(spin)
+    tr.generate()
+    for i in reversed(range(tr.num_Ds)):
+        torch.cuda.synchronize()
+        torch.cuda._sleep(spin)
+        tr.train_joint_Dnet(i, 1)
+    torch.cuda.synchronize()
+    torch.cuda._sleep(spin)
+    tr.engine.g_step(tr.real_cp)
     torch.cuda.synchronize()
     rec, ops.PROFILE = ops.PROFILE, None
     fam = {}
@@ -301,7 +326,7 @@ def kernel_roofline(tr, batch, pk):
     d = fam[top]
     ach = d["flop"] / (d["us"] * 1e-6) / 1e12
     return {"bound": "tensor", "kernel": top, "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-            "frac": ach / pk["bf16_sustained"], "traffic": None, "peak_source": pk["src"] + " (sustained: kernel timed inside a long step)",
+            "frac": ach / pk["bf16_sustained"], "traffic": ncu_traffic(top), "peak_source": pk["src"] + " (sustained: kernel timed inside a long step)",
             "flop_counting": "algorithmic (reference dense-conv count) flops of the launches / sum of their CUDA-event durations",
             "avg_launch_us": d["us"] / d["launches"], "launches_per_step": d["launches"], "families": out}
 
