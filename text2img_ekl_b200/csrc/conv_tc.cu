@@ -10,6 +10,8 @@
 //   warps 2..5  epilogue: tcgen05.ld -> bf16 -> swizzled smem staging -> per-channel sum / sum-of-squares
 //               partials for train-mode BatchNorm -> TMA tensor store.
 // Roofline: tensor pipe (2*128*BN*K flop per tile); operands are re-used from L2 across taps.
+#include <stdlib.h>
+
 #include "conv_plan.h"
 #include "ekl_common.cuh"
 
@@ -384,10 +386,25 @@ int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, i
   const int KC = g->Cin % 64 == 0 ? 64 : (g->Cin % 32 == 0 ? 32 : 16);
   p.ncb = g->Cin / KC;
   const int swz = KC == 64 ? 3 : (KC == 32 ? 2 : 1);
-  int BN = g->N % 256 == 0 ? 256 : (g->N % 128 == 0 ? 128 : (g->N % 64 == 0 ? 64 : (g->N % 32 == 0 ? 32 : 16)));
+  // N-tile width: the kernel is bound by per-SM operand ingest (measured ~85 GB/s per SM whether 48 or 148 SMs are
+  // active), so pick the width that minimises the bytes the busiest CTA has to fetch:
+  //   rounds(BN) * (A tile + B tile(BN)) per k-iteration,  rounds = ceil(#tiles / #SMs);  ties -> wider tile.
   const int sms = ekl_num_sms();
-  // prefer more tiles when the work would not fill the machine
-  while (BN > 64 && (int64_t)mtiles * (g->N / BN) * g->nvar < sms) BN /= 2;
+  int BN = 16;
+  {
+    int64_t best = -1;
+    const int bn_min = g->N % 64 == 0 ? 64 : 16;      // measured: tiles narrower than 64 only add per-iteration overhead
+    for (int bn = 256; bn >= bn_min; bn >>= 1) {
+      if (g->N % bn != 0) continue;
+      const int64_t tiles = (int64_t)mtiles * (g->N / bn) * g->nvar;
+      const int64_t cost = ((tiles + sms - 1) / sms) * (int64_t)(128 + bn);
+      if (best < 0 || cost < best) { best = cost; BN = bn; }
+    }
+  }
+  if (const char* e = getenv("EKL_TC_BN")) {          // experiment knob
+    const int v = atoi(e);
+    if ((v == 16 || v == 32 || v == 64 || v == 128 || v == 256) && g->N % v == 0) BN = v;
+  }
   p.ntn = g->N / BN;
   for (int i = 0; i < g->n_a; ++i) {
     int rc = make_view_map(&p.a_maps[i], g->a[i], KC, tw, th, tb, swz);
