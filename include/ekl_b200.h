@@ -171,6 +171,15 @@ int ekl_caps_agree_fwd(const float* x, const float* u, int B, int I, int O, int 
 int ekl_caps_agree_bwd(const float* x, const float* u, const float* M, const float* Z, const float* gy, int B, int I, int O,
                        int K, float* gu, float* gx, void* stream);
 
+/* ---------------------------------------------------------------- optimiser ---------------------------------
+ * torch.optim.Adam as define_optimizers configures it (cub_trainer_splitz_cap_ca.py:199-215: lr 2e-4, betas (0.5, 0.999),
+ * eps 1e-8, no weight decay) over a network's flat fp32 parameter / gradient / moment buffers (n % 4 == 0, 16-byte
+ * aligned).  state: 3 device floats {step, 1-beta1^t, sqrt(1-beta2^t)}, zero at start; the step advances on the device
+ * (graph-capturable).  shadow_bf16 (may be NULL): bf16 copy of the updated parameters = the packed forward filter operand
+ * of channels_last stride-1 / stride-2 convolutions. */
+int ekl_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float* state, float lr,
+                  float beta1, float beta2, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

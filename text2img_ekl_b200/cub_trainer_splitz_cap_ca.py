@@ -96,16 +96,16 @@ def load_network(gpus, device=None):
 
 
 def define_optimizers(netG, netsD=()):
-    """cub:199-215: Adam(lr 2e-4, betas (0.5, 0.999)) per network; fused + capturable so the step can be graph-captured."""
+    """cub:199-215: Adam(lr 2e-4, betas (0.5, 0.999)) per network.  On the GPU: optim.FlatAdam, the same update as one
+    fused kernel per network over flat parameter / gradient / moment buffers (graph-capturable)."""
     kw = dict(betas=(0.5, 0.999))
     if next(netG.parameters()).is_cuda:
-        kw.update(fused=True, capturable=True)
+        from .optim import FlatAdam
+        optimizersD = [FlatAdam(d.parameters(), lr=cfg.TRAIN.DISCRIMINATOR_LR, **kw) for d in netsD]
+        optimizerG = FlatAdam(netG.parameters(), lr=cfg.TRAIN.GENERATOR_LR, **kw)
+        return optimizerG, optimizersD
     optimizersD = [optim.Adam(d.parameters(), lr=cfg.TRAIN.DISCRIMINATOR_LR, **kw) for d in netsD]
     optimizerG = optim.Adam(netG.parameters(), lr=cfg.TRAIN.GENERATOR_LR, **kw)
-    for opt, net in [(optimizerG, netG)] + list(zip(optimizersD, netsD)):
-        params = list(net.parameters())
-        # fused Adam does not bump parameter version counters: tell the kernels their packed bf16 filters are stale
-        opt.register_step_post_hook(lambda o, a, k, params=params: ops.mark_dirty(params))
     return optimizerG, optimizersD
 
 

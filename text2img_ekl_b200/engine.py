@@ -68,8 +68,11 @@ class tensor_core_matmul:
 class FlatGrads:
     """All gradients of a network as views into one flat fp32 buffer (same memory layout as each parameter)."""
 
-    def __init__(self, params):
+    def __init__(self, params, optimizer=None):
         self.params = [p for p in params if p.requires_grad]
+        if hasattr(optimizer, "make_flat_grads"):        # optim.FlatAdam: gradients share the parameters' flat offsets
+            self.flat = optimizer.make_flat_grads()
+            return
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
@@ -125,8 +128,8 @@ class StepEngine:
         self.netG, self.netsD = netG, netsD
         self.optG, self.optsD = optimizerG, optimizersD
         self.kind, self.cond = kind, cond
-        self.gradsG = FlatGrads(netG.parameters())
-        self.gradsD = [FlatGrads(d.parameters()) for d in netsD]
+        self.gradsG = FlatGrads(netG.parameters(), optimizerG)
+        self.gradsD = [FlatGrads(d.parameters(), o) for d, o in zip(netsD, optimizersD)]
         self.allreduce = allreduce           # callable(flat_tensor) or None
         self.bn_counters = BnCounters([netG] + list(netsD))
         self.comm_stream, self._pending_comm = None, {}

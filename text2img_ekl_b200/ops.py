@@ -73,7 +73,7 @@ _SPECS_OF = {}
 def mark_dirty(params):
     for p in params:
         for spec in _SPECS_OF.get(id(p), ()):
-            spec._ver = None
+            spec._dirty = True
 
 
 class ConvSpec:
@@ -83,9 +83,9 @@ class ConvSpec:
     def __init__(self, mode, cin, cout, impl=L.IMPL_TC, x_fmt=0, y_fmt=0, act=ACT_NONE):
         self.mode, self.cin, self.cout, self.impl = mode, cin, cout, impl
         self.x_fmt, self.y_fmt, self.act = x_fmt, y_fmt, act
-        self._ver = None
+        self._ver, self._dirty = None, False
         self.w_layout = L.W_KCRS
-        self.w_fwd = self.w_dgrad = None
+        self.w_fwd = self.w_dgrad = self._fwd_buf = None
 
     def conv(self, B, H, W, group_b=0):
         return L.EklConv(self.mode, B, H, W, self.cin, self.cout, group_b, self.impl, self.x_fmt, self.y_fmt, self.act,
@@ -103,9 +103,19 @@ class ConvSpec:
         else:
             raise L.EklError("conv filter must be contiguous or channels_last")
 
+    def _shadow(self, weight):
+        """bf16 shadow slice maintained by optim.FlatAdam, usable as the packed forward operand when that operand is a
+        plain cast of the master in memory order: stride-1 / stride-2 plans (one variant, one source tap per packed
+        tap) of a channels_last leaf parameter."""
+        sh = getattr(weight, "_ekl_shadow", None)
+        if sh is None or not weight.is_leaf or self.mode == UP2 or self.w_layout != L.W_KRSC or self.impl != L.IMPL_TC:
+            return None
+        return sh
+
     def packed(self, weight):
         key = (weight._version, weight.data_ptr())
-        if key != self._ver or not weight.is_leaf:      # derived (e.g. zero-padded) filters are rebuilt every step
+        external = key != self._ver or not weight.is_leaf     # derived (e.g. zero-padded) filters are rebuilt every step
+        if external or self._dirty:
             self.bind(weight)
             if weight.is_leaf:
                 lst = _SPECS_OF.setdefault(id(weight), [])
@@ -113,13 +123,23 @@ class ConvSpec:
                     lst.append(self)
             lib = L.lib()
             c = self.conv(1, 4, 4)
-            if self.w_fwd is None:
-                self.w_fwd = torch.empty(lib.ekl_conv_packed_elems(c, 0), device=weight.device, dtype=torch.bfloat16)
+            shadow = self._shadow(weight)
+            if shadow is not None:
+                if external:                       # parameter changed outside the fused optimiser (init / load_state_dict)
+                    shadow.copy_(weight.detach().permute(0, 2, 3, 1).reshape(-1))
+                self.w_fwd = shadow
+            else:
+                if self._fwd_buf is None:
+                    self._fwd_buf = torch.empty(lib.ekl_conv_packed_elems(c, 0), device=weight.device, dtype=torch.bfloat16)
+                self.w_fwd = self._fwd_buf
+            if self.w_dgrad is None:
                 self.w_dgrad = torch.empty(lib.ekl_conv_packed_elems(c, 1), device=weight.device, dtype=torch.bfloat16)
-            with _prof("pack_weights", 0, weight.numel() * 4 + (self.w_fwd.numel() + self.w_dgrad.numel()) * 2):
-                L.check(lib.ekl_conv_pack(c, L.ptr(weight), L.ptr(self.w_fwd), L.ptr(self.w_dgrad), L.stream()))
-            _count(2)
-            self._ver = key
+            w_fwd_arg = None if shadow is not None else self.w_fwd
+            nb = weight.numel() * 4 + ((0 if shadow is not None else self.w_fwd.numel()) + self.w_dgrad.numel()) * 2
+            with _prof("pack_weights", 0, nb):
+                L.check(lib.ekl_conv_pack(c, L.ptr(weight), L.ptr(w_fwd_arg), L.ptr(self.w_dgrad), L.stream()))
+            _count(1 if shadow is not None else 2)
+            self._ver, self._dirty = key, False
         return self.w_fwd, self.w_dgrad
 
 

@@ -1,0 +1,77 @@
+"""Adam for the B200 step: torch.optim.Adam semantics (the reference's define_optimizers, cub_trainer_splitz_cap_ca.py:
+199-215) executed as ONE fused kernel per network over flat buffers (include/ekl_b200.h: ekl_adam_step).
+
+The optimiser re-homes every parameter of the network into one flat fp32 buffer (shapes, strides / channels_last
+layouts and state_dict contents unchanged: each parameter becomes a view), keeps exp_avg / exp_avg_sq flat, and writes a
+bf16 shadow of the updated parameters in the same pass.  ops.ConvSpec uses the shadow slice of a channels_last
+stride-1 / stride-2 conv filter directly as its packed forward operand."""
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+class FlatAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=2e-4, betas=(0.5, 0.999), eps=1e-8):
+        params = [p for p in params if p.requires_grad]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self.plist = params
+        dev = params[0].device
+        assert dev.type == "cuda", "FlatAdam drives the CUDA kernel library; use torch.optim.Adam on the CPU"
+        # every parameter starts at a multiple of 4 elements: 16-byte aligned fp32 views, 8-byte aligned bf16 shadows
+        self.offsets, off = [], 0
+        for p in params:
+            self.offsets.append(off)
+            off += _pad4(p.numel())
+        self.n = off
+        self.flat_p = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        self.shadow = torch.zeros(self.n, device=dev, dtype=torch.bfloat16)
+        self.exp_avg = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        self.state_dev = torch.zeros(3, device=dev, dtype=torch.float32)
+        self.flat_g = None
+        with torch.no_grad():
+            for p, o in zip(params, self.offsets):
+                view = self._view(self.flat_p, p, o)
+                view.copy_(p.data)
+                p.data = view
+                p._ekl_shadow = self.shadow[o:o + p.numel()]
+                self.state[p] = dict(step=self.state_dev[0], exp_avg=self._view(self.exp_avg, p, o),
+                                     exp_avg_sq=self._view(self.exp_avg_sq, p, o))
+            self.shadow.copy_(self.flat_p)
+
+    @staticmethod
+    def _view(flat, p, off):
+        g = flat[off:off + p.numel()]
+        if p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last) and not p.is_contiguous():
+            return g.view(p.shape[0], p.shape[2], p.shape[3], p.shape[1]).permute(0, 3, 1, 2)
+        return g.view(p.shape)
+
+    def make_flat_grads(self):
+        """Gradient buffer with the parameters' offsets; every p.grad becomes a view with the parameter's layout."""
+        self.flat_g = torch.zeros(self.n, device=self.flat_p.device, dtype=torch.float32)
+        for p, o in zip(self.plist, self.offsets):
+            p.grad = self._view(self.flat_g, p, o)
+        return self.flat_g
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if self.flat_g is None or any(p.grad is None or p.grad.data_ptr() != self.flat_g.data_ptr() + 4 * o
+                                      for p, o in zip(self.plist, self.offsets)):
+            # gradients live elsewhere (stand-alone use): gather them into the flat layout
+            old = [p.grad for p in self.plist]
+            self.make_flat_grads()
+            for p, g in zip(self.plist, old):
+                if g is not None:
+                    p.grad.copy_(g)
+        grp = self.param_groups[0]
+        b1, b2 = grp["betas"]
+        L.check(L.lib().ekl_adam_step(L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
+                                      L.ptr(self.shadow), self.n, L.ptr(self.state_dev), float(grp["lr"]), float(b1), float(b2),
+                                      float(grp["eps"]), L.stream()))
+        ops._count(2)
+        ops.mark_dirty(self.plist)          # the packed data-gradient filter operands are stale now

@@ -207,6 +207,30 @@ def run_heads(torch, L, lib, dev, rel):
         ok = all(e < t for e, t in zip(errs, tol))
         print("%s heads G%d B%d C%d E%d %s" % ("PASS" if ok else "FAIL", G, B, C, E1, " ".join("%.1e" % e for e in errs)), flush=True)
         nfail += 0 if ok else 1
+    # fused flat Adam (optim.FlatAdam) against torch.optim.Adam, 3 steps, mixed layouts
+    from text2img_ekl_b200.optim import FlatAdam
+    torch.manual_seed(1)
+    net_a = torch.nn.Sequential(torch.nn.Conv2d(16, 32, 3, bias=False), torch.nn.BatchNorm2d(32), torch.nn.Linear(7, 5)).to(dev)
+    net_a[0].weight.data = net_a[0].weight.data.contiguous(memory_format=torch.channels_last)
+    import copy
+    net_b = copy.deepcopy(net_a)
+    oa = FlatAdam(net_a.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    ob = torch.optim.Adam(net_b.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    worst = 0.0
+    for it in range(3):
+        for pa, pb in zip(net_a.parameters(), net_b.parameters()):
+            g = torch.randn_like(pb) * (10.0 ** (it - 1))
+            pb.grad = g.clone()
+            if pa.grad is None:
+                pa.grad = g.clone()
+            else:
+                pa.grad.copy_(g)
+        oa.step(); ob.step()
+        worst = max([worst] + [rel(pa, pb) for pa, pb in zip(net_a.parameters(), net_b.parameters())])
+    sh = net_a[0].weight._ekl_shadow
+    ok = worst < 1e-6 and bool((sh == net_a[0].weight.detach().permute(0, 2, 3, 1).reshape(-1).bfloat16()).all())
+    print("%s flat_adam 3 steps worst rel %.1e (bf16 shadow exact: %s)" % ("PASS" if ok else "FAIL", worst, ok), flush=True)
+    nfail += 0 if ok else 1
     for (B, D) in [(24, 128), (32, 128), (5, 17)]:
         # fused reparameterisation + KL (model.py:145-152; cub:54-58) on strided halves of one tensor
         x = torch.randn(B, 2 * D, device=dev).requires_grad_(True)
