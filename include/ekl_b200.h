@@ -88,6 +88,12 @@ int ekl_bn_finalize(const float* partial, int rows_per_group, int C, int groups,
                     float* mean, float* rstd, float* running_mean, float* running_var, void* stream);
 int ekl_bn_act_fwd(const void* y, int64_t M, int Cy, int groups, const float* mean, const float* rstd,
                    const float* gamma, const float* beta, int act, const void* residual, void* out, void* stream);
+/* small layers (<= 768 rows per group): ekl_bn_finalize + ekl_bn_act_fwd as ONE launch; also writes mean / rstd
+ * [groups][Cy].  Returns 0 if it ran, 2000 if the layer does not qualify (use the two-call path), else an error code. */
+int ekl_bn_act_fwd_small(const float* partial, int rows_per_group, float count, float eps, float momentum,
+                         float* running_mean, float* running_var, const void* y, int64_t M, int Cy, int groups,
+                         const float* gamma, const float* beta, int act, const void* residual, void* out, float* mean,
+                         float* rstd, void* stream);
 int ekl_bn_act_bwd_rows(int64_t M, int Cy, int groups, int act);
 /* dy from dout; dgamma/dbeta are accumulated (+=). partial: [ekl_bn_act_bwd_rows][2][Cy], sums: [groups][2][Cy] */
 int ekl_bn_act_bwd(const void* y, const void* dout, int64_t M, int Cy, int groups, const float* mean, const float* rstd,

@@ -46,6 +46,7 @@ SIGNATURES = {
     "ekl_col_stats": (_i, [_vp, _i64, _i, _i, _vp, _vp]),
     "ekl_bn_finalize": (_i, [_vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "ekl_bn_act_fwd": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "ekl_bn_act_fwd_small": (_i, [_vp, _i, _f, _f, _f, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "ekl_bn_act_bwd_rows": (_i, [_i64, _i, _i, _i]),
     "ekl_bn_act_bwd": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_lrelu_bwd": (_i, [_vp, _vp, _vp, _i64, _vp]),

@@ -444,6 +444,244 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_kernel(const bf16* __
   }
 }
 
+// ---------------------------------------------------------------- small layers: one launch per direction
+// Layers with few rows per statistics group (the 4x4 / 8x8 discriminator tails, the generator stem's BatchNorm1d) are
+// launch-latency bound: three (backward) / two (forward) kernels of a few microseconds each.  Here a block owns a strip
+// of 8 channel vectors of one group for ALL rows, so the batch statistics never leave the block:
+//   backward: rows -> S1, S2 (warp shuffles + shared memory) -> dy (second sweep hits L1/L2) ; dgamma/dbeta by atomics
+//   forward : partial statistics rows -> mean / rstd (+ running statistics) -> activation sweep
+// Block = 256 threads = 8 vector-threads x 32 row-threads.
+constexpr int SM_CT = 8, SM_RT = 32;
+
+// reduce NV per-thread values over the 32 row-threads that share a vector-thread; result valid in every thread
+template <int NV>
+__device__ __forceinline__ void strip_reduce(float* v, float* sh /*[8 warps][SM_CT][NV]*/, float* tot /*[SM_CT][NV]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ct = threadIdx.x % SM_CT;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] += __shfl_xor_sync(0xffffffffu, v[i], 8);
+    v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+  }
+  __syncthreads();
+  if (lane < SM_CT) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sh[(warp * SM_CT + ct) * NV + i] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < SM_CT * NV) {
+    const int c = threadIdx.x / NV, i = threadIdx.x % NV;
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += sh[(w * SM_CT + c) * NV + i];
+    tot[c * NV + i] = a;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = tot[ct * NV + i];
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(256) bn_act_bwd_small_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dout, int64_t Mg,
+                                                               int Cy, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               float* dgamma, float* dbeta, bf16* __restrict__ dy) {
+  constexpr int VEC = ActVec<ACT>::V;
+  constexpr int NH = ACT == ACT_GLU ? 2 : 1;
+  constexpr int NV = 2 * NH * VEC;
+  using IO = VecIO<VEC>;
+  __shared__ float sh[8 * SM_CT * NV];
+  __shared__ float tot[SM_CT * NV];
+  const int Co = ACT == ACT_GLU ? Cy / 2 : Cy;
+  const int ct = threadIdx.x % SM_CT, rt = threadIdx.x / SM_CT;
+  const int g = blockIdx.y;
+  const int c0 = (blockIdx.x * SM_CT + ct) * VEC;
+  const bf16* yg = y + (int64_t)g * Mg * Cy;
+  const bf16* dg = dout + (int64_t)g * Mg * Co;
+  bf16* dyg = dy + (int64_t)g * Mg * Cy;
+  float sc[VEC], shf[VEC], sc2[VEC], sh2[VEC], rs[VEC], nmr[VEC], rs2[VEC], nmr2[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float mu = mean[g * Cy + c0 + i];
+    rs[i] = rstd[g * Cy + c0 + i]; nmr[i] = -mu * rs[i];
+    sc[i] = gamma[c0 + i] * rs[i]; shf[i] = beta[c0 + i] - mu * sc[i];
+    if (ACT == ACT_GLU) {
+      const int c = Co + c0 + i;
+      const float mu_ = mean[g * Cy + c];
+      rs2[i] = rstd[g * Cy + c]; nmr2[i] = -mu_ * rs2[i];
+      sc2[i] = gamma[c] * rs2[i]; sh2[i] = beta[c] - mu_ * sc2[i];
+    }
+  }
+  float acc[NV];       // [S1 a | S2 a | S1 b | S2 b]
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+  constexpr int U = 4;        // rows in flight per thread
+  for (int64_t rb = rt; rb < Mg; rb += (int64_t)U * SM_RT) {
+    typename IO::T ua[U], ub[U], ud[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = rb + (int64_t)u * SM_RT;
+      if (r < Mg) {
+        ua[u] = *reinterpret_cast<const typename IO::T*>(yg + r * Cy + c0);
+        if (ACT == ACT_GLU) ub[u] = *reinterpret_cast<const typename IO::T*>(yg + r * Cy + Co + c0);
+        ud[u] = *reinterpret_cast<const typename IO::T*>(dg + r * Co + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (rb + (int64_t)u * SM_RT >= Mg) break;
+      float ya[VEC], yb[VEC], d[VEC], dza[VEC], dzb[VEC];
+      IO::unpack(ua[u], ya);
+      if (ACT == ACT_GLU) IO::unpack(ub[u], yb);
+      IO::unpack(ud[u], d);
+      act_bwd<ACT, VEC>(ya, yb, d, sc, shf, sc2, sh2, dza, dzb);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        acc[i] += dza[i]; acc[VEC + i] += dza[i] * (ya[i] * rs[i] + nmr[i]);
+        if (ACT == ACT_GLU) { acc[2 * VEC + i] += dzb[i]; acc[3 * VEC + i] += dzb[i] * (yb[i] * rs2[i] + nmr2[i]); }
+      }
+    }
+  }
+  strip_reduce<NV>(acc, sh, tot);
+  if (rt == 0) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      if (dbeta != nullptr) atomicAdd(dbeta + c0 + i, acc[i]);
+      if (dgamma != nullptr) atomicAdd(dgamma + c0 + i, acc[VEC + i]);
+      if (ACT == ACT_GLU) {
+        if (dbeta != nullptr) atomicAdd(dbeta + Co + c0 + i, acc[2 * VEC + i]);
+        if (dgamma != nullptr) atomicAdd(dgamma + Co + c0 + i, acc[3 * VEC + i]);
+      }
+    }
+  }
+  const float inv_n = 1.f / (float)Mg;
+  float A[VEC], Bc[VEC], A2[VEC], Bc2[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    A[i] = -sc[i] * rs[i] * acc[VEC + i] * inv_n;
+    Bc[i] = -sc[i] * acc[i] * inv_n + A[i] * (nmr[i] / rs[i]);          // - A*mean, mean = -nmr/rs
+    if (ACT == ACT_GLU) {
+      A2[i] = -sc2[i] * rs2[i] * acc[3 * VEC + i] * inv_n;
+      Bc2[i] = -sc2[i] * acc[2 * VEC + i] * inv_n + A2[i] * (nmr2[i] / rs2[i]);
+    }
+  }
+  for (int64_t rb = rt; rb < Mg; rb += (int64_t)U * SM_RT) {
+    typename IO::T ua[U], ub[U], ud[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = rb + (int64_t)u * SM_RT;
+      if (r < Mg) {
+        ua[u] = *reinterpret_cast<const typename IO::T*>(yg + r * Cy + c0);
+        if (ACT == ACT_GLU) ub[u] = *reinterpret_cast<const typename IO::T*>(yg + r * Cy + Co + c0);
+        ud[u] = *reinterpret_cast<const typename IO::T*>(dg + r * Co + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = rb + (int64_t)u * SM_RT;
+      if (r >= Mg) break;
+      float ya[VEC], yb[VEC], d[VEC], dza[VEC], dzb[VEC], o[VEC];
+      IO::unpack(ua[u], ya);
+      if (ACT == ACT_GLU) IO::unpack(ub[u], yb);
+      IO::unpack(ud[u], d);
+      act_bwd<ACT, VEC>(ya, yb, d, sc, shf, sc2, sh2, dza, dzb);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) o[i] = sc[i] * dza[i] + (A[i] * ya[i] + Bc[i]);
+      *reinterpret_cast<typename IO::T*>(dyg + r * Cy + c0) = IO::pack(o);
+      if (ACT == ACT_GLU) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = sc2[i] * dzb[i] + (A2[i] * yb[i] + Bc2[i]);
+        *reinterpret_cast<typename IO::T*>(dyg + r * Cy + Co + c0) = IO::pack(o);
+      }
+    }
+  }
+}
+
+// forward: finalize (partials -> mean/rstd, running statistics) + normalise + activation in one launch
+template <int ACT>
+__global__ void __launch_bounds__(256) bn_act_fwd_small_kernel(const float* __restrict__ partial, int rows_per_group, float count,
+                                                               float eps, float momentum, float* running_mean, float* running_var,
+                                                               const bf16* __restrict__ y, int64_t Mg, int Cy, int groups,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               const bf16* __restrict__ residual, bf16* __restrict__ out,
+                                                               float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  constexpr int VEC = ActVec<ACT>::V;
+  constexpr int NH = ACT == ACT_GLU ? 2 : 1;
+  constexpr int NV = 2 * NH * VEC;
+  using IO = VecIO<VEC>;
+  __shared__ float sh[8 * SM_CT * NV];
+  __shared__ float tot[SM_CT * NV];
+  const int Co = ACT == ACT_GLU ? Cy / 2 : Cy;
+  const int ct = threadIdx.x % SM_CT, rt = threadIdx.x / SM_CT;
+  const int g = blockIdx.y;
+  const int c0 = (blockIdx.x * SM_CT + ct) * VEC;
+  float sc[VEC], shf[VEC], sc2[VEC], sh2[VEC];
+  // Every block reduces its own group's partial statistics; block (strip, 0) walks ALL groups in order so that it can
+  // apply the running-statistics momentum updates sequentially (one per group == one per reference forward call).
+  const int g_first = g, g_last = g == 0 ? groups - 1 : g;
+  for (int gg = g_first; gg <= g_last; ++gg) {
+    float acc[NV];       // [sum a | sumsq a | sum b | sumsq b]
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+    for (int r = rt; r < rows_per_group; r += SM_RT) {
+      const float* pr = partial + ((size_t)gg * rows_per_group + r) * 2 * Cy;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        acc[i] += pr[c0 + i]; acc[VEC + i] += pr[Cy + c0 + i];
+        if (ACT == ACT_GLU) { acc[2 * VEC + i] += pr[Co + c0 + i]; acc[3 * VEC + i] += pr[Cy + Co + c0 + i]; }
+      }
+    }
+    strip_reduce<NV>(acc, sh, tot);
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int c = h * Co + c0 + i;
+        const double md = (double)acc[2 * h * VEC + i] / (double)count;
+        double vd = (double)acc[(2 * h + 1) * VEC + i] / (double)count - md * md;
+        vd = vd < 0.0 ? 0.0 : vd;
+        const float m = (float)md, var = (float)vd;
+        const float r = (float)(1.0 / sqrt(vd + (double)eps));
+        if (gg == g) {
+          const float s_ = gamma[c] * r;
+          if (h == 0) { sc[i] = s_; shf[i] = beta[c] - m * s_; } else { sc2[i] = s_; sh2[i] = beta[c] - m * s_; }
+          if (rt == 0) { mean_out[g * Cy + c] = m; rstd_out[g * Cy + c] = r; }
+        }
+        if (g == 0 && rt == 0 && running_mean != nullptr) {
+          const float unb = count > 1.f ? var * count / (count - 1.f) : var;
+          running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
+          running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
+        }
+      }
+  }
+  const bf16* yg = y + (int64_t)g * Mg * Cy;
+  const bf16* rg = residual != nullptr ? residual + (int64_t)g * Mg * Co : nullptr;
+  bf16* og = out + (int64_t)g * Mg * Co;
+#pragma unroll 2
+  for (int64_t r = rt; r < Mg; r += SM_RT) {
+    float a[VEC], o[VEC];
+    IO::unpack(*reinterpret_cast<const typename IO::T*>(yg + r * Cy + c0), a);
+    if (ACT == ACT_GLU) {
+      float b[VEC];
+      IO::unpack(*reinterpret_cast<const typename IO::T*>(yg + r * Cy + Co + c0), b);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) o[i] = (a[i] * sc[i] + shf[i]) * sigmoidf_(b[i] * sc2[i] + sh2[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float z = a[i] * sc[i] + shf[i];
+        o[i] = ACT == ACT_LRELU ? (z > 0.f ? z : 0.2f * z) : (ACT == ACT_RELU ? fmaxf(z, 0.f) : z);
+      }
+    }
+    if (rg != nullptr) {
+      float q[VEC];
+      IO::unpack(*reinterpret_cast<const typename IO::T*>(rg + r * Co + c0), q);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) o[i] += q[i];
+    }
+    *reinterpret_cast<typename IO::T*>(og + r * Co + c0) = IO::pack(o);
+  }
+}
+
 // ---------------------------------------------------------------- plain LeakyReLU backward / concat helpers
 __global__ void lrelu_bwd_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, bf16* __restrict__ dx, int64_t n8) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
@@ -533,6 +771,11 @@ __global__ void __launch_bounds__(256) cat_code_bwd_kernel(const bf16* __restric
 
 int act_vec(int act) { return act == ACT_GLU ? 4 : 8; }
 
+// small-layer single-launch path: few rows per statistics group, whole strips of 8 channel vectors
+bool bn_small(int64_t M, int Co, int groups, int act) {
+  return M / groups <= 768 && Co % (act_vec(act) * 8) == 0;
+}
+
 int grid_rows(int64_t M, int noct, int groups, dim3* grid) {
   const int CT = noct < 256 ? noct : 256;
   const int RT = 256 / CT;
@@ -597,6 +840,22 @@ extern "C" int ekl_bn_act_fwd(const void* y, int64_t M, int Cy, int groups, cons
   return 0;
 }
 
+// finalize + forward in one launch when the layer is small: returns 0 if it ran, 2000 if the layer does not qualify (the
+// caller then uses ekl_bn_finalize + ekl_bn_act_fwd), any other nonzero value is an error
+extern "C" int ekl_bn_act_fwd_small(const float* partial, int rows_per_group, float count, float eps, float momentum,
+                                    float* running_mean, float* running_var, const void* y, int64_t M, int Cy, int groups,
+                                    const float* gamma, const float* beta, int act, const void* residual, void* out,
+                                    float* mean, float* rstd, void* stream) {
+  const int Co = act == ACT_GLU ? Cy / 2 : Cy;
+  if (!(Co % 8 == 0 && M % groups == 0) || !bn_small(M, Co, groups, act) || rows_per_group > 1024) return 2000;
+  dim3 sg(Co / act_vec(act) / SM_CT, groups);
+  EKL_ACT_SWITCH(act, (bn_act_fwd_small_kernel<A><<<sg, 256, 0, (cudaStream_t)stream>>>(
+                          partial, rows_per_group, count, eps, momentum, running_mean, running_var, (const bf16*)y, M / groups, Cy,
+                          groups, gamma, beta, (const bf16*)residual, (bf16*)out, mean, rstd)));
+  EKL_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int ekl_bn_act_bwd_rows(int64_t M, int Cy, int groups, int act) {
   const int Co = act == ACT_GLU ? Cy / 2 : Cy;
   dim3 grid;
@@ -609,9 +868,16 @@ extern "C" int ekl_bn_act_bwd(const void* y, const void* dout, int64_t M, int Cy
                               float* sums, float* dgamma, float* dbeta, void* dy, void* stream) {
   const int Co = act == ACT_GLU ? Cy / 2 : Cy;
   EKL_REQUIRE(Co % 8 == 0 && M % groups == 0, "bn_act_bwd: bad shape Cy=%d", Cy);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bn_small(M, Co, groups, act)) {
+    dim3 sg(Co / act_vec(act) / SM_CT, groups);
+    EKL_ACT_SWITCH(act, (bn_act_bwd_small_kernel<A><<<sg, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M / groups, Cy, mean, rstd,
+                                                                      gamma, beta, dgamma, dbeta, (bf16*)dy)));
+    EKL_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid;
   const int chunks = grid_rows(M, Co / act_vec(act), groups, &grid);
-  cudaStream_t st = (cudaStream_t)stream;
   EKL_ACT_SWITCH(act, (bn_act_bwd_reduce_kernel<A><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M, Cy, groups,
                                                                          mean, rstd, gamma, beta, partial)));
   EKL_LAUNCH_CHECK();

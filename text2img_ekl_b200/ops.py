@@ -320,15 +320,24 @@ class _BnAct(torch.autograd.Function):
         _log("bn_fwd", M, C, groups, act, residual is not None)
         mean = torch.empty(groups, C, device=dev, dtype=torch.float32)
         rstd = torch.empty(groups, C, device=dev, dtype=torch.float32)
-        with _prof("bn_finalize", 0, stats.numel() * 4):
-            L.check(lib.ekl_bn_finalize(L.ptr(stats), rows_per_group, C, groups, float(M // groups), BN_EPS, BN_MOM,
-                                        L.ptr(mean), L.ptr(rstd), L.ptr(running_mean), L.ptr(running_var), L.stream()))
         Co = C // 2 if act == ACT_GLU else C
         out = torch.empty(*y.shape[:-1], Co, device=dev, dtype=torch.bfloat16)
         with _prof("bn_act_fwd", 0, M * (C + Co + (Co if residual is not None else 0)) * 2):
-            L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, C, groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), act,
-                                       L.ptr(residual), L.ptr(out), L.stream()))
-        _count(2)
+            rc = lib.ekl_bn_act_fwd_small(L.ptr(stats), rows_per_group, float(M // groups), BN_EPS, BN_MOM, L.ptr(running_mean),
+                                          L.ptr(running_var), L.ptr(y), M, C, groups, L.ptr(gamma), L.ptr(beta), act,
+                                          L.ptr(residual), L.ptr(out), L.ptr(mean), L.ptr(rstd), L.stream())
+        if rc == 0:
+            _count(1)
+        elif rc == 2000:       # not a small layer: finalize + streaming pass
+            with _prof("bn_finalize", 0, stats.numel() * 4):
+                L.check(lib.ekl_bn_finalize(L.ptr(stats), rows_per_group, C, groups, float(M // groups), BN_EPS, BN_MOM,
+                                            L.ptr(mean), L.ptr(rstd), L.ptr(running_mean), L.ptr(running_var), L.stream()))
+            with _prof("bn_act_fwd", 0, M * (C + Co + (Co if residual is not None else 0)) * 2):
+                L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, C, groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), act,
+                                           L.ptr(residual), L.ptr(out), L.stream()))
+            _count(2)
+        else:
+            L.check(rc)
         ctx.save_for_backward(y, mean, rstd, gamma, beta)
         ctx.groups, ctx.act, ctx.has_res, ctx.skip_pgrad = groups, act, residual is not None, skip_pgrad
         return out

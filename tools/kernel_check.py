@@ -105,7 +105,8 @@ def run_bn(torch, L, lib, dev, rel):
     nfail = 0
     for (M, Cy, groups, act) in [(3 * 512, 128, 3, L.ACT_GLU), (2048, 64, 1, L.ACT_LRELU), (96, 32768, 1, L.ACT_GLU),
                                  (1536, 512, 3, L.ACT_LRELU), (4096, 64, 1, L.ACT_NONE), (640, 320, 1, L.ACT_GLU),
-                                 (64, 512, 1, L.ACT_RELU)]:
+                                 (64, 512, 1, L.ACT_RELU), (3 * 384, 2048, 3, L.ACT_LRELU), (24, 32768, 1, L.ACT_GLU),
+                                 (384, 512, 1, L.ACT_LRELU), (700, 64, 1, L.ACT_NONE)]:
         y = (torch.randn(M, Cy, device=dev) * 1.5 + 0.3).bfloat16()
         gamma = 1 + 0.1 * torch.randn(Cy, device=dev)
         beta = 0.1 * torch.randn(Cy, device=dev)
@@ -119,10 +120,17 @@ def run_bn(torch, L, lib, dev, rel):
         rm, rv = torch.zeros(Cy, device=dev), torch.ones(Cy, device=dev)
         out = torch.empty(M, Co, device=dev, dtype=torch.bfloat16)
         L.check(lib.ekl_col_stats(L.ptr(y), M, Cy, groups, L.ptr(part), L.stream()))
-        L.check(lib.ekl_bn_finalize(L.ptr(part), rows // groups, Cy, groups, float(M // groups), 1e-5, 0.1, L.ptr(mean),
-                                    L.ptr(rstd), L.ptr(rm), L.ptr(rv), L.stream()))
-        L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, Cy, groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), act,
-                                   L.ptr(res), L.ptr(out), L.stream()))
+        rc = lib.ekl_bn_act_fwd_small(L.ptr(part), rows // groups, float(M // groups), 1e-5, 0.1, L.ptr(rm), L.ptr(rv), L.ptr(y), M, Cy,
+                                      groups, L.ptr(gamma), L.ptr(beta), act, L.ptr(res), L.ptr(out), L.ptr(mean), L.ptr(rstd),
+                                      L.stream())
+        small = rc == 0
+        if rc == 2000:
+            L.check(lib.ekl_bn_finalize(L.ptr(part), rows // groups, Cy, groups, float(M // groups), 1e-5, 0.1, L.ptr(mean),
+                                        L.ptr(rstd), L.ptr(rm), L.ptr(rv), L.stream()))
+            L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, Cy, groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), act,
+                                       L.ptr(res), L.ptr(out), L.stream()))
+        elif rc != 0:
+            L.check(rc)
         prow = lib.ekl_bn_act_bwd_rows(M, Cy, groups, act)
         part2 = torch.empty(prow, 2, Cy, device=dev)
         sums = torch.empty(groups, 2, Cy, device=dev)
@@ -153,7 +161,7 @@ def run_bn(torch, L, lib, dev, rel):
         errs = dict(out=rel(out, o), dy=rel(dy, yr.grad), dgamma=rel(dg, g_.grad), dbeta=rel(db, b_.grad),
                     rmean=rel(rm, rm2), rvar=rel(rv, rv2))
         ok = all(v < 1e-2 for v in errs.values())
-        print("%s bn M%d C%d g%d act%d %s" % ("PASS" if ok else "FAIL", M, Cy, groups, act,
+        print("%s bn%s M%d C%d g%d act%d %s" % ("PASS" if ok else "FAIL", " (single-launch)" if small else "", M, Cy, groups, act,
                                                " ".join("%s %.1e" % kv for kv in errs.items())), flush=True)
         nfail += 0 if ok else 1
     return nfail
