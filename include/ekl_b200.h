@@ -70,6 +70,15 @@ int ekl_conv_fwd_bias9(const ekl_conv* c, const void* x, const void* w_fwd, cons
                        void* stream);
 /* dx = conv^T(dy) */
 int ekl_conv_bwd_data(const ekl_conv* c, const void* dy, const void* w_dgrad, void* dx, void* stream);
+/* Workspace variants.  Plans with few output tiles and a long contraction (the 4x4 / 8x8 discriminator tails) run
+ * split-K: up to 4 work items per tile red-add fp32 partial tiles into `ws`, a finishing pass rounds to bf16 and takes
+ * the BatchNorm partial statistics.  ws: ekl_conv_workspace_elems(c, dgrad) floats owned by the caller, ZERO before the
+ * first call (every call leaves it zero).  ws == NULL or workspace_elems == 0: identical to the plain calls.  On the
+ * split path the statistics buffer has ekl_conv_stats_rows_ws(c) rows. */
+int64_t ekl_conv_workspace_elems(const ekl_conv* c, int dgrad);
+int ekl_conv_stats_rows_ws(const ekl_conv* c);
+int ekl_conv_fwd_ws(const ekl_conv* c, const void* x, const void* w_fwd, void* y, float* stats, float* ws, void* stream);
+int ekl_conv_bwd_data_ws(const ekl_conv* c, const void* dy, const void* w_dgrad, void* dx, float* ws, void* stream);
 /* dw[Cout][KH][KW][Cin] += x (*) dy   (fp32, accumulated: zero it first for a fresh gradient) */
 int ekl_conv_bwd_weight(const ekl_conv* c, const void* x, const void* dy, float* dw, void* stream);
 

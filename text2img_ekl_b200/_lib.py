@@ -38,6 +38,10 @@ SIGNATURES = {
     "ekl_conv_pack": (_i, [_cp, _vp, _vp, _vp, _vp]),
     "ekl_conv_stats_rows": (_i, [_cp]),
     "ekl_conv_fwd": (_i, [_cp, _vp, _vp, _vp, _vp, _vp]),
+    "ekl_conv_workspace_elems": (_i64, [_cp, _i]),
+    "ekl_conv_stats_rows_ws": (_i, [_cp]),
+    "ekl_conv_fwd_ws": (_i, [_cp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ekl_conv_bwd_data_ws": (_i, [_cp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_conv_fwd_bias9": (_i, [_cp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_conv_bwd_data": (_i, [_cp, _vp, _vp, _vp, _vp]),
     "ekl_conv_bwd_weight": (_i, [_cp, _vp, _vp, _vp, _vp]),

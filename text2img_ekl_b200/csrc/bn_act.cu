@@ -77,6 +77,43 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const bf16* __restrict__
   }
 }
 
+// ---------------------------------------------------------------- split-K finish (conv_tc.cu split plans)
+// fp32 scratch [M][C] (sum of the split work items' partial tiles) -> bf16 y, BatchNorm partial statistics of the
+// ROUNDED values (same contract as the conv epilogue), and the scratch is re-zeroed for its next use.
+__global__ void __launch_bounds__(256) splitk_finish_kernel(float* __restrict__ scratch, int64_t M, int C, int groups,
+                                                            bf16* __restrict__ y, float* __restrict__ partial) {
+  __shared__ float red[256 * 16];
+  const Tile t = make_tile(M, C / 8, groups);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+  if (t.active)
+    for (int64_t r = t.r0 + t.rt; r < t.r1; r += t.RT) {
+      float4* src = reinterpret_cast<float4*>(scratch + r * C + t.oct * 8);
+      const float4 a = src[0], b = src[1];
+      src[0] = make_float4(0.f, 0.f, 0.f, 0.f); src[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const uint4 o = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+      *reinterpret_cast<uint4*>(y + r * C + t.oct * 8) = o;
+      float f[8];
+      unpack8(o, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s1[i] += f[i]; s2[i] += f[i] * f[i]; }
+    }
+  if (partial == nullptr) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[threadIdx.x * 16 + i] = s1[i]; red[threadIdx.x * 16 + 8 + i] = s2[i]; }
+  __syncthreads();
+  if (t.active && t.rt == 0) {
+    const int CT = t.CT;
+    for (int k = 1; k < t.RT; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s1[i] += red[(threadIdx.x + k * CT) * 16 + i]; s2[i] += red[(threadIdx.x + k * CT) * 16 + 8 + i]; }
+    float* dst = partial + (size_t)blockIdx.y * 2 * C + t.oct * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dst[i] = s1[i]; dst[C + i] = s2[i]; }
+  }
+}
+
 // ---------------------------------------------------------------- finalize
 // partial [rows][2][C]; rows = groups * rows_per_group (group-contiguous). One block (256 thr) per 32 channels.
 __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partial, int rows_per_group, int C,
@@ -615,29 +652,42 @@ __global__ void __launch_bounds__(256) bn_act_fwd_small_kernel(const float* __re
   const int g = blockIdx.y;
   const int c0 = (blockIdx.x * SM_CT + ct) * VEC;
   float sc[VEC], shf[VEC], sc2[VEC], sh2[VEC];
-  // Every block reduces its own group's partial statistics; block (strip, 0) walks ALL groups in order so that it can
-  // apply the running-statistics momentum updates sequentially (one per group == one per reference forward call).
-  const int g_first = g, g_last = g == 0 ? groups - 1 : g;
-  for (int gg = g_first; gg <= g_last; ++gg) {
-    float acc[NV];       // [sum a | sumsq a | sum b | sumsq b]
+  // Every block reduces its own group's partial statistics; block (strip, 0) reduces ALL groups (their loads are issued
+  // together) so that it can apply the running-statistics momentum updates in group order (one per group == one per
+  // reference forward call).  groups <= 3 on this path.
+  const int ng = g == 0 ? groups : 1;
+  float acc[3][NV];       // per handled group: [sum a | sumsq a | sum b | sumsq b]
 #pragma unroll
-    for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-    for (int r = rt; r < rows_per_group; r += SM_RT) {
-      const float* pr = partial + ((size_t)gg * rows_per_group + r) * 2 * Cy;
+  for (int q = 0; q < 3; ++q)
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        acc[i] += pr[c0 + i]; acc[VEC + i] += pr[Cy + c0 + i];
-        if (ACT == ACT_GLU) { acc[2 * VEC + i] += pr[Co + c0 + i]; acc[3 * VEC + i] += pr[Cy + Co + c0 + i]; }
+    for (int i = 0; i < NV; ++i) acc[q][i] = 0.f;
+#pragma unroll 2
+  for (int r = rt; r < rows_per_group; r += SM_RT) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      if (q < ng) {
+        const int gg = g == 0 ? q : g;
+        const float* pr = partial + ((size_t)gg * rows_per_group + r) * 2 * Cy;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          acc[q][i] += pr[c0 + i]; acc[q][VEC + i] += pr[Cy + c0 + i];
+          if (ACT == ACT_GLU) { acc[q][2 * VEC + i] += pr[Co + c0 + i]; acc[q][3 * VEC + i] += pr[Cy + Co + c0 + i]; }
+        }
       }
     }
-    strip_reduce<NV>(acc, sh, tot);
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    if (q >= ng) break;                  // uniform per block
+    const int gg = g == 0 ? q : g;
+    strip_reduce<NV>(acc[q], sh, tot);
 #pragma unroll
     for (int h = 0; h < NH; ++h)
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         const int c = h * Co + c0 + i;
-        const double md = (double)acc[2 * h * VEC + i] / (double)count;
-        double vd = (double)acc[(2 * h + 1) * VEC + i] / (double)count - md * md;
+        const double md = (double)acc[q][2 * h * VEC + i] / (double)count;
+        double vd = (double)acc[q][(2 * h + 1) * VEC + i] / (double)count - md * md;
         vd = vd < 0.0 ? 0.0 : vd;
         const float m = (float)md, var = (float)vd;
         const float r = (float)(1.0 / sqrt(vd + (double)eps));
@@ -656,29 +706,44 @@ __global__ void __launch_bounds__(256) bn_act_fwd_small_kernel(const float* __re
   const bf16* yg = y + (int64_t)g * Mg * Cy;
   const bf16* rg = residual != nullptr ? residual + (int64_t)g * Mg * Co : nullptr;
   bf16* og = out + (int64_t)g * Mg * Co;
-#pragma unroll 2
-  for (int64_t r = rt; r < Mg; r += SM_RT) {
-    float a[VEC], o[VEC];
-    IO::unpack(*reinterpret_cast<const typename IO::T*>(yg + r * Cy + c0), a);
-    if (ACT == ACT_GLU) {
-      float b[VEC];
-      IO::unpack(*reinterpret_cast<const typename IO::T*>(yg + r * Cy + Co + c0), b);
+  constexpr int U = 4;        // rows in flight per thread
+  for (int64_t rb = rt; rb < Mg; rb += (int64_t)U * SM_RT) {
+    typename IO::T ua[U], ub[U], uq[U];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) o[i] = (a[i] * sc[i] + shf[i]) * sigmoidf_(b[i] * sc2[i] + sh2[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const float z = a[i] * sc[i] + shf[i];
-        o[i] = ACT == ACT_LRELU ? (z > 0.f ? z : 0.2f * z) : (ACT == ACT_RELU ? fmaxf(z, 0.f) : z);
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = rb + (int64_t)u * SM_RT;
+      if (r < Mg) {
+        ua[u] = *reinterpret_cast<const typename IO::T*>(yg + r * Cy + c0);
+        if (ACT == ACT_GLU) ub[u] = *reinterpret_cast<const typename IO::T*>(yg + r * Cy + Co + c0);
+        if (rg != nullptr) uq[u] = *reinterpret_cast<const typename IO::T*>(rg + r * Co + c0);
       }
     }
-    if (rg != nullptr) {
-      float q[VEC];
-      IO::unpack(*reinterpret_cast<const typename IO::T*>(rg + r * Co + c0), q);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) o[i] += q[i];
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = rb + (int64_t)u * SM_RT;
+      if (r >= Mg) break;
+      float a[VEC], o[VEC];
+      IO::unpack(ua[u], a);
+      if (ACT == ACT_GLU) {
+        float b[VEC];
+        IO::unpack(ub[u], b);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = (a[i] * sc[i] + shf[i]) * sigmoidf_(b[i] * sc2[i] + sh2[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const float z = a[i] * sc[i] + shf[i];
+          o[i] = ACT == ACT_LRELU ? (z > 0.f ? z : 0.2f * z) : (ACT == ACT_RELU ? fmaxf(z, 0.f) : z);
+        }
+      }
+      if (rg != nullptr) {
+        float q[VEC];
+        IO::unpack(uq[u], q);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] += q[i];
+      }
+      *reinterpret_cast<typename IO::T*>(og + r * Co + c0) = IO::pack(o);
     }
-    *reinterpret_cast<typename IO::T*>(og + r * Co + c0) = IO::pack(o);
   }
 }
 
@@ -795,6 +860,34 @@ int grid_rows(int64_t M, int noct, int groups, dim3* grid) {
 
 #include "../../include/ekl_b200.h"
 
+// split-K outputs are small (<= a few MB): fine chunks (4 rows per thread) so the pass is not latency bound
+static int finish_grid(int64_t M, int noct, int groups, dim3* grid) {
+  const int CT = noct < 256 ? noct : 256;
+  const int RT = 256 / CT;
+  const int xs = ekl_cdiv(noct, CT);
+  const int64_t Mg = M / groups;
+  int64_t chunks = (Mg + 4 * RT - 1) / (4 * RT);
+  if (chunks > 256) chunks = 256;
+  if (chunks < 1) chunks = 1;
+  *grid = dim3(xs, (unsigned)(chunks * groups));
+  return (int)chunks;
+}
+
+// rows of the partial-statistics buffer splitk_finish writes
+int ekl_splitk_finish_rows(int64_t M, int C, int groups) {
+  dim3 grid;
+  return finish_grid(M, C / 8, groups, &grid) * groups;
+}
+
+int ekl_splitk_finish(float* scratch, int64_t M, int C, int groups, void* y, float* partial, cudaStream_t st) {
+  EKL_REQUIRE(C % 8 == 0 && M % groups == 0, "splitk_finish: C %% 8 and M %% groups required (C=%d)", C);
+  dim3 grid;
+  finish_grid(M, C / 8, groups, &grid);
+  splitk_finish_kernel<<<grid, 256, 0, st>>>(scratch, M, C, groups, (bf16*)y, partial);
+  EKL_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int ekl_col_stats_rows(int64_t M, int C, int groups) {
   dim3 grid;
   return grid_rows(M, C / 8, groups, &grid) * groups;
@@ -847,7 +940,7 @@ extern "C" int ekl_bn_act_fwd_small(const float* partial, int rows_per_group, fl
                                     const float* gamma, const float* beta, int act, const void* residual, void* out,
                                     float* mean, float* rstd, void* stream) {
   const int Co = act == ACT_GLU ? Cy / 2 : Cy;
-  if (!(Co % 8 == 0 && M % groups == 0) || !bn_small(M, Co, groups, act) || rows_per_group > 1024) return 2000;
+  if (!(Co % 8 == 0 && M % groups == 0) || !bn_small(M, Co, groups, act) || rows_per_group > 1024 || groups > 3) return 2000;
   dim3 sg(Co / act_vec(act) / SM_CT, groups);
   EKL_ACT_SWITCH(act, (bn_act_fwd_small_kernel<A><<<sg, 256, 0, (cudaStream_t)stream>>>(
                           partial, rows_per_group, count, eps, momentum, running_mean, running_var, (const bf16*)y, M / groups, Cy,

@@ -7,7 +7,10 @@ int ekl_tc_supported(const EklGather* g);
 int ekl_tc_stats_rows(const EklGather* g, int group_b);
 void ekl_tc_geometry(const EklGather* g, int group_b, int* tb, int* th, int* tw);
 int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, int group_b, int act, const float* bias9,
-                       int* mtiles_out, cudaStream_t st);
+                       float* scratch, int* mtiles_out, cudaStream_t st);
+int64_t ekl_tc_split_elems(const EklGather* g, int group_b);
+int ekl_splitk_finish_rows(int64_t M, int C, int groups);
+int ekl_splitk_finish(float* scratch, int64_t M, int C, int groups, void* y, float* partial, cudaStream_t st);
 int ekl_rw_supported(const EklGather* g, int group_b);
 int ekl_conv3x3_rw(const EklGather* g, const void* w_packed, float* stats, int act, const float* bias9, cudaStream_t st);
 int ekl_gather_simt(const EklGather* g, const void* w_packed, int act, cudaStream_t st);
@@ -31,7 +34,23 @@ bool rw_enabled() {
 // generic gather-GEMM kernel (conv_tc.cu)
 int run_tc(const EklGather* g, const void* w, float* stats, int group_b, int act, const float* bias9, cudaStream_t st) {
   if (rw_enabled() && ekl_rw_supported(g, group_b)) return ekl_conv3x3_rw(g, w, stats, act, bias9, st);
-  return ekl_gather_gemm_tc(g, w, stats, group_b, act, bias9, nullptr, st);
+  return ekl_gather_gemm_tc(g, w, stats, group_b, act, bias9, nullptr, nullptr, st);
+}
+
+// fp32 workspace elements of the split-K path for this plan (0 = the plan does not split)
+int64_t split_elems(const ekl_conv* c, const EklGather* g, int group_b) {
+  if (c->impl != EKL_IMPL_TC || c->act != EKL_ACT_NONE || c->x_fmt != 0 || c->y_fmt != 0) return 0;
+  if (rw_enabled() && ekl_rw_supported(g, group_b)) return 0;
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("EKL_DISABLE_SPLITK"); on = (e && e[0] == '1') ? 0 : 1; }
+  return on ? ekl_tc_split_elems(g, group_b) : 0;
+}
+
+// split-K conv into `ws` (zero on entry, zero on exit) + finish into the bf16 output `out` (+ statistics)
+int run_split(const EklGather* g, const void* w, int group_b, float* ws, void* out, float* stats, cudaStream_t st) {
+  if (int rc = ekl_gather_gemm_tc(g, w, nullptr, group_b, 0, nullptr, ws, nullptr, st)) return rc;
+  const int groups = (group_b > 0 && g->mB % group_b == 0) ? g->mB / group_b : 1;
+  return ekl_splitk_finish(ws, (int64_t)g->mB * g->mH * g->mW, g->N, stats ? groups : 1, out, stats, st);
 }
 
 void out_extent(const ekl_conv* c, int* Ho, int* Wo) {
@@ -135,6 +154,43 @@ extern "C" int ekl_conv_bwd_data(const ekl_conv* c, const void* dy, const void* 
   if (c->impl == EKL_IMPL_SIMT) return ekl_gather_simt(&g, w_dgrad, 0, (cudaStream_t)stream);
   EKL_REQUIRE(c->x_fmt == 0 && c->y_fmt == 0, "TC conv: NHWC bf16 only");
   return run_tc(&g, w_dgrad, nullptr, 0, 0, nullptr, (cudaStream_t)stream);
+}
+
+// ---- workspace variants: few-tile / long-contraction plans run split-K through an fp32 workspace the caller owns
+// (ekl_conv_workspace_elems floats, ZERO before the first call; every call leaves it zero again).  With ws == NULL or a
+// plan that does not split they are the plain calls.  The statistics buffer of the split path has
+// ekl_conv_stats_rows_ws rows.
+extern "C" int64_t ekl_conv_workspace_elems(const ekl_conv* c, int dgrad) {
+  if (check(c)) return -1;
+  EklGather g;
+  plan(c, dgrad, nullptr, nullptr, &g);
+  return split_elems(c, &g, dgrad ? 0 : c->group_b);
+}
+
+extern "C" int ekl_conv_stats_rows_ws(const ekl_conv* c) {
+  if (check(c)) return -1;
+  EklGather g;
+  plan(c, 0, nullptr, nullptr, &g);
+  if (split_elems(c, &g, c->group_b) == 0) return ekl_tc_stats_rows(&g, c->group_b);
+  const int groups = (c->group_b > 0 && g.mB % c->group_b == 0) ? g.mB / c->group_b : 1;
+  return ekl_splitk_finish_rows((int64_t)g.mB * g.mH * g.mW, g.N, groups);
+}
+
+extern "C" int ekl_conv_fwd_ws(const ekl_conv* c, const void* x, const void* w_fwd, void* y, float* stats, float* ws,
+                               void* stream) {
+  if (int rc = check(c)) return rc;
+  EklGather g;
+  plan(c, 0, x, y, &g);
+  if (ws == nullptr || split_elems(c, &g, c->group_b) == 0) return ekl_conv_fwd(c, x, w_fwd, y, stats, stream);
+  return run_split(&g, w_fwd, c->group_b, ws, y, stats, (cudaStream_t)stream);
+}
+
+extern "C" int ekl_conv_bwd_data_ws(const ekl_conv* c, const void* dy, const void* w_dgrad, void* dx, float* ws, void* stream) {
+  if (int rc = check(c)) return rc;
+  EklGather g;
+  plan(c, 1, dx, dy, &g);
+  if (ws == nullptr || split_elems(c, &g, 0) == 0) return ekl_conv_bwd_data(c, dy, w_dgrad, dx, stream);
+  return run_split(&g, w_dgrad, 0, ws, dx, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int ekl_conv_bwd_weight(const ekl_conv* c, const void* x, const void* dy, float* dw, void* stream) {

@@ -32,6 +32,9 @@ struct TcParams {
   int act;            // epilogue activation on the fp32 accumulator: 0 none, 2 LeakyReLU(0.2), 4 tanh
   const float* bias9; // [B][9][N] per-sample, per-border-class bias added to the accumulator (folded code channels) or null
   int H, W;           // M-grid extents (border classes of bias9)
+  int ksplit;         // split-K: the (tap, channel-block) iterations of a tile are divided over ksplit work items ...
+  float* scratch;     // ... whose fp32 partial tiles are red-added into scratch[pixel][N] (finished by splitk_finish)
+  int mB;             // batch extent of the M grid (bounds of the scratch rows)
 };
 
 template <int BN, int KC>
@@ -90,7 +93,8 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grid = gridDim.x, cta = blockIdx.x;
   const int n_iters = p.ntaps * p.ncb;
-  const int rounds = p.nvar * p.ntn * p.groups;
+  const int rounds = p.nvar * p.ntn * p.groups * p.ksplit;
+  const int k_per = (n_iters + p.ksplit - 1) / p.ksplit;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -104,7 +108,8 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   // schedule helpers (identical in every role)
-  auto round_vng = [&](int r, int& v, int& n, int& g) { g = r % p.groups; int q = r / p.groups; n = q % p.ntn; v = q / p.ntn; };
+  auto round_vng = [&](int r, int& v, int& n, int& g) { r /= p.ksplit; g = r % p.groups; int q = r / p.groups; n = q % p.ntn; v = q / p.ntn; };
+  auto k_range = [&](int r, int& it0, int& it1) { const int ks = r % p.ksplit; it0 = ks * k_per; it1 = (it0 + k_per) < n_iters ? (it0 + k_per) : n_iters; };
   auto first_tile = [&](int r) { int rot = (int)(((long long)r * p.mtg) % grid); int c = cta - rot; if (c < 0) c += grid; return c; };
   auto tile_origin = [&](int g, int mloc, int& w0, int& h0, int& b0) {
     int mt = g * p.mtg + mloc;
@@ -119,12 +124,13 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
       const uint32_t tx = (uint32_t)(p.rows_valid * KC * 2 + C::B_BYTES);
       uint32_t kit = 0;                      // global k-iteration counter -> smem ring position
       for (int r = 0; r < rounds; ++r) {
-        int v, n, g;
+        int v, n, g, it0, it1;
         round_vng(r, v, n, g);
+        k_range(r, it0, it1);
         for (int mloc = first_tile(r); mloc < p.mtg; mloc += grid) {
           int w0, h0, b0;
           tile_origin(g, mloc, w0, h0, b0);
-          for (int it = 0; it < n_iters; ++it, ++kit) {
+          for (int it = it0; it < it1; ++it, ++kit) {
             const int s = kit % C::STAGES;
             const uint32_t ph = (kit / C::STAGES) & 1u;
             mbar_wait(&empty[s], ph ^ 1u);
@@ -142,12 +148,14 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
     constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
     uint32_t kit = 0, tile = 0;
     for (int r = 0; r < rounds; ++r) {
+      int it0, it1;
+      k_range(r, it0, it1);
       for (int mloc = first_tile(r); mloc < p.mtg; mloc += grid, ++tile) {
         const uint32_t buf = tile & 1u, use = tile >> 1;
         mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);        // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + buf * BN;
-        for (int it = 0; it < n_iters; ++it, ++kit) {
+        for (int it = it0; it < it1; ++it, ++kit) {
           const int s = kit % C::STAGES;
           const uint32_t ph = (kit / C::STAGES) & 1u;
           mbar_wait(&full[s], ph);
@@ -159,10 +167,10 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
             for (int k = 0; k < KC / 16; ++k) {
               const uint64_t da = umma_desc(sa + k * 32, 16, C::SBO, C::LAYOUT);
               const uint64_t db = umma_desc(sb + k * 32, 16, C::SBO, C::LAYOUT);
-              tc_mma_bf16(tacc, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+              tc_mma_bf16(tacc, da, db, idesc, (it != it0 || k != 0) ? 1u : 0u);
             }
             tc_commit(&empty[s]);                              // smem stage reusable once these MMAs retire
-            if (it == n_iters - 1) tc_commit(&tmem_full[buf]); // accumulator complete
+            if (it == it1 - 1) tc_commit(&tmem_full[buf]);     // accumulator complete
           }
           __syncwarp();
         }
@@ -198,6 +206,28 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
           const int hh = h0 + hi, ww = w0 + wi;
           const int cls = (hh == 0 ? 0 : (hh == p.H - 1 ? 2 : 1)) * 3 + (ww == 0 ? 0 : (ww == p.W - 1 ? 2 : 1));
           brow = p.bias9 + ((size_t)(b0 + bi) * 9 + cls) * p.N + n * BN;
+        }
+        if (p.scratch != nullptr) {
+          // split-K work item: red-add the fp32 partial tile into scratch[pixel][N]; no staging / statistics / store
+          const int wi = row % p.tw, hi = (row / p.tw) % p.th, bi = row / (p.tw * p.th);
+          const bool live = row < p.rows_valid && (b0 + bi) < p.mB && (h0 + hi) < p.H && (w0 + wi) < p.W;
+          float* dst = p.scratch + ((size_t)((b0 + bi) * p.H + h0 + hi) * p.W + w0 + wi) * p.N + n * BN;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t rr[16];
+            tmem_ld16(tacc + (uint32_t)c0, rr);
+            tmem_ld_wait();
+            if (live) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + i), "f"(__uint_as_float(rr[i])),
+                             "f"(__uint_as_float(rr[i + 1])), "f"(__uint_as_float(rr[i + 2])), "f"(__uint_as_float(rr[i + 3]))
+                             : "memory");
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[buf]);
+          continue;
         }
         if constexpr (BN == 16) {
           uint32_t rr[16];
@@ -364,8 +394,47 @@ int ekl_tc_stats_rows(const EklGather* g, int group_b) {
 }
 
 // stats: [((grp*grid + cta)*nvar + v)][2][N] fp32 partials or null.
+// Split-K plan of a gather-GEMM (0 = not split): few tiles and a long contraction (the 4x4 / 8x8 discriminator tails:
+// M = 384..1152 rows, K up to 18432) leave most SMs idle while each busy SM is bound by its own operand ingest, so the
+// (tap, channel-block) iterations of a tile are spread over up to 4 work items that red-add fp32 partial tiles into a
+// scratch buffer; splitk_finish (bn_act.cu) rounds to bf16, takes the BatchNorm statistics and re-zeroes the scratch.
+static void tc_tile_plan(const EklGather* g, int group_b, bool allow_split, int* BN_out, int* ks_out) {
+  int tb, th, tw;
+  ekl_tc_geometry(g, group_b, &tb, &th, &tw);
+  const int groups = (group_b > 0 && g->mB % group_b == 0) ? g->mB / group_b : 1;
+  const int mtiles = ekl_cdiv(g->mW, tw) * ekl_cdiv(g->mH, th) * ekl_cdiv(g->mB / groups, tb) * groups;
+  const int KC = g->Cin % 64 == 0 ? 64 : (g->Cin % 32 == 0 ? 32 : 16);
+  const int n_iters = g->ntaps * (g->Cin / KC);
+  const int sms = ekl_num_sms();
+  const int bn_min = g->N % 64 == 0 ? 64 : 16;      // measured: tiles narrower than 64 only add per-iteration overhead
+  double best = -1.0;
+  int BN = 16, KS = 1;
+  for (int bn = 256; bn >= bn_min; bn >>= 1) {
+    if (g->N % bn != 0) continue;
+    const int64_t tiles = (int64_t)mtiles * (g->N / bn) * g->nvar;
+    int ks = 1;
+    if (allow_split && g->nvar == 1 && KC == 64 && tiles * 3 <= sms && n_iters >= 64) {
+      ks = (int)(sms / tiles);
+      if (ks > n_iters / 16) ks = n_iters / 16;
+      if (ks > 4) ks = 4;
+      if (ks < 1) ks = 1;
+    }
+    // bytes the busiest CTA fetches (per-SM operand ingest is the bound: ~85 GB/s measured whether 48 or 148 SMs run)
+    const double cost = (double)((tiles * ks + sms - 1) / sms) * (128 + bn) / ks;
+    if (best < 0 || cost < best) { best = cost; BN = bn; KS = ks; }
+  }
+  *BN_out = BN; *ks_out = KS;
+}
+
+// fp32 scratch elements the split-K path of this plan needs (0: the plan is not split)
+int64_t ekl_tc_split_elems(const EklGather* g, int group_b) {
+  int BN, ks;
+  tc_tile_plan(g, group_b, true, &BN, &ks);
+  return ks > 1 ? (int64_t)g->mB * g->mH * g->mW * g->N : 0;
+}
+
 int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, int group_b, int act, const float* bias9,
-                       int* mtiles_out, cudaStream_t st) {
+                       float* scratch, int* mtiles_out, cudaStream_t st) {
   EKL_REQUIRE(ekl_tc_supported(g), "gather_gemm_tc: unsupported shape Cin=%d N=%d mH=%d mW=%d", g->Cin, g->N, g->mH, g->mW);
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -386,24 +455,14 @@ int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, i
   const int KC = g->Cin % 64 == 0 ? 64 : (g->Cin % 32 == 0 ? 32 : 16);
   p.ncb = g->Cin / KC;
   const int swz = KC == 64 ? 3 : (KC == 32 ? 2 : 1);
-  // N-tile width: the kernel is bound by per-SM operand ingest (measured ~85 GB/s per SM whether 48 or 148 SMs are
-  // active), so pick the width that minimises the bytes the busiest CTA has to fetch:
-  //   rounds(BN) * (A tile + B tile(BN)) per k-iteration,  rounds = ceil(#tiles / #SMs);  ties -> wider tile.
-  const int sms = ekl_num_sms();
-  int BN = 16;
-  {
-    int64_t best = -1;
-    const int bn_min = g->N % 64 == 0 ? 64 : 16;      // measured: tiles narrower than 64 only add per-iteration overhead
-    for (int bn = 256; bn >= bn_min; bn >>= 1) {
-      if (g->N % bn != 0) continue;
-      const int64_t tiles = (int64_t)mtiles * (g->N / bn) * g->nvar;
-      const int64_t cost = ((tiles + sms - 1) / sms) * (int64_t)(128 + bn);
-      if (best < 0 || cost < best) { best = cost; BN = bn; }
-    }
-  }
-  if (const char* e = getenv("EKL_TC_BN")) {          // experiment knob
+  int BN, ksplit;
+  tc_tile_plan(g, group_b, scratch != nullptr, &BN, &ksplit);
+  EKL_REQUIRE(scratch == nullptr || (ksplit > 1 && act == 0 && bias9 == nullptr), "split-K scratch passed to a plan that is not split");
+  p.ksplit = ksplit; p.scratch = ksplit > 1 ? scratch : nullptr; p.mB = g->mB;
+  if (ksplit > 1) p.stats = nullptr;      // statistics come from splitk_finish
+  if (const char* e = getenv("EKL_TC_BN")) {          // experiment knob (unsplit plans only)
     const int v = atoi(e);
-    if ((v == 16 || v == 32 || v == 64 || v == 128 || v == 256) && g->N % v == 0) BN = v;
+    if (ksplit == 1 && (v == 16 || v == 32 || v == 64 || v == 128 || v == 256) && g->N % v == 0) BN = v;
   }
   p.ntn = g->N / BN;
   for (int i = 0; i < g->n_a; ++i) {
@@ -423,7 +482,7 @@ int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, i
     if (rc) return rc;
   }
   // the statistics layout is indexed by the full-machine grid, so the grid is always #SMs
-  const int grid = sms;
+  const int grid = ekl_num_sms();
 #define EKL_TC_CASE(bn, kc) if (BN == bn && KC == kc) return launch_tc<bn, kc>(g, p, grid, st);
   EKL_TC_CASE(256, 64) EKL_TC_CASE(128, 64) EKL_TC_CASE(64, 64) EKL_TC_CASE(32, 64) EKL_TC_CASE(16, 64)
   EKL_TC_CASE(256, 32) EKL_TC_CASE(128, 32) EKL_TC_CASE(64, 32) EKL_TC_CASE(32, 32) EKL_TC_CASE(16, 32)

@@ -86,10 +86,20 @@ class ConvSpec:
         self._ver, self._dirty = None, False
         self.w_layout = L.W_KCRS
         self.w_fwd = self.w_dgrad = self._fwd_buf = None
+        self._ws = {}
 
     def conv(self, B, H, W, group_b=0):
         return L.EklConv(self.mode, B, H, W, self.cin, self.cout, group_b, self.impl, self.x_fmt, self.y_fmt, self.act,
                          self.w_layout)
+
+    def workspace(self, c, dgrad, device):
+        """fp32 split-K workspace of this layer for descriptor c (None when the plan does not split).  Allocated once
+        per (shape, direction), zero-filled; the kernels leave it zero."""
+        key = (c.B, c.H, c.W, c.group_b, dgrad)
+        if key not in self._ws:
+            n = L.lib().ekl_conv_workspace_elems(c, dgrad) if self.impl == L.IMPL_TC else 0
+            self._ws[key] = torch.zeros(n, device=device, dtype=torch.float32) if n > 0 else None
+        return self._ws[key]
 
     def out_hw(self, H, W):
         return (2 * H, 2 * W) if self.mode == UP2 else ((H // 2, W // 2) if self.mode == DOWN2 else (H, W))
@@ -164,13 +174,18 @@ class _Conv(torch.autograd.Function):
         else:
             y = torch.empty(B, Ho, Wo, spec.cout, device=x.device, dtype=torch.bfloat16)
         stats = None
+        ws = spec.workspace(c, 0, x.device) if spec.act == ACT_NONE else None
         if want_stats and spec.impl == L.IMPL_TC:
-            stats = torch.empty(lib.ekl_conv_stats_rows(c), 2, spec.cout, device=x.device, dtype=torch.float32)
+            rows = lib.ekl_conv_stats_rows_ws(c) if ws is not None else lib.ekl_conv_stats_rows(c)
+            stats = torch.empty(rows, 2, spec.cout, device=x.device, dtype=torch.float32)
         fam = "conv_tc" if spec.impl == L.IMPL_TC else "conv_simt"
         _log("fwd", fam, spec.mode, B, H, W, spec.cin, spec.cout, group_b)
         with _prof(fam + "_fwd", _conv_flops(spec, B, H, W), x.numel() * x.element_size() + y.numel() * y.element_size()):
-            L.check(lib.ekl_conv_fwd(c, L.ptr(x), L.ptr(w_fwd), L.ptr(y), L.ptr(stats), L.stream()))
-        _count()
+            if ws is not None:
+                L.check(lib.ekl_conv_fwd_ws(c, L.ptr(x), L.ptr(w_fwd), L.ptr(y), L.ptr(stats), L.ptr(ws), L.stream()))
+            else:
+                L.check(lib.ekl_conv_fwd(c, L.ptr(x), L.ptr(w_fwd), L.ptr(y), L.ptr(stats), L.stream()))
+        _count(2 if ws is not None else 1)
         ctx.dims = (B, H, W)
         if spec.act != ACT_NONE and spec.impl == L.IMPL_TC:
             ctx.save_for_backward(x, weight, y)        # fused epilogue activation: its derivative needs the output
@@ -203,9 +218,13 @@ class _Conv(torch.autograd.Function):
             _, w_dgrad = spec.packed(weight)
             dx = torch.empty_like(x)
             _log("dgrad", fam, spec.mode, *ctx.dims, spec.cin, spec.cout, 0)
+            ws = spec.workspace(c, 1, dx.device)
             with _prof(fam + "_dgrad", _conv_flops(spec, *ctx.dims), dx.numel() * dx.element_size() + dy.numel() * dy.element_size()):
-                L.check(lib.ekl_conv_bwd_data(c, L.ptr(dy), L.ptr(w_dgrad), L.ptr(dx), L.stream()))
-            _count()
+                if ws is not None:
+                    L.check(lib.ekl_conv_bwd_data_ws(c, L.ptr(dy), L.ptr(w_dgrad), L.ptr(dx), L.ptr(ws), L.stream()))
+                else:
+                    L.check(lib.ekl_conv_bwd_data(c, L.ptr(dy), L.ptr(w_dgrad), L.ptr(dx), L.stream()))
+            _count(2 if ws is not None else 1)
         dw = None
         if ctx.needs_input_grad[1] and not ctx.skip_wgrad:
             if ctx.w_leaf:

@@ -20,7 +20,7 @@ SHAPES = {  # mode -> list of (B, H, W, Cin, Cout)
     1: [(4, 4, 4, 128, 128), (2, 8, 8, 64, 64), (3, 16, 16, 64, 128), (2, 32, 32, 32, 32), (2, 4, 4, 256, 512)],
     2: [(4, 16, 16, 64, 128), (2, 8, 8, 128, 256), (3, 32, 32, 64, 64), (2, 8, 8, 512, 1024), (2, 64, 64, 32, 64)],
 }
-GROUPS = ["tc_fwd", "tc_dgrad", "tc_wgrad", "simt_fwd", "simt_dgrad", "simt_wgrad", "bn", "misc", "heads"]
+GROUPS = ["tc_fwd", "tc_dgrad", "tc_wgrad", "simt_fwd", "simt_dgrad", "simt_wgrad", "bn", "misc", "heads", "tc_split"]
 
 
 def run_group(group):
@@ -42,6 +42,8 @@ def run_group(group):
         return run_misc(torch, L, lib, dev, rel)
     if group == "heads":
         return run_heads(torch, L, lib, dev, rel)
+    if group == "tc_split":
+        return run_split(torch, L, lib, dev, rel)
     impl = L.IMPL_TC if group.startswith("tc") else L.IMPL_SIMT
     what = group.split("_")[1]
     for mode, shapes in SHAPES.items():
@@ -163,6 +165,55 @@ def run_bn(torch, L, lib, dev, rel):
         ok = all(v < 1e-2 for v in errs.values())
         print("%s bn%s M%d C%d g%d act%d %s" % ("PASS" if ok else "FAIL", " (single-launch)" if small else "", M, Cy, groups, act,
                                                " ".join("%s %.1e" % kv for kv in errs.items())), flush=True)
+        nfail += 0 if ok else 1
+    return nfail
+
+
+def run_split(torch, L, lib, dev, rel):
+    """Split-K workspace path (ekl_conv_fwd_ws / ekl_conv_bwd_data_ws): few output tiles, long contraction."""
+    import torch.nn.functional as F
+    torch.backends.cudnn.allow_tf32 = False
+    nfail = 0
+    for (mode, B, H, W, Cin, Cout, gb) in [(0, 6, 4, 4, 512, 256, 2), (2, 8, 8, 8, 256, 512, 0), (0, 24, 4, 4, 1024, 512, 8),
+                                           (0, 3, 4, 4, 640, 512, 0)]:
+        K = 4 if mode == 2 else 3
+        Ho, Wo = (H // 2, W // 2) if mode == 2 else (H, W)
+        x = torch.randn(B, H, W, Cin, device=dev).bfloat16()
+        wm = (torch.randn(Cout, K, K, Cin, device=dev) / (K * K * Cin) ** 0.5).bfloat16().float()
+        conv = L.EklConv(mode, B, H, W, Cin, Cout, gb, L.IMPL_TC, 0, 0, 0, 0)
+        wf = torch.empty(lib.ekl_conv_packed_elems(conv, 0), device=dev, dtype=torch.bfloat16)
+        wd = torch.empty(lib.ekl_conv_packed_elems(conv, 1), device=dev, dtype=torch.bfloat16)
+        L.check(lib.ekl_conv_pack(conv, L.ptr(wm), L.ptr(wf), L.ptr(wd), L.stream()))
+        xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+        yr = F.conv2d(xr, wm.permute(0, 3, 1, 2).contiguous(), stride=2 if mode == 2 else 1, padding=1)
+        dyn = torch.randn(B, Ho, Wo, Cout, device=dev).bfloat16()
+        yr.backward(dyn.float().permute(0, 3, 1, 2))
+        nf, nd = lib.ekl_conv_workspace_elems(conv, 0), lib.ekl_conv_workspace_elems(conv, 1)
+        msg, ok = "ws fwd %d dgrad %d" % (nf, nd), nf > 0
+        if nf > 0:
+            ws = torch.zeros(nf, device=dev)
+            rows = lib.ekl_conv_stats_rows_ws(conv)
+            for rep in range(2):                      # second pass proves the workspace was left zero
+                y = torch.full((B, Ho, Wo, Cout), float("nan"), device=dev, dtype=torch.bfloat16)
+                stats = torch.full((rows, 2, Cout), float("nan"), device=dev)
+                L.check(lib.ekl_conv_fwd_ws(conv, L.ptr(x), L.ptr(wf), L.ptr(y), L.ptr(stats), L.ptr(ws), L.stream()))
+                torch.cuda.synchronize()
+                e = rel(y.permute(0, 3, 1, 2), yr)
+                groups = B // gb if gb else 1
+                sg = stats.view(groups, rows // groups, 2, Cout).sum(1)
+                yf = y.float().reshape(groups, -1, Cout)
+                e2 = rel(sg[:, 1], (yf * yf).sum(1))
+                ok = ok and e < 6e-3 and e2 < 1e-3 and float(ws.abs().max()) == 0.0
+                msg += " | y %.1e stats %.1e" % (e, e2)
+        if nd > 0:
+            ws = torch.zeros(nd, device=dev)
+            dx = torch.full((B, H, W, Cin), float("nan"), device=dev, dtype=torch.bfloat16)
+            L.check(lib.ekl_conv_bwd_data_ws(conv, L.ptr(dyn), L.ptr(wd), L.ptr(dx), L.ptr(ws), L.stream()))
+            torch.cuda.synchronize()
+            e = rel(dx.permute(0, 3, 1, 2), xr.grad)
+            ok = ok and e < 6e-3 and float(ws.abs().max()) == 0.0
+            msg += " | dx %.1e" % e
+        print("%s tc_split mode%d B%d %dx%d %d>%d gb%d %s" % ("PASS" if ok else "FAIL", mode, B, H, W, Cin, Cout, gb, msg), flush=True)
         nfail += 0 if ok else 1
     return nfail
 
