@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libekl_b200.so")
+LIB_PATH = os.environ.get("EKL_LIB_PATH") or os.path.join(HERE, "libekl_b200.so")
 
 S1, UP2, DOWN2 = 0, 1, 2
 IMPL_TC, IMPL_SIMT = 0, 1

@@ -12,8 +12,19 @@
 //   * the 9 filter taps [BN][Cin] of the current output-channel tile stay in shared memory for all tiles of a round.
 // Pipeline roles / TMEM double buffering / epilogue (bf16 pack, BatchNorm partial sums, TMA store, optional fused
 // activation and border-class bias) follow conv_tc.cu.  Forward and data-gradient of EKL_S1 (taps differ only in sign).
+#include <stdlib.h>
+
 #include "conv_plan.h"
 #include "ekl_common.cuh"
+
+// -DEKL_RW_TIMING: per-role cycle accounting of CTA 0, printed at kernel exit (development aid)
+#ifdef EKL_RW_TIMING
+#define RW_T0() long long t0_ = clock64()
+#define RW_ACC(x) do { const long long t1_ = clock64(); (x) += t1_ - t0_; t0_ = t1_; } while (0)
+#else
+#define RW_T0() do {} while (0)
+#define RW_ACC(x) do {} while (0)
+#endif
 
 namespace {
 
@@ -23,6 +34,7 @@ struct RwParams {
   float* stats;          // [cta][2][N] or null
   const float* bias9;    // [B][9][N] or null
   int N, ntn, H, W, nTh, nTw, tiles, act;
+  int halo1;             // experiment: ONE [Cin][10 w][18 h] halo box per tile, taps = row-shifted descriptors
 };
 
 template <int BN, int KC>
@@ -37,7 +49,8 @@ struct RwCfg {
   static constexpr int STAGES = STAGES_RAW > 4 ? 4 : STAGES_RAW;
   static_assert(STAGES >= 2, "not enough shared memory for two stages");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + W_BYTES + OUT_BYTES + 1024 + 512 + 2 * 2 * BN * 4 * (256 / BN);
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int NBUF = 4;                                        // TMEM accumulators in flight (4 x BN <= 256 columns)
+  static constexpr int TMEM_COLS = NBUF * BN < 32 ? 32 : NBUF * BN;
   static constexpr uint32_t LAYOUT = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);
   static constexpr uint32_t SBO = 8 * ROWB;
   static constexpr int QUADS = BN / 4;
@@ -66,9 +79,9 @@ __global__ void __launch_bounds__(192, 1) conv3x3_rw_kernel(const __grid_constan
   uint8_t* stage_out = wsm + C::W_BYTES;
   uint64_t* full = (uint64_t*)(stage_out + C::OUT_BYTES);
   uint64_t* empty = full + C::STAGES;
-  uint64_t* tmem_full = empty + C::STAGES;      // [2]
-  uint64_t* tmem_empty = tmem_full + 2;         // [2]
-  uint64_t* wfull = tmem_empty + 2;
+  uint64_t* tmem_full = empty + C::STAGES;      // [NBUF]
+  uint64_t* tmem_empty = tmem_full + C::NBUF;   // [NBUF]
+  uint64_t* wfull = tmem_empty + C::NBUF;
   uint64_t* wfree = wfull + 1;
   uint32_t* tmem_slot = (uint32_t*)(wfree + 1);
   float* red = (float*)(stage_out + C::OUT_BYTES + 512);
@@ -78,7 +91,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_rw_kernel(const __grid_constan
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+    for (int b = 0; b < C::NBUF; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
     mbar_init(wfull, 1); mbar_init(wfree, 1);
     fence_barrier_init();
   }
@@ -100,6 +113,10 @@ __global__ void __launch_bounds__(192, 1) conv3x3_rw_kernel(const __grid_constan
       tma_prefetch_desc(&p.w_map);
       tma_prefetch_desc(&p.a_map);
       uint32_t kit = 0;
+#ifdef EKL_RW_TIMING
+      long long tp_wait = 0, tp_issue = 0;
+#endif
+      RW_T0();
       for (int n = 0; n < p.ntn; ++n) {
         // the filter tile may be overwritten once every MMA of the previous round has retired
         if (n > 0) mbar_wait(wfree, (uint32_t)(n - 1) & 1u);
@@ -111,49 +128,77 @@ __global__ void __launch_bounds__(192, 1) conv3x3_rw_kernel(const __grid_constan
           int w0, h0, b0;
           tile_origin(tile, w0, h0, b0);
           mbar_wait(&empty[s], ph ^ 1u);
+          RW_ACC(tp_wait);
           uint8_t* sa = smem + s * C::STAGE_BYTES;
-          mbar_expect_tx(&full[s], (uint32_t)(3 * 144 * C::ROWB));
+          if (p.halo1) {
+            mbar_expect_tx(&full[s], (uint32_t)(180 * C::ROWB));
+            tma_load_4d(&p.a_map, &full[s], sa, 0, w0 - 1, h0 - 1, b0);
+          } else {
+            mbar_expect_tx(&full[s], (uint32_t)(3 * 144 * C::ROWB));
 #pragma unroll
-          for (int j = 0; j < 3; ++j) tma_load_4d(&p.a_map, &full[s], sa + j * C::BOX_BYTES, 0, w0 + j - 1, h0 - 1, b0);
+            for (int j = 0; j < 3; ++j) tma_load_4d(&p.a_map, &full[s], sa + j * C::BOX_BYTES, 0, w0 + j - 1, h0 - 1, b0);
+          }
+          RW_ACC(tp_issue);
         }
       }
+#ifdef EKL_RW_TIMING
+      if (cta == 0) printf("rw producer: wait_empty %lld issue %lld cycles, %u tiles\n", tp_wait, tp_issue, kit);
+#endif
     }
   } else if (warp == 1) {
     if (has_tiles) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
       uint32_t kit = 0;
+      // descriptors are affine in the shared address: desc(base + off) = desc(base) + (off >> 4) (no carry out of the
+      // 14-bit start field for offsets inside one CTA's shared memory).  Per-tap A offsets are tile-invariant.
+      uint32_t a_off[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const EklTap tap = p.taps[t];
+        a_off[t] = (p.halo1 ? (uint32_t)((tap.dh + 1) * 10 + tap.dw + 1) * C::ROWB
+                            : (uint32_t)(tap.dw + 1) * C::BOX_BYTES + (uint32_t)(tap.dh + 1) * C::SBO) >> 4;
+      }
+      const uint32_t a_sbo = p.halo1 ? 10u * C::ROWB : C::SBO;
+      const uint64_t bdesc0 = umma_desc(smem_u32(wsm), 16, C::SBO, C::LAYOUT);
+#ifdef EKL_RW_TIMING
+      long long tm_tmem = 0, tm_full = 0, tm_issue = 0, tm_w = 0;
+#endif
+      RW_T0();
       for (int n = 0; n < p.ntn; ++n) {
         mbar_wait(wfull, (uint32_t)n & 1u);
         tc_fence_after();
+        RW_ACC(tm_w);
         for (int tile = cta; tile < p.tiles; tile += grid, ++kit) {
           const int s = kit % C::STAGES;
           const uint32_t ph = (kit / C::STAGES) & 1u;
-          const uint32_t buf = kit & 1u, use = kit >> 1;
+          const uint32_t buf = kit % C::NBUF, use = kit / C::NBUF;
           mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);
+          RW_ACC(tm_tmem);
           mbar_wait(&full[s], ph);
           tc_fence_after();
+          RW_ACC(tm_full);
           if (elect_one()) {
-            const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
-            const uint32_t sw = smem_u32(wsm);
+            const uint64_t adesc0 = umma_desc(smem_u32(smem + s * C::STAGE_BYTES), 16, a_sbo, C::LAYOUT);
             const uint32_t tacc = tmem_base + buf * BN;
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
-              const EklTap tap = p.taps[t];
-              const uint32_t a0 = sa + (uint32_t)(tap.dw + 1) * C::BOX_BYTES + (uint32_t)(tap.dh + 1) * C::SBO;
-              const uint32_t b0 = sw + (uint32_t)t * C::WT_BYTES;
 #pragma unroll
               for (int k = 0; k < KC / 16; ++k)
-                tc_mma_bf16(tacc, umma_desc(a0 + k * 32, 16, C::SBO, C::LAYOUT), umma_desc(b0 + k * 32, 16, C::SBO, C::LAYOUT),
-                            idesc, (t | k) != 0 ? 1u : 0u);
+                tc_mma_bf16(tacc, adesc0 + (uint64_t)(a_off[t] + 2 * k), bdesc0 + (uint64_t)((t * C::WT_BYTES + k * 32) >> 4), idesc,
+                            (t | k) != 0 ? 1u : 0u);
             }
             tc_commit(&empty[s]);
             tc_commit(&tmem_full[buf]);
           }
           __syncwarp();
+          RW_ACC(tm_issue);
         }
         if (elect_one()) tc_commit(wfree);       // all MMAs of this round retired -> filter tile reusable
         __syncwarp();
       }
+#ifdef EKL_RW_TIMING
+      if (cta == 0 && lane == 0) printf("rw mma: wait_w %lld wait_tmem_empty %lld wait_full %lld issue %lld\n", tm_w, tm_tmem, tm_full, tm_issue);
+#endif
     }
   } else {
     const int q = warp & 3;
@@ -163,17 +208,23 @@ __global__ void __launch_bounds__(192, 1) conv3x3_rw_kernel(const __grid_constan
     const uint32_t so = smem_u32(stage_out);
     uint32_t kit = 0;
     bool store_pending = false;
+#ifdef EKL_RW_TIMING
+    long long te_full = 0, te_store = 0, te_ld = 0, te_bar = 0, te_stats = 0;
+#endif
+    RW_T0();
     for (int n = 0; n < p.ntn; ++n) {
       float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
       if (has_tiles)
         for (int tile = cta; tile < p.tiles; tile += grid, ++kit) {
-          const uint32_t buf = kit & 1u, use = kit >> 1;
+          const uint32_t buf = kit % C::NBUF, use = kit / C::NBUF;
           int w0, h0, b0;
           tile_origin(tile, w0, h0, b0);
           mbar_wait(&tmem_full[buf], use & 1u);
           tc_fence_after();
+          RW_ACC(te_full);
           if (store_pending && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           asm volatile("bar.sync 1, 128;" ::: "memory");
+          RW_ACC(te_store);
           const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
           const float* brow = nullptr;
           if (p.bias9 != nullptr) {
@@ -209,6 +260,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_rw_kernel(const __grid_constan
           }
           tc_fence_before();
           mbar_arrive(&tmem_empty[buf]);
+          RW_ACC(te_ld);
           fence_proxy_async_smem();
           asm volatile("bar.sync 1, 128;" ::: "memory");
           if (et == 0) {
@@ -216,10 +268,11 @@ __global__ void __launch_bounds__(192, 1) conv3x3_rw_kernel(const __grid_constan
             tma_store_commit();
           }
           store_pending = true;
+          RW_ACC(te_bar);
           if (p.stats != nullptr) {
             constexpr int RPS = 128 / C::SLICES;
             const int r0 = slice * RPS;
-#pragma unroll 4
+#pragma unroll
             for (int rr = r0; rr < r0 + RPS; ++rr) {
               const uint2 u = lds64(so + rw_stage_off<BN>(rr, 4 * quad));
               const float x0 = bf16_lo(u.x), x1 = bf16_hi(u.x), x2 = bf16_lo(u.y), x3 = bf16_hi(u.y);
@@ -227,6 +280,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_rw_kernel(const __grid_constan
               s1[2] += x2; s2[2] += x2 * x2; s1[3] += x3; s2[3] += x3 * x3;
             }
           }
+          RW_ACC(te_stats);
         }
       if (p.stats != nullptr) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -244,6 +298,11 @@ __global__ void __launch_bounds__(192, 1) conv3x3_rw_kernel(const __grid_constan
       }
     }
     if (store_pending && et == 0) tma_store_wait_all();
+#ifdef EKL_RW_TIMING
+    if (cta == 0 && et == 0)
+      printf("rw epilogue: wait_tmem_full %lld wait_store_read+bar %lld ld/pack/sts %lld fence+bar+store %lld stats %lld\n", te_full,
+             te_store, te_ld, te_bar, te_stats);
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -296,7 +355,9 @@ int ekl_conv3x3_rw(const EklGather* g, const void* w_packed, float* stats, int a
     const EklView& v = g->a[0];
     uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)v.dW, (uint64_t)v.dH, (uint64_t)v.dB};
     uint64_t strides[3] = {(uint64_t)v.sW * 2, (uint64_t)v.sH * 2, (uint64_t)v.sB * 2};
-    uint32_t box[4] = {(uint32_t)KC, 8, 18, 1};
+    const char* e = getenv("EKL_RW_HALO");
+    p.halo1 = (e && e[0] == '1') ? 1 : 0;
+    uint32_t box[4] = {(uint32_t)KC, (uint32_t)(p.halo1 ? 10 : 8), 18, 1};
     if (int rc = ekl_make_tmap(&p.a_map, v.base, 4, dims, strides, box, swz, 2)) return rc;
   }
   {
