@@ -79,6 +79,11 @@ int64_t ekl_conv_workspace_elems(const ekl_conv* c, int dgrad);
 int ekl_conv_stats_rows_ws(const ekl_conv* c);
 int ekl_conv_fwd_ws(const ekl_conv* c, const void* x, const void* w_fwd, void* y, float* stats, float* ws, void* stream);
 int ekl_conv_bwd_data_ws(const ekl_conv* c, const void* dy, const void* w_dgrad, void* dx, float* ws, void* stream);
+/* Data-gradient straight from the FORWARD-packed filter (MN-major tensor-core operand; no transposed copy).  Usable
+ * when ekl_conv_dgrad_from_fwd(c) != 0: stride-1 / stride-2 convs with Cin, Cout multiples of 64 on the generic kernel.
+ * ws: split-K workspace as for ekl_conv_bwd_data_ws (may be NULL). */
+int ekl_conv_dgrad_from_fwd(const ekl_conv* c);
+int ekl_conv_bwd_data_fw(const ekl_conv* c, const void* dy, const void* w_fwd, void* dx, float* ws, void* stream);
 /* dw[Cout][KH][KW][Cin] += x (*) dy   (fp32, accumulated: zero it first for a fresh gradient) */
 int ekl_conv_bwd_weight(const ekl_conv* c, const void* x, const void* dy, float* dw, void* stream);
 

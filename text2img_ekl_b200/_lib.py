@@ -42,6 +42,8 @@ SIGNATURES = {
     "ekl_conv_stats_rows_ws": (_i, [_cp]),
     "ekl_conv_fwd_ws": (_i, [_cp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_conv_bwd_data_ws": (_i, [_cp, _vp, _vp, _vp, _vp, _vp]),
+    "ekl_conv_dgrad_from_fwd": (_i, [_cp]),
+    "ekl_conv_bwd_data_fw": (_i, [_cp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_conv_fwd_bias9": (_i, [_cp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_conv_bwd_data": (_i, [_cp, _vp, _vp, _vp, _vp]),
     "ekl_conv_bwd_weight": (_i, [_cp, _vp, _vp, _vp, _vp]),

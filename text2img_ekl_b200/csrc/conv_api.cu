@@ -7,7 +7,8 @@ int ekl_tc_supported(const EklGather* g);
 int ekl_tc_stats_rows(const EklGather* g, int group_b);
 void ekl_tc_geometry(const EklGather* g, int group_b, int* tb, int* th, int* tw);
 int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, int group_b, int act, const float* bias9,
-                       float* scratch, int* mtiles_out, cudaStream_t st);
+                       float* scratch, int* mtiles_out, cudaStream_t st, int w_is_fwd_packed = 0);
+int ekl_tc_dgrad_from_fwd_ok(const EklGather* g);
 int64_t ekl_tc_split_elems(const EklGather* g, int group_b);
 int ekl_splitk_finish_rows(int64_t M, int C, int groups);
 int ekl_splitk_finish(float* scratch, int64_t M, int C, int groups, void* y, float* partial, cudaStream_t st);
@@ -47,8 +48,9 @@ int64_t split_elems(const ekl_conv* c, const EklGather* g, int group_b) {
 }
 
 // split-K conv into `ws` (zero on entry, zero on exit) + finish into the bf16 output `out` (+ statistics)
-int run_split(const EklGather* g, const void* w, int group_b, float* ws, void* out, float* stats, cudaStream_t st) {
-  if (int rc = ekl_gather_gemm_tc(g, w, nullptr, group_b, 0, nullptr, ws, nullptr, st)) return rc;
+int run_split(const EklGather* g, const void* w, int group_b, float* ws, void* out, float* stats, cudaStream_t st,
+              int w_is_fwd = 0) {
+  if (int rc = ekl_gather_gemm_tc(g, w, nullptr, group_b, 0, nullptr, ws, nullptr, st, w_is_fwd)) return rc;
   const int groups = (group_b > 0 && g->mB % group_b == 0) ? g->mB / group_b : 1;
   return ekl_splitk_finish(ws, (int64_t)g->mB * g->mH * g->mW, g->N, stats ? groups : 1, out, stats, st);
 }
@@ -119,6 +121,7 @@ extern "C" int ekl_conv_stats_rows(const ekl_conv* c) {
 
 extern "C" int ekl_conv_fwd(const ekl_conv* c, const void* x, const void* w_fwd, void* y, float* stats, void* stream) {
   if (int rc = check(c)) return rc;
+  EKL_REQUIRE(x != nullptr && w_fwd != nullptr && y != nullptr, "conv_fwd: null pointer argument");
   EklGather g;
   plan(c, 0, x, y, &g);
   if (c->impl == EKL_IMPL_SIMT) {
@@ -149,6 +152,7 @@ extern "C" int ekl_conv_fwd_bias9(const ekl_conv* c, const void* x, const void* 
 
 extern "C" int ekl_conv_bwd_data(const ekl_conv* c, const void* dy, const void* w_dgrad, void* dx, void* stream) {
   if (int rc = check(c)) return rc;
+  EKL_REQUIRE(dy != nullptr && w_dgrad != nullptr && dx != nullptr, "conv_bwd_data: null pointer argument");
   EklGather g;
   plan(c, 1, dx, dy, &g);
   if (c->impl == EKL_IMPL_SIMT) return ekl_gather_simt(&g, w_dgrad, 0, (cudaStream_t)stream);
@@ -191,6 +195,27 @@ extern "C" int ekl_conv_bwd_data_ws(const ekl_conv* c, const void* dy, const voi
   plan(c, 1, dx, dy, &g);
   if (ws == nullptr || split_elems(c, &g, 0) == 0) return ekl_conv_bwd_data(c, dy, w_dgrad, dx, stream);
   return run_split(&g, w_dgrad, 0, ws, dx, nullptr, (cudaStream_t)stream);
+}
+
+// Data-gradient reading the FORWARD-packed filter (ekl_conv_pack's w_fwd, or the optimiser's bf16 shadow of a
+// channels_last master) as an MN-major tensor-core operand: no transposed copy of the filter is needed.  Available when
+// ekl_conv_dgrad_from_fwd(c) != 0 (stride-1 / stride-2 convs, Cin and Cout multiples of 64, generic tcgen05 kernel).
+extern "C" int ekl_conv_dgrad_from_fwd(const ekl_conv* c) {
+  if (check(c) || c->impl != EKL_IMPL_TC || c->x_fmt != 0 || c->y_fmt != 0 || c->mode == EKL_UP2) return 0;
+  EklGather g;
+  plan(c, 1, nullptr, nullptr, &g);
+  if (rw_enabled() && ekl_rw_supported(&g, 0)) return 0;
+  return ekl_tc_dgrad_from_fwd_ok(&g);
+}
+
+extern "C" int ekl_conv_bwd_data_fw(const ekl_conv* c, const void* dy, const void* w_fwd, void* dx, float* ws, void* stream) {
+  if (int rc = check(c)) return rc;
+  EKL_REQUIRE(ekl_conv_dgrad_from_fwd(c), "conv_bwd_data_fw: this layer needs the transposed operand (ekl_conv_bwd_data)");
+  EKL_REQUIRE(dy != nullptr && w_fwd != nullptr && dx != nullptr, "conv_bwd_data_fw: null pointer argument");
+  EklGather g;
+  plan(c, 1, dx, dy, &g);
+  if (ws != nullptr && split_elems(c, &g, 0) > 0) return run_split(&g, w_fwd, 0, ws, dx, nullptr, (cudaStream_t)stream, 1);
+  return ekl_gather_gemm_tc(&g, w_fwd, nullptr, 0, 0, nullptr, nullptr, nullptr, (cudaStream_t)stream, 1);
 }
 
 extern "C" int ekl_conv_bwd_weight(const ekl_conv* c, const void* x, const void* dy, float* dw, void* stream) {

@@ -35,6 +35,8 @@ struct TcParams {
   int ksplit;         // split-K: the (tap, channel-block) iterations of a tile are divided over ksplit work items ...
   float* scratch;     // ... whose fp32 partial tiles are red-added into scratch[pixel][N] (finished by splitk_finish)
   int mB;             // batch extent of the M grid (bounds of the scratch rows)
+  int b_mn;           // data-gradient reading the FORWARD-packed filter [Cout][tap][Cin] as an MN-major B operand
+  int Nm;             // b_mn: master Cin (row pitch of the forward-packed filter = ntaps_master * Nm)
 };
 
 template <int BN, int KC>
@@ -139,13 +141,21 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
             uint8_t* sa = smem + s * C::STAGE_BYTES;
             mbar_expect_tx(&full[s], tx);
             tma_load_4d(&p.a_maps[tap.map], &full[s], sa, cb * KC, w0 + tap.dw, h0 + tap.dh, b0);
-            tma_load_2d(&p.w_map, &full[s], sa + C::A_BYTES, t * p.Cin + cb * KC, v * p.N + n * BN);
+            if (p.b_mn) {
+              // K rows = output channels [cb*KC, +KC), N columns = input channels of master tap src: 64-wide boxes
+#pragma unroll
+              for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j)
+                tma_load_2d(&p.w_map, &full[s], sa + C::A_BYTES + j * (KC * 128), tap.src[0] * p.Nm + n * BN + j * 64, cb * KC);
+            } else {
+              tma_load_2d(&p.w_map, &full[s], sa + C::A_BYTES, t * p.Cin + cb * KC, v * p.N + n * BN);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    constexpr uint32_t idesc_mn = umma_idesc_bf16(128, BN, 0, 1);
     uint32_t kit = 0, tile = 0;
     for (int r = 0; r < rounds; ++r) {
       int it0, it1;
@@ -161,13 +171,20 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
           mbar_wait(&full[s], ph);
           tc_fence_after();
           if (elect_one()) {
+            // descriptors are affine in the shared address: +32 bytes along K == +2 in the (addr >> 4) start field
             const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
-            const uint32_t sb = sa + C::A_BYTES;
+            const uint64_t da0 = umma_desc(sa, 16, C::SBO, C::LAYOUT);
+            if (p.b_mn) {
+              // MN-major B: boxes of [KC k-rows][64 n] (128-byte rows, SWIZZLE_128B); 16 k-rows per MMA = +2048 bytes
+              const uint64_t db0 = umma_desc(sa + C::A_BYTES, KC * 128, 8 * 128, 2u);
 #pragma unroll
-            for (int k = 0; k < KC / 16; ++k) {
-              const uint64_t da = umma_desc(sa + k * 32, 16, C::SBO, C::LAYOUT);
-              const uint64_t db = umma_desc(sb + k * 32, 16, C::SBO, C::LAYOUT);
-              tc_mma_bf16(tacc, da, db, idesc, (it != it0 || k != 0) ? 1u : 0u);
+              for (int k = 0; k < KC / 16; ++k)
+                tc_mma_bf16(tacc, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(128 * k), idesc_mn, (it != it0 || k != 0) ? 1u : 0u);
+            } else {
+              const uint64_t db0 = umma_desc(sa + C::A_BYTES, 16, C::SBO, C::LAYOUT);
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k)
+                tc_mma_bf16(tacc, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, (it != it0 || k != 0) ? 1u : 0u);
             }
             tc_commit(&empty[s]);                              // smem stage reusable once these MMAs retire
             if (it == it1 - 1) tc_commit(&tmem_full[buf]);     // accumulator complete
@@ -433,8 +450,18 @@ int64_t ekl_tc_split_elems(const EklGather* g, int group_b) {
   return ks > 1 ? (int64_t)g->mB * g->mH * g->mW * g->N : 0;
 }
 
+// 1 if the data-gradient plan g can read the FORWARD-packed filter ([Cout][tap][Cin], i.e. the bf16 shadow of a
+// channels_last master) as an MN-major B operand: one master tap per packed tap, 64-channel K blocks, N % 64 == 0
+int ekl_tc_dgrad_from_fwd_ok(const EklGather* g) {
+  if (!g->transposed || g->Cin % 64 != 0 || g->N % 64 != 0) return 0;
+  for (int v = 0; v < g->nvar; ++v)
+    for (int t = 0; t < g->ntaps; ++t)
+      if (g->taps[v][t].nsrc != 1) return 0;
+  return 1;
+}
+
 int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, int group_b, int act, const float* bias9,
-                       float* scratch, int* mtiles_out, cudaStream_t st) {
+                       float* scratch, int* mtiles_out, cudaStream_t st, int w_is_fwd_packed) {
   EKL_REQUIRE(ekl_tc_supported(g), "gather_gemm_tc: unsupported shape Cin=%d N=%d mH=%d mW=%d", g->Cin, g->N, g->mH, g->mW);
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -474,7 +501,16 @@ int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, i
     int rc = make_view_map(&p.o_maps[i], g->o[i], obox, tw, th, tb, BN >= 64 ? 3 : (BN == 32 ? 2 : 0));
     if (rc) return rc;
   }
-  {
+  if (w_is_fwd_packed) {
+    EKL_REQUIRE(ekl_tc_dgrad_from_fwd_ok(g) && KC == 64 && BN >= 64, "dgrad from the forward-packed filter: unsupported plan");
+    p.b_mn = 1; p.Nm = g->N;
+    const int KK = g->KH * g->KW;
+    uint64_t dims[2] = {(uint64_t)KK * g->N, (uint64_t)g->Cin};            // [Cout rows][tap][Cin]
+    uint64_t strides[1] = {(uint64_t)KK * g->N * 2};
+    uint32_t box[2] = {64u, (uint32_t)KC};
+    int rc = ekl_make_tmap(&p.w_map, w_packed, 2, dims, strides, box, 3, 2);
+    if (rc) return rc;
+  } else {
     uint64_t dims[2] = {(uint64_t)g->ntaps * g->Cin, (uint64_t)g->nvar * g->N};
     uint64_t strides[1] = {(uint64_t)g->ntaps * g->Cin * 2};
     uint32_t box[2] = {(uint32_t)KC, (uint32_t)BN};

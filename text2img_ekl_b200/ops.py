@@ -113,6 +113,12 @@ class ConvSpec:
         else:
             raise L.EklError("conv filter must be contiguous or channels_last")
 
+    def dgrad_from_fwd(self):
+        """The data-gradient kernel can read the forward-packed filter as an MN-major operand (no transposed pack):
+        stride-1 / stride-2 convs with 64-multiple channel counts that never take the resident-filter path."""
+        return (self.impl == L.IMPL_TC and self.mode != UP2 and self.w_layout == L.W_KRSC and self.cin % 64 == 0
+                and self.cout % 64 == 0 and self.cout > 64 and self.x_fmt == 0 and self.y_fmt == 0)
+
     def _shadow(self, weight):
         """bf16 shadow slice maintained by optim.FlatAdam, usable as the packed forward operand when that operand is a
         plain cast of the master in memory order: stride-1 / stride-2 plans (one variant, one source tap per packed
@@ -142,15 +148,36 @@ class ConvSpec:
                 if self._fwd_buf is None:
                     self._fwd_buf = torch.empty(lib.ekl_conv_packed_elems(c, 0), device=weight.device, dtype=torch.bfloat16)
                 self.w_fwd = self._fwd_buf
-            if self.w_dgrad is None:
+            need_dgrad = not self.dgrad_from_fwd()
+            if need_dgrad and self.w_dgrad is None:
                 self.w_dgrad = torch.empty(lib.ekl_conv_packed_elems(c, 1), device=weight.device, dtype=torch.bfloat16)
             w_fwd_arg = None if shadow is not None else self.w_fwd
-            nb = weight.numel() * 4 + ((0 if shadow is not None else self.w_fwd.numel()) + self.w_dgrad.numel()) * 2
-            with _prof("pack_weights", 0, nb):
-                L.check(lib.ekl_conv_pack(c, L.ptr(weight), L.ptr(w_fwd_arg), L.ptr(self.w_dgrad), L.stream()))
-            _count(1 if shadow is not None else 2)
+            w_dgrad_arg = self.w_dgrad if need_dgrad else None
+            if w_fwd_arg is not None or w_dgrad_arg is not None:
+                nb = weight.numel() * 4 + ((w_fwd_arg.numel() if w_fwd_arg is not None else 0) +
+                                           (w_dgrad_arg.numel() if w_dgrad_arg is not None else 0)) * 2
+                with _prof("pack_weights", 0, nb):
+                    L.check(lib.ekl_conv_pack(c, L.ptr(weight), L.ptr(w_fwd_arg), L.ptr(w_dgrad_arg), L.stream()))
+                _count((w_fwd_arg is not None) + (w_dgrad_arg is not None))
             self._ver, self._dirty = key, False
         return self.w_fwd, self.w_dgrad
+
+
+def _run_dgrad(spec, c, weight, dy, dx):
+    """dx = conv^T(dy) through whichever operand the layer keeps: the forward-packed filter read as an MN-major operand
+    (no transposed pack), else the packed data-gradient operand; split-K workspace when the plan has one."""
+    lib = L.lib()
+    ws = spec.workspace(c, 1, dx.device)
+    if spec.dgrad_from_fwd():
+        w_fwd, _ = spec.packed(weight)
+        L.check(lib.ekl_conv_bwd_data_fw(c, L.ptr(dy), L.ptr(w_fwd), L.ptr(dx), L.ptr(ws), L.stream()))
+    else:
+        _, w_dgrad = spec.packed(weight)
+        if ws is not None:
+            L.check(lib.ekl_conv_bwd_data_ws(c, L.ptr(dy), L.ptr(w_dgrad), L.ptr(dx), L.ptr(ws), L.stream()))
+        else:
+            L.check(lib.ekl_conv_bwd_data(c, L.ptr(dy), L.ptr(w_dgrad), L.ptr(dx), L.stream()))
+    _count(2 if ws is not None else 1)
 
 
 class _Conv(torch.autograd.Function):
@@ -215,16 +242,10 @@ class _Conv(torch.autograd.Function):
                 dy = dy * (1.0 - y.float() ** 2).to(dy.dtype)
         dx = None
         if ctx.needs_input_grad[0]:
-            _, w_dgrad = spec.packed(weight)
             dx = torch.empty_like(x)
             _log("dgrad", fam, spec.mode, *ctx.dims, spec.cin, spec.cout, 0)
-            ws = spec.workspace(c, 1, dx.device)
             with _prof(fam + "_dgrad", _conv_flops(spec, *ctx.dims), dx.numel() * dx.element_size() + dy.numel() * dy.element_size()):
-                if ws is not None:
-                    L.check(lib.ekl_conv_bwd_data_ws(c, L.ptr(dy), L.ptr(w_dgrad), L.ptr(dx), L.ptr(ws), L.stream()))
-                else:
-                    L.check(lib.ekl_conv_bwd_data(c, L.ptr(dy), L.ptr(w_dgrad), L.ptr(dx), L.stream()))
-            _count(2 if ws is not None else 1)
+                _run_dgrad(spec, c, weight, dy, dx)
         dw = None
         if ctx.needs_input_grad[1] and not ctx.skip_wgrad:
             if ctx.w_leaf:
@@ -298,12 +319,10 @@ class _ConvBias9(torch.autograd.Function):
         dy = dy.contiguous()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            _, w_dgrad = spec.packed(weight)
             dx = torch.empty_like(x)
             _log("dgrad", "conv_tc", spec.mode, *ctx.dims, spec.cin, spec.cout, 0)
             with _prof("conv_tc_dgrad", _conv_flops(spec, *ctx.dims), dx.numel() * 2 + dy.numel() * 2):
-                L.check(lib.ekl_conv_bwd_data(c, L.ptr(dy), L.ptr(w_dgrad), L.ptr(dx), L.stream()))
-            _count()
+                _run_dgrad(spec, c, weight, dy, dx)
         if ctx.needs_input_grad[1]:
             buf = _grad_buffer(weight) if ctx.w_leaf else torch.zeros_like(weight, memory_format=torch.preserve_format)
             dw = None if ctx.w_leaf else buf

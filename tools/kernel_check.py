@@ -90,6 +90,14 @@ def run_group(group):
                     torch.cuda.synchronize()
                     e = rel(dx.permute(0, 3, 1, 2), xr.grad)
                     msg, ok = "rel %.2e" % e, e < 6e-3
+                    if impl == L.IMPL_TC and lib.ekl_conv_dgrad_from_fwd(conv):
+                        # same gradient from the FORWARD-packed filter (MN-major B operand)
+                        dx2 = torch.full((B, H, W, Cin), float("nan"), device=dev, dtype=torch.bfloat16)
+                        L.check(lib.ekl_conv_bwd_data_fw(conv, L.ptr(dyn), L.ptr(wf), L.ptr(dx2), None, L.stream()))
+                        torch.cuda.synchronize()
+                        e2 = rel(dx2.permute(0, 3, 1, 2), xr.grad)
+                        msg += " from-fwd %.2e" % e2
+                        ok = ok and e2 < 6e-3
                 else:
                     dw = torch.zeros(Cout, K, K, Cin, device=dev)
                     L.check(lib.ekl_conv_bwd_weight(conv, L.ptr(x), L.ptr(dyn), L.ptr(dw), L.stream()))
@@ -213,6 +221,13 @@ def run_split(torch, L, lib, dev, rel):
             e = rel(dx.permute(0, 3, 1, 2), xr.grad)
             ok = ok and e < 6e-3 and float(ws.abs().max()) == 0.0
             msg += " | dx %.1e" % e
+            if lib.ekl_conv_dgrad_from_fwd(conv):
+                dx2 = torch.full((B, H, W, Cin), float("nan"), device=dev, dtype=torch.bfloat16)
+                L.check(lib.ekl_conv_bwd_data_fw(conv, L.ptr(dyn), L.ptr(wf), L.ptr(dx2), L.ptr(ws), L.stream()))
+                torch.cuda.synchronize()
+                e2 = rel(dx2.permute(0, 3, 1, 2), xr.grad)
+                ok = ok and e2 < 6e-3 and float(ws.abs().max()) == 0.0
+                msg += " from-fwd %.1e" % e2
         print("%s tc_split mode%d B%d %dx%d %d>%d gb%d %s" % ("PASS" if ok else "FAIL", mode, B, H, W, Cin, Cout, gb, msg), flush=True)
         nfail += 0 if ok else 1
     return nfail
