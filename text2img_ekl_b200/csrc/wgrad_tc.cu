@@ -322,6 +322,157 @@ __global__ void __launch_bounds__(192) conv_wgrad_co_kernel(const __grid_constan
   if (warp == 1) tmem_dealloc<256>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Halo variant for the small-channel stride-1 3x3 layers (Cin in {16, 32}: ResBlocks / folded jointConv of stage 3,
+// image heads, discriminator stem): huge pixel count, tiny filter.  The generic kernel re-fetches the x tile for each of
+// the 9 taps and the dY tile for each (tap, channel-block) group; here a CTA walks 16-row x 8-column pixel tiles and per
+// tile loads ONE 18 x 10 halo box of x and ONE dY box.  Accumulator D[co 128 lanes][(tap, ci) 9*Cin columns] stays in
+// TMEM over all of the CTA's tiles (split-K over tiles across CTAs), so a tap is an MMA with
+//   A = dY tile        (pixel-major = MN-major, M = co; channels beyond Cout are TMA zero fill)
+//   B = x halo rows shifted by the tap offset (MN-major, N = Cin; UMMA descriptors swizzle on absolute address bits, so
+//       a row-shifted start inside the swizzled box is legal -- verified against the reference in conv_rw.cu's halo mode)
+// and the epilogue is the transposed-accumulator one: 16-byte red.global.add per lane into dw[co][tap][ci].
+struct WgHaloParams {
+  CUtensorMap x_map, y_map;
+  EklTap taps[9];
+  float* dw;
+  int Cin, Cout, nTh, nTw, tiles;
+};
+
+template <int CIN>
+struct WgHaloCfg {
+  static constexpr int ROWB = CIN * 2;
+  static constexpr int X_BYTES = ((180 * ROWB + 1023) / 1024) * 1024;
+  static constexpr int Y_BOX = 128 * 128;                  // [128 px][64 co]
+  static constexpr int STAGE_BYTES = X_BYTES + 2 * Y_BOX;
+  static constexpr int STAGES = 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 512;                    // 9 * CIN <= 288 columns used
+  static constexpr uint32_t X_LAYOUT = CIN == 32 ? 4u : 6u; // SW64 / SW32
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(192, 1) conv_wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
+  using C = WgHaloCfg<CIN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tmem_full = empty + C::STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grid = gridDim.x, cta = blockIdx.x;
+  const int ybox = p.Cout > 64 ? 2 : 1;
+  const bool has_tiles = cta < p.tiles;
+
+  // the second dY box is never written when Cout <= 64: zero it once so accumulator rows 64..127 stay finite
+  if (ybox == 1)
+    for (int s = 0; s < C::STAGES; ++s)
+      for (int i = threadIdx.x; i < C::Y_BOX / 16; i += 192)
+        reinterpret_cast<uint4*>(smem + s * C::STAGE_BYTES + C::X_BYTES + C::Y_BOX)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (has_tiles) {
+    if (warp == 0) {
+      if (elect_one()) {
+        tma_prefetch_desc(&p.x_map);
+        tma_prefetch_desc(&p.y_map);
+        uint32_t kit = 0;
+        for (int tile = cta; tile < p.tiles; tile += grid, ++kit) {
+          const int s = kit % C::STAGES;
+          const uint32_t ph = (kit / C::STAGES) & 1u;
+          int t = tile;
+          const int twi = t % p.nTw; t /= p.nTw;
+          const int thi = t % p.nTh; t /= p.nTh;
+          const int w0 = twi * 8, h0 = thi * 16, b0 = t;
+          mbar_wait(&empty[s], ph ^ 1u);
+          uint8_t* sx = smem + s * C::STAGE_BYTES;
+          mbar_expect_tx(&full[s], (uint32_t)(180 * C::ROWB + ybox * C::Y_BOX));
+          tma_load_4d(&p.x_map, &full[s], sx, 0, w0 - 1, h0 - 1, b0);
+          for (int j = 0; j < ybox; ++j) tma_load_4d(&p.y_map, &full[s], sx + C::X_BYTES + j * C::Y_BOX, j * 64, w0, h0, b0);
+        }
+      }
+    } else if (warp == 1) {
+      // The three taps of one filter row (dw = -1, 0, +1) are the SAME pixel rows shifted by one row each, so they are
+      // issued as ONE MMA with N = 3*CIN whose N-atoms are ROWB bytes apart (LBO = one pixel row: overlapping atoms);
+      // the dY operand is then read from shared memory 3 times per k-step instead of 9.
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 3 * CIN, 1, 1);
+      uint32_t kit = 0;
+      for (int tile = cta; tile < p.tiles; tile += grid, ++kit) {
+        const int s = kit % C::STAGES;
+        const uint32_t ph = (kit / C::STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sx = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint32_t sy = sx + C::X_BYTES;
+#pragma unroll 1
+          for (int j = 0; j < 8; ++j) {                       // 16 pixels = image rows 2j, 2j+1 of the tile
+            const uint64_t da = umma_desc(sy + j * 16 * 128, C::Y_BOX, 8 * 128, 2u);
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              // K rows of B: 8 pixels of halo row (2j + kh), halo column 0.., then the next halo row (SBO = 10 rows)
+              const uint64_t db = umma_desc(sx + (uint32_t)((2 * j + kh) * 10) * C::ROWB, C::ROWB, 10 * C::ROWB, C::X_LAYOUT);
+              tc_mma_bf16(tmem_base + (uint32_t)(kh * 3 * CIN), da, db, idesc, (kit | (uint32_t)j) != 0 ? 1u : 0u);
+            }
+          }
+          tc_commit(&empty[s]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) tc_commit(tmem_full);
+      __syncwarp();
+    } else {
+      // epilogue: lane = output channel; 9*CIN columns = (tap, ci); 32x32 blocks transposed through smem (free by now)
+      const int q = warp & 3;
+      float* stg = reinterpret_cast<float*>(smem) + q * (32 * 36);
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      const int rsub = lane >> 3, col = (lane & 7) * 4;
+      if (q * 32 < p.Cout) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < 9 * CIN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+          tmem_ld_wait();
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(stg + lane * 36 + i) =
+                make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+          __syncwarp();
+          // columns c0+col .. c0+col+3 belong to one tap (CIN is a multiple of 16 >= 16 and col % 4 == 0)
+          const int cc = c0 + col;
+          const bool in_range = cc < 9 * CIN;                  // CIN = 16: the last 32-column chunk is half used
+          const int t = in_range ? cc / CIN : 0, ci = cc - t * CIN;
+          const int src = p.taps[t].src[0];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int co = q * 32 + it * 4 + rsub;
+            if (in_range && co < p.Cout) {
+              const float4 v = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * 36 + col);
+              red_add_v4(p.dw + ((int64_t)co * 9 + src) * p.Cin + ci, v.x, v.y, v.z, v.w);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
 int make_map(CUtensorMap* m, const EklView& v, int boxC, int tw, int th, int tb, int swz) {
   uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)v.dW, (uint64_t)v.dH, (uint64_t)v.dB};
   uint64_t strides[3] = {(uint64_t)v.sW * 2, (uint64_t)v.sH * 2, (uint64_t)v.sB * 2};
@@ -404,9 +555,65 @@ static int wgrad_co(const EklGather* g, float* dw, cudaStream_t st) {
   return 0;
 }
 
+// halo variant: see conv_wgrad_halo_kernel
+static int wgrad_halo_ok(const EklGather* g) {
+  if (g->w_kcrs || g->nvar != 1 || g->ntaps != 9 || g->n_a != 1) return 0;
+  if (!(g->Cin == 16 || g->Cin == 32) || g->N % 16 != 0 || g->N > 128) return 0;
+  if (g->mH % 16 != 0 || g->mW % 8 != 0) return 0;
+  for (int t = 0; t < 9; ++t) {      // taps in (kh, kw) raster order: tap t reads pixel offset (t/3 - 1, t%3 - 1)
+    const EklTap& tp = g->taps[0][t];
+    if (tp.nsrc != 1 || tp.dh != t / 3 - 1 || tp.dw != t % 3 - 1) return 0;
+  }
+  return 1;
+}
+
+template <int CIN>
+static int launch_wgrad_halo(WgHaloParams& p, int grid, cudaStream_t st) {
+  using C = WgHaloCfg<CIN>;
+  auto kern = conv_wgrad_halo_kernel<CIN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EKL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  kern<<<grid, 192, C::SMEM_BYTES, st>>>(p);
+  EKL_LAUNCH_CHECK();
+  return 0;
+}
+
+static int wgrad_halo(const EklGather* g, float* dw, cudaStream_t st) {
+  WgHaloParams p;
+  memset(&p, 0, sizeof(p));
+  memcpy(p.taps, g->taps[0], sizeof(p.taps));
+  p.dw = dw; p.Cin = g->Cin; p.Cout = g->N;
+  p.nTh = g->mH / 16; p.nTw = g->mW / 8; p.tiles = g->mB * p.nTh * p.nTw;
+  {
+    const EklView& v = g->a[0];
+    uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)v.dW, (uint64_t)v.dH, (uint64_t)v.dB};
+    uint64_t strides[3] = {(uint64_t)v.sW * 2, (uint64_t)v.sH * 2, (uint64_t)v.sB * 2};
+    uint32_t box[4] = {(uint32_t)g->Cin, 10, 18, 1};
+    if (int rc = ekl_make_tmap(&p.x_map, v.base, 4, dims, strides, box, g->Cin == 32 ? 2 : 1, 2)) return rc;
+  }
+  {
+    const EklView& v = g->o[0];
+    uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)v.dW, (uint64_t)v.dH, (uint64_t)v.dB};
+    uint64_t strides[3] = {(uint64_t)v.sW * 2, (uint64_t)v.sH * 2, (uint64_t)v.sB * 2};
+    uint32_t box[4] = {64, 8, 16, 1};
+    if (int rc = ekl_make_tmap(&p.y_map, v.base, 4, dims, strides, box, 3, 2)) return rc;
+  }
+  int grid = ekl_num_sms();
+  if (grid > p.tiles) grid = p.tiles;
+  return g->Cin == 32 ? launch_wgrad_halo<32>(p, grid, st) : launch_wgrad_halo<16>(p, grid, st);
+}
+
 // fwd_plan: forward plan whose `o` views hold dY.  dw: master-layout fp32 gradient, ACCUMULATED into.
 int ekl_wgrad_tc(const EklGather* g, float* dw, cudaStream_t st) {
   EKL_REQUIRE(ekl_wgrad_tc_supported(g), "wgrad_tc: unsupported shape Cin=%d Cout=%d", g->Cin, g->N);
+  {
+    static int halo_on = -1;
+    if (halo_on < 0) { const char* e = getenv("EKL_DISABLE_WGRAD_HALO"); halo_on = (e && e[0] == '1') ? 0 : 1; }
+    if (halo_on && wgrad_halo_ok(g)) return wgrad_halo(g, dw, st);
+  }
   {
     static int co_on = -1;
     if (co_on < 0) { const char* e = getenv("EKL_DISABLE_WGRAD_CO"); co_on = (e && e[0] == '1') ? 0 : 1; }
