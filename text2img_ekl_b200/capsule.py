@@ -32,6 +32,11 @@ def _k():
     return L, L.lib()
 
 
+def _count(n=1):
+    from . import ops
+    ops._count(n)
+
+
 class _ProjU(torch.autograd.Function):
     """u[b,o,:] = W[o]^T v[b,o,:]"""
 
@@ -43,6 +48,7 @@ class _ProjU(torch.autograd.Function):
         W, v = W.contiguous(), v.contiguous()
         u = torch.empty(B, O, K, device=v.device)
         L.check(lib.ekl_caps_proj_u(L.ptr(W), L.ptr(v), B, O, Lh, K, L.ptr(u), L.stream()))
+        _count()
         ctx.save_for_backward(W, v)
         return u
 
@@ -57,6 +63,7 @@ class _ProjU(torch.autograd.Function):
         L.check(lib.ekl_caps_proj_s(L.ptr(W), L.ptr(gu), B, O, Lh, K, L.ptr(gv), None, L.stream()))      # gv = W gu
         gW = torch.zeros_like(W)
         L.check(lib.ekl_caps_outer(L.ptr(v), L.ptr(gu), B, O, Lh, K, L.ptr(gW), L.stream()))
+        _count(2)
         return gW, gv
 
 
@@ -72,6 +79,7 @@ class _SSquash(torch.autograd.Function):
         s = torch.empty(B, O, Lh, device=y.device)
         v = torch.empty(B, O, Lh, device=y.device)
         L.check(lib.ekl_caps_proj_s(L.ptr(W), L.ptr(y), B, O, Lh, K, L.ptr(s), L.ptr(v), L.stream()))
+        _count()
         ctx.save_for_backward(W, y, s)
         return v
 
@@ -86,6 +94,7 @@ class _SSquash(torch.autograd.Function):
         L.check(lib.ekl_caps_squash_bwd(L.ptr(W), L.ptr(s), L.ptr(gv), B, O, Lh, K, L.ptr(gs), L.ptr(gy), L.stream()))
         gW = torch.zeros_like(W)
         L.check(lib.ekl_caps_outer(L.ptr(gs), L.ptr(y), B, O, Lh, K, L.ptr(gW), L.stream()))
+        _count(2)
         return gW, gy
 
 
@@ -101,6 +110,7 @@ class _Agree(torch.autograd.Function):
         y = torch.empty(B, O, K, device=x.device)
         M, Z = torch.empty(B, I, device=x.device), torch.empty(B, I, device=x.device)
         L.check(lib.ekl_caps_agree_fwd(L.ptr(x), L.ptr(u), B, I, O, K, L.ptr(y), L.ptr(M), L.ptr(Z), L.stream()))
+        _count()
         ctx.save_for_backward(x, u, M, Z)
         return y
 
@@ -114,6 +124,7 @@ class _Agree(torch.autograd.Function):
         gu, gx = torch.empty_like(u), torch.empty_like(x)
         L.check(lib.ekl_caps_agree_bwd(L.ptr(x), L.ptr(u), L.ptr(M), L.ptr(Z), L.ptr(gy), B, I, O, K, L.ptr(gu), L.ptr(gx),
                                        L.stream()))
+        _count()
         return gx, gu
 
 
