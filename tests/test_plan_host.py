@@ -156,3 +156,43 @@ def test_joint_conv_fold_identity():
     q = cls_h.view(H, 1) * 3 + cls_w.view(1, W)                      # [H, W]
     got = F.conv2d(h, w[:, Cc:], padding=1) + bias9[:, q].permute(0, 3, 1, 2)
     assert torch.allclose(ref, got, atol=1e-4)
+
+
+def test_split_k_and_operand_planning_host_logic():
+    """Host-side planning that needs no GPU: which plans get a split-K workspace, which data-gradients can read the
+    forward-packed filter, and the statistics-row count of the workspace path (include/ekl_b200.h)."""
+    lib = L.lib()
+    mk = lambda mode, B, H, W, Cin, Cout, gb=0: L.EklConv(mode, B, H, W, Cin, Cout, gb, L.IMPL_TC, 0, 0, 0, L.W_KRSC)
+    # 4x4 discriminator tail, batch 24: 3 output tiles of 128 rows, contraction 9*2048 -> split
+    tail = mk(L.S1, 24, 4, 4, 2048, 1024, 24)
+    assert lib.ekl_conv_workspace_elems(tail, 0) == 24 * 16 * 1024
+    assert lib.ekl_conv_workspace_elems(tail, 1) == 24 * 16 * 2048
+    assert lib.ekl_conv_stats_rows_ws(tail) != lib.ekl_conv_stats_rows(tail)
+    # a layer that fills the machine is never split
+    big = mk(L.DOWN2, 72, 64, 64, 128, 256, 24)
+    assert lib.ekl_conv_workspace_elems(big, 0) == 0 and lib.ekl_conv_workspace_elems(big, 1) == 0
+    assert lib.ekl_conv_stats_rows_ws(big) == lib.ekl_conv_stats_rows(big)
+    # small-channel 3x3 layers run on the resident-filter kernel: no workspace, transposed operand still packed
+    res = mk(L.S1, 24, 128, 128, 32, 64, 24)
+    assert lib.ekl_conv_workspace_elems(res, 0) == 0
+    assert lib.ekl_conv_dgrad_from_fwd(res) == 0
+    # stride-1 / stride-2 convs with 64-multiple channels: data-gradient straight from the forward-packed filter
+    assert lib.ekl_conv_dgrad_from_fwd(tail) == 1 and lib.ekl_conv_dgrad_from_fwd(big) == 1
+    assert lib.ekl_conv_dgrad_from_fwd(mk(L.UP2, 24, 8, 8, 512, 512)) == 0          # pre-summed taps need their own pack
+
+
+def test_bn_counters_single_vector_add():
+    """engine.BnCounters: every num_batches_tracked becomes a view into one int64 tensor, the per-call increments are
+    tallied on the host and added once; state_dict keys / values stay those of nn.BatchNorm."""
+    from text2img_ekl_b200.engine import BnCounters
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4), torch.nn.BatchNorm2d(4))
+    net[1].num_batches_tracked.fill_(7)
+    bc = BnCounters([net])
+    assert net[1]._ekl_counted and int(net[1].num_batches_tracked) == 7
+    net[1]._ekl_calls += 3          # what ops.bn_act does per call (groups = 3)
+    net[2]._ekl_calls += 1
+    bc.flush()
+    bc.flush()                      # nothing pending: no-op
+    sd = net.state_dict()
+    assert int(sd["1.num_batches_tracked"]) == 10 and int(sd["2.num_batches_tracked"]) == 1
+    assert sd["1.num_batches_tracked"].dtype == torch.int64 and sd["1.num_batches_tracked"].dim() == 0
