@@ -135,3 +135,29 @@ def test_training_step_matches_oracle(name, B):
         report.append(("params %s (floor %.1e)" % (tag, f), r))
         assert r <= max(GRAD_SLACK * f, 3e-3), (name, tag, r, f)
     print("\n" + "\n".join("%-50s %.3e" % kv for kv in report))
+
+
+def test_eval_mode_generation_is_per_sample():
+    """Generation path (cub_trainer_splitz_cap_ca.py:776-911 evaluate(): netG.eval(), BatchNorm on running statistics):
+    runs through the same kernels (no statistics epilogue, eval-mode normalisation), is finite, and a sample's images do
+    not depend on what else is in the batch."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    tr, oc, orc, _ = build("splitz_cap_ca", 4)
+    dev = tr.device
+    b = synth.make_batch(oc, 4, "eval")
+    # one training step first so that the running statistics are not the initial (0, 1)
+    tr.train_step((b["imgs"], b["wrong_imgs"], b["embedding"], b["cls"], None),
+                  noise=b["noise"].to(dev), eps=b["eps"].to(dev), seed=b["seed"].to(dev))
+    netG = tr.netG.eval()
+    cls = torch.zeros(4, oc.ENTITY_DIM, device=dev)
+    cls[torch.arange(4), (b["cls"].long() - 1).to(dev)] = 1
+    args = [b["noise"].to(dev), b["embedding"].to(dev), cls]
+    kw = dict(eps=b["eps"].to(dev), seed=b["seed"].to(dev))
+    with torch.no_grad():
+        imgs4 = netG.image(netG(*args, **kw)[0])
+        imgs2 = netG.image(netG(*[a[:2] for a in args], **{k: v[:2] for k, v in kw.items()})[0])
+    torch.cuda.synchronize()
+    for i4, i2 in zip(imgs4, imgs2):
+        assert torch.isfinite(i4).all() and float(i4.abs().max()) <= 1.0
+        assert rel(i4[:2], i2) < 2e-3, rel(i4[:2], i2)
+    netG.train()
