@@ -193,9 +193,8 @@ class condGANTrainer(object):
         else:
             self.noise.copy_(noise)
         self.generate(eps, seed)
-        errDs = [None] * self.num_Ds
-        for i in reversed(range(self.num_Ds)):        # independent updates; largest first (engine.StepEngine.step)
-            errDs[i] = self.train_joint_Dnet(i, count)
+        # the discriminator updates are independent: engine.d_steps runs them as parallel stream branches
+        errDs = self.engine.d_steps(self.real_imgs, self.wrong_imgs, self.real_cp, self.fake_cp)
         errG = self.engine.g_step(self.real_cp)
         return errDs, errG
 

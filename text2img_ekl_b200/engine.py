@@ -10,6 +10,8 @@ What changes against the reference, with semantics preserved:
   * label tensors (one-hot / multi-hot normalisation) are built on the device.
 RNG draws (noise, CA eps, VC seed) can be injected for parity tests; otherwise they are drawn on the device.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -133,6 +135,9 @@ class StepEngine:
         self.allreduce = allreduce           # callable(flat_tensor) or None
         self.bn_counters = BnCounters([netG] + list(netsD))
         self.comm_stream, self._pending_comm = None, {}
+        # EKL_PARALLEL_D=0 runs the discriminators one after the other on the caller's stream
+        self.parallel_d = os.environ.get("EKL_PARALLEL_D", "1") != "0" and len(netsD) > 1
+        self.d_streams, self._on_d_stream = None, False
         self.d_logits = {}                   # idx -> (real, wrong, fake) x [match p, uncond p, class log-probs]
         self.uncond = float(cfg.TRAIN.COEFF.UNCOND_LOSS)
         self.kl_coeff = float(cfg.TRAIN.COEFF.KL)
@@ -208,7 +213,10 @@ class StepEngine:
         updates are independent: cub:594-596 loops over the discriminators); g_step joins the side stream before the
         updated discriminators are used."""
         grads, opt = self.gradsD[idx], self.optsD[idx]
-        if self.allreduce is None:
+        if self.allreduce is None or self._on_d_stream:
+            # (on a per-discriminator stream the all-reduce already overlaps the other discriminators' work)
+            if self.allreduce is not None:
+                self.allreduce(grads.flat)
             opt.step()
             return
         if self.comm_stream is None:
@@ -229,16 +237,63 @@ class StepEngine:
             if ev is not None:
                 torch.cuda.current_stream().wait_event(ev)
 
+    def _streams(self):
+        if self.d_streams is None:
+            self.d_streams = [torch.cuda.Stream() for _ in self.netsD]
+        return self.d_streams
+
+    def d_steps(self, real_imgs, wrong_imgs, real_cp, fake_cp):
+        """All discriminator updates of one iteration (cub:594-596).  They are independent of each other (own
+        parameters, gradients, optimiser; inputs are the detached fakes), so each runs on its own stream: the
+        latency-bound tails of one discriminator (4x4 / 8x8 maps: kernels of 50-150 CTAs) fill the SMs another one
+        leaves idle, and with several ranks its gradient all-reduce hides behind the others' compute.  Captured into the
+        step graph as parallel branches.  Returns the per-discriminator loss tuples in index order."""
+        n = len(self.netsD)
+        errDs = [None] * n
+        if not self.parallel_d:
+            for i in reversed(range(n)):          # largest first: its all-reduce (side stream) hides behind the others
+                errDs[i] = self.d_step(i, real_imgs[i], wrong_imgs[i], real_cp, fake_cp)
+            return errDs
+        main = torch.cuda.current_stream()
+        streams = self._streams()
+        self._on_d_stream = True
+        try:
+            for i in reversed(range(n)):
+                streams[i].wait_stream(main)
+                with torch.cuda.stream(streams[i]):
+                    errDs[i] = self.d_step(i, real_imgs[i], wrong_imgs[i], real_cp, fake_cp)
+        finally:
+            self._on_d_stream = False
+        for st in streams:
+            main.wait_stream(st)
+        return errDs
+
     # ---- (3) generator loss through the UPDATED discriminators: cub:463-490
     def g_loss(self, real_cp):
         self._join_comm()
         errGs_match = errGs_uncond = errGs_cls = errGs_total_fused = 0
         self.last_g_logits = []
+        main = torch.cuda.current_stream()
+        par = self.parallel_d and all(hasattr(d, "heads_raw") for d in self.netsD) and self.uncond > 0
+        per_d = []
+        if par:
+            # the discriminators judge their own stage's fake independently: one stream each (autograd replays every
+            # branch's backward on the stream of its forward), joined before the losses are summed
+            for i, netD in enumerate(self.netsD):
+                st = self._streams()[i]
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    lm, lu, lc = netD.heads_raw(self.fake_imgs[i], self.mu)
+                    per_d.append(ops.d_loss(lm, lu, lc, real_cp, None, 1, lm.shape[0], (1,), (1,), (0,), self.uncond))
+            for st in self._streams():
+                main.wait_stream(st)
         for i, netD in enumerate(self.netsD):
             if hasattr(netD, "heads_raw") and self.uncond > 0:
-                lm, lu, lc = netD.heads_raw(self.fake_imgs[i], self.mu)
-                B = lm.shape[0]
-                losses, pm, pu, logp = ops.d_loss(lm, lu, lc, real_cp, None, 1, B, (1,), (1,), (0,), self.uncond)
+                if par:
+                    losses, pm, pu, logp = per_d[i]
+                else:
+                    lm, lu, lc = netD.heads_raw(self.fake_imgs[i], self.mu)
+                    losses, pm, pu, logp = ops.d_loss(lm, lu, lc, real_cp, None, 1, lm.shape[0], (1,), (1,), (0,), self.uncond)
                 d = losses.detach()
                 errGs_match, errGs_uncond, errGs_cls = errGs_match + d[1], errGs_uncond + d[2], errGs_cls + d[3]
                 errGs_total_fused = errGs_total_fused + losses[0]
@@ -292,9 +347,7 @@ class StepEngine:
         self.generate(noise, txt, cls_cond, eps, seed)
         # the discriminator updates are independent (cub:594-596); the largest goes first so that its gradient
         # all-reduce + Adam (side stream, N > 1) hide behind the smaller ones' compute
-        errDs = [None] * len(self.netsD)
-        for i in reversed(range(len(self.netsD))):
-            errDs[i] = self.d_step(i, real_imgs[i], wrong_imgs[i], real_cp, fake_cp)
+        errDs = self.d_steps(real_imgs, wrong_imgs, real_cp, fake_cp)
         errG = self.g_step(real_cp)
         return errDs, errG
 
@@ -343,9 +396,7 @@ class GraphedStep:
         self.eps.normal_(0, 1)
         self.seed.normal_(0, 1)
         tr.generate(self.eps, self.seed)
-        errDs = [None] * tr.num_Ds
-        for i in reversed(range(tr.num_Ds)):          # largest discriminator first (see StepEngine.step)
-            errDs[i] = tr.train_joint_Dnet(i, 1)
+        errDs = tr.engine.d_steps(tr.real_imgs, tr.wrong_imgs, tr.real_cp, tr.fake_cp)
         errG = tr.engine.g_step(tr.real_cp)
         return torch.stack([torch.stack([x.detach().float() for x in e]) for e in errDs]), \
             torch.stack([x.detach().float() for x in errG])
