@@ -161,3 +161,44 @@ def test_eval_mode_generation_is_per_sample():
         assert torch.isfinite(i4).all() and float(i4.abs().max()) <= 1.0
         assert rel(i4[:2], i2) < 2e-3, rel(i4[:2], i2)
     netG.train()
+
+
+def _graphed(parallel, monkeypatch):
+    from text2img_ekl_b200.engine import GraphedStep
+    from text2img_ekl_b200.synthetic import SyntheticLoader
+    monkeypatch.setenv("EKL_PARALLEL_D", "1" if parallel else "0")
+    tr, _, _, _ = build("3stages", 4)
+    assert tr.engine.parallel_d == parallel
+    pool = SyntheticLoader(4, getattr(tr, "CLS_KIND", "index"), pool=3).pool
+    torch.manual_seed(77)
+    return tr, GraphedStep(tr, pool[0], warmup=1), pool
+
+
+def test_graphed_step_parallel_branches_match_serial_and_prefetch(monkeypatch):
+    """The captured step (engine.GraphedStep: the bench / production path).  (1) Running the discriminator updates and
+    the generator-loss discriminator passes as parallel stream branches must not change the result: same weights, same
+    batches, same device RNG seed -> the losses of every replay agree with the serial-order capture (only fp32 atomic
+    summation order differs; a missing dependency between branches would show up as an O(1) difference).  (2) A batch
+    uploaded ahead of time through prefetch() reaches the graph's input buffers intact."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    outs = []
+    for parallel in (True, False):
+        tr, gs, pool = _graphed(parallel, monkeypatch)
+        torch.manual_seed(5)
+        seq = []
+        for k in range(3):
+            errDs, errG = gs.step(pool[k % 3], pool[(k + 1) % 3])
+            seq.append((errDs.clone(), errG.clone()))
+        torch.cuda.synchronize()
+        # step 2 consumed pool[2] from the staging buffers; pool[0] is staged for a fourth call
+        nxt = pool[2]
+        for i in range(tr.num_Ds):
+            assert torch.equal(gs.s_imgs[i].cpu(), nxt[0][i]) and torch.equal(gs.s_wrong[i].cpu(), nxt[1][i])
+        assert torch.equal(gs.s_emb.cpu(), nxt[2]) and torch.equal(gs.s_cls.cpu(), nxt[3])
+        assert gs._staged is pool[0] and torch.equal(gs._stage[0].cpu(), pool[0][0][0])
+        outs.append((seq, [p.detach().clone() for p in tr.netG.parameters()]))
+        assert all(torch.isfinite(d).all() and torch.isfinite(g).all() for d, g in seq)
+    for k, ((dp, gp), (ds, gs_)) in enumerate(zip(outs[0][0], outs[1][0])):
+        assert rel(dp, ds) < 2e-2 and rel(gp, gs_) < 2e-2, (k, rel(dp, ds), rel(gp, gs_))
+    pa, pb = torch.cat([p.flatten() for p in outs[0][1]]), torch.cat([p.flatten() for p in outs[1][1]])
+    assert rel(pa, pb) < 1e-2, rel(pa, pb)
