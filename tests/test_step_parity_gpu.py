@@ -202,3 +202,25 @@ def test_graphed_step_parallel_branches_match_serial_and_prefetch(monkeypatch):
         assert rel(dp, ds) < 2e-2 and rel(gp, gs_) < 2e-2, (k, rel(dp, ds), rel(gp, gs_))
     pa, pb = torch.cat([p.flatten() for p in outs[0][1]]), torch.cat([p.flatten() for p in outs[1][1]])
     assert rel(pa, pb) < 1e-2, rel(pa, pb)
+
+
+def test_train_loop_captures_after_eager_steps():
+    """condGANTrainer.train() (cub:492-672), the call a user of the reference makes: two eager iterations, then one
+    capture (which must execute nothing) and graph replays for the rest.  Every BatchNorm of the generator is applied
+    once per iteration, so its num_batches_tracked counts iterations exactly: 2 eager + 4 replays = 6."""
+    from text2img_ekl_b200 import configs
+    from text2img_ekl_b200.synthetic import SyntheticLoader
+    torch.backends.cuda.matmul.allow_tf32 = False
+    Trainer = configs.setup("catcls", batch=4)
+    loader = SyntheticLoader(4, getattr(Trainer, "CLS_KIND", "index"), pool=3, length=6)
+    tr = Trainer(None, loader, 64)
+    tr.max_epoch = 1
+    tr.train()
+    torch.cuda.synchronize()
+    assert getattr(tr, "_graphed", None) is not None and tr._eager_done == 2
+    bns = [m for m in tr.netG.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
+    assert bns and all(int(m.num_batches_tracked) == 6 for m in bns), [int(m.num_batches_tracked) for m in bns]
+    for net in [tr.netG] + list(tr.netsD):
+        assert all(torch.isfinite(p).all() for p in net.parameters())
+    errDs, errG = tr._graphed.out
+    assert torch.isfinite(errDs).all() and torch.isfinite(errG).all()

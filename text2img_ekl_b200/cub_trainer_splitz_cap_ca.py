@@ -198,16 +198,49 @@ class condGANTrainer(object):
         errG = self.engine.g_step(self.real_cp)
         return errDs, errG
 
+    EAGER_STEPS_BEFORE_CAPTURE = 2
+
+    def _loop_step(self, data, nxt, count):
+        """One iteration of train()'s loop.  On a GPU the first EAGER_STEPS_BEFORE_CAPTURE batches run eagerly (they
+        initialise the library handles and buffers that must exist before a capture), then the whole step is captured
+        once (engine.GraphedStep; the capture itself executes nothing) and every following full-size batch is one graph
+        replay with the next batch's upload hidden behind it.  Batches of another shape (a loader without drop_last;
+        the reference uses drop_last=True, main.py:135) take the eager path.  EKL_GRAPH=0 keeps everything eager."""
+        if self.device.type == "cuda" and os.environ.get("EKL_GRAPH", "1") != "0":
+            gs = getattr(self, "_graphed", None)
+            if gs is None and getattr(self, "_eager_done", 0) >= self.EAGER_STEPS_BEFORE_CAPTURE:
+                from .engine import GraphedStep
+                gs = self._graphed = GraphedStep(self, data, warmup=0)
+            if gs is not None and gs.accepts(data):
+                return gs.step(data, nxt if nxt is not None and gs.accepts(nxt) else None)
+        self._eager_done = getattr(self, "_eager_done", 0) + 1
+        return self.train_step(data, count)
+
     def train(self):
+        """cub:492-672.  On a GPU the loop runs on a side stream: autograd pins each parameter's gradient accumulation to
+        the stream of its first use, and work pinned to the legacy default stream cannot be captured into a graph."""
+        if getattr(self, "device", None) is None or torch.device(self.device).type != "cuda":
+            return self._train_loop()
+        cur, side = torch.cuda.current_stream(), torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self._train_loop()
+        cur.wait_stream(side)
+
+    def _train_loop(self):
         start_count = self.setup()
         count = start_count
         start_epoch = start_count // max(self.num_batches, 1)
         for epoch in range(start_epoch, self.max_epoch):
             start_t = time.time()
             errDs = errG = None
-            for step, data in enumerate(self.data_loader, 0):
-                errDs, errG = self.train_step(data, count)
+            it = iter(self.data_loader)
+            data = next(it, None)
+            while data is not None:
+                nxt = next(it, None)
+                errDs, errG = self._loop_step(data, nxt, count)
                 count += 1
+                data = nxt
             if errG is None:
                 break
             end_t = time.time()

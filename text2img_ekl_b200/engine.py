@@ -395,7 +395,8 @@ class GraphedStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = ops.LAUNCHES[0]
-        with torch.cuda.graph(self.graph):
+        # thread_local: a DataLoader's pin-memory thread may allocate page-locked memory while the capture is open
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.out = self._body()
         self.launches_per_step = ops.LAUNCHES[0] - n0
         torch.cuda.synchronize()
@@ -424,6 +425,13 @@ class GraphedStep:
     def replay(self):
         self.graph.replay()
         return self.out
+
+    def accepts(self, data):
+        """True when the host batch has the shapes / dtypes the graph was captured for."""
+        imgs, wrong, emb, cls, _ = data
+        n = self.tr.num_Ds
+        srcs = [imgs[i] for i in range(n)] + [wrong[i] for i in range(n)] + [emb, cls]
+        return all(s.shape == d.shape and s.dtype == d.dtype for s, d in zip(srcs, self._stage))
 
     def prefetch(self, data):
         """Start the host->device copy of a FUTURE batch on the copy stream into the staging buffers; it overlaps the
