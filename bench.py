@@ -119,6 +119,46 @@ def cpu_step_rate(config, batch, steps, warmup, budget_s, threads=None):
     return batch / t, kind, cores, "%d timed step(s) of batch %d (full reference step, fp32 torch CPU), %.2f s/step" % (len(times), batch, t), t
 
 
+def gpu_eager_rate(config, batch, steps=3, warmup=2):
+    """The reference's step as plain PyTorch eager ops on this GPU (cuDNN / cuBLAS kernels, fp32 NCHW): the oracle port
+    with every tensor on the device -- what a user of the unmodified reference gets from a B200 ("the real bar
+    to beat").  'stock' = torch's default precision flags (TF32 allowed for cuDNN convolutions, fp32 matmuls);
+    'strict_fp32' = TF32 off everywhere.  A reported baseline like cpu_baseline, never part of the product path."""
+    import torch
+    from oracle import configs as ocfg, shapes, synth
+    from oracle.ekl_oracle import OracleTrainer
+    dev = torch.device("cuda", torch.cuda.current_device())
+    oc = ocfg.oracle_cfg(config, batch=batch)
+    to_dev = lambda v: [t.to(dev) for t in v] if isinstance(v, (list, tuple)) else (v.to(dev) if torch.is_tensor(v) else v)
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    res = {}
+    try:
+        for mode, conv_tf32 in (("stock", True), ("strict_fp32", False)):
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = conv_tf32, False
+            gsh = shapes.g_shapes(oc, cond_dim=ocfg.cond_dim(oc))
+            dsh = [shapes.d_shapes(oc, r, True, oc.D_CAPSULE) for r in [64, 128, 256][: oc.BRANCH_NUM]]
+            on_dev = lambda sd: {k: v.to(dev) for k, v in sd.items()}
+            stepper = OracleTrainer(oc, on_dev(shapes.make_state_dict(gsh, "G")),
+                                    [on_dev(shapes.make_state_dict(s, "D%d" % i)) for i, s in enumerate(dsh)])
+            b = {k: to_dev(v) for k, v in synth.make_batch(oc, batch, "bench").items()}
+            for _ in range(warmup):
+                stepper.step(**b)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                stepper.step(**b)
+            e1.record()
+            torch.cuda.synchronize()
+            res[mode] = batch / (e0.elapsed_time(e1) / steps * 1e-3)
+            del stepper, b
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    return {"unit": UNIT, "kind": "port, torch eager on cuda:0 (cuDNN / cuBLAS, fp32 NCHW)", "batch": batch,
+            "sample": "%d timed steps after %d warm-up" % (steps, warmup), **res}
+
+
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -259,6 +299,11 @@ def run_ours(a):
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %s" % ex}
+    if rank == 0 and ws == 1 and not a.no_cpu:
+        try:
+            line["gpu_eager_baseline"] = gpu_eager_rate(a.config, B)
+        except Exception as ex:  # noqa: BLE001
+            line["gpu_eager_baseline"] = {"unit": UNIT, "failed": str(ex)[:200]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if ws > 1:

@@ -360,8 +360,8 @@ def mean_covariance(img):
 
 def onehot(cls, n):
     """cub:322-331."""
-    out = torch.zeros(cls.shape[0], n)
-    out[torch.arange(cls.shape[0]), cls] = 1
+    out = torch.zeros(cls.shape[0], n, device=cls.device)
+    out[torch.arange(cls.shape[0], device=cls.device), cls] = 1
     return out
 
 
@@ -378,7 +378,7 @@ def d_loss(real, wrong, fake, real_cp, fake_cp, cfg):
         e_unc = u * bce(real[1], 1) + u * bce(wrong[1], 1) + u * bce(fake[1], 0)     # wrong -> REAL (cub:430)
         e_cls = ce_loss(real[2], real_cp) + ce_loss(fake[2], fake_cp)
         return e_match + e_unc + e_cls, e_match, e_unc, e_cls
-    z = torch.zeros(())
+    z = torch.zeros((), device=real[0].device)
     return bce(real[0], 1) + 0.5 * (bce(wrong[0], 0) + bce(fake[0], 0)), e_match, z, z
 
 
@@ -436,7 +436,7 @@ class OracleTrainer:
             cls_multi = cls.float()
             real_cp = cls_multi / cls_multi.sum(1).view(-1, 1)
             cls_onehot = cls_multi
-        fake_cp = torch.zeros(B, E + 1)
+        fake_cp = torch.zeros(B, E + 1, device=embedding.device)
         fake_cp[:, -1] = 1                                                                # cub:520-521
         out["real_cp"], out["fake_cp"], out["cls_onehot"] = real_cp, fake_cp, cls_onehot
         # (1) generate: cub:567-587
@@ -481,7 +481,7 @@ class OracleTrainer:
         errG.backward()
         out["gradG"] = {k: p.grad.clone() for k, p in self.pG.items() if p.grad is not None}
         self.optG.step()
-        z = torch.zeros(())
+        z = torch.zeros((), device=errG.device)
         out["errG"] = torch.stack([errG.detach(), (e_match + z).detach(), (e_unc + z).detach(), (e_cls + z).detach()]
                                   + [k.detach() for k in kl])
         return out
