@@ -135,6 +135,14 @@ int ekl_img_s2d_bwd(const void* dxs, int B, int H, int W, float* dx, void* strea
 int ekl_head_tanh_fwd(const void* y, int B, int HW, int C, float* img, void* stream);
 int ekl_head_tanh_bwd(const void* y, const float* dimg, int B, int HW, int C, void* dy, void* stream);
 
+/* ---------------------------------------------------------------- colour-consistency statistics -----------
+ * compute_mean_covariance (cub_trainer_splitz_cap_ca.py:33-52): img fp32 NCHW [B,3,HW] -> mean [B,3] and channel
+ * covariance [B,3,3] (divided by HW).  `scratch`: 9*B doubles of caller workspace (zeroed here).  HW % 4 == 0.
+ * The backward pass takes the gradients of both outputs (either may be NULL) and writes dimg [B,3,HW]. */
+int ekl_color_stats_fwd(const float* img, int B, int HW, double* scratch, float* mean, float* cov, void* stream);
+int ekl_color_stats_bwd(const float* img, const float* mean, const float* dmean, const float* dcov, int B, int HW,
+                        float* dimg, void* stream);
+
 /* ---------------------------------------------------------------- discriminator heads + GAN losses -----------
  * Heads: `logits` / `uncond_logits` = Conv2d(8ndf, 1, 4, stride 4) + Sigmoid on the 4x4 code map (model.py:886-888,
  * 935-952) == one dot of length K = 16*8ndf per sample.  x_code / h_c: bf16 [GB][K] (NHWC-flattened trunk output /

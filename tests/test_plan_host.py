@@ -196,3 +196,80 @@ def test_bn_counters_single_vector_add():
     sd = net.state_dict()
     assert int(sd["1.num_batches_tracked"]) == 10 and int(sd["2.num_batches_tracked"]) == 1
     assert sd["1.num_batches_tracked"].dtype == torch.int64 and sd["1.num_batches_tracked"].dim() == 0
+
+
+def test_generation_image_writers(tmp_path):
+    """evaluate()'s output side (cub:733-775): uint8 conversion truncates like the reference's .byte(); the tile sheet
+    equals torchvision's save_image(nrow=10, normalize=True) pixels; file names follow the reference's pattern."""
+    import numpy as np
+    from PIL import Image
+    from torchvision.utils import make_grid
+    from text2img_ekl_b200 import cub_trainer_splitz_cap_ca as T
+    g = torch.Generator().manual_seed(3)
+    imgs = torch.rand(13, 3, 16, 16, generator=g) * 2.4 - 1.2          # beyond [-1, 1]: the clamp matters
+    ref = imgs.add(1).div(2).mul(255).clamp(0, 255).byte().permute(0, 2, 3, 1)
+    assert torch.equal(T.to_uint8_nhwc(imgs), ref)
+    want = make_grid(imgs, nrow=10, padding=2, normalize=True).mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to(torch.uint8)
+    assert torch.equal(T.image_grid_uint8(imgs, nrow=10), want)
+    keys = ["001.Bird/a_%d" % i for i in range(4)]
+    T.condGANTrainer.save_singleimages(None, imgs[:4], keys, str(tmp_path), "test", 2, torch.tensor([5, 6, 7, 8]), 16, 0)
+    f = tmp_path / "single_samples" / "001.Bird" / "a_1_16_class6_sid2_nid0.png"
+    assert f.exists() and np.array_equal(np.asarray(Image.open(f)), ref[1].numpy())
+    T.condGANTrainer.save_superimages(None, [imgs[:4], imgs[4:8], imgs[8:12]], keys, str(tmp_path), "test", 16)
+    sheet = np.asarray(Image.open(tmp_path / "super" / "test" / "001.Bird" / "a_3_16.png"))
+    assert sheet.shape == (2 + 18, 2 + 3 * 18, 3)
+    assert np.array_equal(sheet, T.image_grid_uint8(torch.stack([imgs[3], imgs[7], imgs[11]])).numpy())
+
+
+def test_evaluate_control_flow_with_stub_generator(tmp_path, monkeypatch):
+    """evaluate() (cub:776-911) host logic on the CPU with a stand-in generator: snapshot loading with the 'module.'
+    prefix, one noise draw per batch, one generation per sentence embedding (at most 10), zero-based class one-hots,
+    single-PNG and tile-sheet outputs, image count.  (The real generator under evaluate() runs in the GPU suite.)"""
+    import numpy as np
+    from PIL import Image
+    from text2img_ekl_b200 import configs, cub_trainer_splitz_cap_ca as T, model
+    from text2img_ekl_b200.miscc.config import cfg
+    Trainer = configs.setup("splitz_cap_ca", batch=3)
+    calls = []
+
+    class StubG(model.COND_G_NET_CATZ_CA):
+        def __init__(self):
+            torch.nn.Module.__init__(self)
+            self.w = torch.nn.Parameter(torch.ones(1))
+
+        def forward(self, noise, sen, cls=None, cls_prior=None, eps=None, seed=None):
+            calls.append((noise.clone(), sen.clone(), None if cls is None else cls.clone(), self.training))
+            return [sen[:, :3].reshape(-1, 3, 1, 1) * self.w], 0, 0, 0, 0, 0, 0
+
+        def image(self, hcodes):
+            h = torch.tanh(hcodes[0])
+            return [h.expand(-1, 3, 64, 64).contiguous(), (h.expand(-1, 3, 128, 128) * torch.linspace(-1, 1, 128)).contiguous()]
+
+    monkeypatch.setattr(T, "build_G", lambda use_cap=None: (StubG(), None))
+    monkeypatch.setattr(model, "to_kernel_layout", lambda net: net)
+    torch.save({"module.w": torch.full((1,), 2.0)}, tmp_path / "netG_epoch7.pth")
+    g = torch.Generator().manual_seed(1)
+    batches = [([torch.zeros(3, 3, 64, 64)], torch.randn(3, 12, cfg.TEXT.DIMENSION, generator=g),
+                torch.tensor([1, 5, 200]), ["c%d/k%d" % (b, i) for i in range(3)]) for b in range(2)]
+    ev = object.__new__(Trainer)
+    ev.device, ev.data_loader, ev.num_batches, ev.batch_size = torch.device("cpu"), batches, 2, 3
+    try:
+        cfg.TRAIN.NET_G = str(tmp_path / "netG_epoch7.pth")
+        cfg.TEST.B_EXAMPLE = False
+        n = ev.evaluate("test", save_dir=str(tmp_path / "o1"))
+        assert n == 2 * 10 * 3 and len(calls) == 20
+        assert all(not c[3] for c in calls)                                        # cfg.TEST.EVAL_MODE -> eval()
+        assert all(torch.equal(calls[i][0], calls[0][0]) for i in range(10)) and not torch.equal(calls[10][0], calls[0][0])
+        assert torch.equal(calls[3][1], batches[0][1][:, 3]) and torch.equal(calls[13][1], batches[1][1][:, 3])
+        assert calls[0][2].shape == (3, cfg.GAN.ENTITY_DIM) and calls[0][2].argmax(1).tolist() == [0, 4, 199]
+        files = sorted(p.name for p in (tmp_path / "o1" / "single_samples" / "c0").glob("*.png"))
+        assert len(files) == 30 and "k1_128_class4_sid9_nid0.png" in files
+        assert np.asarray(Image.open(tmp_path / "o1" / "single_samples" / "c1" / "k2_128_class199_sid0_nid0.png")).shape == (128, 128, 3)
+        cfg.TEST.B_EXAMPLE = True
+        assert ev.evaluate("test", save_dir=str(tmp_path / "o2")) == 60
+        sheet = np.asarray(Image.open(tmp_path / "o2" / "super" / "test" / "c0" / "k0_128.png"))
+        assert sheet.shape == (2 + 130, 2 + 10 * 130, 3)
+        assert "Testset_evalmode_fixednoise_epoch7_" in ev._eval_save_dir()
+    finally:
+        cfg.TRAIN.NET_G = ""
+        cfg.TEST.B_EXAMPLE = True

@@ -199,7 +199,10 @@ def test_graphed_step_parallel_branches_match_serial_and_prefetch(monkeypatch):
         outs.append((seq, [p.detach().clone() for p in tr.netG.parameters()]))
         assert all(torch.isfinite(d).all() and torch.isfinite(g).all() for d, g in seq)
     for k, ((dp, gp), (ds, gs_)) in enumerate(zip(outs[0][0], outs[1][0])):
-        assert rel(dp, ds) < 2e-2 and rel(gp, gs_) < 2e-2, (k, rel(dp, ds), rel(gp, gs_))
+        # fp32 atomic summation order differs between the two schedules and GAN training at batch 4 amplifies it from
+        # replay to replay (observed: up to 2.1 % on the loss vectors by the third replay); a branch running ahead of
+        # its inputs gives O(1) differences or NaNs
+        assert rel(dp, ds) < 1e-1 and rel(gp, gs_) < 1e-1, (k, rel(dp, ds), rel(gp, gs_))
     pa, pb = torch.cat([p.flatten() for p in outs[0][1]]), torch.cat([p.flatten() for p in outs[1][1]])
     assert rel(pa, pb) < 1e-2, rel(pa, pb)
 
@@ -224,3 +227,95 @@ def test_train_loop_captures_after_eager_steps():
         assert all(torch.isfinite(p).all() for p in net.parameters())
     errDs, errG = tr._graphed.out
     assert torch.isfinite(errDs).all() and torch.isfinite(errG).all()
+
+
+def test_checkpoint_resume_restores_networks_and_adam_moments(tmp_path, monkeypatch):
+    """save_checkpoint / load_checkpoint restore networks AND Adam moments in place.  After three
+    iterations the next update (same batch, same injected noise) is taken twice, the second time after restoring the
+    checkpoint: parameters are restored bit-exactly and the update is reproduced up to the chaotic amplification of
+    fp32 summation order at batch 4 (observed 5.7 %); with zeroed moments and step count Adam's first-step update
+    lr*sign(g) would differ from lr*m/sqrt(v) by O(1)."""
+    from text2img_ekl_b200 import configs
+    from text2img_ekl_b200.miscc.config import cfg
+    from text2img_ekl_b200.synthetic import SyntheticLoader
+    torch.backends.cuda.matmul.allow_tf32 = False
+    monkeypatch.setenv("EKL_GRAPH", "0")
+    Trainer = configs.setup("splitz_cap_ca", batch=4)
+    loader = SyntheticLoader(4, "index", pool=2, length=3)
+    tr = Trainer(None, loader, 64)
+    tr.max_epoch = 1
+    tr.train()                                     # three eager iterations: running statistics and Adam moments exist
+    dev = tr.device
+    nets = [tr.netG] + list(tr.netsD)
+    flat = lambda: torch.cat([p.detach().flatten() for n in nets for p in n.parameters()]).clone()
+    tr.save_checkpoint(str(tmp_path / "ck.pth"), 3)
+    p0 = flat()
+    g = torch.Generator(device="cpu").manual_seed(21)
+    inj = dict(noise=torch.randn(4, cfg.GAN.Z_DIM, generator=g).to(dev), eps=torch.randn(4, cfg.GAN.EMBEDDING_DIM, generator=g).to(dev),
+               seed=torch.randn(4, cfg.GAN.MANIFD_DIM, generator=g).to(dev))
+    tr.train_step(loader.pool[0], **inj)
+    da = flat() - p0
+    assert float(da.abs().max()) > 0
+    assert tr.load_checkpoint(str(tmp_path / "ck.pth")) == 3
+    assert torch.equal(flat(), p0)
+    tr.train_step(loader.pool[0], **inj)
+    db = flat() - p0
+    assert rel(db, da) < 0.25, rel(db, da)
+
+
+def test_color_statistics_kernel_and_consistency_loss():
+    """compute_mean_covariance (cub:33-52; the oracle's restatement of it is pinned to the reference in
+    tests/test_oracle_golden.py) as a kernel: forward and gradient against the same formula in float64, including a
+    nearly flat image where raw moments would cancel; then the colour-consistency term the generator loss assembles
+    from it when COEFF.COLOR_LOSS > 0 (engine.StepEngine.color_consistency)."""
+    from text2img_ekl_b200 import configs, engine, ops
+    from text2img_ekl_b200.miscc.config import cfg
+    from text2img_ekl_b200.synthetic import SyntheticLoader
+    dev = torch.device("cuda", 0)
+
+    def formula(x):
+        b, c, h, w = x.shape
+        mu = x.mean(2, keepdim=True).mean(3, keepdim=True)
+        d = (x - mu).reshape(b, c, h * w)
+        return mu, torch.bmm(d, d.transpose(1, 2)) / (h * w)
+
+    g = torch.Generator().manual_seed(4)
+    cases = [(torch.rand(4, 3, 64, 64, generator=g) * 2 - 1) * torch.rand(4, 3, 1, 1, generator=g) + 0.3 * torch.randn(4, 3, 1, 1, generator=g),
+             torch.rand(3, 3, 128, 128, generator=g) * 2 - 1, torch.tanh(2 * torch.randn(2, 3, 256, 256, generator=g)),
+             0.7 + 1e-3 * torch.randn(2, 3, 64, 64, generator=g)]
+    for x0 in cases:
+        x = x0.to(dev).contiguous().requires_grad_(True)
+        assert ops.color_stats_supported(x)
+        mu, cov = engine.compute_mean_covariance(x)
+        xr = x0.to(dev).double().requires_grad_(True)
+        mur, covr = formula(xr)
+        assert mu.shape == mur.shape and cov.shape == covr.shape
+        assert rel(mu, mur) < 1e-5 and rel(cov, covr) < 1e-4, (rel(mu, mur), rel(cov, covr))
+        gm, gc = torch.randn(mu.shape, generator=g).to(dev), torch.randn(cov.shape, generator=g).to(dev)
+        ((mu * gm).sum() + (cov * gc).sum()).backward()
+        ((mur * gm.double()).sum() + (covr * gc.double()).sum()).backward()
+        assert rel(x.grad, xr.grad) < 1e-4, rel(x.grad, xr.grad)
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    Trainer = configs.setup("3stages", batch=4)
+    try:
+        cfg.TRAIN.COEFF.COLOR_LOSS = 1.0
+        tr = Trainer(None, None, 64)
+        tr.setup()
+        assert tr.engine.color_coeff == 1.0
+        batch = SyntheticLoader(4, getattr(tr, "CLS_KIND", "index"), pool=1).pool[0]
+        errDs, errG = tr.train_step(batch)
+        torch.cuda.synchronize()
+        assert len(tr.engine.last_color) == 2
+        want = 0.0
+        for i in (1, 2):
+            (m1, c1), (m2, c2) = formula(tr.engine.fake_imgs[i].detach().double()), formula(tr.engine.fake_imgs[i - 1].detach().double())
+            lm, lc = float(((m1 - m2) ** 2).mean()), 5 * float(((c1 - c2) ** 2).mean())
+            got_m, got_c = (float(v) for v in tr.engine.last_color[i - 1])
+            assert abs(got_m - lm) <= 1e-3 * abs(lm) + 1e-9 and abs(got_c - lc) <= 1e-3 * abs(lc) + 1e-9, (i, got_m, lm, got_c, lc)
+            want += lm + lc
+        parts = float(errG[1]) + float(errG[2]) + float(errG[3]) + cfg.TRAIN.COEFF.KL * sum(float(k) for k in errG[4:])
+        assert abs(float(errG[0]) - parts - want) <= 2e-3 * abs(float(errG[0])) + 1e-6, (float(errG[0]), parts, want)
+        assert all(torch.isfinite(p).all() for p in tr.netG.parameters())
+    finally:
+        cfg.TRAIN.COEFF.COLOR_LOSS = 0.0

@@ -62,6 +62,8 @@ SIGNATURES = {
     "ekl_img_s2d_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "ekl_head_tanh_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "ekl_head_tanh_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "ekl_color_stats_fwd": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "ekl_color_stats_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "ekl_dhead_dots": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "ekl_dhead_dots_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_dloss_fwd": (_i, [_i, _i, _i, _ip, _ip, _ip, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -88,7 +88,133 @@ __global__ void __launch_bounds__(256) head_tanh_bwd_kernel(const bf16* __restri
   }
 }
 
+// Colour statistics of an image batch (cub_trainer_splitz_cap_ca.py:33-52 compute_mean_covariance): per image the
+// channel mean mu[3] and the channel covariance cov[3][3] = (1/HW) sum_p (x_p - mu)(x_p - mu)^T.  HBM-bound: every
+// pixel is read exactly once.  Pass 1 accumulates, per image, the first and second moments of y = x - s with the shift
+// s = the image's first pixel (kills the cancellation of raw moments on nearly flat images): fp32 per thread (<= 64
+// pixels), warp shuffles, then one fp64 atomic per block and moment.  acc[b] = {sum y_c (3), sum y_i y_j (i <= j: 6)}.
+__global__ void __launch_bounds__(256) color_moments_kernel(const float* __restrict__ img, int HW, double* __restrict__ acc) {
+  const int b = blockIdx.y;
+  const float* x = img + (int64_t)b * 3 * HW;
+  const float s0 = x[0], s1 = x[HW], s2 = x[2 * (int64_t)HW];
+  float m[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) m[k] = 0.f;
+  const int n4 = HW / 4;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n4; i += gridDim.x * 256) {
+    const float4 a = reinterpret_cast<const float4*>(x)[i];
+    const float4 c = reinterpret_cast<const float4*>(x + HW)[i];
+    const float4 d = reinterpret_cast<const float4*>(x + 2 * (int64_t)HW)[i];
+    const float r[4] = {a.x - s0, a.y - s0, a.z - s0, a.w - s0};
+    const float g[4] = {c.x - s1, c.y - s1, c.z - s1, c.w - s1};
+    const float u[4] = {d.x - s2, d.y - s2, d.z - s2, d.w - s2};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      m[0] += r[k]; m[1] += g[k]; m[2] += u[k];
+      m[3] += r[k] * r[k]; m[4] += r[k] * g[k]; m[5] += r[k] * u[k];
+      m[6] += g[k] * g[k]; m[7] += g[k] * u[k]; m[8] += u[k] * u[k];
+    }
+  }
+  __shared__ float part[8][9];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float v = warp_sum(m[k]);
+    if (lane == 0) part[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += (double)part[w][threadIdx.x];
+    atomicAdd(acc + (int64_t)b * 9 + threadIdx.x, t);
+  }
+}
+
+// Pass 2 (one thread per image): mu = s + E[y], cov_ij = E[y_i y_j] - E[y_i] E[y_j], in fp64.
+__global__ void color_finalize_kernel(const float* __restrict__ img, const double* __restrict__ acc, int B, int HW,
+                                      float* __restrict__ mean, float* __restrict__ cov) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* x = img + (int64_t)b * 3 * HW;
+  const double* a = acc + (int64_t)b * 9;
+  const double inv = 1.0 / (double)HW;
+  const double e[3] = {a[0] * inv, a[1] * inv, a[2] * inv};
+  const double sft[3] = {(double)x[0], (double)x[HW], (double)x[2 * (int64_t)HW]};
+  const int idx[3][3] = {{3, 4, 5}, {4, 6, 7}, {5, 7, 8}};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    mean[b * 3 + i] = (float)(sft[i] + e[i]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) cov[b * 9 + i * 3 + j] = (float)(a[idx[i][j]] * inv - e[i] * e[j]);
+  }
+}
+
+// Gradient: d mean_k / d x_kp = 1/HW;  d cov_ij / d x_kp = (delta_ik (x_jp - mu_j) + delta_jk (x_ip - mu_i)) / HW
+// (the terms through mu vanish because sum_p (x_p - mu) = 0), so
+//   dx[k][p] = ( dmean[k] + sum_j (dcov[k][j] + dcov[j][k]) (x[j][p] - mu[j]) ) / HW .      One read, one write per element.
+__global__ void __launch_bounds__(256) color_stats_bwd_kernel(const float* __restrict__ img, const float* __restrict__ mean,
+                                                              const float* __restrict__ dmean, const float* __restrict__ dcov,
+                                                              int HW, float* __restrict__ dimg) {
+  const int b = blockIdx.y;
+  const float* x = img + (int64_t)b * 3 * HW;
+  float* dx = dimg + (int64_t)b * 3 * HW;
+  const float inv = 1.f / (float)HW;
+  float mu[3], dm[3], sym[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    mu[i] = mean[b * 3 + i];
+    dm[i] = dmean ? dmean[b * 3 + i] * inv : 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) sym[i][j] = dcov ? (dcov[b * 9 + i * 3 + j] + dcov[b * 9 + j * 3 + i]) * inv : 0.f;
+  }
+  const int n4 = HW / 4;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n4; i += gridDim.x * 256) {
+    const float4 a = reinterpret_cast<const float4*>(x)[i];
+    const float4 c = reinterpret_cast<const float4*>(x + HW)[i];
+    const float4 d = reinterpret_cast<const float4*>(x + 2 * (int64_t)HW)[i];
+    const float r[4] = {a.x - mu[0], a.y - mu[0], a.z - mu[0], a.w - mu[0]};
+    const float g[4] = {c.x - mu[1], c.y - mu[1], c.z - mu[1], c.w - mu[1]};
+    const float u[4] = {d.x - mu[2], d.y - mu[2], d.z - mu[2], d.w - mu[2]};
+    float o[3][4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[k][q] = dm[k] + sym[k][0] * r[q] + sym[k][1] * g[q] + sym[k][2] * u[q];
+    reinterpret_cast<float4*>(dx)[i] = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
+    reinterpret_cast<float4*>(dx + HW)[i] = make_float4(o[1][0], o[1][1], o[1][2], o[1][3]);
+    reinterpret_cast<float4*>(dx + 2 * (int64_t)HW)[i] = make_float4(o[2][0], o[2][1], o[2][2], o[2][3]);
+  }
+}
+
+int color_slices(int HW) {
+  int s = HW / 4096;          // >= 4 float4 loads per thread and channel
+  return s < 1 ? 1 : (s > 64 ? 64 : s);
+}
+
 }  // namespace
+
+extern "C" int ekl_color_stats_fwd(const float* img, int B, int HW, double* scratch, float* mean, float* cov, void* stream) {
+  EKL_REQUIRE(img && scratch && mean && cov, "color_stats_fwd: null pointer");
+  EKL_REQUIRE(B > 0 && B <= 65535 && HW >= 4 && HW % 4 == 0, "color_stats_fwd: HW must be a positive multiple of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double) * 9 * (size_t)B, st);
+  if (e != cudaSuccess) return (int)e;
+  color_moments_kernel<<<dim3(color_slices(HW), B), 256, 0, st>>>(img, HW, scratch);
+  EKL_LAUNCH_CHECK();
+  color_finalize_kernel<<<ekl_cdiv(B, 64), 64, 0, st>>>(img, scratch, B, HW, mean, cov);
+  EKL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ekl_color_stats_bwd(const float* img, const float* mean, const float* dmean, const float* dcov, int B, int HW,
+                                   float* dimg, void* stream) {
+  EKL_REQUIRE(img && mean && dimg, "color_stats_bwd: null pointer");
+  EKL_REQUIRE(B > 0 && B <= 65535 && HW >= 4 && HW % 4 == 0, "color_stats_bwd: HW must be a positive multiple of 4");
+  color_stats_bwd_kernel<<<dim3(color_slices(HW), B), 256, 0, (cudaStream_t)stream>>>(img, mean, dmean, dcov, HW, dimg);
+  EKL_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int ekl_head_tanh_fwd(const void* y, int B, int HW, int C, float* img, void* stream) {
   EKL_REQUIRE(C % 8 == 0 && C >= 8 && B > 0 && HW > 0, "head_tanh_fwd: C %% 8");

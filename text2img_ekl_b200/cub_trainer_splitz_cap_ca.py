@@ -46,14 +46,54 @@ def load_params(net, new_param):
         p.data.copy_(new_p)
 
 
-def build_G():
+def build_G(use_cap=None):
+    """The generator train() builds (cub:130-135); evaluate() passes cfg.TEST.G_CAPSULE (cub:787)."""
+    use_cap = cfg.TRAIN.G_CAPSULE if use_cap is None else use_cap
     shareGs = model.get_shareGs(cfg.GAN.GF_DIM)
     if USE_CLS and SPLIT_Z:
-        netG = model.COND_G_NET_CATZ_CA(cfg.TEXT.DIMENSION, cfg.GAN.ENTITY_DIM, shareGs, use_cap=cfg.TRAIN.G_CAPSULE,
+        netG = model.COND_G_NET_CATZ_CA(cfg.TEXT.DIMENSION, cfg.GAN.ENTITY_DIM, shareGs, use_cap=use_cap,
                                         cat=cfg.TRAIN.CAT_Z, exchange=cfg.TRAIN.EXCHANGE)            # cub:130
     else:
-        netG = model.COND_G_NET(cfg.TEXT.DIMENSION, shareGs, use_cap=cfg.TRAIN.G_CAPSULE)           # cub:135
+        netG = model.COND_G_NET(cfg.TEXT.DIMENSION, shareGs, use_cap=use_cap)                       # cub:135
     return netG, shareGs
+
+
+def _strip_module(state_dict):
+    """Reference snapshots are saved from the nn.DataParallel wrapper: keys carry a 'module.' prefix (cub:663)."""
+    return {k[7:] if k.startswith("module.") else k: v for k, v in state_dict.items()}
+
+
+def save_model(netG, avg_param_G, netsD, epoch, model_dir):
+    """cub:218-228: netG_<epoch>.pth (with avg_param_G loaded first when given) and netD<i>.pth, the files
+    cfg.TRAIN.NET_G / cfg.TRAIN.NET_D point load_network at.  Keys carry the reference's 'module.' prefix."""
+    if avg_param_G is not None:
+        load_params(netG, avg_param_G)
+    wrap = lambda net: {"module." + k: v.detach().cpu() for k, v in net.state_dict().items()}
+    torch.save(wrap(netG), "%s/netG_%d.pth" % (model_dir, epoch))
+    for i, netD in enumerate(netsD):
+        torch.save(wrap(netD), "%s/netD%d.pth" % (model_dir, i))
+
+
+def to_uint8_nhwc(images):
+    """cub:771-772: [-1, 1] float NCHW -> uint8 NHWC (add 1, /2, *255, clamp, truncate), computed where the images live."""
+    return images.detach().add(1).div(2).mul(255).clamp(0, 255).byte().permute(0, 2, 3, 1).contiguous()
+
+
+def image_grid_uint8(images, nrow=10, padding=2):
+    """The tile sheet the reference writes through torchvision's save_image(nrow=10, normalize=True) (cub:756): min-max
+    normalisation over the whole stack, `nrow` tiles per row, 2-pixel black gutters, round to uint8.  [N,3,H,W] -> HWC."""
+    x = images.detach().float()
+    lo, hi = x.min(), x.max()
+    x = (x - lo) / (hi - lo).clamp_min(1e-5)
+    n, c, h, w = x.shape
+    cols = min(nrow, n)
+    rows = (n + cols - 1) // cols
+    sheet = x.new_zeros(c, rows * (h + padding) + padding, cols * (w + padding) + padding)
+    for k in range(n):
+        r, q = divmod(k, cols)
+        sheet[:, padding + r * (h + padding):padding + r * (h + padding) + h,
+              padding + q * (w + padding):padding + q * (w + padding) + w] = x[k]
+    return sheet.mul(255).add(0.5).clamp(0, 255).byte().permute(1, 2, 0).contiguous()
 
 
 def build_Ds(allow_three=False):
@@ -79,14 +119,14 @@ def load_network(gpus, device=None):
     count = 0
     if cfg.TRAIN.NET_G != "":
         state_dict = torch.load(cfg.TRAIN.NET_G, map_location="cpu")
-        netG.load_state_dict({k[7:] if k.startswith("module.") else k: v for k, v in state_dict.items()})
+        netG.load_state_dict(_strip_module(state_dict))
         name = os.path.basename(cfg.TRAIN.NET_G)
         digits = "".join(ch for ch in name[name.rfind("_") + 1:name.rfind(".")] if ch.isdigit())
         count = int(digits) + 1 if digits else 0
     if cfg.TRAIN.NET_D != "":
         for i, d in enumerate(netsD):
             sd = torch.load("%s%d.pth" % (cfg.TRAIN.NET_D, i), map_location="cpu")
-            d.load_state_dict({k[7:] if k.startswith("module.") else k: v for k, v in sd.items()})
+            d.load_state_dict(_strip_module(sd))
     netG.to(device)
     model.to_kernel_layout(netG)
     for d in netsD:
@@ -250,7 +290,118 @@ class condGANTrainer(object):
                   % (epoch, self.max_epoch, self.num_batches, self.num_Ds, tot[0], tot[1], tot[2], tot[3],
                      errG[0].item(), float(errG[1]), float(errG[2]), float(errG[3]),
                      " ".join("%.3f" % float(k) for k in errG[4:]), end_t - start_t))
-            if hasattr(self, "model_dir") and (epoch % self.snapshot_interval == 0 or epoch > 199):
+            si = self.snapshot_interval
+            if hasattr(self, "model_dir") and (epoch % si == si - 1 or epoch > 199):          # cub:664-669
                 # keys carry the DataParallel "module." prefix like the reference's snapshots (cub:662-667)
                 sd = {"module." + k: v for k, v in self.netG.state_dict().items()}
                 torch.save(sd, "%s/netG_epoch%d.pth" % (self.model_dir, epoch))
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def save_checkpoint(self, path, count):
+        """Everything a bit-faithful resume needs in one file: G, every D (reference key layout, 'module.' prefix),
+        the Adam state of each optimiser in torch.optim.Adam's state_dict format, and the iteration count.  The
+        reference itself only snapshots netG (cub:662-669) and re-creates the optimisers on restart."""
+        wrap = lambda net: {"module." + k: v.detach().cpu() for k, v in net.state_dict().items()}
+
+        def opt_state(opt):         # compact host copies: the fused optimiser's moments are views into flat buffers
+            sd = opt.state_dict()
+            host = lambda v: v.detach().cpu().clone() if torch.is_tensor(v) else v
+            return {"state": {i: {k: host(v) for k, v in st.items()} for i, st in sd["state"].items()},
+                    "param_groups": sd["param_groups"]}
+        torch.save({"netG": wrap(self.netG), "netsD": [wrap(d) for d in self.netsD],
+                    "optimizerG": opt_state(self.optimizerG),
+                    "optimizersD": [opt_state(o) for o in self.optimizersD], "count": int(count)}, path)
+
+    def load_checkpoint(self, path):
+        """Inverse of save_checkpoint, IN PLACE (parameter / moment storage keeps its addresses, so a captured step graph
+        stays valid).  Returns the stored iteration count."""
+        ck = torch.load(path, map_location="cpu")
+        self.netG.load_state_dict(_strip_module(ck["netG"]))
+        for d, sd in zip(self.netsD, ck["netsD"]):
+            d.load_state_dict(_strip_module(sd))
+        self.optimizerG.load_state_dict(ck["optimizerG"])
+        for o, sd in zip(self.optimizersD, ck["optimizersD"]):
+            o.load_state_dict(sd)
+        for o in [self.optimizerG] + list(self.optimizersD):
+            if hasattr(o, "refresh_shadow"):
+                o.refresh_shadow()
+        return int(ck["count"])
+
+    # ------------------------------------------------------------------ generation path (cub:720-911; SURVEY 8f row 1)
+    def save_singleimages(self, images, filenames, save_dir, split_dir, sentenceID, cls, imsize, noiseID):
+        """cub:759-775: one PNG per sample, <save_dir>/single_samples/<key>_<size>_class<c>_sid<s>_nid<n>.png."""
+        arr = to_uint8_nhwc(images).cpu().numpy()
+        from PIL import Image
+        for i in range(arr.shape[0]):
+            stem = "%s/single_samples/%s" % (save_dir, filenames[i])
+            mkdir_p(os.path.dirname(stem))
+            Image.fromarray(arr[i]).save("%s_%d_class%d_sid%d_nid%d.png" % (stem, imsize, int(cls[i]), sentenceID, noiseID))
+
+    def save_superimages(self, images_list, filenames, save_dir, split_dir, imsize):
+        """cub:733-756: per sample, one sheet of its images for every sentence (10 per row, min-max normalised)."""
+        from PIL import Image
+        for i in range(images_list[0].size(0)):
+            stem = "%s/super/%s/%s" % (save_dir, split_dir, filenames[i])
+            mkdir_p(os.path.dirname(stem))
+            tiles = torch.stack([imgs[i].view(3, imsize, imsize) for imgs in images_list])
+            Image.fromarray(image_grid_uint8(tiles, nrow=10).cpu().numpy()).save("%s_%d.png" % (stem, imsize))
+
+    def _eval_save_dir(self):
+        """cub:829-844 naming: eval/Testset_<mode>_fixednoise[_clsprior-random]_<epoch tag>_<run directory>."""
+        path = cfg.TRAIN.NET_G
+        tag = os.path.splitext(path)[0].split("_")[-1]
+        parts = path.split("/")
+        run = parts[-3] if len(parts) >= 3 else "run"
+        mode = "evalmode" if cfg.TEST.EVAL_MODE else "trainmode"
+        prior = "_clsprior-random" if cfg.TEST.CLS_PRIOR else ""
+        return "eval/Testset_%s_fixednoise%s_%s_%s" % (mode, prior, tag, run)
+
+    MAX_EVAL_SENTENCES = 10            # cub:826 embedding_dim
+
+    def evaluate(self, split_dir, save_dir=None):
+        """cub:776-911: load cfg.TRAIN.NET_G into a freshly built generator, and for every batch of the test loader
+        `(imgs, t_embeddings[B, n_sentences, T], cls (1-based), keys)` draw ONE noise batch, generate the final-stage
+        image for each of the first 10 sentence embeddings, and write tile sheets (cfg.TEST.B_EXAMPLE) or single PNGs.
+        BatchNorm runs on the running statistics when cfg.TEST.EVAL_MODE (the kernels' eval-mode normalisation).
+        Returns the number of images written."""
+        if cfg.TRAIN.NET_G == "":
+            print("Error: cfg.TRAIN.NET_G is empty, no generator snapshot to evaluate")
+            return 0
+        netG, _ = build_G(use_cap=cfg.TEST.G_CAPSULE)
+        netG.load_state_dict(_strip_module(torch.load(cfg.TRAIN.NET_G, map_location="cpu")))
+        netG.to(self.device)
+        model.to_kernel_layout(netG)
+        netG.eval() if cfg.TEST.EVAL_MODE else netG.train()
+        save_dir = save_dir or self._eval_save_dir()
+        final = cfg.TREE.BASE_SIZE * cfg.TREE.SCALE ** (cfg.TREE.BRANCH_NUM - 1)
+        split_z = isinstance(netG, model.COND_G_NET_CATZ_CA)
+        from .engine import tensor_core_matmul
+        count = 0
+        for step, data in enumerate(self.data_loader, 0):
+            imgs, t_embeddings, cls, filenames = data
+            cls = cls.long() - 1
+            emb = t_embeddings.to(self.device, non_blocking=True)
+            cls_onehot = self.onehot(cls.to(self.device), cfg.GAN.ENTITY_DIM)
+            B = emb.shape[0]
+            noise = torch.randn(B, cfg.GAN.Z_DIM, device=self.device)           # one draw per batch (cub:866-867)
+            sheets = []
+            with torch.no_grad(), tensor_core_matmul():
+                for i in range(min(self.MAX_EVAL_SENTENCES, emb.shape[1])):
+                    sen = emb[:, i, :].contiguous()
+                    if not split_z:
+                        hcodes = netG(noise, sen)[0]                            # USE_CLS False branch (cub:135)
+                    elif cfg.TEST.CLS_PRIOR:
+                        hcodes = netG(noise, sen)[0]                            # class code from the N(0,1) prior (model.py:491-495)
+                    else:
+                        hcodes = netG(noise, sen, cls_onehot)[0]
+                    fake = netG.image(hcodes)[-1]
+                    if cfg.TEST.B_EXAMPLE:
+                        sheets.append(fake)
+                    else:
+                        self.save_singleimages(fake, filenames, save_dir, split_dir, i, cls, final, 0)
+                    count += B
+            if cfg.TEST.B_EXAMPLE:
+                self.save_superimages(sheets, filenames, save_dir, split_dir, final)
+            print("[%d/%d]" % (step, self.num_batches))
+        print("Number of images: %d -> %s" % (count, save_dir))
+        return count

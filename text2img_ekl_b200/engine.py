@@ -32,6 +32,8 @@ def ce_loss(logq, p, average=True):
 
 def compute_mean_covariance(img):
     """cub:33-52: per-image channel mean [B,C,1,1] and channel covariance [B,C,C] (colour-consistency statistics)."""
+    if ops.color_stats_supported(img):
+        return ops.color_stats(img)           # one pass over the images (include/ekl_b200.h: ekl_color_stats_fwd)
     b, c, h, w = img.shape
     mu = img.mean(2, keepdim=True).mean(3, keepdim=True)
     d = (img - mu).reshape(b, c, h * w)
@@ -141,6 +143,8 @@ class StepEngine:
         self.d_logits = {}                   # idx -> (real, wrong, fake) x [match p, uncond p, class log-probs]
         self.uncond = float(cfg.TRAIN.COEFF.UNCOND_LOSS)
         self.kl_coeff = float(cfg.TRAIN.COEFF.KL)
+        self.color_coeff = float(cfg.TRAIN.COEFF.COLOR_LOSS)      # 0.0 in every shipped yml (config.py:61)
+        self.last_color = []
         self.cat_z = cfg.TRAIN.CAT_Z
 
     # ---- (1) generate: cub:567-587 / trainer.py:524-528
@@ -268,6 +272,27 @@ class StepEngine:
             main.wait_stream(st)
         return errDs
 
+    def color_consistency(self, fake_imgs):
+        """Colour-consistency regulariser between adjacent stages, the StackGAN++ term the reference keeps the statistics
+        function and the coefficient for (cub:33-52 compute_mean_covariance, config.py:61 COEFF.COLOR_LOSS) but never
+        assembles:  sum_{i>=1} coeff * ( MSE(mu_i, mu_{i-1}) + 5 * MSE(cov_i, cov_{i-1}) ), the lower stage detached.
+        Each stage's statistics are computed once (ekl_color_stats_fwd); the lower role uses them detached."""
+        stats = []
+        for i, img in enumerate(fake_imgs):
+            if i == 0:
+                with torch.no_grad():
+                    stats.append(compute_mean_covariance(img))
+            else:
+                stats.append(compute_mean_covariance(img))
+        total, self.last_color = 0, []
+        for i in range(1, len(fake_imgs)):
+            (mu1, cov1), (mu2, cov2) = stats[i], stats[i - 1]
+            like_mu = self.color_coeff * F.mse_loss(mu1, mu2.detach())
+            like_cov = self.color_coeff * 5 * F.mse_loss(cov1, cov2.detach())
+            self.last_color.append((like_mu.detach(), like_cov.detach()))
+            total = total + like_mu + like_cov
+        return total
+
     # ---- (3) generator loss through the UPDATED discriminators: cub:463-490
     def g_loss(self, real_cp):
         self._join_comm()
@@ -310,6 +335,8 @@ class StepEngine:
         kl = [self._kl(m, lv) for m, lv in self.kls]
         # only losses[0] of the fused kernel carries gradient: the total is assembled from it (components are reported)
         errG_total = errGs_total_fused + sum(kl) * self.kl_coeff
+        if self.color_coeff > 0 and len(self.fake_imgs) > 1:
+            errG_total = errG_total + self.color_consistency(self.fake_imgs)
         return (errG_total, errGs_match, errGs_uncond, errGs_cls) + tuple(kl)
 
     def _kl(self, mu, logvar):

@@ -689,3 +689,43 @@ class _ReparamKL(torch.autograd.Function):
 
 def reparam_kl(mu, logvar, eps):
     return _ReparamKL.apply(mu, logvar, eps)
+
+
+class _ColorStats(torch.autograd.Function):
+    """Per-image channel mean [B,3,1,1] and covariance [B,3,3] of an fp32 NCHW image batch (cub:33-52
+    compute_mean_covariance; include/ekl_b200.h: ekl_color_stats_fwd / _bwd): one read of the images forward, one read +
+    one write backward."""
+
+    @staticmethod
+    def forward(ctx, img):
+        ctx.set_materialize_grads(False)
+        B, C, H, W = img.shape
+        mean = torch.empty(B, 3, 1, 1, device=img.device)
+        cov = torch.empty(B, 3, 3, device=img.device)
+        scratch = torch.empty(B * 9, device=img.device, dtype=torch.float64)
+        L.check(L.lib().ekl_color_stats_fwd(L.ptr(img), B, H * W, L.ptr(scratch), L.ptr(mean), L.ptr(cov), L.stream()))
+        _count(2)
+        ctx.save_for_backward(img, mean)
+        return mean, cov
+
+    @staticmethod
+    def backward(ctx, dmean, dcov):
+        if dmean is None and dcov is None:
+            return None
+        img, mean = ctx.saved_tensors
+        B, C, H, W = img.shape
+        dmean = dmean.float().contiguous() if dmean is not None else None
+        dcov = dcov.float().contiguous() if dcov is not None else None
+        dimg = torch.empty_like(img)
+        L.check(L.lib().ekl_color_stats_bwd(L.ptr(img), L.ptr(mean), L.ptr(dmean), L.ptr(dcov), B, H * W, L.ptr(dimg), L.stream()))
+        _count()
+        return dimg
+
+
+def color_stats_supported(img):
+    return (img.is_cuda and img.dim() == 4 and img.shape[1] == 3 and img.dtype == torch.float32 and img.is_contiguous()
+            and (img.shape[2] * img.shape[3]) % 4 == 0)
+
+
+def color_stats(img):
+    return _ColorStats.apply(img)

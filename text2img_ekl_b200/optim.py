@@ -51,6 +51,37 @@ class FlatAdam(torch.optim.Optimizer):
             return g.view(p.shape[0], p.shape[2], p.shape[3], p.shape[1]).permute(0, 3, 1, 2)
         return g.view(p.shape)
 
+    def refresh_shadow(self):
+        """Re-derive the bf16 shadow from the fp32 masters (after the parameters were written from outside)."""
+        with torch.no_grad():
+            self.shadow.copy_(self.flat_p)
+        ops.mark_dirty(self.plist)
+
+    def load_state_dict(self, state_dict):
+        """Accepts the state_dict of torch.optim.Adam or of this class (same format: per-parameter `step`, `exp_avg`,
+        `exp_avg_sq`, indexed in parameter order).  The moments are copied INTO the flat buffers: the views held by
+        self.state, and any captured graph, keep pointing at live storage."""
+        ids = [i for g in state_dict["param_groups"] for i in g["params"]]
+        if len(ids) != len(self.plist):
+            raise ValueError("optimizer state has %d parameters, this optimizer %d" % (len(ids), len(self.plist)))
+        step = None
+        with torch.no_grad():
+            for idx, p in zip(ids, self.plist):
+                st = state_dict["state"].get(idx)
+                if st is None:
+                    continue
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError("optimizer state %d has shape %s, parameter %s" % (idx, tuple(st["exp_avg"].shape), tuple(p.shape)))
+                self.state[p]["exp_avg"].copy_(st["exp_avg"])
+                self.state[p]["exp_avg_sq"].copy_(st["exp_avg_sq"])
+                step = float(st["step"]) if step is None else step
+            if step is not None:
+                self.state_dev[0] = step          # the kernel derives both bias corrections from the count
+        grp, src = self.param_groups[0], state_dict["param_groups"][0]
+        for k in ("lr", "betas", "eps"):
+            if k in src:
+                grp[k] = tuple(src[k]) if k == "betas" else src[k]
+
     def make_flat_grads(self):
         """Gradient buffer with the parameters' offsets; every p.grad becomes a view with the parameter's layout."""
         self.flat_g = torch.zeros(self.n, device=self.flat_p.device, dtype=torch.float32)
