@@ -1,11 +1,7 @@
-import errno
+"""Small host helpers shared by the trainers (reference: miscc/utils.py keeps the same public name)."""
 import os
 
 
 def mkdir_p(path):
-    try:
-        os.makedirs(path)
-    except OSError as exc:
-        if exc.errno == errno.EEXIST and os.path.isdir(path):
-            return
-        raise
+    """`mkdir -p`: create `path` with its parents; an existing directory is fine, an existing file is an error."""
+    os.makedirs(path, exist_ok=True)
