@@ -318,16 +318,17 @@ def run_ours(a):
 
 def ncu_traffic(family):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
-    capture (profiles/r01_conv_full.json, written by tools/ncu_summary.py); None when no capture is committed."""
+    capture (profiles/r01_conv_full.json, written by tools/ncu_summary.py) -> (bytes per launch, provenance);
+    (None, None) when no capture is committed."""
     p = os.path.join(ROOT, "profiles", "r01_conv_full.json")
     if not os.path.exists(p):
-        return None
+        return None, None
     key = "conv_wgrad" if "wgrad" in family else "conv_gemm_tc"
     rows = [r for r in json.load(open(p)) if key in r.get("kernel", "")]
     if not rows:
-        return None
+        return None, None
     tot = sum(r.get("dram__bytes_read.sum", 0.0) + r.get("dram__bytes_write.sum", 0.0) for r in rows)
-    return {"bytes_per_launch": tot / len(rows), "launches_captured": len(rows), "source": "profiles/r01_conv_full.json"}
+    return tot / len(rows), {"launches_captured": len(rows), "source": "profiles/r01_conv_full.json"}
 
 
 def kernel_roofline(tr, batch, pk):
@@ -372,8 +373,9 @@ def kernel_roofline(tr, batch, pk):
         return None
     d = fam[top]
     ach = d["flop"] / (d["us"] * 1e-6) / 1e12
+    traffic, traffic_src = ncu_traffic(top)
     return {"bound": "tensor", "kernel": top, "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-            "frac": ach / pk["bf16_sustained"], "traffic": ncu_traffic(top), "peak_source": pk["src"] + " (sustained: kernel timed inside a long step)",
+            "frac": ach / pk["bf16_sustained"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk["src"] + " (sustained: kernel timed inside a long step)",
             "flop_counting": "algorithmic (reference dense-conv count) flops of the launches / sum of their CUDA-event durations",
             "avg_launch_us": d["us"] / d["launches"], "launches_per_step": d["launches"], "families": out}
 
