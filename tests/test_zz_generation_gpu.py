@@ -131,3 +131,44 @@ def test_stackgan_original_modules_match_oracle():
         ((out[0] * w0.to(dev)).sum() + (out[1] * w1.to(dev)).sum()).backward()
         ((ref[0] * w0).sum() + (ref[1] * w1).sum()).backward()
         assert torch.isfinite(xg.grad).all() and _rel(xg.grad, xo.grad) < 0.5, (res, _rel(xg.grad, xo.grad))
+
+
+def test_full_size_step_is_batch_permutation_equivariant():
+    """Size-independent property at the benchmark's full size (config 2, B = 24, all three stages and discriminators):
+    train-mode BatchNorm statistics are symmetric in the batch, so permuting the samples of every input permutes the
+    generated images and the discriminator outputs and leaves the mean-reduced losses unchanged (up to summation order
+    and bf16 rounding: the same 1e-2 / 2e-2 bounds as the oracle parity tests).  No optimiser step is taken."""
+    from text2img_ekl_b200 import configs
+    from text2img_ekl_b200.miscc.config import cfg
+    from text2img_ekl_b200.synthetic import SyntheticLoader
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B = 24
+    Trainer = configs.setup("3stages", batch=B)
+    tr = Trainer(None, None, 64)
+    tr.setup()
+    dev = tr.device
+    batch = SyntheticLoader(B, getattr(tr, "CLS_KIND", "index"), pool=1).pool[0]
+    g = torch.Generator().manual_seed(12)
+    noise, seed = torch.randn(B, cfg.GAN.Z_DIM, generator=g), torch.randn(B, cfg.GAN.MANIFD_DIM, generator=g)
+    perm = torch.randperm(B, generator=g)
+
+    def run(p):
+        imgs, wrong, emb, cls, _ = batch
+        data = ([t[p] for t in imgs], [t[p] for t in wrong], emb[p], cls[p], None)
+        tr.imgs_tcpu, tr.real_imgs, tr.wrong_imgs, tr.txt_embedding, tr.cls_label = tr.prepare_data(data)
+        tr.noise.copy_(noise[p].to(dev))
+        with torch.no_grad():
+            tr.generate(None, seed[p].to(dev))
+            fakes = tr.fake_imgs
+            outs = [netD(tr.real_imgs[i], tr.mu) for i, netD in enumerate(tr.netsD)]
+        torch.cuda.synchronize()
+        return [f.float().cpu() for f in fakes], [[o.float().cpu() for o in out] for out in outs]
+
+    ident = torch.arange(B)
+    f0, d0 = run(ident)
+    f1, d1 = run(perm)
+    for i in range(3):
+        assert tuple(f0[i].shape) == (B, 3, 64 << i, 64 << i)
+        assert _rel(f1[i], f0[i][perm]) < (1e-2 if i == 0 else 2e-2), (i, _rel(f1[i], f0[i][perm]))
+        for a, b in zip(d1[i], d0[i]):
+            assert _rel(a, b[perm]) < 2e-2, (i, _rel(a, b[perm]))
