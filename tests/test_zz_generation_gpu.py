@@ -172,3 +172,55 @@ def test_full_size_step_is_batch_permutation_equivariant():
         assert _rel(f1[i], f0[i][perm]) < (1e-2 if i == 0 else 2e-2), (i, _rel(f1[i], f0[i][perm]))
         for a, b in zip(d1[i], d0[i]):
             assert _rel(a, b[perm]) < 2e-2, (i, _rel(a, b[perm]))
+
+
+# cfg overrides on top of config 4 (cfg/birds_2stg_splitz_cap_ca.realcls.yml) -> the OracleCfg fields they imply
+VARIANTS = {
+    "cat_sum": ({"TRAIN.CAT_Z": "sum"}, dict(CAT_Z="sum")),                         # model.py:500-505, cub:577-582
+    "cat_product": ({"TRAIN.CAT_Z": "product"}, dict(CAT_Z="product")),
+    "exchange_cap": ({"TRAIN.EXCHANGE": True}, dict(EXCHANGE=True)),                # model.py:280-333
+    "scale4_sum": ({"TREE.SCALE": 4, "TRAIN.CAT_Z": "sum"}, dict(SCALE=4, CAT_Z="sum")),   # model.py:406-407, cub:151-154
+}
+
+
+@pytest.mark.timeout(300, method="thread")
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_conditioning_variants_match_oracle(variant, monkeypatch):
+    """the remaining conditioning variants of the split-z generator run through the SAME whole-step
+    parity check as the five BASELINE configs (tests/test_step_parity_gpu.py), with the config-4 yml plus one override:
+    CAT_Z sum / product, the exchange capsule stem, and TREE.SCALE 4 (upsample2 in NEXT_STAGE_G, JOINT_D_NET256 as the
+    second discriminator; only composable with a non-concat CAT_Z in the reference, whose JOINT_D_NET256 ignores CAT_Z).
+    The oracle side of every variant and the state_dict compatibility were dry-run on the CPU."""
+    import dataclasses
+    import test_step_parity_gpu as P
+    from oracle import configs as ocfg, shapes
+    from oracle.ekl_oracle import OracleTrainer
+    over, oover = VARIANTS[variant]
+
+    def build(name, B):
+        from text2img_ekl_b200 import configs
+        from text2img_ekl_b200.miscc.config import cfg
+        Trainer = configs.setup(name, batch=B)
+        for key, v in over.items():
+            node = cfg
+            *path, leaf = key.split(".")
+            for part in path:
+                node = getattr(node, part)
+            setattr(node, leaf, v)
+        tr = Trainer(None, None, 64)
+        tr.setup()
+        oc = dataclasses.replace(ocfg.oracle_cfg(name, batch=B), **oover)
+        gsh = shapes.g_shapes(oc, cond_dim=ocfg.cond_dim(oc))
+        d_res = [64, 128 if oc.SCALE == 2 else 256, 256][: oc.BRANCH_NUM]
+        dsh = [shapes.d_shapes(oc, r, joint=True, use_cap=oc.D_CAPSULE and r != 256) for r in d_res]
+        sdG = shapes.make_state_dict(gsh, "G")
+        sdDs = [shapes.make_state_dict(s, "D%d" % i) for i, s in enumerate(dsh)]
+        tr.netG.load_state_dict(sdG)
+        for d, sd in zip(tr.netsD, sdDs):
+            d.load_state_dict(sd)
+        clone = lambda sd: {k: v.detach().clone() for k, v in sd.items()}
+        orc16 = OracleTrainer(oc, clone(sdG), [clone(s) for s in sdDs])
+        return tr, oc, OracleTrainer(oc, sdG, sdDs), orc16
+
+    monkeypatch.setattr(P, "build", build)
+    P.test_training_step_matches_oracle("splitz_cap_ca", 4)
