@@ -273,3 +273,50 @@ def test_evaluate_control_flow_with_stub_generator(tmp_path, monkeypatch):
     finally:
         cfg.TRAIN.NET_G = ""
         cfg.TEST.B_EXAMPLE = True
+
+
+def test_flat_adam_state_dict_round_trip_and_no_cpu_step():
+    """optim.FlatAdam's host logic: parameters / moments become views into flat buffers without changing shapes, layouts
+    or values; its state_dict is interchangeable with torch.optim.Adam's in both directions and loading copies INTO the
+    flat buffers (addresses stay valid for a captured graph); step() on CPU tensors fails loudly (no CPU path)."""
+    import io
+    from text2img_ekl_b200 import _lib
+    from text2img_ekl_b200.optim import FlatAdam
+    mk = lambda: torch.nn.Sequential(torch.nn.Conv2d(4, 8, 3), torch.nn.BatchNorm2d(8), torch.nn.Linear(8, 3))
+    torch.manual_seed(0)
+    net, net2 = mk(), mk()
+    net[0].weight.data = net[0].weight.data.contiguous(memory_format=torch.channels_last)
+    before = [p.detach().clone() for p in net.parameters()]
+    strides = [p.stride() for p in net.parameters()]
+    opt = FlatAdam(net.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    for p, b, st in zip(net.parameters(), before, strides):
+        assert torch.equal(p, b) and p.stride() == st
+        assert opt.flat_p.data_ptr() <= p.data_ptr() < opt.flat_p.data_ptr() + 4 * opt.n
+    assert all(o % 4 == 0 for o in opt.offsets)                       # 16-byte aligned fp32 views
+    opt.exp_avg.normal_()
+    opt.exp_avg_sq.uniform_()
+    opt.state_dev[0] = 7
+    buf = io.BytesIO()
+    torch.save(opt.state_dict(), buf)
+    buf.seek(0)
+    sd = torch.load(buf)
+    adam = torch.optim.Adam(net2.parameters(), lr=1e-3, betas=(0.9, 0.99))
+    adam.load_state_dict(sd)                                           # FlatAdam -> torch.optim.Adam
+    for p, q in zip(opt.plist, net2.parameters()):
+        assert float(adam.state[q]["step"]) == 7.0
+        assert torch.equal(adam.state[q]["exp_avg"], opt.state[p]["exp_avg"])
+        assert torch.equal(adam.state[q]["exp_avg_sq"], opt.state[p]["exp_avg_sq"])
+    opt2 = FlatAdam(mk().parameters(), lr=5e-4)
+    ptrs = (opt2.exp_avg.data_ptr(), opt2.exp_avg_sq.data_ptr())
+    opt2.load_state_dict(adam.state_dict())                            # torch.optim.Adam -> FlatAdam, in place
+    assert (opt2.exp_avg.data_ptr(), opt2.exp_avg_sq.data_ptr()) == ptrs and float(opt2.state_dev[0]) == 7.0
+    for p, q in zip(opt.plist, opt2.plist):
+        assert torch.equal(opt2.state[q]["exp_avg"], opt.state[p]["exp_avg"])
+        assert torch.equal(opt2.state[q]["exp_avg_sq"], opt.state[p]["exp_avg_sq"])
+    assert opt2.param_groups[0]["lr"] == 2e-4 and tuple(opt2.param_groups[0]["betas"]) == (0.5, 0.999)
+    with pytest.raises(ValueError):
+        FlatAdam(torch.nn.Linear(2, 2).parameters()).load_state_dict(adam.state_dict())
+    for p in net.parameters():
+        p.grad = torch.zeros_like(p)
+    with pytest.raises(_lib.EklError):
+        opt.step()

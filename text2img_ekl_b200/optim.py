@@ -21,7 +21,6 @@ class FlatAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self.plist = params
         dev = params[0].device
-        assert dev.type == "cuda", "FlatAdam drives the CUDA kernel library; use torch.optim.Adam on the CPU"
         # every parameter starts at a multiple of 4 elements: 16-byte aligned fp32 views, 8-byte aligned bf16 shadows
         self.offsets, off = [], 0
         for p in params:
@@ -91,6 +90,9 @@ class FlatAdam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None):
+        if self.flat_p.device.type != "cuda":
+            raise L.EklError("FlatAdam.step drives the CUDA kernel library (ekl_adam_step): there is no CPU path; "
+                             "use torch.optim.Adam for CPU tensors")
         if self.flat_g is None or any(p.grad is None or p.grad.data_ptr() != self.flat_g.data_ptr() + 4 * o
                                       for p, o in zip(self.plist, self.offsets)):
             # gradients live elsewhere (stand-alone use): gather them into the flat layout
