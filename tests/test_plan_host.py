@@ -320,3 +320,29 @@ def test_flat_adam_state_dict_round_trip_and_no_cpu_step():
         p.grad = torch.zeros_like(p)
     with pytest.raises(_lib.EklError):
         opt.step()
+
+
+def test_color_consistency_term_formula_and_gradient_routing():
+    """engine.StepEngine.color_consistency on CPU tensors (the statistics fall back to the torch formula there):
+    sum over adjacent stages of coeff * (MSE(mu_i, mu_{i-1}) + 5 * MSE(cov_i, cov_{i-1})) with the LOWER stage detached
+    -- stage 0 receives no gradient, the middle stage only through its 'upper' role."""
+    import types
+    from oracle import ekl_oracle as O
+    from text2img_ekl_b200.engine import StepEngine
+    g = torch.Generator().manual_seed(2)
+    imgs = [torch.tanh(torch.randn(3, 3, 8 << i, 8 << i, generator=g)).requires_grad_(True) for i in range(3)]
+    eng = types.SimpleNamespace(color_coeff=2.0, last_color=[])
+    total = StepEngine.color_consistency(eng, imgs)
+    want = 0.0
+    for i in (1, 2):
+        (m1, c1), (m2, c2) = O.mean_covariance(imgs[i].detach()), O.mean_covariance(imgs[i - 1].detach())
+        want += 2.0 * float(((m1 - m2) ** 2).mean()) + 2.0 * 5 * float(((c1 - c2) ** 2).mean())
+    assert abs(float(total.detach()) - want) < 1e-6 * max(1.0, abs(want)) and len(eng.last_color) == 2
+    total.backward()
+    assert imgs[0].grad is None and imgs[1].grad is not None and imgs[2].grad is not None
+    # the middle stage's gradient is that of its pair with stage 0 only (its role under stage 2 is detached)
+    mid = imgs[1].detach().clone().requires_grad_(True)
+    m1, c1 = O.mean_covariance(mid)
+    m2, c2 = O.mean_covariance(imgs[0].detach())
+    (2.0 * ((m1 - m2) ** 2).mean() + 10.0 * ((c1 - c2) ** 2).mean()).backward()
+    assert torch.allclose(imgs[1].grad, mid.grad, rtol=1e-4, atol=1e-9)
