@@ -346,3 +346,21 @@ def test_color_consistency_term_formula_and_gradient_routing():
     m2, c2 = O.mean_covariance(imgs[0].detach())
     (2.0 * ((m1 - m2) ** 2).mean() + 10.0 * ((c1 - c2) ** 2).mean()).backward()
     assert torch.allclose(imgs[1].grad, mid.grad, rtol=1e-4, atol=1e-9)
+
+
+def test_public_loss_helpers_match_oracle_on_cpu():
+    """The reference-named module functions the trainers export (KL_loss, ce_loss, compute_mean_covariance, onehot:
+    cub:33-65, 322-331) against the oracle's restatements, which tests/test_oracle_golden.py pins to the real reference."""
+    from oracle import ekl_oracle as O
+    from text2img_ekl_b200 import cub_trainer_splitz_cap_ca as T
+    g = torch.Generator().manual_seed(8)
+    mu, lv = torch.randn(6, 128, generator=g), 0.3 * torch.randn(6, 128, generator=g)
+    assert torch.allclose(T.KL_loss(mu, lv), O.kl_loss(mu, lv), rtol=1e-6)
+    logq = torch.log_softmax(torch.randn(6, 201, generator=g), 1)
+    p = torch.softmax(torch.randn(6, 201, generator=g), 1)
+    assert torch.allclose(T.ce_loss(logq, p), O.ce_loss(logq, p), rtol=1e-6)
+    img = torch.rand(3, 3, 16, 16, generator=g) * 2 - 1
+    (m, c), (mo, co) = T.compute_mean_covariance(img), O.mean_covariance(img)
+    assert m.shape == (3, 3, 1, 1) and c.shape == (3, 3, 3) and torch.equal(m, mo) and torch.equal(c, co)
+    cls = torch.randint(0, 200, (9,), generator=g)
+    assert torch.equal(T.onehot(cls, 201), O.onehot(cls, 201))                   # bit-exact class targets
