@@ -364,3 +364,35 @@ def test_public_loss_helpers_match_oracle_on_cpu():
     assert m.shape == (3, 3, 1, 1) and c.shape == (3, 3, 3) and torch.equal(m, mo) and torch.equal(c, co)
     cls = torch.randint(0, 200, (9,), generator=g)
     assert torch.equal(T.onehot(cls, 201), O.onehot(cls, 201))                   # bit-exact class targets
+
+
+def test_product_state_dicts_equal_the_reference_golden_lists():
+    """Drop-in boundary: the package's own modules, built from each BASELINE config, expose exactly the
+    reference's state_dict keys, shapes AND registration order -- compared with the lists tests/golden/*.npz recorded
+    from the real reference (`shapes/G`, `shapes/D<i>`, `gnet/shapes`, `dnet<res>/shapes`), so reference snapshots load."""
+    import glob
+    import os
+    import numpy as np
+    from text2img_ekl_b200 import configs, cub_trainer_splitz_cap_ca as T, model
+    from text2img_ekl_b200.miscc.config import cfg
+    fmt = lambda net: ["%s|%s" % (k, ",".join(map(str, v.shape))) for k, v in net.state_dict().items()]
+    seen = 0
+    for path in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "step_*.npz"))):
+        name, b, w = os.path.basename(path)[5:-4].rsplit("_", 2)
+        gold = np.load(path)
+        Trainer = configs.setup(name, batch=int(b[1:]), width=int(w[1:]))
+        if name == "splitz_cap_ca":
+            netG = T.build_G()[0]
+        else:
+            cond_dim = cfg.TEXT.DIMENSION + (cfg.GAN.ENTITY_DIM + 1 if Trainer.COND == "txt+cls" else 0)
+            netG = model.COND_G_NET(cond_dim, model.get_shareGs(cfg.GAN.GF_DIM), use_cap=cfg.TRAIN.G_CAPSULE)
+        assert fmt(netG) == list(gold["shapes/G"]), path
+        for i, d in enumerate(T.build_Ds()):
+            assert fmt(d) == list(gold["shapes/D%d" % i]), (path, i)
+        seen += 1
+    assert seen >= 5
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "modules.npz"))
+    configs.setup("3stages", batch=4, width=8)
+    assert fmt(model.G_NET(model.get_shareGs(cfg.GAN.GF_DIM))) == list(gold["gnet/shapes"])
+    for res, D in ((64, model.D_NET64), (128, model.D_NET128), (256, model.D_NET256)):
+        assert fmt(D()) == list(gold["dnet%d/shapes" % res])
