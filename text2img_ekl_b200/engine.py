@@ -32,9 +32,13 @@ def ce_loss(logq, p, average=True):
 
 def compute_mean_covariance(img):
     """cub:33-52: per-image channel mean [B,C,1,1] and channel covariance [B,C,C] (colour-consistency statistics)."""
-    if ops.color_stats_supported(img):
-        return ops.color_stats(img)           # one pass over the images (include/ekl_b200.h: ekl_color_stats_fwd)
-    b, c, h, w = img.shape
+    if img.is_cuda:
+        x = img.float().contiguous()
+        if not ops.color_stats_supported(x):
+            raise ops.L.EklError("compute_mean_covariance on the GPU takes [B,3,H,W] images with H*W %% 4 == 0, got %s"
+                                 % (tuple(img.shape),))
+        return ops.color_stats(x)             # one pass over the images (include/ekl_b200.h: ekl_color_stats_fwd)
+    b, c, h, w = img.shape                    # host tensors (tests, tooling): the reference formula
     mu = img.mean(2, keepdim=True).mean(3, keepdim=True)
     d = (img - mu).reshape(b, c, h * w)
     return mu, torch.bmm(d, d.transpose(1, 2)) / (h * w)
