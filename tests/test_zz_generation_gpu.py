@@ -27,6 +27,7 @@ class _TestSetLoader:
         return iter(self.batches)
 
 
+@pytest.mark.timeout(120, method="thread")
 def test_save_model_load_network_and_evaluate(tmp_path, monkeypatch):
     """(1) save_model writes the files cfg.TRAIN.NET_G / NET_D name (cub:218-228); load_network reads them back
     ('module.' prefix stripped, count parsed from the file name, cub:171-184).  (2) evaluate() (cub:776-911) generates
@@ -79,6 +80,7 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-12))
 
 
+@pytest.mark.timeout(120, method="thread")
 def test_stackgan_original_modules_match_oracle():
     """G_NET (model.py:747-808, composed from its sub-modules as its own forward is broken) and the two-head
     D_NET64/128/256 (model.py:874-914, 1006-1050, 1154-1202) are in scope as modules.  Forward parity against the oracle
@@ -133,6 +135,7 @@ def test_stackgan_original_modules_match_oracle():
         assert torch.isfinite(xg.grad).all() and _rel(xg.grad, xo.grad) < 0.6, (res, _rel(xg.grad, xo.grad))
 
 
+@pytest.mark.timeout(120, method="thread")
 def test_full_size_step_is_batch_permutation_equivariant():
     """Size-independent property at the benchmark's full size (config 2, B = 24, all three stages and discriminators):
     train-mode BatchNorm statistics are symmetric in the batch, so permuting the samples of every input permutes the
@@ -183,7 +186,7 @@ VARIANTS = {
 }
 
 
-@pytest.mark.timeout(300, method="thread")
+@pytest.mark.timeout(120, method="thread")
 @pytest.mark.parametrize("variant", list(VARIANTS))
 def test_conditioning_variants_match_oracle(variant, monkeypatch):
     """the remaining conditioning variants of the split-z generator run through the SAME whole-step
