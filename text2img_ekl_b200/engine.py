@@ -247,7 +247,12 @@ class StepEngine:
 
     def _streams(self):
         if self.d_streams is None:
-            self.d_streams = [torch.cuda.Stream() for _ in self.netsD]
+            # EKL_D_PRIO=1 (experiment, off by default): the deepest discriminator's branch is the critical path of the
+            # parallel section; a high-priority stream lets its kernels win SMs over the fillers (captured kernel nodes
+            # inherit the stream priority)
+            prio = os.environ.get("EKL_D_PRIO", "0") == "1"
+            last = len(self.netsD) - 1
+            self.d_streams = [torch.cuda.Stream(priority=-1 if (prio and i == last) else 0) for i in range(len(self.netsD))]
         return self.d_streams
 
     def d_steps(self, real_imgs, wrong_imgs, real_cp, fake_cp):
