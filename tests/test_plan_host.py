@@ -396,3 +396,36 @@ def test_product_state_dicts_equal_the_reference_golden_lists():
     assert fmt(model.G_NET(model.get_shareGs(cfg.GAN.GF_DIM))) == list(gold["gnet/shapes"])
     for res, D in ((64, model.D_NET64), (128, model.D_NET128), (256, model.D_NET256)):
         assert fmt(D()) == list(gold["dnet%d/shapes" % res])
+
+
+def test_discriminator_trunk_marks_fire_deepest_first():
+    """model._DBase._trunk drops an ops.grad_mark behind its blocks (no-op unless a tail-first all-reduce is registered
+    for the network, parallel.TailAllreduce): with stand-in blocks on the CPU the block order of all three trunk depths is
+    unchanged, and registered marks fire in backward order, deepest block first."""
+    from text2img_ekl_b200 import model, ops
+
+    class Blk(torch.nn.Module):
+        def __init__(self, tag, log):
+            super().__init__()
+            self.tag, self.log, self.w = tag, log, torch.nn.Parameter(torch.ones(1))
+
+        def forward(self, x, groups):
+            self.log.append(self.tag)
+            return x * self.w + groups
+
+    for names in (["img_code_s16"], ["img_code_s16", "img_code_s32", "img_code_s32_1"],
+                  ["img_code_s16", "img_code_s32", "img_code_s64", "img_code_s64_1", "img_code_s64_2"]):
+        order, fired = [], []
+        d = model._DBase()
+        for n in names:
+            setattr(d, n, Blk(n, order))
+        x = torch.ones(2, 3, 4, 4, requires_grad=True)
+        y = d._trunk(x, 1)                                   # no registration: plain pass-through
+        assert order == names and y.shape == (2, 4, 4, 3)
+        ops.GRAD_MARKS[id(d)] = lambda after: fired.append(after.tag)
+        try:
+            d._trunk(x, 1).sum().backward()
+        finally:
+            ops.GRAD_MARKS.clear()
+        marked = [n for n in names if n not in ("img_code_s32_1", "img_code_s64_2")]
+        assert fired == marked[::-1], (names, fired)

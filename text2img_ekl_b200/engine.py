@@ -150,6 +150,22 @@ class StepEngine:
         self.color_coeff = float(cfg.TRAIN.COEFF.COLOR_LOSS)      # 0.0 in every shipped yml (config.py:61)
         self.last_color = []
         self.cat_z = cfg.TRAIN.CAT_Z
+        # EKL_BUCKET_AR=1 (experiment, off by default, N > 1): each discriminator's gradient all-reduce starts from the
+        # tail of its flat buffer while its backward is still running (parallel.TailAllreduce)
+        self.tail_ar = [None] * len(netsD)
+        if allreduce is not None and os.environ.get("EKL_BUCKET_AR", "0") == "1":
+            from .parallel import TailAllreduce
+            for i, (d, opt, g) in enumerate(zip(netsD, optimizersD, self.gradsD)):
+                if hasattr(opt, "offsets"):
+                    self.tail_ar[i] = TailAllreduce(d, opt.plist, opt.offsets, opt.n, g.flat)
+                    ops.GRAD_MARKS[id(d)] = self.tail_ar[i].on_mark
+
+    def _reduce_d(self, idx):
+        """Average discriminator idx's gradients over the ranks (no-op for a single process)."""
+        if self.tail_ar[idx] is not None:
+            self.tail_ar[idx].finish()
+        elif self.allreduce is not None:
+            self.allreduce(self.gradsD[idx].flat)
 
     # ---- (1) generate: cub:567-587 / trainer.py:524-528
     def generate(self, noise, txt, cls_cond, eps=None, seed=None):
@@ -188,6 +204,8 @@ class StepEngine:
             # fused path: raw logits of the stacked real / wrong / fake pass -> one loss kernel (cub:423-448)
             lm, lu, lc = netD.heads_raw((real_imgs, wrong_imgs, self.fake_imgs[idx].detach()), self.mu.detach(), groups=3)
             losses, pm, pu, logp = ops.d_loss(lm, lu, lc, real_cp, fake_cp, 3, B, (1, 0, 0), (1, 1, 0), (0, -1, 1), self.uncond)
+            if self.tail_ar[idx] is not None:
+                self.tail_ar[idx].begin()
             losses[0].backward()
             self._d_update(idx)
             self.d_logits[idx] = tuple([pm[i * B:(i + 1) * B], pu[i * B:(i + 1) * B], logp[i * B:(i + 1) * B]] for i in range(3))
@@ -205,6 +223,8 @@ class StepEngine:
         else:
             errD_uncond = errD_cls = torch.zeros((), device=real_imgs.device)
             errD = _bce_const(real[0], 1) + 0.5 * (_bce_const(wrong[0], 0) + _bce_const(fake[0], 0))
+        if self.tail_ar[idx] is not None:
+            self.tail_ar[idx].begin()
         errD.backward()
         self._d_update(idx)
         self.d_logits[idx] = (real, wrong, fake)
@@ -223,8 +243,7 @@ class StepEngine:
         grads, opt = self.gradsD[idx], self.optsD[idx]
         if self.allreduce is None or self._on_d_stream:
             # (on a per-discriminator stream the all-reduce already overlaps the other discriminators' work)
-            if self.allreduce is not None:
-                self.allreduce(grads.flat)
+            self._reduce_d(idx)
             opt.step()
             return
         if self.comm_stream is None:
@@ -232,7 +251,7 @@ class StepEngine:
         main = torch.cuda.current_stream()
         self.comm_stream.wait_stream(main)
         with torch.cuda.stream(self.comm_stream):
-            self.allreduce(grads.flat)
+            self._reduce_d(idx)
             opt.step()
             ev = torch.cuda.Event()
             ev.record()

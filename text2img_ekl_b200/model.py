@@ -638,12 +638,13 @@ def _head_logit(head, feat_nhwc):
 
 class _DBase(nn.Module):
     def _trunk(self, x_var, groups):
-        x = self.img_code_s16(x_var, groups)
+        # ops.grad_mark: no-op unless a tail-first gradient all-reduce is registered for this network (parallel.py)
+        x = ops.grad_mark(self.img_code_s16(x_var, groups), self, self.img_code_s16)
         if hasattr(self, "img_code_s32"):
-            x = self.img_code_s32(x, groups)
+            x = ops.grad_mark(self.img_code_s32(x, groups), self, self.img_code_s32)
         if hasattr(self, "img_code_s64"):
-            x = self.img_code_s64(x, groups)
-            x = self.img_code_s64_1(x, groups)
+            x = ops.grad_mark(self.img_code_s64(x, groups), self, self.img_code_s64)
+            x = ops.grad_mark(self.img_code_s64_1(x, groups), self, self.img_code_s64_1)
             x = self.img_code_s64_2(x, groups)
         elif hasattr(self, "img_code_s32_1"):
             x = self.img_code_s32_1(x, groups)

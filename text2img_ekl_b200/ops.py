@@ -28,6 +28,23 @@ PROFILE = None
 SHAPE_LOG = None
 
 
+# parallel.TailAllreduce (opt-in, N > 1): id(network) -> callback(module).  A network's forward drops a mark behind a
+# block; when autograd has produced the gradient of the marked activation, every parameter registered AFTER that block
+# has its final gradient, and the callback may start reducing that tail of the flat gradient buffer.
+GRAD_MARKS = {}
+
+
+def grad_mark(x, owner, after):
+    cb = GRAD_MARKS.get(id(owner)) if GRAD_MARKS else None
+    if cb is None or not x.requires_grad:
+        return x
+
+    def fire(grad, after=after, cb=cb):
+        cb(after)                  # returns None: the gradient passes through unchanged
+    x.register_hook(fire)
+    return x
+
+
 def _log(*key):
     if SHAPE_LOG is not None:
         SHAPE_LOG.append(key)

@@ -57,3 +57,62 @@ def shard_range(n_units, rank=None, ws=None):
     per, rem = divmod(n_units, ws)
     lo = rank * per + min(rank, rem)
     return lo, lo + per + (1 if rank < rem else 0)
+
+
+class TailAllreduce:
+    """Gradient all-reduce of one network, started from the END of its flat gradient buffer while backward is still
+    running (opt-in: EKL_BUCKET_AR=1, N > 1).
+
+    Parameters sit in the flat buffer in registration order = forward order, so the deepest layers -- whose gradients
+    backward produces FIRST, and which hold most of a discriminator's weights (the 1024->2048 4x4 and 2048->1024 3x3
+    filters are 52 M of JOINT_D_NET256's 73 M parameters) -- form its tail.  The network's forward marks block boundaries
+    (ops.grad_mark); when the gradient of a marked activation arrives, everything registered after that block is final:
+    the slice [end of that block, start of what is already in flight) goes out as an asynchronous all-reduce that
+    overlaps the rest of backward.  finish() sends the remaining head slice and makes the current stream wait for all
+    of them.  Collectives are issued in the same order on every rank (same graph, same marks)."""
+
+    def __init__(self, net, params, offsets, total, flat, min_bytes=4 << 20):
+        self.flat, self.total = flat, total
+        self.min_elems = max(1, min_bytes // 4)
+        end_of_param = {id(p): o + p.numel() for p, o in zip(params, offsets)}
+        self.end_of = {}
+        for m in net.modules():
+            ends = [end_of_param[id(p)] for p in m.parameters() if id(p) in end_of_param]
+            if ends:
+                self.end_of[id(m)] = (max(ends) + 3) // 4 * 4 if max(ends) < total else total
+        self.ws = dist.get_world_size()
+        self.avg = dist.get_backend() == "nccl"
+        self.active, self.lo, self.works = False, total, []
+
+    def begin(self):
+        """Call right before backward of this network's own update (marks fired at any other time are ignored)."""
+        self.active, self.lo, self.works = True, self.total, []
+
+    def on_mark(self, after_module):
+        if not self.active:
+            return
+        lo = self.end_of.get(id(after_module))
+        if lo is None or self.lo - lo < self.min_elems:
+            return
+        self._launch(lo, self.lo)
+        self.lo = lo
+
+    def _launch(self, lo, hi):
+        t = self.flat[lo:hi]
+        w = dist.all_reduce(t, op=dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM, async_op=True)
+        self.works.append((w, lo, hi))
+
+    def finish(self):
+        """Reduce what is left (the head of the buffer) and wait for every slice: afterwards the whole buffer holds the
+        mean over ranks, exactly as one all-reduce of the flat buffer would."""
+        self.active = False
+        if self.lo > 0:
+            self._launch(0, self.lo)
+            self.lo = 0
+        for w, lo, hi in self.works:
+            w.wait()
+            if not self.avg:
+                self.flat[lo:hi].div_(self.ws)
+        n = len(self.works)
+        self.works = []
+        return n

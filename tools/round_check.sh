@@ -16,4 +16,10 @@ print('value', round(d['value']), 'img/s', round(d['ms_per_step'], 2), 'ms; e2e'
 EKL_PARALLEL_D=0 timeout 90 python bench.py --steps 20 --warmup 5 --no-cpu --no-profile 2>/dev/null | grep '^{' | python -c "
 import sys, json
 d = json.loads(sys.stdin.read()); print('serial discriminators:', round(d['value']), 'img/s')"
+EKL_D_PRIO=1 timeout 90 python bench.py --steps 20 --warmup 5 --no-cpu --no-profile 2>/dev/null | grep '^{' | python -c "
+import sys, json
+d = json.loads(sys.stdin.read()); print('high-priority deepest branch (EKL_D_PRIO=1):', round(d['value']), 'img/s')"
+# 2-GPU experiments (run under gpurun --gpus 2, one at a time, always inside `timeout`):
+#   [EKL_BUCKET_AR=1] timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+#       --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 5 --no-cpu --no-profile
 timeout 120 python tools/step_profile.py --config 3stages > gpurun_out/rc_step_profile.log 2>&1; tail -25 gpurun_out/rc_step_profile.log
