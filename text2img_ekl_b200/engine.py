@@ -158,7 +158,7 @@ class StepEngine:
             for i, (d, opt, g) in enumerate(zip(netsD, optimizersD, self.gradsD)):
                 if hasattr(opt, "offsets"):
                     self.tail_ar[i] = TailAllreduce(d, opt.plist, opt.offsets, opt.n, g.flat)
-                    ops.GRAD_MARKS[id(d)] = self.tail_ar[i].on_mark
+                    ops.GRAD_MARKS[id(d)] = lambda m, t=self.tail_ar[i]: (ops.join_wgrad(), t.on_mark(m))[1]
 
     def _reduce_d(self, idx):
         """Average discriminator idx's gradients over the ranks (no-op for a single process)."""
@@ -241,6 +241,7 @@ class StepEngine:
         updates are independent: cub:594-596 loops over the discriminators); g_step joins the side stream before the
         updated discriminators are used."""
         grads, opt = self.gradsD[idx], self.optsD[idx]
+        ops.join_wgrad()                     # (EKL_WGRAD_STREAM experiment: side-stream weight gradients must have landed)
         if self.allreduce is None or self._on_d_stream:
             # (on a per-discriminator stream the all-reduce already overlaps the other discriminators' work)
             self._reduce_d(idx)
@@ -388,6 +389,7 @@ class StepEngine:
         try:
             res = self.g_loss(real_cp)
             res[0].backward()
+            ops.join_wgrad()
         finally:
             for d in self.netsD:
                 d.requires_grad_(True)

@@ -19,6 +19,10 @@ d = json.loads(sys.stdin.read()); print('serial discriminators:', round(d['value
 EKL_D_PRIO=1 timeout 90 python bench.py --steps 20 --warmup 5 --no-cpu --no-profile 2>/dev/null | grep '^{' | python -c "
 import sys, json
 d = json.loads(sys.stdin.read()); print('high-priority deepest branch (EKL_D_PRIO=1):', round(d['value']), 'img/s')"
+EKL_WGRAD_STREAM=1 timeout 90 python bench.py --steps 20 --warmup 5 --no-cpu --no-profile 2>/dev/null | grep '^{' | python -c "
+import sys, json
+d = json.loads(sys.stdin.read()); print('weight gradients on side streams (EKL_WGRAD_STREAM=1):', round(d['value']), 'img/s')"
+EKL_WGRAD_STREAM=1 timeout 120 python -m pytest tests/test_step_parity_gpu.py -m gpu -q -k "3stages or splitz" 2>&1 | tail -2
 # 2-GPU experiments (run under gpurun --gpus 2, one at a time, always inside `timeout`):
 #   [EKL_BUCKET_AR=1] timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
 #       --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 5 --no-cpu --no-profile
