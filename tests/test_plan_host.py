@@ -429,3 +429,39 @@ def test_discriminator_trunk_marks_fire_deepest_first():
             ops.GRAD_MARKS.clear()
         marked = [n for n in names if n not in ("img_code_s32_1", "img_code_s64_2")]
         assert fired == marked[::-1], (names, fired)
+
+
+def test_step_engine_update_paths_run_on_cpu_stand_ins(monkeypatch):
+    """Host-side control flow of engine.StepEngine that every step takes -- construction (flat gradient buffers, BN
+    counters, experiment switches off by default), the discriminator update (_d_update -> _reduce_d -> optimiser) and the
+    generator update (_g_step: loss -> backward -> join -> optimiser -> counters) -- exercised with tiny CPU stand-in
+    networks and torch.optim.Adam, so that a Python-level slip in these paths shows up before a GPU run."""
+    from text2img_ekl_b200 import configs, ops
+    from text2img_ekl_b200.engine import StepEngine
+    for k in ("EKL_BUCKET_AR", "EKL_WGRAD_STREAM", "EKL_D_PRIO"):
+        monkeypatch.delenv(k, raising=False)
+    configs.setup("3stages", batch=4)
+    torch.manual_seed(0)
+    netG = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.BatchNorm1d(4))
+    netsD = [torch.nn.Linear(4, 1), torch.nn.Linear(4, 1)]
+    optG = torch.optim.Adam(netG.parameters(), lr=1e-2)
+    optsD = [torch.optim.Adam(d.parameters(), lr=1e-2) for d in netsD]
+    eng = StepEngine(netG, netsD, optG, optsD, "cond")
+    assert eng.tail_ar == [None, None] and eng.allreduce is None and eng.parallel_d and not ops.GRAD_MARKS
+    assert not ops.WGRAD_STREAM and ops.join_wgrad() is None
+    x = torch.randn(6, 4)
+    # discriminator update: gradients are views of the flat buffer, _d_update applies them
+    w0 = netsD[1].weight.detach().clone()
+    eng.gradsD[1].zero()
+    netsD[1](x).square().mean().backward()
+    assert netsD[1].weight.grad.data_ptr() == eng.gradsD[1].flat.data_ptr() and float(eng.gradsD[1].flat.abs().sum()) > 0
+    eng._d_update(1)
+    assert not torch.equal(netsD[1].weight.detach(), w0) and eng._pending_comm == {}
+    # generator update with a stand-in loss
+    g0 = netG[0].weight.detach().clone()
+    monkeypatch.setattr(eng, "g_loss", lambda real_cp: (netsD[0](netG(x)).square().mean(),) + (torch.zeros(()),) * 3)
+    d0 = netsD[0].weight.detach().clone()
+    res = eng.g_step(None)
+    assert len(res) == 4 and not torch.equal(netG[0].weight.detach(), g0)
+    assert torch.equal(netsD[0].weight.detach(), d0) and netsD[0].weight.requires_grad      # D frozen during, restored after
+    assert int(netG[1].num_batches_tracked) == 1
