@@ -63,7 +63,10 @@ def run_gather(A, out_shape, info, taps, wp):
     return out
 
 
-CASES = [(0, 2, 6, 5, 4, 6), (1, 2, 3, 4, 5, 3), (2, 2, 8, 6, 3, 5), (0, 1, 4, 4, 8, 8), (1, 1, 4, 4, 2, 2), (2, 3, 4, 4, 4, 2)]
+CASES = [(0, 2, 6, 5, 4, 6), (1, 2, 3, 4, 5, 3), (2, 2, 8, 6, 3, 5), (0, 1, 4, 4, 8, 8), (1, 1, 4, 4, 2, 2), (2, 3, 4, 4, 4, 2),
+         # edge shapes: single row / column maps, one channel, one sample, strongly non-square, the 2x2 -> 1x1 stride-2 case
+         (0, 1, 1, 7, 3, 2), (0, 2, 5, 1, 1, 4), (0, 1, 1, 1, 2, 3), (1, 1, 1, 1, 3, 2), (1, 2, 1, 5, 2, 1), (1, 1, 7, 2, 1, 3),
+         (2, 1, 2, 2, 3, 2), (2, 2, 2, 10, 1, 3), (2, 1, 12, 2, 2, 1)]
 
 
 @pytest.mark.parametrize("mode,B,H,W,Cin,Cout", CASES)
