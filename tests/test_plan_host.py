@@ -468,3 +468,31 @@ def test_step_engine_update_paths_run_on_cpu_stand_ins(monkeypatch):
     assert len(res) == 4 and not torch.equal(netG[0].weight.detach(), g0)
     assert torch.equal(netsD[0].weight.detach(), d0) and netsD[0].weight.requires_grad      # D frozen during, restored after
     assert int(netG[1].num_batches_tracked) == 1
+
+
+def test_abi_rejects_bad_arguments_with_status_and_message():
+    """SURVEY 8b error contract of the C ABI: int status (negative = invalid argument), never an exception or a launch,
+    and a thread-local message from ekl_last_error().  Argument checks run before any CUDA call, so they are testable
+    without a device."""
+    lib = L.lib()
+    p = C.c_void_p(256)                      # a non-null dummy address: must never be dereferenced on these paths
+
+    def rejected(rc, needle):
+        msg = lib.ekl_last_error().decode()
+        assert rc < 0 and needle in msg, (rc, msg)
+
+    rejected(lib.ekl_color_stats_fwd(None, 2, 64, None, None, None, None), "null pointer")
+    rejected(lib.ekl_color_stats_fwd(p, 2, 63, p, p, p, None), "multiple of 4")
+    rejected(lib.ekl_color_stats_bwd(p, p, None, None, 0, 64, p, None), "multiple of 4")
+    rejected(lib.ekl_head_tanh_fwd(p, 2, 64, 7, p, None), "C % 8")
+    rejected(lib.ekl_img_s2d(p, None, None, 4, 2, 8, 8, p, None), "bad arguments")
+    rejected(lib.ekl_img_s2d(p, None, None, 1, 2, 7, 8, p, None), "bad arguments")
+    rejected(lib.ekl_lrelu_bwd(p, p, p, 12, None), "n % 8")
+    rejected(lib.ekl_cat_code(p, 12, p, 64, 2, 16, p, None), "channels % 8")
+    bad_mode = L.EklConv(7, 2, 8, 8, 16, 16, 0, L.IMPL_TC, 0, 0, 0)
+    rejected(lib.ekl_conv_fwd(bad_mode, p, p, p, None, None), "bad conv mode")
+    odd = L.EklConv(L.DOWN2, 2, 7, 8, 16, 16, 0, L.IMPL_TC, 0, 0, 0)
+    rejected(lib.ekl_conv_fwd(odd, p, p, p, None, None), "even H, W")
+    ok = L.EklConv(L.S1, 2, 8, 8, 16, 16, 0, L.IMPL_TC, 0, 0, 0)
+    rejected(lib.ekl_conv_fwd(ok, None, p, p, None, None), "null pointer")
+    rejected(lib.ekl_conv_bwd_data(ok, p, None, p, None), "null pointer")
