@@ -9,10 +9,15 @@ G backward + Adam, gradient all-reduce when N > 1.  The whole step is one CUDA-g
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = same metric through the public
 trainer API with host batches (pinned H2D copies and a D2H loss read inside the timed region).
 `--impl reference` times the reference's own CPU step (oracle port, or the real reference tree when present).
+
+Every rank executes exactly the same sequence of steps (timed regions, the roofline pass, the barriers): any step
+issues gradient all-reduces when N > 1, so nothing that runs a step may be rank-conditional.
 """
 import argparse
+import gc
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -28,6 +33,7 @@ GFLOP_PER_IMAGE = {"catcls": 48.98, "3stages": 143.1, "onlycapsule": 50.20, "spl
 WORKLOAD = {"catcls": "cfg/birds_2stgs_catcls.yml", "3stages": "cfg/birds_3stages.yml",
             "onlycapsule": "cfg/birds_2stgs_onlycapsule.yml",
             "splitz_cap_ca": "cfg/birds_2stg_splitz_cap_ca.realcls.yml", "coco": "cfg/coco_2stgs.yml"}
+DEFAULT_BATCH = {"catcls": 24, "3stages": 24, "onlycapsule": 32, "splitz_cap_ca": 32, "coco": 64}
 
 
 def peaks():
@@ -82,9 +88,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
-def cpu_step_rate(config, batch, steps, warmup, budget_s, threads=None):
+def cpu_step_rate(config, batch, steps, warmup, budget_s, threads=None, min_steps=1):
     """Reference CPU step (fp32, torch CPU): the real reference tree when present, else the oracle port.
-    Returns (images/s, kind, cores, sample description)."""
+    Runs `warmup` untimed + up to `steps` timed steps of the FULL batch; stops early (never below min_steps timed
+    steps) once budget_s is used up.  Returns (images/s, kind, cores, sample description, s/step, timed steps)."""
     import torch
     from oracle import configs as ocfg, ref_harness, shapes, synth
     from oracle.ekl_oracle import OracleTrainer
@@ -113,103 +120,158 @@ def cpu_step_rate(config, batch, steps, warmup, budget_s, threads=None):
         dt = time.time() - t0
         if i >= warmup:
             times.append(dt)
-        if time.time() - t_start > budget_s and times:
+        if time.time() - t_start > budget_s and len(times) >= min_steps:
             break
     t = sum(times) / len(times)
-    return batch / t, kind, cores, "%d timed step(s) of batch %d (full reference step, fp32 torch CPU), %.2f s/step" % (len(times), batch, t), t
+    sample = "%d timed step(s) after %d warm-up of batch %d (full reference step, fp32 torch CPU, %d threads), %.2f s/step" % (
+        len(times), min(warmup, i), batch, cores, t)
+    return batch / t, kind, cores, sample, t, len(times)
 
 
 def gpu_eager_rate(config, batch, steps=3, warmup=2):
-    """The reference's step as plain PyTorch eager ops on this GPU (cuDNN / cuBLAS kernels, fp32 NCHW): the oracle port
-    with every tensor on the device -- what a user of the unmodified reference gets from a B200 ("the real bar
-    to beat").  'stock' = torch's default precision flags (TF32 allowed for cuDNN convolutions, fp32 matmuls);
-    'strict_fp32' = TF32 off everywhere.  A reported baseline like cpu_baseline, never part of the product path."""
+    """The reference's step as plain PyTorch eager ops on this GPU (cuDNN / cuBLAS kernels): the oracle port with every
+    tensor on the device -- what a user of the unmodified reference gets from a B200 ("the real bar to
+    beat").  'stock' = fp32 NCHW with torch's default precision flags (TF32 allowed for cuDNN convolutions, fp32
+    matmuls); 'strict_fp32' = TF32 off everywhere; 'bf16_autocast_channels_last' = torch.autocast(bfloat16) with
+    filters and images stored channels_last (cuDNN's tensor-core NHWC kernels), the strongest eager configuration.
+    A reported baseline like cpu_baseline, never part of the product path."""
     import torch
     from oracle import configs as ocfg, shapes, synth
     from oracle.ekl_oracle import OracleTrainer
     dev = torch.device("cuda", torch.cuda.current_device())
     oc = ocfg.oracle_cfg(config, batch=batch)
-    to_dev = lambda v: [t.to(dev) for t in v] if isinstance(v, (list, tuple)) else (v.to(dev) if torch.is_tensor(v) else v)
-    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
     res = {}
     try:
-        for mode, conv_tf32 in (("stock", True), ("strict_fp32", False)):
-            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = conv_tf32, False
+        for mode, conv_tf32, autocast in (("stock", True, False), ("strict_fp32", False, False),
+                                          ("bf16_autocast_channels_last", True, True)):
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = conv_tf32, autocast
+            torch.backends.cudnn.benchmark = True            # the reference sets it (cub:286)
+            cl = (lambda t: t.contiguous(memory_format=torch.channels_last) if t.dim() == 4 else t) if autocast else (lambda t: t)
             gsh = shapes.g_shapes(oc, cond_dim=ocfg.cond_dim(oc))
             dsh = [shapes.d_shapes(oc, r, True, oc.D_CAPSULE) for r in [64, 128, 256][: oc.BRANCH_NUM]]
-            on_dev = lambda sd: {k: v.to(dev) for k, v in sd.items()}
+            on_dev = lambda sd: {k: cl(v.to(dev)) for k, v in sd.items()}
             stepper = OracleTrainer(oc, on_dev(shapes.make_state_dict(gsh, "G")),
                                     [on_dev(shapes.make_state_dict(s, "D%d" % i)) for i, s in enumerate(dsh)])
+            to_dev = lambda v: [cl(t.to(dev)) for t in v] if isinstance(v, (list, tuple)) else (v.to(dev) if torch.is_tensor(v) else v)
             b = {k: to_dev(v) for k, v in synth.make_batch(oc, batch, "bench").items()}
-            for _ in range(warmup):
-                stepper.step(**b)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(steps):
-                stepper.step(**b)
-            e1.record()
-            torch.cuda.synchronize()
-            res[mode] = batch / (e0.elapsed_time(e1) / steps * 1e-3)
+
+            def one():
+                if autocast:
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        stepper.step(**b)
+                else:
+                    stepper.step(**b)
+            try:
+                for _ in range(warmup):
+                    one()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    one()
+                e1.record()
+                torch.cuda.synchronize()
+                res[mode] = batch / (e0.elapsed_time(e1) / steps * 1e-3)
+            except Exception as ex:  # noqa: BLE001
+                res[mode + "_failed"] = str(ex)[:160]
             del stepper, b
             torch.cuda.empty_cache()
     finally:
-        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
-    return {"unit": UNIT, "kind": "port, torch eager on cuda:0 (cuDNN / cuBLAS, fp32 NCHW)", "batch": batch,
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    return {"unit": UNIT, "kind": "port, torch eager on cuda:0 (cuDNN / cuBLAS)", "batch": batch,
             "sample": "%d timed steps after %d warm-up" % (steps, warmup), **res}
 
 
 def run_reference_arm(a):
+    """The reference's own CPU implementation of the step on the host cores, on the SAME config and batch as the GPU
+    arm.  Bounded: one untimed warm-up step, then as many of the requested timed steps as fit EKL_REF_BUDGET_S (never
+    fewer than one; the batch is never shrunk)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     batch = a.batch or DEFAULT_BATCH[a.config]
-    # bounded sample: shrink the batch until (steps + warmup) steps fit the budget (BatchNorm keeps work/image ~constant)
-    budget = float(os.environ.get("EKL_REF_BUDGET_S", "240"))
-    import torch
-    probe_b = min(batch, 4)
-    rate, kind, cores, sample, t = cpu_step_rate(a.config, probe_b, 1, 0, 1e9)
-    per_img = t / probe_b
-    b = batch
-    while b > 2 and per_img * b * (a.steps + a.warmup) > budget:
-        b //= 2
-    rate, kind, cores, sample, t = cpu_step_rate(a.config, b, a.steps, a.warmup, budget)
+    budget = float(os.environ.get("EKL_REF_BUDGET_S", "200"))
+    rate, kind, cores, sample, t, n = cpu_step_rate(a.config, batch, max(a.steps, 1), min(a.warmup, 1), budget)
     line = {"metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD[a.config], "resolved_config": a.config, "batch_per_step": b,
-                       "note": "reference CPU training step on host cores; rank 0 only"},
+            "config": {"workload": WORKLOAD[a.config], "resolved_config": a.config, "batch_per_gpu": batch,
+                       "global_batch": batch, "steps_timed": n,
+                       "note": "reference CPU training step on host cores at the GPU arm's batch; rank 0 only; bounded sample: "
+                               "the requested steps are cut short when they exceed %.0f s" % budget},
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-DEFAULT_BATCH = {"catcls": 24, "3stages": 24, "onlycapsule": 32, "splitz_cap_ca": 32, "coco": 64}
-
-
 # ------------------------------------------------------------------------------------------------ GPU arm
-def run_ours(a):
+def make_trainer(config, B):
     import torch
-    import torch.distributed as dist
-    from text2img_ekl_b200 import _lib, configs, ops, parallel
-    from text2img_ekl_b200.engine import GraphedStep
-    from text2img_ekl_b200.synthetic import SyntheticLoader
-    rank, ws = parallel.init_from_env()
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    _lib.check(_lib.lib().ekl_require_sm100())
-    torch.backends.cuda.matmul.allow_tf32 = False
-    B = a.batch or DEFAULT_BATCH[a.config]
-    Trainer = configs.setup(a.config, batch=B)
+    from text2img_ekl_b200 import configs
+    Trainer = configs.setup(config, batch=B)
     torch.manual_seed(0)
     tr = Trainer(None, None, 64)
-    tr.setup()
-    parallel.broadcast_params([tr.netG] + tr.netsD)
-    cls_kind = getattr(tr, "CLS_KIND", "index")
-    loader = SyntheticLoader(B, cls_kind, rank=rank, pool=4)
+    tr.setup()                      # initialises torch.distributed from the environment and broadcasts rank 0's weights
+    return tr
+
+
+def timed_region(fn, steps, warmup, ws, on_gpu=True):
+    """W untimed + K timed calls of fn, bracketed by barrier + synchronize; CUDA-event time, max over ranks (ms).
+    on_gpu=False (the CPU control-flow test): wall clock, gloo."""
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        if on_gpu:
+            torch.cuda.synchronize()
+    for i in range(warmup):
+        fn(i)
+    barrier()
+    if on_gpu:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    else:
+        t0 = time.perf_counter()
+    for i in range(steps):
+        fn(i)
+    if on_gpu:
+        e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) if on_gpu else (time.perf_counter() - t0) * 1e3
+    if ws > 1:
+        t = torch.tensor([ms], device="cuda" if on_gpu else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    return ms
+
+
+def drive(resident, e2e, roofline, a, ws, on_gpu=True, after_resident=None):
+    """The part of the benchmark that runs training steps, in the order every rank must follow: device-resident timed
+    region, end-to-end timed region, roofline pass.  A step issues gradient all-reduces when ws > 1, so this sequence is
+    identical on all ranks; only printing is rank-conditional (tests/test_parallel_gloo.py drives it with a stub step
+    under gloo).  Returns (ms resident, ms e2e, roofline)."""
+    ms = timed_region(resident, a.steps, a.warmup, ws, on_gpu)
+    if after_resident is not None:
+        after_resident()               # host-only bookkeeping (the clock sampler stops here)
+    ms2 = timed_region(e2e, a.steps, max(a.warmup, 1), ws, on_gpu)
+    roof = roofline() if (roofline is not None and not a.no_profile) else None
+    return ms, ms2, roof
+
+
+def measure(tr, a, ws, rank, local_rank, B, pk=None):
+    """The timed regions (and, with pk, the roofline pass) of one configured trainer -> dict."""
+    import torch
+    from text2img_ekl_b200 import ops
+    from text2img_ekl_b200.engine import GraphedStep
+    from text2img_ekl_b200.synthetic import SyntheticLoader
+    loader = SyntheticLoader(B, getattr(tr, "CLS_KIND", "index"), rank=rank, pool=4)
     pool = loader.pool
     use_graph = not a.no_graph
+    gs = None
     if use_graph:
         gs = GraphedStep(tr, pool[0])
         launches_per_step = gs.launches_per_step
@@ -225,38 +287,6 @@ def run_ours(a):
         step_resident = lambda: tr.train_step(dev_batches[0])
         step_e2e = lambda d, nxt=None: tr.train_step(d)
         h2d = sum(t.numel() * t.element_size() for t in pool[0][0] + pool[0][1] + [pool[0][2], pool[0][3]])
-
-    def barrier():
-        if ws > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup):
-        for i in range(warmup):
-            fn(i)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if ws > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms
-
-    # ---- device-resident throughput (inputs already in HBM)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ms = timed(lambda i: step_resident(), a.steps, a.warmup)
-    clocks = sampler.stop() if rank == 0 else None
-    ms_per_step = ms / a.steps
-    value = ws * B / (ms_per_step * 1e-3)
-
     # ---- end to end through the public API: pinned host batch -> H2D -> step -> D2H loss read, every step
     host_loss = torch.zeros(8, pin_memory=True)
 
@@ -266,118 +296,232 @@ def run_ours(a):
         v = errG if torch.is_tensor(errG) else torch.stack([x.detach().float() for x in errG])
         host_loss[: v.numel()].copy_(v.reshape(-1), non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the user reads the loss: a real D2H dependency every step
-    ms2 = timed(e2e_step, a.steps, max(a.warmup, 1))
-    e2e_value = ws * B / (ms2 / a.steps * 1e-3)
-    d2h = 4 * 6
 
-    line = None
+    def roofline():
+        try:
+            return kernel_roofline(tr, gs, pool[0], pk)
+        except Exception as ex:  # noqa: BLE001
+            if ws > 1:
+                raise                # ranks must not diverge silently
+            return {"failed": str(ex)[:300]}
+    # ---- device-resident throughput (inputs already in HBM), then e2e, then the roofline pass: same order on all ranks
+    sampler, clocks = ClockSampler(local_rank), []
     if rank == 0:
-        pk = peaks()
-        gf = GFLOP_PER_IMAGE[a.config]
-        roof = kernel_roofline(tr, pool[0], pk) if not a.no_profile else None
-        step_tf = gf * (value / ws) / 1e3
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": WORKLOAD[a.config], "resolved_config": a.config, "batch_per_gpu": B,
-                           "global_batch": ws * B, "parallelism": "dp%d" % ws, "cuda_graph": use_graph,
-                           "l2": "working set per step (activations + weights, > 1 GB) exceeds the 126 MB L2; no flush",
-                           "gflop_per_image_reference_count": gf},
-                "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms2 / a.steps,
-                        "pipeline": "one upload per step; batch k+1 goes up on a copy stream behind step k" if use_graph
-                        else "upload on the critical path"},
-                "gpu_launches": launches_per_step * a.steps,
-                "step_tflops_reference_count": step_tf,
-                "step_frac_of_bf16_sustained": step_tf / pk["bf16_sustained"],
-                "roofline": roof}
-    if rank == 0 and ws == 1 and not a.no_cpu:
+        sampler.start()
+    ms, ms2, roof = drive(lambda i: step_resident(), e2e_step, roofline if pk is not None else None, a, ws,
+                          after_resident=lambda: clocks.append(sampler.stop() if rank == 0 else None))
+    clocks = clocks[0]
+    return dict(ms_per_step=ms / a.steps, value=ws * B / (ms / a.steps * 1e-3), e2e_ms=ms2 / a.steps,
+                e2e_value=ws * B / (ms2 / a.steps * 1e-3), h2d=h2d, d2h=4 * 6, launches=launches_per_step, clocks=clocks,
+                graph=gs, use_graph=use_graph, roofline=roof)
+
+
+def teardown(ws, *objs):
+    """Leave cleanly: captured graphs hold NCCL kernels, so they are destroyed (and the device drained) BEFORE the
+    process group.  A watchdog ends the process if the communicator teardown does not return (seen once in round 1
+    when the group was destroyed under live graphs); the result line has already been printed by then."""
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if ws <= 1:
+        return
+    dist.barrier()
+    torch.cuda.synchronize()
+    for o in objs:
+        if o is not None and getattr(o, "graph", None) is not None:
+            o.graph.reset()
+            o.graph = None
+    gc.collect()
+    torch.cuda.synchronize()
+    killer = threading.Timer(20.0, lambda: os._exit(0))
+    killer.daemon = True
+    killer.start()
+    dist.destroy_process_group()
+    killer.cancel()
+
+
+def run_ours(a):
+    import torch
+    from text2img_ekl_b200 import _lib, parallel
+    rank, ws = parallel.init_from_env()
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    _lib.check(_lib.lib().ekl_require_sm100())
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B = a.batch or DEFAULT_BATCH[a.config]
+    tr = make_trainer(a.config, B)
+    pk = peaks()
+    m = measure(tr, a, ws, rank, local_rank, B, pk)
+    gf = GFLOP_PER_IMAGE[a.config]
+    roof = m["roofline"]
+    step_tf = gf * (m["value"] / ws) / 1e3
+    line = {"metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": ws, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD[a.config], "resolved_config": a.config, "batch_per_gpu": B,
+                       "global_batch": ws * B, "parallelism": "dp%d" % ws, "cuda_graph": m["use_graph"],
+                       "grad_comm": os.environ.get("EKL_GRAD_COMM", "bf16") if ws > 1 else None,
+                       "l2": "working set per step (activations + weights, > 1 GB) exceeds the 126 MB L2; no flush",
+                       "gflop_per_image_reference_count": gf},
+            "clocks": m["clocks"],
+            "e2e": {"value": m["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
+                    "ms_per_step": m["e2e_ms"],
+                    "pipeline": "one upload per step; batch k+1 goes up on a copy stream behind step k" if m["use_graph"]
+                    else "upload on the critical path"},
+            "gpu_launches": m["launches"] * a.steps,
+            "step_tflops_reference_count": step_tf,
+            "step_frac_of_bf16_sustained": step_tf / pk["bf16_sustained"],
+            "roofline": roof}
+    single = rank == 0 and ws == 1
+    if single and not a.no_cpu:
         try:
             cb = min(B, int(os.environ.get("EKL_CPU_BASELINE_BATCH", "8")))
-            rate, kind, cores, sample, _ = cpu_step_rate(a.config, cb, 1, 1, float(os.environ.get("EKL_CPU_BUDGET_S", "40")))
+            rate, kind, cores, sample, _, _ = cpu_step_rate(a.config, cb, 3, 1, float(os.environ.get("EKL_CPU_BUDGET_S", "45")),
+                                                            min_steps=3)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %s" % ex}
-    if rank == 0 and ws == 1 and not a.no_cpu:
         try:
             line["gpu_eager_baseline"] = gpu_eager_rate(a.config, B)
         except Exception as ex:  # noqa: BLE001
             line["gpu_eager_baseline"] = {"unit": UNIT, "failed": str(ex)[:200]}
+    if single and not a.no_extra:
+        # the other BASELINE configs at their own batch sizes: one short child run each (a fault there cannot take the
+        # headline line down with it); the headline above is config `a.config`
+        extra = {a.config: {"batch_per_gpu": B, "value": m["value"], "ms_per_step": m["ms_per_step"], "e2e": m["e2e_value"],
+                            "frac_of_bf16_sustained": step_tf / pk["bf16_sustained"]}}
+        m["graph"] = None
+        del tr
+        gc.collect()
+        torch.cuda.empty_cache()
+        ks, kw = min(a.steps, 10), min(max(a.warmup, 3), 3)
+        for name in sorted(WORKLOAD):
+            if name in extra:
+                continue
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", name, "--steps", str(ks), "--warmup", str(kw),
+                                    "--no-cpu", "--no-profile", "--no-extra"], capture_output=True, text=True, timeout=150)
+                d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+                extra[name] = {"batch_per_gpu": d["config"]["batch_per_gpu"], "value": d["value"], "ms_per_step": d["ms_per_step"],
+                               "e2e": d["e2e"]["value"], "frac_of_bf16_sustained": d["step_frac_of_bf16_sustained"]}
+            except Exception as ex:  # noqa: BLE001
+                extra[name] = {"failed": str(ex)[:200]}
+        line["extra"] = {"all_configs": extra, "unit": UNIT,
+                         "note": "each BASELINE config at its own batch per GPU, %d timed steps after %d warm-up, 1 GPU" % (ks, kw)}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    if ws > 1:
-        # every rank is past its timed region; leave without tearing the NCCL communicator down under live CUDA
-        # graphs that captured its kernels (destroy_process_group was seen to hang there)
-        dist.barrier()
-        torch.cuda.synchronize()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+    teardown(ws, m.get("graph"))
+
+
+# ------------------------------------------------------------------------------------------------ roofline
+# kernel-name pattern -> family (first match wins).  Names are the demangled CUPTI kernel names.
+FAMILIES = [
+    ("conv_gemm_tc", r"conv_gemm_tc_kernel"),
+    ("conv3x3_rw", r"conv3x3_rw_kernel"),
+    ("conv_wgrad", r"conv_wgrad_"),
+    ("splitk_finish", r"splitk_finish"),
+    ("batchnorm", r"bn_|col_stats"),
+    ("adam", r"adam_step"),
+    ("pack_weights", r"pack_"),
+    ("capsule", r"caps_|dcaps_"),
+    ("nccl", r"nccl"),
+    ("ekl_small", r"ekl|anonymous namespace|<unnamed>"),
+    ("library_gemm", r"gemm|cutlass|cublas|sm\d+_xmma|gemv"),
+    ("torch_glue", r"."),
+]
+# ops-side accounting name -> family its flops / bytes belong to
+ACCOUNT_FAMILY = {"conv_tc:generic": "conv_gemm_tc", "conv_tc:split": "conv_gemm_tc", "conv_tc:rw": "conv3x3_rw",
+                  "conv_wgrad": "conv_wgrad", "bn": "batchnorm", "adam": "adam", "pack_weights": "pack_weights"}
+
+
+def _family(name):
+    for fam, pat in FAMILIES:
+        if re.search(pat, name):
+            return fam
+    return "torch_glue"
 
 
 def ncu_traffic(family):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
-    capture (profiles/r01_conv_full.json, written by tools/ncu_summary.py) -> (bytes per launch, provenance);
-    (None, None) when no capture is committed."""
-    p = os.path.join(ROOT, "profiles", "r01_conv_full.json")
-    if not os.path.exists(p):
-        return None, None
-    key = "conv_wgrad" if "wgrad" in family else "conv_gemm_tc"
-    rows = [r for r in json.load(open(p)) if key in r.get("kernel", "")]
-    if not rows:
-        return None, None
-    tot = sum(r.get("dram__bytes_read.sum", 0.0) + r.get("dram__bytes_write.sum", 0.0) for r in rows)
-    return tot / len(rows), {"launches_captured": len(rows), "source": "profiles/r01_conv_full.json"}
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the newest committed
+    `ncu --set full` capture (profiles/r0N_conv_full.json, written by tools/ncu_summary.py) -> (bytes per launch,
+    provenance); (None, None) when no capture is committed."""
+    pdir = os.path.join(ROOT, "profiles")
+    cands = sorted((f for f in os.listdir(pdir) if re.match(r"r\d+_conv_full\.json$", f)), reverse=True) if os.path.isdir(pdir) else []
+    key = {"conv_gemm_tc": "conv_gemm_tc", "conv3x3_rw": "conv3x3_rw", "conv_wgrad": "conv_wgrad"}.get(family, family)
+    for f in cands:
+        rows = [r for r in json.load(open(os.path.join(pdir, f))) if key in r.get("kernel", "")]
+        if rows:
+            tot = sum(r.get("dram__bytes_read.sum", 0.0) + r.get("dram__bytes_write.sum", 0.0) for r in rows)
+            return tot / len(rows), {"launches_captured": len(rows), "source": "profiles/" + f}
+    return None, None
 
 
-def kernel_roofline(tr, batch, pk):
-    """One eager step with a CUDA-event pair around every kernel-library call (on the launching stream), aggregated
-    per kernel family; `roofline` describes the dominant family (tcgen05 conv forward/dgrad kernel)."""
+def kernel_roofline(tr, gs, batch, pk, replays=3):
+    """Per-kernel-family device time of the step AS BENCHED (CUDA-graph replay; CUPTI kernel records through
+    torch.profiler, taken after the timed regions -- no bench value is measured under the profiler) joined with the
+    algorithmic work of the same launches (one eager step with ops.ACCOUNT on: reference-count flops, executed flops and
+    algorithmic bytes per library call, keyed by the kernel the call routes to).  `roofline` describes the dominant
+    tensor-core family."""
     import torch
+    from torch.profiler import ProfilerActivity, profile
     from text2img_ekl_b200 import ops
-    ops.PROFILE = []
-    # Park the GPU behind a ~120 ms spin before every phase of the step (generate, each discriminator update, generator
-    # update) so that the host enqueues the whole phase ahead of the device (each phase stays below the launch-queue
-    # depth): every event pair then brackets back-to-back device execution of its kernel(s), not host launch latency.
-    spin = int(0.12 * 1.9e9)
+    ops.ACCOUNT = []
+    tr.train_step(batch)
     torch.cuda.synchronize()
-    tr.imgs_tcpu, tr.real_imgs, tr.wrong_imgs, tr.txt_embedding, tr.cls_label = tr.prepare_data(batch)
-    tr.noise.normal_(0, 1)
-    torch.cuda._sleep(spin)
-    tr.generate()
-    for i in reversed(range(tr.num_Ds)):
+    acc, ops.ACCOUNT = ops.ACCOUNT, None
+    work = {}
+    for name, ref_flops, exe_flops, nbytes in acc:
+        d = work.setdefault(ACCOUNT_FAMILY.get(name, name), dict(ref=0.0, exe=0.0, bytes=0.0, calls=0))
+        d["ref"] += ref_flops; d["exe"] += exe_flops; d["bytes"] += nbytes; d["calls"] += 1
+    run = gs.replay if gs is not None else (lambda: tr.train_step(batch))
+    run()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(replays):
+            run()
         torch.cuda.synchronize()
-        torch.cuda._sleep(spin)
-        tr.train_joint_Dnet(i, 1)
-    torch.cuda.synchronize()
-    torch.cuda._sleep(spin)
-    tr.engine.g_step(tr.real_cp)
-    torch.cuda.synchronize()
-    rec, ops.PROFILE = ops.PROFILE, None
     fam = {}
-    for name, flops, nbytes, e0, e1 in rec:
-        d = fam.setdefault(name, dict(us=0.0, flop=0.0, bytes=0.0, launches=0))
-        d["us"] += e0.elapsed_time(e1) * 1e3
-        d["flop"] += flops
-        d["bytes"] += nbytes
-        d["launches"] += 1
+    for ev in prof.key_averages():
+        t = getattr(ev, "device_time_total", None)
+        if t is None:
+            t = getattr(ev, "cuda_time_total", 0.0)
+        if t <= 0:
+            continue
+        d = fam.setdefault(_family(ev.key), dict(us=0.0, launches=0.0))
+        d["us"] += t / replays
+        d["launches"] += ev.count / replays
     total = sum(d["us"] for d in fam.values()) or 1.0
     out = {}
     for k, d in sorted(fam.items(), key=lambda kv: -kv[1]["us"]):
-        out[k] = {"us": round(d["us"], 1), "share": round(d["us"] / total, 4), "launches": d["launches"],
-                  "tflops": round(d["flop"] / (d["us"] * 1e-6) / 1e12, 1) if d["flop"] else None,
-                  "gbs": round(d["bytes"] / (d["us"] * 1e-6) / 1e9, 1) if d["bytes"] else None}
-    top = max((k for k in fam if fam[k]["flop"] > 0), key=lambda k: fam[k]["us"], default=None)
-    if top is None:
-        return None
-    d = fam[top]
-    ach = d["flop"] / (d["us"] * 1e-6) / 1e12
+        w = work.get(k, {})
+        sec = d["us"] * 1e-6
+        out[k] = {"us_per_step": round(d["us"], 1), "share": round(d["us"] / total, 4), "launches_per_step": round(d["launches"], 1),
+                  "tflops_reference_count": round(w["ref"] / sec / 1e12, 1) if w.get("ref") else None,
+                  "tflops_executed": round(w["exe"] / sec / 1e12, 1) if w.get("exe") else None,
+                  "gbs_algorithmic": round(w["bytes"] / sec / 1e9, 1) if w.get("bytes") and not w.get("ref") else None}
+    tensor = [k for k in fam if work.get(k, {}).get("ref")]
+    if not tensor:
+        return {"families": out, "kernel_us_per_step": round(total, 1)}
+    top = max(tensor, key=lambda k: fam[k]["us"])
+    d, w = fam[top], work[top]
+    ach = w["ref"] / (d["us"] * 1e-6) / 1e12
+    conv_us = sum(fam[k]["us"] for k in tensor)
+    conv_ref = sum(work[k]["ref"] for k in tensor)
+    conv_exe = sum(work[k]["exe"] for k in tensor)
     traffic, traffic_src = ncu_traffic(top)
-    return {"bound": "tensor", "kernel": top, "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-            "frac": ach / pk["bf16_sustained"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk["src"] + " (sustained: kernel timed inside a long step)",
-            "flop_counting": "algorithmic (reference dense-conv count) flops of the launches / sum of their CUDA-event durations",
-            "avg_launch_us": d["us"] / d["launches"], "launches_per_step": d["launches"], "families": out}
+    return {"bound": "tensor", "kernel": top + "_kernel", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+            "frac": ach / pk["bf16_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": pk["src"] + " (sustained: kernel timed inside a long step)",
+            "method": "CUPTI kernel durations of %d CUDA-graph replays of the benched step (after the timed regions) / "
+                      "algorithmic flops of the same launches from one accounted eager step" % replays,
+            "flop_counting": "reference dense-conv count (upsampled grid for up-convs, tiled code channels included)",
+            "achieved_executed": w["exe"] / (d["us"] * 1e-6) / 1e12,
+            "avg_launch_us": d["us"] / max(d["launches"], 1), "launches_per_step": d["launches"],
+            "all_conv_kernels": {"us_per_step": round(conv_us, 1), "tflops_reference_count": round(conv_ref / conv_us / 1e6, 1),
+                                 "tflops_executed": round(conv_exe / conv_us / 1e6, 1),
+                                 "frac_reference_count": conv_ref / conv_us / 1e6 / pk["bf16_sustained"]},
+            "kernel_us_per_step": round(total, 1), "families": out}
 
 
 def main():
@@ -389,8 +533,9 @@ def main():
     ap.add_argument("--config", default="3stages", choices=sorted(WORKLOAD))
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and gpu_eager_baseline legs")
+    ap.add_argument("--no-profile", action="store_true", help="skip the roofline pass")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other four BASELINE configs (`extra`, N=1 only)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference_arm(a)

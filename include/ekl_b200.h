@@ -84,6 +84,9 @@ int ekl_conv_bwd_data_ws(const ekl_conv* c, const void* dy, const void* w_dgrad,
  * ws: split-K workspace as for ekl_conv_bwd_data_ws (may be NULL). */
 int ekl_conv_dgrad_from_fwd(const ekl_conv* c);
 int ekl_conv_bwd_data_fw(const ekl_conv* c, const void* dy, const void* w_fwd, void* dx, float* ws, void* stream);
+/* accounting only: the kernel family a call runs on -- 0 generic gather-GEMM kernel, 1 resident-filter 3x3 kernel,
+ * 2 generic kernel with split-K + finishing pass (-1: not a tcgen05 plan) */
+int ekl_conv_route(const ekl_conv* c, int dgrad);
 /* dw[Cout][KH][KW][Cin] += x (*) dy   (fp32, accumulated: zero it first for a fresh gradient) */
 int ekl_conv_bwd_weight(const ekl_conv* c, const void* x, const void* dy, float* dw, void* stream);
 
@@ -207,6 +210,12 @@ int ekl_caps_agree_bwd(const float* x, const float* u, const float* M, const flo
  * of channels_last stride-1 / stride-2 convolutions. */
 int ekl_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float* state, float lr,
                   float beta1, float beta2, float eps, void* stream);
+/* Data-parallel gradient exchange (replaces nn.DataParallel's fp32 reduce-to-GPU0, cub_trainer_splitz_cap_ca.py:139,163):
+ * ekl_cast_bf16 rounds a slice of the flat fp32 gradient buffer to bf16 (the NCCL all-reduce payload: half the NVLink
+ * bytes), ekl_adam_step_g16 is ekl_adam_step reading the averaged gradient from that bf16 buffer.  n % 4 == 0. */
+int ekl_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+int ekl_adam_step_g16(float* p, const void* g_bf16, float* m, float* v, void* shadow_bf16, int64_t n, float* state, float lr,
+                      float beta1, float beta2, float eps, void* stream);
 
 #ifdef __cplusplus
 }

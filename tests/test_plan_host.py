@@ -402,8 +402,8 @@ def test_product_state_dicts_equal_the_reference_golden_lists():
 
 
 def test_discriminator_trunk_marks_fire_deepest_first():
-    """model._DBase._trunk drops an ops.grad_mark behind its blocks (no-op unless a tail-first all-reduce is registered
-    for the network, parallel.TailAllreduce): with stand-in blocks on the CPU the block order of all three trunk depths is
+    """model._DBase._trunk drops an ops.grad_mark behind its blocks (no-op unless a gradient reducer is registered
+    for the network, parallel.GradReducer): with stand-in blocks on the CPU the block order of all three trunk depths is
     unchanged, and registered marks fire in backward order, deepest block first."""
     from text2img_ekl_b200 import model, ops
 
@@ -436,12 +436,12 @@ def test_discriminator_trunk_marks_fire_deepest_first():
 
 def test_step_engine_update_paths_run_on_cpu_stand_ins(monkeypatch):
     """Host-side control flow of engine.StepEngine that every step takes -- construction (flat gradient buffers, BN
-    counters, experiment switches off by default), the discriminator update (_d_update -> _reduce_d -> optimiser) and the
+    counters, no gradient reducers in a single process), the discriminator update (_d_update -> optimiser) and the
     generator update (_g_step: loss -> backward -> join -> optimiser -> counters) -- exercised with tiny CPU stand-in
     networks and torch.optim.Adam, so that a Python-level slip in these paths shows up before a GPU run."""
     from text2img_ekl_b200 import configs, ops
     from text2img_ekl_b200.engine import StepEngine
-    for k in ("EKL_BUCKET_AR", "EKL_WGRAD_STREAM", "EKL_D_PRIO"):
+    for k in ("EKL_WGRAD_STREAM", "EKL_D_PRIO"):
         monkeypatch.delenv(k, raising=False)
     configs.setup("3stages", batch=4)
     torch.manual_seed(0)
@@ -450,7 +450,7 @@ def test_step_engine_update_paths_run_on_cpu_stand_ins(monkeypatch):
     optG = torch.optim.Adam(netG.parameters(), lr=1e-2)
     optsD = [torch.optim.Adam(d.parameters(), lr=1e-2) for d in netsD]
     eng = StepEngine(netG, netsD, optG, optsD, "cond")
-    assert eng.tail_ar == [None, None] and eng.allreduce is None and eng.parallel_d and not ops.GRAD_MARKS
+    assert eng.redD == [None, None] and eng.redG is None and eng.parallel_d and not ops.GRAD_MARKS
     assert not ops.WGRAD_STREAM and ops.join_wgrad() is None
     x = torch.randn(6, 4)
     # discriminator update: gradients are views of the flat buffer, _d_update applies them
@@ -459,7 +459,7 @@ def test_step_engine_update_paths_run_on_cpu_stand_ins(monkeypatch):
     netsD[1](x).square().mean().backward()
     assert netsD[1].weight.grad.data_ptr() == eng.gradsD[1].flat.data_ptr() and float(eng.gradsD[1].flat.abs().sum()) > 0
     eng._d_update(1)
-    assert not torch.equal(netsD[1].weight.detach(), w0) and eng._pending_comm == {}
+    assert not torch.equal(netsD[1].weight.detach(), w0)
     # generator update with a stand-in loss
     g0 = netG[0].weight.detach().clone()
     monkeypatch.setattr(eng, "g_loss", lambda real_cp: (netsD[0](netG(x)).square().mean(),) + (torch.zeros(()),) * 3)

@@ -43,6 +43,7 @@ SIGNATURES = {
     "ekl_conv_fwd_ws": (_i, [_cp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_conv_bwd_data_ws": (_i, [_cp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_conv_dgrad_from_fwd": (_i, [_cp]),
+    "ekl_conv_route": (_i, [_cp, _i]),
     "ekl_conv_bwd_data_fw": (_i, [_cp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_conv_fwd_bias9": (_i, [_cp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_conv_bwd_data": (_i, [_cp, _vp, _vp, _vp, _vp]),
@@ -77,6 +78,8 @@ SIGNATURES = {
     "ekl_caps_agree_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ekl_caps_agree_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "ekl_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _vp]),
+    "ekl_adam_step_g16": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _vp]),
+    "ekl_cast_bf16": (_i, [_vp, _vp, _i64, _vp]),
     "ekl_dloss_bwd": (_i, [_i, _i, _i, _ip, _ip, _ip, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

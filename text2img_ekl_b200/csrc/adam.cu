@@ -17,7 +17,15 @@ __global__ void adam_tick_kernel(float* state, float beta1, float beta2) {
   state[2] = (float)sqrt(1.0 - pow((double)beta2, t));
 }
 
-__global__ void __launch_bounds__(256) adam_step_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+__device__ __forceinline__ float4 load_grad4(const float4* g, int64_t i) { return g[i]; }
+__device__ __forceinline__ float4 load_grad4(const uint2* g, int64_t i) {      // 4 bf16 gradients (the all-reduced staging buffer)
+  const uint2 r = g[i];
+  return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                     __uint_as_float(r.y & 0xffff0000u));
+}
+
+template <typename G4>
+__global__ void __launch_bounds__(256) adam_step_kernel(float4* __restrict__ p, const G4* __restrict__ g, float4* __restrict__ m,
                                                         float4* __restrict__ v, uint2* __restrict__ shadow, int64_t n4,
                                                         const float* __restrict__ state, float lr, float beta1, float beta2,
                                                         float eps) {
@@ -25,7 +33,7 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float4* __restrict__ p, 
   const float inv_bc2 = 1.f / state[2];
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
     float4 pp = p[i], mm = m[i], vv = v[i];
-    const float4 gg = g[i];
+    const float4 gg = load_grad4(g, i);
 #define EKL_ADAM1(c)                                                   \
     mm.c = beta1 * mm.c + (1.f - beta1) * gg.c;                        \
     vv.c = beta2 * vv.c + (1.f - beta2) * gg.c * gg.c;                 \
@@ -37,20 +45,54 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float4* __restrict__ p, 
   }
 }
 
+// fp32 -> bf16 (round to nearest even) of a gradient slice: the NVLink payload of the data-parallel gradient average
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const float4 a = src[i];
+    dst[i] = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+  }
+}
+
+int adam_launch(float* p, const void* g, int g_bf16, float* m, float* v, void* shadow_bf16, int64_t n, float* state, float lr,
+                float beta1, float beta2, float eps, cudaStream_t st) {
+  EKL_REQUIRE(n % 4 == 0 && n > 0, "adam_step: n %% 4");
+  adam_tick_kernel<<<1, 1, 0, st>>>(state, beta1, beta2);
+  EKL_LAUNCH_CHECK();
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (g_bf16)
+    adam_step_kernel<uint2><<<(int)blocks, 256, 0, st>>>((float4*)p, (const uint2*)g, (float4*)m, (float4*)v, (uint2*)shadow_bf16,
+                                                         n / 4, state, lr, beta1, beta2, eps);
+  else
+    adam_step_kernel<float4><<<(int)blocks, 256, 0, st>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v,
+                                                          (uint2*)shadow_bf16, n / 4, state, lr, beta1, beta2, eps);
+  EKL_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
 
 // n must be a multiple of 4 and all buffers 16-byte aligned.  state: 3 device floats {step, 1-b1^t, sqrt(1-b2^t)},
 // zero-initialised by the caller; every call advances the step (device side, so the call is CUDA-graph capturable).
 extern "C" int ekl_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float* state,
                              float lr, float beta1, float beta2, float eps, void* stream) {
-  EKL_REQUIRE(n % 4 == 0 && n > 0, "adam_step: n %% 4");
-  cudaStream_t st = (cudaStream_t)stream;
-  adam_tick_kernel<<<1, 1, 0, st>>>(state, beta1, beta2);
-  EKL_LAUNCH_CHECK();
+  return adam_launch(p, g, 0, m, v, shadow_bf16, n, state, lr, beta1, beta2, eps, (cudaStream_t)stream);
+}
+
+// Same update with the gradient read from a bf16 buffer: the data-parallel path all-reduces gradients as bf16 (half the
+// NVLink bytes of the reference's fp32 DataParallel reduce) and the optimiser consumes that staging buffer directly.
+extern "C" int ekl_adam_step_g16(float* p, const void* g_bf16, float* m, float* v, void* shadow_bf16, int64_t n, float* state,
+                                 float lr, float beta1, float beta2, float eps, void* stream) {
+  return adam_launch(p, g_bf16, 1, m, v, shadow_bf16, n, state, lr, beta1, beta2, eps, (cudaStream_t)stream);
+}
+
+// dst[i] = bf16(src[i]), n % 4 == 0, both 16 / 8-byte aligned: gradient slice -> NVLink payload
+extern "C" int ekl_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream) {
+  EKL_REQUIRE(n % 4 == 0 && n > 0, "cast_bf16: n %% 4");
+  EKL_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst_bf16 & 7) == 0, "cast_bf16: alignment");
   int64_t blocks = (n / 4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  adam_step_kernel<<<(int)blocks, 256, 0, st>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v, (uint2*)shadow_bf16, n / 4,
-                                               state, lr, beta1, beta2, eps);
+  cast_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)src, (uint2*)dst_bf16, n / 4);
   EKL_LAUNCH_CHECK();
   return 0;
 }

@@ -208,6 +208,17 @@ extern "C" int ekl_conv_dgrad_from_fwd(const ekl_conv* c) {
   return ekl_tc_dgrad_from_fwd_ok(&g);
 }
 
+// Which kernel family a conv call of this descriptor runs on (accounting / profiling only):
+// 0 generic gather-GEMM kernel, 1 resident-filter 3x3 kernel, 2 generic kernel split-K (+ finishing pass).
+extern "C" int ekl_conv_route(const ekl_conv* c, int dgrad) {
+  if (check(c) || c->impl != EKL_IMPL_TC) return -1;
+  EklGather g;
+  plan(c, dgrad, nullptr, nullptr, &g);
+  const int group_b = dgrad ? 0 : c->group_b;
+  if (rw_enabled() && ekl_rw_supported(&g, group_b)) return 1;
+  return split_elems(c, &g, group_b) > 0 ? 2 : 0;
+}
+
 extern "C" int ekl_conv_bwd_data_fw(const ekl_conv* c, const void* dy, const void* w_fwd, void* dx, float* ws, void* stream) {
   if (int rc = check(c)) return rc;
   EKL_REQUIRE(ekl_conv_dgrad_from_fwd(c), "conv_bwd_data_fw: this layer needs the transposed operand (ekl_conv_bwd_data)");

@@ -17,7 +17,7 @@ from . import ops
 from .engine import (KL_loss, StepEngine, ce_loss, compute_mean_covariance, onehot)  # noqa: F401  (reference names)
 from .miscc.config import cfg
 from .miscc.utils import mkdir_p
-from .parallel import make_allreduce
+from . import parallel
 
 USE_CLS = True
 SPLIT_Z = True
@@ -108,14 +108,10 @@ def build_Ds(allow_three=False):
     return netsD
 
 
-def load_network(gpus, device=None):
-    """cub:113-196.  Returns (netG, shareGs, netsD, num_Ds, count)."""
-    device = device or (torch.device("cuda", gpus[0]) if gpus else torch.device("cuda"))
-    netG, shareGs = build_G()
-    netG.apply(weights_init)
-    netsD = build_Ds()
-    for d in netsD:
-        d.apply(weights_init)
+def load_snapshots(netG, netsD):
+    """cub:171-184 / trainer.py:138-152: load cfg.TRAIN.NET_G into the generator and cfg.TRAIN.NET_D<i>.pth into the
+    discriminators; the start count is the number in the generator file name + 1 (the reference's int() of the name
+    tail fails on the 'netG_epoch%d.pth' files its own loop writes, SURVEY app. A #11: only the digits are used here)."""
     count = 0
     if cfg.TRAIN.NET_G != "":
         state_dict = torch.load(cfg.TRAIN.NET_G, map_location="cpu")
@@ -127,6 +123,18 @@ def load_network(gpus, device=None):
         for i, d in enumerate(netsD):
             sd = torch.load("%s%d.pth" % (cfg.TRAIN.NET_D, i), map_location="cpu")
             d.load_state_dict(_strip_module(sd))
+    return count
+
+
+def load_network(gpus, device=None):
+    """cub:113-196.  Returns (netG, shareGs, netsD, num_Ds, count)."""
+    device = device or (torch.device("cuda", gpus[0]) if gpus else torch.device("cuda"))
+    netG, shareGs = build_G()
+    netG.apply(weights_init)
+    netsD = build_Ds()
+    for d in netsD:
+        d.apply(weights_init)
+    count = load_snapshots(netG, netsD)
     netG.to(device)
     model.to_kernel_layout(netG)
     for d in netsD:
@@ -187,8 +195,22 @@ class condGANTrainer(object):
         return onehot(cls_vec, n)
 
     # ------------------------------------------------------------------ setup (cub:494-537)
+    def _replicate(self):
+        """One process per GPU (the nn.DataParallel replacement, cub:139,163): join the process group torchrun described
+        in the environment, start every replica from rank 0's weights and buffers (DataParallel replicates GPU0's), and
+        give each rank its own device RNG stream for the in-step noise / eps / seed draws.  No-op for one process."""
+        rank, ws = parallel.init_from_env()
+        if ws > 1:
+            parallel.broadcast_params([self.netG] + list(self.netsD))
+            if self.device.type == "cuda":
+                torch.cuda.manual_seed(torch.cuda.initial_seed() + rank)
+            else:
+                torch.manual_seed(torch.initial_seed() + rank)
+        self.rank, self.world_size = rank, ws
+
     def setup(self):
         self.netG, self.shareGs, self.netsD, self.num_Ds, start_count = load_network(self.gpus, self.device)
+        self._replicate()                    # before the optimisers re-home the parameters into flat buffers
         self.optimizerG, self.optimizersD = define_optimizers(self.netG, self.netsD)
         self.criterion = nn.BCELoss()
         self.CE = ce_loss
@@ -198,8 +220,7 @@ class condGANTrainer(object):
         self.fake_cp = torch.zeros(B, cfg.GAN.ENTITY_DIM + 1, device=self.device)
         self.fake_cp[:, -1] = 1
         self.noise = torch.zeros(B, cfg.GAN.Z_DIM, device=self.device)
-        self.engine = StepEngine(self.netG, self.netsD, self.optimizerG, self.optimizersD, self.KIND, self.COND,
-                                 allreduce=make_allreduce())
+        self.engine = StepEngine(self.netG, self.netsD, self.optimizerG, self.optimizersD, self.KIND, self.COND)
         return start_count
 
     # ------------------------------------------------------------------ reference-named step pieces
@@ -292,9 +313,13 @@ class condGANTrainer(object):
                      " ".join("%.3f" % float(k) for k in errG[4:]), end_t - start_t))
             si = self.snapshot_interval
             if hasattr(self, "model_dir") and (epoch % si == si - 1 or epoch > 199):          # cub:664-669
-                # keys carry the DataParallel "module." prefix like the reference's snapshots (cub:662-667)
-                sd = {"module." + k: v for k, v in self.netG.state_dict().items()}
-                torch.save(sd, "%s/netG_epoch%d.pth" % (self.model_dir, epoch))
+                # keys carry the DataParallel "module." prefix like the reference's snapshots (cub:662-667); replicas
+                # are identical, so rank 0 alone writes and the others wait for the file to be complete
+                if getattr(self, "rank", 0) == 0:
+                    sd = {"module." + k: v for k, v in self.netG.state_dict().items()}
+                    torch.save(sd, "%s/netG_epoch%d.pth" % (self.model_dir, epoch))
+                if getattr(self, "world_size", 1) > 1:
+                    torch.distributed.barrier()
 
     # ------------------------------------------------------------------ checkpoint / resume
     def save_checkpoint(self, path, count):

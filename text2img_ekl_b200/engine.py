@@ -80,19 +80,22 @@ class FlatGrads:
         self.params = [p for p in params if p.requires_grad]
         if hasattr(optimizer, "make_flat_grads"):        # optim.FlatAdam: gradients share the parameters' flat offsets
             self.flat = optimizer.make_flat_grads()
+            self.offsets = list(optimizer.offsets)
             return
-        n = sum(p.numel() for p in self.params)
-        dev = self.params[0].device
-        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
-        off = 0
+        pad4 = lambda n: (n + 3) // 4 * 4                 # 16-byte aligned slices (the gradient reducer's granularity)
+        self.offsets, off = [], 0
         for p in self.params:
+            self.offsets.append(off)
+            off += pad4(p.numel())
+        dev = self.params[0].device
+        self.flat = torch.zeros(off, device=dev, dtype=torch.float32)
+        for p, off in zip(self.params, self.offsets):
             g = self.flat[off:off + p.numel()]
             if p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last) and not p.is_contiguous():
                 g = g.view(p.shape[0], p.shape[2], p.shape[3], p.shape[1]).permute(0, 3, 1, 2)
             else:
                 g = g.view(p.shape)
             p.grad = g
-            off += p.numel()
 
     def zero(self):
         self.flat.zero_()
@@ -132,40 +135,45 @@ class BnCounters:
 class StepEngine:
     """kind 'catz_ca': COND_G_NET_CATZ_CA flavour (cub trainer); 'cond': COND_G_NET flavour (trainer.py)."""
 
-    def __init__(self, netG, netsD, optimizerG, optimizersD, kind, cond="txt+cls", allreduce=None):
+    def __init__(self, netG, netsD, optimizerG, optimizersD, kind, cond="txt+cls", data_parallel=None):
         self.netG, self.netsD = netG, netsD
         self.optG, self.optsD = optimizerG, optimizersD
         self.kind, self.cond = kind, cond
         self.gradsG = FlatGrads(netG.parameters(), optimizerG)
         self.gradsD = [FlatGrads(d.parameters(), o) for d, o in zip(netsD, optimizersD)]
-        self.allreduce = allreduce           # callable(flat_tensor) or None
+        # data parallelism (the nn.DataParallel replacement, cub:139,163): one gradient reducer per network when the
+        # process group has several ranks (data_parallel=None: decided by the process group; False: never).  A
+        # discriminator's reducer starts from the tail of its flat buffer while its backward is still running.
+        from . import parallel
+        dp = parallel.world()[1] > 1 if data_parallel is None else data_parallel
+        self.redG = parallel.make_reducer(self.gradsG.flat) if dp else None
+        self.redD = [parallel.make_reducer(g.flat, d, g.params, g.offsets) if dp else None for d, g in zip(netsD, self.gradsD)]
+        for d, r in zip(netsD, self.redD):
+            if r is not None:
+                ops.GRAD_MARKS[id(d)] = lambda m, r=r: (ops.join_wgrad(), r.on_mark(m))[1]
         self.bn_counters = BnCounters([netG] + list(netsD))
-        self.comm_stream, self._pending_comm = None, {}
         # EKL_PARALLEL_D=0 runs the discriminators one after the other on the caller's stream
         self.parallel_d = os.environ.get("EKL_PARALLEL_D", "1") != "0" and len(netsD) > 1
-        self.d_streams, self._on_d_stream = None, False
+        self.d_streams = None
         self.d_logits = {}                   # idx -> (real, wrong, fake) x [match p, uncond p, class log-probs]
         self.uncond = float(cfg.TRAIN.COEFF.UNCOND_LOSS)
         self.kl_coeff = float(cfg.TRAIN.COEFF.KL)
         self.color_coeff = float(cfg.TRAIN.COEFF.COLOR_LOSS)      # 0.0 in every shipped yml (config.py:61)
         self.last_color = []
         self.cat_z = cfg.TRAIN.CAT_Z
-        # EKL_BUCKET_AR=1 (experiment, off by default, N > 1): each discriminator's gradient all-reduce starts from the
-        # tail of its flat buffer while its backward is still running (parallel.TailAllreduce)
-        self.tail_ar = [None] * len(netsD)
-        if allreduce is not None and os.environ.get("EKL_BUCKET_AR", "0") == "1":
-            from .parallel import TailAllreduce
-            for i, (d, opt, g) in enumerate(zip(netsD, optimizersD, self.gradsD)):
-                if hasattr(opt, "offsets"):
-                    self.tail_ar[i] = TailAllreduce(d, opt.plist, opt.offsets, opt.n, g.flat)
-                    ops.GRAD_MARKS[id(d)] = lambda m, t=self.tail_ar[i]: (ops.join_wgrad(), t.on_mark(m))[1]
 
-    def _reduce_d(self, idx):
-        """Average discriminator idx's gradients over the ranks (no-op for a single process)."""
-        if self.tail_ar[idx] is not None:
-            self.tail_ar[idx].finish()
-        elif self.allreduce is not None:
-            self.allreduce(self.gradsD[idx].flat)
+    @staticmethod
+    def _apply(opt, red):
+        """Optimiser step on the (rank-averaged) gradients: with a reducer, its remaining slices go out, the side stream
+        is joined and the optimiser reads the buffer the reducer hands back (bf16 staging or the fp32 flat buffer)."""
+        if red is None:
+            opt.step()
+            return
+        g, is_bf16 = red.finish()
+        if is_bf16:
+            opt.step(grads_bf16=g)
+        else:
+            opt.step()
 
     # ---- (1) generate: cub:567-587 / trainer.py:524-528
     def generate(self, noise, txt, cls_cond, eps=None, seed=None):
@@ -198,14 +206,13 @@ class StepEngine:
     def _d_step(self, idx, real_imgs, wrong_imgs, real_cp, fake_cp):
         netD, opt, grads = self.netsD[idx], self.optsD[idx], self.gradsD[idx]
         B = real_imgs.shape[0]
-        self._join_comm(idx)                 # a still-pending update of this same discriminator must land first
         grads.zero()
         if hasattr(netD, "heads_raw") and self.uncond > 0:
             # fused path: raw logits of the stacked real / wrong / fake pass -> one loss kernel (cub:423-448)
             lm, lu, lc = netD.heads_raw((real_imgs, wrong_imgs, self.fake_imgs[idx].detach()), self.mu.detach(), groups=3)
             losses, pm, pu, logp = ops.d_loss(lm, lu, lc, real_cp, fake_cp, 3, B, (1, 0, 0), (1, 1, 0), (0, -1, 1), self.uncond)
-            if self.tail_ar[idx] is not None:
-                self.tail_ar[idx].begin()
+            if self.redD[idx] is not None:
+                self.redD[idx].begin()
             losses[0].backward()
             self._d_update(idx)
             self.d_logits[idx] = tuple([pm[i * B:(i + 1) * B], pu[i * B:(i + 1) * B], logp[i * B:(i + 1) * B]] for i in range(3))
@@ -223,8 +230,8 @@ class StepEngine:
         else:
             errD_uncond = errD_cls = torch.zeros((), device=real_imgs.device)
             errD = _bce_const(real[0], 1) + 0.5 * (_bce_const(wrong[0], 0) + _bce_const(fake[0], 0))
-        if self.tail_ar[idx] is not None:
-            self.tail_ar[idx].begin()
+        if self.redD[idx] is not None:
+            self.redD[idx].begin()
         errD.backward()
         self._d_update(idx)
         self.d_logits[idx] = (real, wrong, fake)
@@ -236,34 +243,11 @@ class StepEngine:
         return self.d_logits[max(self.d_logits)]
 
     def _d_update(self, idx):
-        """Gradient all-reduce (N > 1) + Adam step of discriminator idx.  With several ranks it runs on a side stream, so
-        the all-reduce over NVLink and the optimiser pass of D_i overlap the forward / backward of D_{i+1} (their
-        updates are independent: cub:594-596 loops over the discriminators); g_step joins the side stream before the
-        updated discriminators are used."""
-        grads, opt = self.gradsD[idx], self.optsD[idx]
+        """Gradient average over the ranks (N > 1: the slices still outstanding, see parallel.GradReducer) + Adam step of
+        discriminator idx.  The updates of the discriminators are independent (cub:594-596 loops over them) and run as
+        parallel stream branches (d_steps), so one discriminator's exchange also overlaps the others' compute."""
         ops.join_wgrad()                     # (EKL_WGRAD_STREAM experiment: side-stream weight gradients must have landed)
-        if self.allreduce is None or self._on_d_stream:
-            # (on a per-discriminator stream the all-reduce already overlaps the other discriminators' work)
-            self._reduce_d(idx)
-            opt.step()
-            return
-        if self.comm_stream is None:
-            self.comm_stream = torch.cuda.Stream()
-        main = torch.cuda.current_stream()
-        self.comm_stream.wait_stream(main)
-        with torch.cuda.stream(self.comm_stream):
-            self._reduce_d(idx)
-            opt.step()
-            ev = torch.cuda.Event()
-            ev.record()
-        self._pending_comm[idx] = ev
-
-    def _join_comm(self, idx=None):
-        """Make the current stream wait for the side-stream update of discriminator idx (all of them if None)."""
-        for k in ([idx] if idx is not None else list(self._pending_comm)):
-            ev = self._pending_comm.pop(k, None)
-            if ev is not None:
-                torch.cuda.current_stream().wait_event(ev)
+        self._apply(self.optsD[idx], self.redD[idx])
 
     def _streams(self):
         if self.d_streams is None:
@@ -279,24 +263,20 @@ class StepEngine:
         """All discriminator updates of one iteration (cub:594-596).  They are independent of each other (own
         parameters, gradients, optimiser; inputs are the detached fakes), so each runs on its own stream: the
         latency-bound tails of one discriminator (4x4 / 8x8 maps: kernels of 50-150 CTAs) fill the SMs another one
-        leaves idle, and with several ranks its gradient all-reduce hides behind the others' compute.  Captured into the
+        leaves idle, and with several ranks its gradient exchange hides behind the others' compute.  Captured into the
         step graph as parallel branches.  Returns the per-discriminator loss tuples in index order."""
         n = len(self.netsD)
         errDs = [None] * n
         if not self.parallel_d:
-            for i in reversed(range(n)):          # largest first: its all-reduce (side stream) hides behind the others
+            for i in reversed(range(n)):
                 errDs[i] = self.d_step(i, real_imgs[i], wrong_imgs[i], real_cp, fake_cp)
             return errDs
         main = torch.cuda.current_stream()
         streams = self._streams()
-        self._on_d_stream = True
-        try:
-            for i in reversed(range(n)):
-                streams[i].wait_stream(main)
-                with torch.cuda.stream(streams[i]):
-                    errDs[i] = self.d_step(i, real_imgs[i], wrong_imgs[i], real_cp, fake_cp)
-        finally:
-            self._on_d_stream = False
+        for i in reversed(range(n)):              # largest first
+            streams[i].wait_stream(main)
+            with torch.cuda.stream(streams[i]):
+                errDs[i] = self.d_step(i, real_imgs[i], wrong_imgs[i], real_cp, fake_cp)
         for st in streams:
             main.wait_stream(st)
         return errDs
@@ -324,7 +304,6 @@ class StepEngine:
 
     # ---- (3) generator loss through the UPDATED discriminators: cub:463-490
     def g_loss(self, real_cp):
-        self._join_comm()
         errGs_match = errGs_uncond = errGs_cls = errGs_total_fused = 0
         self.last_g_logits = []
         main = torch.cuda.current_stream()
@@ -382,7 +361,6 @@ class StepEngine:
             return self._g_step(real_cp)
 
     def _g_step(self, real_cp):
-        self._join_comm()                    # discriminator updates issued on the side stream must have landed
         self.gradsG.zero()
         for d in self.netsD:
             d.requires_grad_(False)          # the reference computes and discards these
@@ -393,17 +371,16 @@ class StepEngine:
         finally:
             for d in self.netsD:
                 d.requires_grad_(True)
-        if self.allreduce is not None:
-            self.allreduce(self.gradsG.flat)
-        self.optG.step()
+        if self.redG is not None:
+            self.redG.begin()
+        self._apply(self.optG, self.redG)
         self.bn_counters.flush()
         return res
 
     # ---- whole step on device-resident inputs
     def step(self, real_imgs, wrong_imgs, txt, cls_cond, real_cp, fake_cp, noise, eps=None, seed=None):
         self.generate(noise, txt, cls_cond, eps, seed)
-        # the discriminator updates are independent (cub:594-596); the largest goes first so that its gradient
-        # all-reduce + Adam (side stream, N > 1) hide behind the smaller ones' compute
+        # the discriminator updates are independent (cub:594-596): parallel stream branches, the largest issued first
         errDs = self.d_steps(real_imgs, wrong_imgs, real_cp, fake_cp)
         errG = self.g_step(real_cp)
         return errDs, errG

@@ -334,6 +334,8 @@ class NEXT_STAGE_G(nn.Module):
             self.upsample2 = upBlock(ngf // 2, ngf // 4)
         self._fold = ngf % 16 == 0 and (2 * ngf) % 32 == 0
         self._spec_x = ops.ConvSpec(ops.S1, ngf, 2 * ngf, impl=L.IMPL_TC) if self._fold else None
+        if self._fold:
+            self._spec_x.ref = (ngf + self.ef_dim, 2 * ngf, 9)          # the reference convolves the tiled code channels too
         self._valid = None
 
     def _joint(self, h_code, c_code):
@@ -384,6 +386,7 @@ class GET_IMAGE_G(nn.Module):
         self.img = nn.Sequential(conv3x3(ngf, 3), nn.Tanh())
         if ngf % 16 == 0:
             self._spec = ops.ConvSpec(ops.S1, ngf, self.PAD, impl=L.IMPL_TC)
+            self._spec.ref = (ngf, 3, 9)
         else:
             self._spec = ops.ConvSpec(ops.S1, ngf, 3, impl=L.IMPL_SIMT, y_fmt=L.FMT_NCHW_F32, act=ops.ACT_TANH)
 
@@ -599,6 +602,7 @@ class _Encode16(nn.Sequential):
         self._tc0 = ndf % 32 == 0
         if self._tc0:
             self._s0 = ops.ConvSpec(ops.S1, 16, ndf, impl=L.IMPL_TC, act=ops.ACT_LRELU)
+            self._s0.ref = (3, ndf, 16)              # conv4x4 s2 over 3 channels, counted on its own output grid
             self._s2d = None
         else:
             self._s0 = ops.ConvSpec(ops.DOWN2, 3, ndf, impl=L.IMPL_SIMT, x_fmt=L.FMT_NCHW_F32, act=ops.ACT_LRELU)

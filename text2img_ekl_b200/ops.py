@@ -23,9 +23,9 @@ def _count(n=1):
     LAUNCHES[0] += n
 
 
-# bench.py's kernel_roofline(): when a list, every library call appends (family, algorithmic flops, algorithmic bytes,
-# start event, end event) recorded on the launching stream
-PROFILE = None
+# bench.py's kernel_roofline(): when a list, every library call appends (accounting name, reference-count flops,
+# executed flops, algorithmic bytes).  Device times come from CUPTI records of the graph replay, not from here.
+ACCOUNT = None
 # tools/layer_bench.py: when a list, every conv / BatchNorm call appends its shape key
 SHAPE_LOG = None
 
@@ -52,28 +52,32 @@ def _log(*key):
         SHAPE_LOG.append(key)
 
 
-class _prof:
-    def __init__(self, name, flops=0.0, nbytes=0.0):
-        self.a = (name, float(flops), float(nbytes))
-
-    def __enter__(self):
-        if PROFILE is not None:
-            self.e0 = torch.cuda.Event(enable_timing=True)
-            self.e0.record()
-        return self
-
-    def __exit__(self, *exc):
-        if PROFILE is not None:
-            e1 = torch.cuda.Event(enable_timing=True)
-            e1.record()
-            PROFILE.append(self.a + (self.e0, e1))
-        return False
+def _acct(name, flops=(0.0, 0.0), nbytes=0.0):
+    if ACCOUNT is not None:
+        ACCOUNT.append((name, float(flops[0]), float(flops[1]), float(nbytes)))
 
 
 def _conv_flops(spec, B, H, W):
+    """(reference-count flops, executed flops) of one conv pass.  Reference count = the dense conv the reference runs
+    (SURVEY 8d): 2*B*Ho*Wo*Cout*Cin*KH*KW on the upsampled grid for up-convs, with the layer's real channel / tap
+    counts (spec.ref = (cin, cout, taps) where they differ from what the kernel contracts: folded code channels, padded
+    image-head outputs, the space-to-depth stem).  Executed = what the kernel multiplies (sub-pixel up-convs: 16 taps per
+    2x2 output block instead of 36)."""
     Ho, Wo = spec.out_hw(H, W)
     k = 16 if spec.mode == DOWN2 else 9
-    return 2.0 * B * Ho * Wo * spec.cout * spec.cin * k       # reference dense-conv count (upsampled grid for UP2)
+    rcin, rcout, rk = spec.ref or (spec.cin, spec.cout, k)
+    ref = 2.0 * B * Ho * Wo * rcout * rcin * rk
+    exe = 2.0 * B * Ho * Wo * spec.cout * spec.cin * k / (2.25 if spec.mode == UP2 else 1.0)
+    return ref, exe
+
+
+def _route(spec, c, dgrad):
+    """accounting name of the kernel family a conv call runs on (include/ekl_b200.h: ekl_conv_route)."""
+    if ACCOUNT is None:
+        return ""
+    if spec.impl != L.IMPL_TC:
+        return "conv_simt"
+    return "conv_tc:" + ("generic", "rw", "split")[L.lib().ekl_conv_route(c, dgrad)]
 
 
 def _grad_buffer(p):
@@ -102,6 +106,7 @@ class ConvSpec:
     def __init__(self, mode, cin, cout, impl=L.IMPL_TC, x_fmt=0, y_fmt=0, act=ACT_NONE):
         self.mode, self.cin, self.cout, self.impl = mode, cin, cout, impl
         self.x_fmt, self.y_fmt, self.act = x_fmt, y_fmt, act
+        self.ref = None                  # (cin, cout, taps) of the reference layer when they differ (flop accounting only)
         self._ver, self._dirty = None, False
         self.w_layout = L.W_KCRS
         self.w_fwd = self.w_dgrad = self._fwd_buf = None
@@ -175,8 +180,8 @@ class ConvSpec:
             if w_fwd_arg is not None or w_dgrad_arg is not None:
                 nb = weight.numel() * 4 + ((w_fwd_arg.numel() if w_fwd_arg is not None else 0) +
                                            (w_dgrad_arg.numel() if w_dgrad_arg is not None else 0)) * 2
-                with _prof("pack_weights", 0, nb):
-                    L.check(lib.ekl_conv_pack(c, L.ptr(weight), L.ptr(w_fwd_arg), L.ptr(w_dgrad_arg), L.stream()))
+                _acct("pack_weights", nbytes=nb)
+                L.check(lib.ekl_conv_pack(c, L.ptr(weight), L.ptr(w_fwd_arg), L.ptr(w_dgrad_arg), L.stream()))
                 _count((w_fwd_arg is not None) + (w_dgrad_arg is not None))
             self._ver, self._dirty = key, False
         return self.w_fwd, self.w_dgrad
@@ -257,11 +262,11 @@ class _Conv(torch.autograd.Function):
             stats = torch.empty(rows, 2, spec.cout, device=x.device, dtype=torch.float32)
         fam = "conv_tc" if spec.impl == L.IMPL_TC else "conv_simt"
         _log("fwd", fam, spec.mode, B, H, W, spec.cin, spec.cout, group_b)
-        with _prof(fam + "_fwd", _conv_flops(spec, B, H, W), x.numel() * x.element_size() + y.numel() * y.element_size()):
-            if ws is not None:
-                L.check(lib.ekl_conv_fwd_ws(c, L.ptr(x), L.ptr(w_fwd), L.ptr(y), L.ptr(stats), L.ptr(ws), L.stream()))
-            else:
-                L.check(lib.ekl_conv_fwd(c, L.ptr(x), L.ptr(w_fwd), L.ptr(y), L.ptr(stats), L.stream()))
+        _acct(_route(spec, c, 0), _conv_flops(spec, B, H, W), x.numel() * x.element_size() + y.numel() * y.element_size())
+        if ws is not None:
+            L.check(lib.ekl_conv_fwd_ws(c, L.ptr(x), L.ptr(w_fwd), L.ptr(y), L.ptr(stats), L.ptr(ws), L.stream()))
+        else:
+            L.check(lib.ekl_conv_fwd(c, L.ptr(x), L.ptr(w_fwd), L.ptr(y), L.ptr(stats), L.stream()))
         _count(2 if ws is not None else 1)
         ctx.dims = (B, H, W)
         if spec.act != ACT_NONE and spec.impl == L.IMPL_TC:
@@ -292,7 +297,7 @@ class _Conv(torch.autograd.Function):
                 dy = dy * (1.0 - y.float() ** 2).to(dy.dtype)
         dx = None
         want_w = ctx.needs_input_grad[1] and not ctx.skip_wgrad
-        if want_w and ctx.w_leaf and WGRAD_STREAM and PROFILE is None:
+        if want_w and ctx.w_leaf and WGRAD_STREAM:
             _log("wgrad", fam, spec.mode, *ctx.dims, spec.cin, spec.cout, 0)
             _wgrad_side_launch(c, x, dy, _grad_buffer(weight))       # ahead of the data gradient, on the side stream
             _count()
@@ -300,8 +305,8 @@ class _Conv(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             _log("dgrad", fam, spec.mode, *ctx.dims, spec.cin, spec.cout, 0)
-            with _prof(fam + "_dgrad", _conv_flops(spec, *ctx.dims), dx.numel() * dx.element_size() + dy.numel() * dy.element_size()):
-                _run_dgrad(spec, c, weight, dy, dx)
+            _acct(_route(spec, c, 1), _conv_flops(spec, *ctx.dims), dx.numel() * dx.element_size() + dy.numel() * dy.element_size())
+            _run_dgrad(spec, c, weight, dy, dx)
         dw = None
         if want_w:
             if ctx.w_leaf:
@@ -309,8 +314,9 @@ class _Conv(torch.autograd.Function):
             else:
                 buf = dw = torch.zeros_like(weight, memory_format=torch.preserve_format)
             _log("wgrad", fam, spec.mode, *ctx.dims, spec.cin, spec.cout, 0)
-            with _prof(fam + "_wgrad", _conv_flops(spec, *ctx.dims), x.numel() * x.element_size() + dy.numel() * dy.element_size()):
-                L.check(lib.ekl_conv_bwd_weight(c, L.ptr(x), L.ptr(dy), L.ptr(buf), L.stream()))
+            _acct("conv_wgrad" if spec.impl == L.IMPL_TC else "conv_simt", _conv_flops(spec, *ctx.dims),
+                  x.numel() * x.element_size() + dy.numel() * dy.element_size())
+            L.check(lib.ekl_conv_bwd_weight(c, L.ptr(x), L.ptr(dy), L.ptr(buf), L.stream()))
             _count()
         return dx, dw, None, None, None, None
 
@@ -356,8 +362,8 @@ class _ConvBias9(torch.autograd.Function):
             stats = torch.empty(lib.ekl_conv_stats_rows(c), 2, spec.cout, device=x.device, dtype=torch.float32)
         bias9 = bias9.float().contiguous()
         _log("fwd", "conv_tc", spec.mode, B, H, W, spec.cin, spec.cout, 0)
-        with _prof("conv_tc_fwd", _conv_flops(spec, B, H, W), x.numel() * 2 + y.numel() * 2):
-            L.check(lib.ekl_conv_fwd_bias9(c, L.ptr(x), L.ptr(w_fwd), L.ptr(bias9), L.ptr(y), L.ptr(stats), L.stream()))
+        _acct(_route(spec, c, 0), _conv_flops(spec, B, H, W), x.numel() * 2 + y.numel() * 2)
+        L.check(lib.ekl_conv_fwd_bias9(c, L.ptr(x), L.ptr(w_fwd), L.ptr(bias9), L.ptr(y), L.ptr(stats), L.stream()))
         _count()
         ctx.dims = (B, H, W)
         ctx.save_for_backward(x, weight)
@@ -377,14 +383,14 @@ class _ConvBias9(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             _log("dgrad", "conv_tc", spec.mode, *ctx.dims, spec.cin, spec.cout, 0)
-            with _prof("conv_tc_dgrad", _conv_flops(spec, *ctx.dims), dx.numel() * 2 + dy.numel() * 2):
-                _run_dgrad(spec, c, weight, dy, dx)
+            _acct(_route(spec, c, 1), _conv_flops(spec, *ctx.dims), dx.numel() * 2 + dy.numel() * 2)
+            _run_dgrad(spec, c, weight, dy, dx)
         if ctx.needs_input_grad[1]:
             buf = _grad_buffer(weight) if ctx.w_leaf else torch.zeros_like(weight, memory_format=torch.preserve_format)
             dw = None if ctx.w_leaf else buf
             _log("wgrad", "conv_tc", spec.mode, *ctx.dims, spec.cin, spec.cout, 0)
-            with _prof("conv_tc_wgrad", _conv_flops(spec, *ctx.dims), x.numel() * 2 + dy.numel() * 2):
-                L.check(lib.ekl_conv_bwd_weight(c, L.ptr(x), L.ptr(dy), L.ptr(buf), L.stream()))
+            _acct("conv_wgrad", _conv_flops(spec, *ctx.dims), x.numel() * 2 + dy.numel() * 2)
+            L.check(lib.ekl_conv_bwd_weight(c, L.ptr(x), L.ptr(dy), L.ptr(buf), L.stream()))
             _count()
         if ctx.needs_input_grad[2]:
             db = border_class_sums(dy)
@@ -407,8 +413,8 @@ class _BnAct(torch.autograd.Function):
         if stats is None:
             rows = lib.ekl_col_stats_rows(M, C, groups)
             stats = torch.empty(rows, 2, C, device=dev, dtype=torch.float32)
-            with _prof("bn_col_stats", 0, M * C * 2):
-                L.check(lib.ekl_col_stats(L.ptr(y), M, C, groups, L.ptr(stats), L.stream()))
+            _acct("bn", nbytes=M * C * 2)
+            L.check(lib.ekl_col_stats(L.ptr(y), M, C, groups, L.ptr(stats), L.stream()))
             _count()
         rows_per_group = stats.shape[0] // groups
         _log("bn_fwd", M, C, groups, act, residual is not None)
@@ -416,19 +422,18 @@ class _BnAct(torch.autograd.Function):
         rstd = torch.empty(groups, C, device=dev, dtype=torch.float32)
         Co = C // 2 if act == ACT_GLU else C
         out = torch.empty(*y.shape[:-1], Co, device=dev, dtype=torch.bfloat16)
-        with _prof("bn_act_fwd", 0, M * (C + Co + (Co if residual is not None else 0)) * 2):
-            rc = lib.ekl_bn_act_fwd_small(L.ptr(stats), rows_per_group, float(M // groups), BN_EPS, BN_MOM, L.ptr(running_mean),
+        # algorithmic bytes (minimal-traffic model): y read once, out written once (+ the residual read)
+        _acct("bn", nbytes=M * (C + Co + (Co if residual is not None else 0)) * 2)
+        rc = lib.ekl_bn_act_fwd_small(L.ptr(stats), rows_per_group, float(M // groups), BN_EPS, BN_MOM, L.ptr(running_mean),
                                           L.ptr(running_var), L.ptr(y), M, C, groups, L.ptr(gamma), L.ptr(beta), act,
                                           L.ptr(residual), L.ptr(out), L.ptr(mean), L.ptr(rstd), L.stream())
         if rc == 0:
             _count(1)
         elif rc == 2000:       # not a small layer: finalize + streaming pass
-            with _prof("bn_finalize", 0, stats.numel() * 4):
-                L.check(lib.ekl_bn_finalize(L.ptr(stats), rows_per_group, C, groups, float(M // groups), BN_EPS, BN_MOM,
-                                            L.ptr(mean), L.ptr(rstd), L.ptr(running_mean), L.ptr(running_var), L.stream()))
-            with _prof("bn_act_fwd", 0, M * (C + Co + (Co if residual is not None else 0)) * 2):
-                L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, C, groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), act,
-                                           L.ptr(residual), L.ptr(out), L.stream()))
+            L.check(lib.ekl_bn_finalize(L.ptr(stats), rows_per_group, C, groups, float(M // groups), BN_EPS, BN_MOM,
+                                        L.ptr(mean), L.ptr(rstd), L.ptr(running_mean), L.ptr(running_var), L.stream()))
+            L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, C, groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), act,
+                                       L.ptr(residual), L.ptr(out), L.stream()))
             _count(2)
         else:
             L.check(rc)
@@ -450,11 +455,12 @@ class _BnAct(torch.autograd.Function):
         pg = gamma.requires_grad and not ctx.skip_pgrad
         Co = C // 2 if ctx.act == ACT_GLU else C
         _log("bn_bwd", M, C, ctx.groups, ctx.act, ctx.has_res)
-        with _prof("bn_act_bwd", 0, M * (2 * C + 2 * Co + C) * 2):     # two passes over y and dout, one write of dy
-            L.check(lib.ekl_bn_act_bwd(L.ptr(y), L.ptr(dout), M, C, ctx.groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma),
-                                       L.ptr(beta), ctx.act, L.ptr(partial), L.ptr(sums),
-                                       L.ptr(_grad_buffer(gamma)) if pg else None, L.ptr(_grad_buffer(beta)) if pg else None,
-                                       L.ptr(dy), L.stream()))
+        # algorithmic bytes (minimal-traffic model): y and dout read once, dy written once (the kernel makes two passes)
+        _acct("bn", nbytes=M * (2 * C + Co) * 2)
+        L.check(lib.ekl_bn_act_bwd(L.ptr(y), L.ptr(dout), M, C, ctx.groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma),
+                                   L.ptr(beta), ctx.act, L.ptr(partial), L.ptr(sums),
+                                   L.ptr(_grad_buffer(gamma)) if pg else None, L.ptr(_grad_buffer(beta)) if pg else None,
+                                   L.ptr(dy), L.stream()))
         _count(3)
         return dy, None, None, None, None, None, None, None, (dout if ctx.has_res else None), None
 

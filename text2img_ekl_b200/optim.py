@@ -89,7 +89,9 @@ class FlatAdam(torch.optim.Optimizer):
         return self.flat_g
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, grads_bf16=None):
+        """grads_bf16: optional bf16 buffer in the flat layout holding the gradients to apply instead of the fp32 flat
+        buffer (the rank-averaged staging buffer of parallel.GradReducer)."""
         if self.flat_p.device.type != "cuda":
             raise L.EklError("FlatAdam.step drives the CUDA kernel library (ekl_adam_step): there is no CPU path; "
                              "use torch.optim.Adam for CPU tensors")
@@ -103,8 +105,15 @@ class FlatAdam(torch.optim.Optimizer):
                     p.grad.copy_(g)
         grp = self.param_groups[0]
         b1, b2 = grp["betas"]
-        L.check(L.lib().ekl_adam_step(L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
-                                      L.ptr(self.shadow), self.n, L.ptr(self.state_dev), float(grp["lr"]), float(b1), float(b2),
-                                      float(grp["eps"]), L.stream()))
+        if grads_bf16 is not None:
+            assert grads_bf16.dtype == torch.bfloat16 and grads_bf16.numel() == self.n
+            L.check(L.lib().ekl_adam_step_g16(L.ptr(self.flat_p), L.ptr(grads_bf16), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
+                                              L.ptr(self.shadow), self.n, L.ptr(self.state_dev), float(grp["lr"]), float(b1),
+                                              float(b2), float(grp["eps"]), L.stream()))
+        else:
+            L.check(L.lib().ekl_adam_step(L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
+                                          L.ptr(self.shadow), self.n, L.ptr(self.state_dev), float(grp["lr"]), float(b1),
+                                          float(b2), float(grp["eps"]), L.stream()))
         ops._count(2)
+        ops._acct("adam", nbytes=30.0 * self.n)          # 16 B read (p, g, m, v) + 14 B written (p, m, v, bf16 shadow) per parameter
         ops.mark_dirty(self.plist)          # the packed data-gradient filter operands are stale now

@@ -21,12 +21,13 @@ def load_network(gpus, device=None, cond="txt+cls"):
     netsD = _cub.build_Ds()
     for d in netsD:
         d.apply(weights_init)
+    count = _cub.load_snapshots(netG, netsD)           # trainer.py:138-152: cfg.TRAIN.NET_G / NET_D resume
     netG.to(device)
     model.to_kernel_layout(netG)
     for d in netsD:
         d.to(device)
         model.to_kernel_layout(d)
-    return netG, shareGs, netsD, len(netsD), 0
+    return netG, shareGs, netsD, len(netsD), count
 
 
 class condGANTrainer(_cub.condGANTrainer):
@@ -46,15 +47,14 @@ class condGANTrainer(_cub.condGANTrainer):
 
     def setup(self):
         self.netG, self.shareGs, self.netsD, self.num_Ds, start_count = load_network(self.gpus, self.device, self.COND)
+        self._replicate()
         self.optimizerG, self.optimizersD = define_optimizers(self.netG, self.netsD)
         B = self.batch_size
         self.fake_cp = torch.zeros(B, cfg.GAN.ENTITY_DIM + 1, device=self.device)
         self.fake_cp[:, -1] = 1
         self.noise = torch.zeros(B, cfg.GAN.Z_DIM, device=self.device)
         from .engine import StepEngine
-        from .parallel import make_allreduce
-        self.engine = StepEngine(self.netG, self.netsD, self.optimizerG, self.optimizersD, self.KIND, self.COND,
-                                 allreduce=make_allreduce())
+        self.engine = StepEngine(self.netG, self.netsD, self.optimizerG, self.optimizersD, self.KIND, self.COND)
         return start_count
 
     def labels(self):
