@@ -31,7 +31,28 @@ CONFIGS = {
                  over={"TRAIN.CAT_Z": "sum"},
                  ocfg=dict(G_KIND="cond", COND="txt+cls", CLS_KIND="multihot", CAT_Z="sum", Z_DIM=100,
                            ENTITY_DIM=90)),
+    # ---- conditioning variants of config 4 (one cfg override each), pinned by the real reference too
+    # CAT_Z sum / product (model.py:500-505, cub:577-582)
+    "splitz_cat_sum": dict(yml="birds_2stg_splitz_cap_ca.realcls.yml", batch=32, over={"TRAIN.CAT_Z": "sum"},
+                           ocfg=dict(G_KIND="catz_ca", CLS_KIND="index", CAT_Z="sum", Z_DIM=128, G_CAPSULE=True, D_CAPSULE=True)),
+    "splitz_cat_product": dict(yml="birds_2stg_splitz_cap_ca.realcls.yml", batch=32, over={"TRAIN.CAT_Z": "product"},
+                               ocfg=dict(G_KIND="catz_ca", CLS_KIND="index", CAT_Z="product", Z_DIM=128, G_CAPSULE=True,
+                                         D_CAPSULE=True)),
+    # TREE.SCALE 4: upsample2 in NEXT_STAGE_G (model.py:406-407, 420-421), JOINT_D_NET256 as the stage-2 discriminator
+    # (cub:151-154); composable only with a non-concat CAT_Z because JOINT_D_NET256 ignores CAT_Z (model.py:1210)
+    "splitz_scale4_sum": dict(yml="birds_2stg_splitz_cap_ca.realcls.yml", batch=32, over={"TRAIN.CAT_Z": "sum", "TREE.SCALE": 4},
+                              ocfg=dict(G_KIND="catz_ca", CLS_KIND="index", CAT_Z="sum", SCALE=4, Z_DIM=128, G_CAPSULE=True,
+                                        D_CAPSULE=True)),
+    # COND_G_NET_CATZ (model.py:567-665: two VC_NETs; no shipped trainer builds it): with the exchange capsule stem
+    # (COND_INIT_STAGE_G_Exchange_Cap, model.py:280-333) and with the plain Linear stem, driven through the cub step
+    "catz_exchange": dict(yml="birds_2stg_splitz_cap_ca.realcls.yml", batch=32, over={"TRAIN.EXCHANGE": True},
+                          ocfg=dict(G_KIND="catz", CLS_KIND="index", CAT_Z="concat", EXCHANGE=True, Z_DIM=128, G_CAPSULE=True,
+                                    D_CAPSULE=True)),
+    "catz_plain": dict(yml="birds_2stg_splitz_cap_ca.realcls.yml", batch=32, over={"TRAIN.G_CAPSULE": False, "TRAIN.D_CAPSULE": False},
+                       ocfg=dict(G_KIND="catz", CLS_KIND="index", CAT_Z="concat", Z_DIM=128, G_CAPSULE=False, D_CAPSULE=False)),
 }
+
+BASELINE = ("catcls", "3stages", "onlycapsule", "splitz_cap_ca", "coco")      # the five BASELINE.json configs
 
 
 def oracle_cfg(name, batch=None, gf=None, df=None):

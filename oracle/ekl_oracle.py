@@ -88,7 +88,7 @@ class OracleCfg:
     MANIFD_DIM: int = 128
     TEXT_DIM: int = 1024           # TEXT.DIMENSION
     # which generator assembly / step flavour (SURVEY 8 "config resolution")
-    G_KIND: str = "catz_ca"        # catz_ca | cond | gnet
+    G_KIND: str = "catz_ca"        # catz_ca | catz | cond | gnet
     COND: str = "txt+cls"          # cond-G input: 'txt+cls' (trainer.py:525) or 'txt' (cub:571)
     CLS_KIND: str = "index"        # 'index' (birds, cub:303-304,556-557) | 'multihot' (coco, trainer.py:518)
     ROUTING: str = "dynamic"
@@ -245,6 +245,26 @@ def g_forward_catz_ca(sd, cfg, noise, sen, cls, eps, seed):
         h1 = init_stage_cap(c, noise, sd, "h_net1", ngf, cfg)        # model.py:512
     else:
         raise TypeError("reference defect: COND_INIT_STAGE_G.forward takes one arg (SURVEY app. A #2)")
+    return _stages(c, h1, sd, cfg), mu1, mu2, lv1, lv2, std1, std2
+
+
+def g_forward_catz(sd, cfg, noise, sen, cls, seed1, seed2):
+    """model.py:592-628 COND_G_NET_CATZ.forward: both codes come from VC_NETs; h_net1 takes c_code alone (:614)."""
+    c1, mu1, lv1, std1 = vc_net(noise, sen, sd, "vc_net1", seed1)
+    c2, mu2, lv2, std2 = vc_net(noise, cls, sd, "vc_net2", seed2)
+    if cfg.EXCHANGE or cfg.CAT_Z == "concat":
+        c = torch.cat((c1, c2), 1)
+    elif cfg.CAT_Z == "product":
+        c = c1 * c2
+    else:
+        c = c1 + c2
+    ngf = cfg.GF_DIM * 16
+    if cfg.G_CAPSULE and cfg.EXCHANGE:
+        h1 = init_stage_exchange_cap(c, sd, "h_net1", ngf, cfg)
+    elif cfg.G_CAPSULE:
+        h1 = init_stage_cap(c, None, sd, "h_net1", ngf, cfg)
+    else:
+        h1 = init_stage_fc(c, sd, "h_net1", ngf)
     return _stages(c, h1, sd, cfg), mu1, mu2, lv1, lv2, std1, std2
 
 
@@ -440,8 +460,11 @@ class OracleTrainer:
         fake_cp[:, -1] = 1                                                                # cub:520-521
         out["real_cp"], out["fake_cp"], out["cls_onehot"] = real_cp, fake_cp, cls_onehot
         # (1) generate: cub:567-587
-        if c.G_KIND == "catz_ca":
-            hs, mu1, mu2, lv1, lv2, std1, std2 = g_forward_catz_ca(self.sdG, c, noise, embedding, cls_onehot, eps, seed)
+        if c.G_KIND in ("catz_ca", "catz"):
+            if c.G_KIND == "catz":          # eps plays the role of the sentence VC_NET's seed (first host draw)
+                hs, mu1, mu2, lv1, lv2, std1, std2 = g_forward_catz(self.sdG, c, noise, embedding, cls_onehot, eps, seed)
+            else:
+                hs, mu1, mu2, lv1, lv2, std1, std2 = g_forward_catz_ca(self.sdG, c, noise, embedding, cls_onehot, eps, seed)
             mu = torch.cat((mu1, mu2), 1) if c.CAT_Z == "concat" else (mu1 * mu2 if c.CAT_Z == "product" else mu1 + mu2)
             kls = [(mu1, lv1), (mu2, lv2)]
         elif c.G_KIND == "cond":

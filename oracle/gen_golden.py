@@ -21,6 +21,7 @@ GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
 
 # (config, batch, gf/df width, iterations)
 CASES = [(n, 4, 8, 2) for n in configs.CONFIGS] + [("splitz_cap_ca", 4, 64, 1), ("catcls", 2, 64, 1)]
+# the five BASELINE configs + the conditioning variants of SURVEY 8f row 2 (configs.CONFIGS lists both)
 
 
 def run_case(name, B, width, iters):
@@ -101,12 +102,18 @@ def module_cases():
 
 
 def main():
+    """python -m oracle.gen_golden [--only name,name,...]  (--only: just those step cases, modules.npz untouched)"""
     os.makedirs(GOLD, exist_ok=True)
+    only = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else None
     for name, B, width, iters in CASES:
+        if only is not None and name not in only:
+            continue
         flat = run_case(name, B, width, iters)
         path = os.path.join(GOLD, "step_%s_b%d_w%d.npz" % (name, B, width))
         np.savez_compressed(path, **flat)
         print(path, len(flat), os.path.getsize(path))
+    if only is not None:
+        return
     flat = module_cases()
     path = os.path.join(GOLD, "modules.npz")
     np.savez_compressed(path, **flat)

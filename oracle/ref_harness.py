@@ -116,12 +116,15 @@ def build_nets(name, batch=None, gf=None, df=None):
     if spec["ocfg"]["G_KIND"] == "catz_ca":
         netG = m.COND_G_NET_CATZ_CA(cfg.TEXT.DIMENSION, cfg.GAN.ENTITY_DIM, share, use_cap=cfg.TRAIN.G_CAPSULE,
                                     cat=cfg.TRAIN.CAT_Z, exchange=cfg.TRAIN.EXCHANGE)          # cub:130
+    elif spec["ocfg"]["G_KIND"] == "catz":
+        netG = m.COND_G_NET_CATZ(cfg.TEXT.DIMENSION, cfg.GAN.ENTITY_DIM, share, use_cap=cfg.TRAIN.G_CAPSULE,
+                                 cat=cfg.TRAIN.CAT_Z, exchange=cfg.TRAIN.EXCHANGE)             # model.py:567
     else:
         cd = cfg.TEXT.DIMENSION + (cfg.GAN.ENTITY_DIM + 1 if spec["ocfg"]["COND"] == "txt+cls" else 0)
         netG = m.COND_G_NET(cd, share, use_cap=cfg.TRAIN.G_CAPSULE)                            # trainer.py:116 | cub:135
     netsD = [m.JOINT_D_NET64(use_cap=cfg.TRAIN.D_CAPSULE)]
-    if cfg.TREE.BRANCH_NUM > 1:
-        netsD.append(m.JOINT_D_NET128(use_cap=cfg.TRAIN.D_CAPSULE))
+    if cfg.TREE.BRANCH_NUM > 1:                                                              # cub:150-154
+        netsD.append(m.JOINT_D_NET128(use_cap=cfg.TRAIN.D_CAPSULE) if cfg.TREE.SCALE == 2 else m.JOINT_D_NET256())
     if cfg.TREE.BRANCH_NUM > 2:
         netsD.append(m.JOINT_D_NET256())
     return cfg, netG, netsD
@@ -135,7 +138,7 @@ class RefStepper:
         R = import_reference()
         self.R, self.cfg, self.spec = R, R["cfg"], CONFIGS[name]
         self.kind = self.spec["ocfg"]["G_KIND"]
-        mod = R["cub"] if self.kind == "catz_ca" else R["trainer"]
+        mod = R["cub"] if self.kind in ("catz_ca", "catz") else R["trainer"]
         self.mod = mod
         t = mod.condGANTrainer.__new__(mod.condGANTrainer)      # skip __init__ (mkdirs, set_device)
         cfg = self.cfg
@@ -157,10 +160,12 @@ class RefStepper:
         data = ([i.clone() for i in imgs], [i.clone() for i in wrong_imgs], embedding.clone(), cls.clone(), None)
         t.imgs_tcpu, t.real_imgs, t.wrong_imgs, t.txt_embedding, t.cls_label = t.prepare_data(data)
         count = 1            # count % 100 != 0 -> skips the .data[0] logging path (trainer.py:433)
-        if self.kind == "catz_ca":
+        if self.kind in ("catz_ca", "catz"):
             t.cls_onehot = t.onehot(t.cls_label, cfg.GAN.ENTITY_DIM)
             t.real_cp = t.onehot(t.cls_label, cfg.GAN.ENTITY_DIM + 1)
-            with rng_tape([noise, eps], [seed]):
+            # draws: catz_ca = noise.normal_, CA eps (device normal_), VC seed (host randn); catz = noise, two host randn
+            tape = rng_tape([noise, eps], [seed]) if self.kind == "catz_ca" else rng_tape([noise], [eps, seed])
+            with tape:
                 self.noise.data.normal_(0, 1)
                 (t.hcodes, t.mu1, t.mu2, t.logvar1, t.logvar2, t.std1, t.std2) = \
                     t.netG(self.noise, t.txt_embedding, t.cls_onehot)
@@ -189,7 +194,7 @@ class RefStepper:
         for i in range(t.num_Ds):
             rec = []
             h = t.netsD[i].register_forward_hook(lambda m, a, o, rec=rec: rec.append([x.detach() for x in o]))
-            if self.kind == "catz_ca":
+            if self.kind in ("catz_ca", "catz"):
                 res = t.train_joint_Dnet(i, count)
             else:
                 res = self._old_train_joint_Dnet(i, count)

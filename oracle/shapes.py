@@ -72,6 +72,11 @@ def g_shapes(c, kind=None, cond_dim=None):
         _vc(sd, "vc_net2", c.ENTITY_DIM, c)
         in_dim = c.MANIFD_DIM * 2 if c.CAT_Z == "concat" else c.MANIFD_DIM
         _init_stage(sd, "h_net1", gf * 16, c, in_dim, c.G_CAPSULE, c.EXCHANGE)
+    elif kind == "catz":                           # model.py:567-590 COND_G_NET_CATZ: two VC_NETs
+        _vc(sd, "vc_net1", c.TEXT_DIM, c)
+        _vc(sd, "vc_net2", c.ENTITY_DIM, c)
+        in_dim = c.MANIFD_DIM * 2 if c.CAT_Z == "concat" else c.MANIFD_DIM
+        _init_stage(sd, "h_net1", gf * 16, c, in_dim, c.G_CAPSULE, c.EXCHANGE)
     elif kind == "cond":
         _vc(sd, "vc_net", cond_dim, c)
         in_dim = c.MANIFD_DIM * 2 if c.CAT_Z == "concat" else c.MANIFD_DIM

@@ -1,6 +1,8 @@
 """Pin the CPU oracle (oracle/ekl_oracle.py) against fixtures produced by the REAL reference
 (oracle/gen_golden.py -> tests/golden/*.npz): every loss, logit, image/h_code checksum, every gradient
-checksum and the post-Adam parameter norms, for all five resolved BASELINE configs."""
+checksum and the post-Adam parameter norms, for all five resolved BASELINE configs and the conditioning variants of
+SURVEY 8f row 2 (CAT_Z sum / product, TREE.SCALE 4, COND_G_NET_CATZ with the exchange capsule stem and with the Linear
+stem)."""
 import glob
 import os
 
@@ -31,7 +33,7 @@ def _shape_list(sh):
 def build_oracle(name, B, width):
     oc = configs.oracle_cfg(name, batch=B, gf=width, df=width)
     gsh = shapes.g_shapes(oc, cond_dim=configs.cond_dim(oc))
-    res = [64, 128, 256][: oc.BRANCH_NUM]
+    res = [64, 128 if oc.SCALE == 2 else 256, 256][: oc.BRANCH_NUM]                    # cub:144-154
     dsh = [shapes.d_shapes(oc, r, joint=True, use_cap=oc.D_CAPSULE) for r in res]
     sdG = shapes.make_state_dict(gsh, "G")
     sdDs = [shapes.make_state_dict(s, "D%d" % i) for i, s in enumerate(dsh)]

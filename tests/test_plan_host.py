@@ -384,8 +384,8 @@ def test_product_state_dicts_equal_the_reference_golden_lists():
         name, b, w = os.path.basename(path)[5:-4].rsplit("_", 2)
         gold = np.load(path)
         Trainer = configs.setup(name, batch=int(b[1:]), width=int(w[1:]))
-        if name == "splitz_cap_ca":
-            netG = T.build_G()[0]
+        if Trainer.KIND == "catz_ca":                   # cub flavour: config 4 and its conditioning variants
+            netG = T.build_G(g_class=Trainer.G_CLASS)[0]
         else:
             cond_dim = cfg.TEXT.DIMENSION + (cfg.GAN.ENTITY_DIM + 1 if Trainer.COND == "txt+cls" else 0)
             netG = model.COND_G_NET(cond_dim, model.get_shareGs(cfg.GAN.GF_DIM), use_cap=cfg.TRAIN.G_CAPSULE)
@@ -393,12 +393,33 @@ def test_product_state_dicts_equal_the_reference_golden_lists():
         for i, d in enumerate(T.build_Ds()):
             assert fmt(d) == list(gold["shapes/D%d" % i]), (path, i)
         seen += 1
-    assert seen >= 5
+    assert seen >= 12             # 5 BASELINE configs + 2 full-width cases + 5 conditioning variants
     gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "modules.npz"))
     configs.setup("3stages", batch=4, width=8)
     assert fmt(model.G_NET(model.get_shareGs(cfg.GAN.GF_DIM))) == list(gold["gnet/shapes"])
     for res, D in ((64, model.D_NET64), (128, model.D_NET128), (256, model.D_NET256)):
         assert fmt(D()) == list(gold["dnet%d/shapes" % res])
+
+
+def test_reference_yml_plus_overrides_equals_the_shipped_resolved_yml():
+    import os
+    """configs.setup builds each config from the REFERENCE's own cfg/*.yml + the documented override dict when the
+    reference tree is present, and from the package's resolved copy otherwise (the GPU box): both routes must give the
+    identical cfg, for the five BASELINE configs and every conditioning variant."""
+    import copy
+    from text2img_ekl_b200 import configs
+    from text2img_ekl_b200.miscc.config import cfg
+    if not os.path.isdir(os.path.join(configs.REF_ROOT, "cfg")):
+        pytest.skip("reference tree not present")
+    for name in list(configs.RESOLVED) + list(configs.VARIANTS):
+        assert configs.yml_path(name, True)[0].startswith(configs.REF_ROOT)
+        configs.setup(name, prefer_reference=True)
+        a = copy.deepcopy(cfg)
+        configs.setup(name, prefer_reference=False)
+        assert a == cfg, name
+    configs.setup("splitz_scale4_sum")
+    assert cfg.TREE.SCALE == 4 and cfg.TRAIN.CAT_Z == "sum"
+    assert configs.setup("catz_exchange").G_CLASS == "COND_G_NET_CATZ" and cfg.TRAIN.EXCHANGE is True
 
 
 def test_discriminator_trunk_marks_fire_deepest_first():

@@ -44,7 +44,8 @@ def build(name, B):
     tr.setup()
     oc = ocfg.oracle_cfg(name, batch=B)
     gsh = shapes.g_shapes(oc, cond_dim=ocfg.cond_dim(oc))
-    dsh = [shapes.d_shapes(oc, r, joint=True, use_cap=oc.D_CAPSULE) for r in [64, 128, 256][: oc.BRANCH_NUM]]
+    d_res = [64, 128 if oc.SCALE == 2 else 256, 256][: oc.BRANCH_NUM]                  # cub:144-154
+    dsh = [shapes.d_shapes(oc, r, joint=True, use_cap=oc.D_CAPSULE) for r in d_res]
     sdG = shapes.make_state_dict(gsh, "G")
     sdDs = [shapes.make_state_dict(s, "D%d" % i) for i, s in enumerate(dsh)]
     tr.netG.load_state_dict(sdG)
@@ -55,7 +56,9 @@ def build(name, B):
     return tr, oc, OracleTrainer(oc, sdG, sdDs), orc16
 
 
-CASES = [("splitz_cap_ca", 4), ("catcls", 4), ("onlycapsule", 4), ("coco", 4), ("3stages", 4)]
+# every BASELINE config at batch 4 (fast) AND at the batch BASELINE.json names for it (24 / 24 / 32 / 32 / 64 per GPU)
+CASES = [("splitz_cap_ca", 4), ("catcls", 4), ("onlycapsule", 4), ("coco", 4), ("3stages", 4),
+         ("3stages", 24), ("catcls", 24), ("onlycapsule", 32), ("splitz_cap_ca", 32), ("coco", 64)]
 
 
 @pytest.mark.parametrize("name,B", CASES)
@@ -99,11 +102,14 @@ def test_training_step_matches_oracle(name, B):
                 r = rel(grp[q], want["d_logits"][last][j][q])
                 report.append(("it%d dlogit D%d group%d head%d" % (it, last, j, q), r))
                 assert r <= 3e-2, (name, it, "d_logits", j, q, r)   # [B] sigmoid outputs of the deepest D on 13-19-layer-deep fakes
-        # generator-step logits come from the discriminators AFTER their Adam update (sign-like first step) and are
-        # partly saturated probabilities: reported with the bf16-storage floor, asserted through errG above
+        # generator-step logits come from the discriminators AFTER their Adam update (a sign-like first step: every
+        # weight moves by ~lr, tiny gradients flip sign under bf16 storage), so their bound is the deviation the
+        # bf16-storage oracle shows for the same tensor, never below the north-star 1e-2
         for i, (g, w) in enumerate(zip(tr.engine.last_g_logits, want["g_logits"])):
             for q in range(len(w)):
-                report.append(("it%d glogit%d_%d (floor %.1e)" % (it, i, q, rel(w16["g_logits"][i][q], w[q])), rel(g[q], w[q])))
+                r, f = rel(g[q], w[q]), rel(w16["g_logits"][i][q], w[q])
+                report.append(("it%d glogit%d_%d (floor %.1e)" % (it, i, q, f), r))
+                assert r <= max(GRAD_SLACK * f, TOL_OUT), (name, it, "g_logits", i, q, r, f)
         # gradients: deviation from fp32 bounded by the bf16-storage floor of the same tensor
         def check_grads(tag, named, want_g, floor_g):
             rs, fl = [], []
@@ -134,7 +140,7 @@ def test_training_step_matches_oracle(name, B):
         r, f = (num / den) ** 0.5, (fnum / den) ** 0.5
         report.append(("params %s (floor %.1e)" % (tag, f), r))
         assert r <= max(GRAD_SLACK * f, 3e-3), (name, tag, r, f)
-    print("\n" + "\n".join("%-50s %.3e" % kv for kv in report))
+    print("\n[%s B=%d]\n" % (name, B) + "\n".join("%-50s %.3e" % kv for kv in report))
 
 
 def test_eval_mode_generation_is_per_sample():

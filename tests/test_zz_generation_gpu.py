@@ -1,8 +1,7 @@
 """GPU tests of the generation path and of the reference's file-based resume.
 Collected last (file name) so that a problem here cannot mask the parity tests under `pytest -x`.
-Status: written after round 1's GPU budget was spent -- the host side of every test was dry-run on the CPU (state-dict
-loading, oracle outputs, file writers, evaluate() control flow with a stub generator in tests/test_plan_host.py), the
-device side has not run on a B200 yet."""
+The host side of every test is also dry-run on the CPU (state-dict loading, oracle outputs, file writers, evaluate()
+control flow with a stub generator in tests/test_plan_host.py)."""
 import numpy as np
 import pytest
 import torch
@@ -86,7 +85,8 @@ def test_stackgan_original_modules_match_oracle():
     D_NET64/128/256 (model.py:874-914, 1006-1050, 1154-1202) are in scope as modules.  Forward parity against the oracle
     restatement (itself pinned to the real reference in tests/test_oracle_golden.py::test_modules_match_reference) on
     identical deterministic weights and inputs; tolerances as in test_step_parity_gpu.py.  The input-image gradient of
-    the discriminators is only sanity-bounded (bf16 storage moves it by 5-30 %, see tests/test_bf16_sensitivity.py)."""
+    the discriminators is held to the same rule as the parameter gradients there: its deviation from the fp32 oracle may
+    not exceed 2.5 x the deviation the bf16-storage oracle shows for the same tensor (absolute allowance 3e-2)."""
     from oracle import configs as ocfg, detfill, shapes, synth
     from oracle import ekl_oracle as O
     from text2img_ekl_b200 import configs, model
@@ -132,7 +132,13 @@ def test_stackgan_original_modules_match_oracle():
         assert _rel(out[0], ref[0]) < 2e-2 and _rel(out[1], ref[1]) < 2e-2, (res, _rel(out[0], ref[0]), _rel(out[1], ref[1]))
         ((out[0] * w0.to(dev)).sum() + (out[1] * w1.to(dev)).sum()).backward()
         ((ref[0] * w0).sum() + (ref[1] * w1).sum()).backward()
-        assert torch.isfinite(xg.grad).all() and _rel(xg.grad, xo.grad) < 0.6, (res, _rel(xg.grad, xo.grad))
+        x16 = x.clone().requires_grad_(True)
+        with O.storage("bf16"):                       # the same oracle with feature maps merely STORED in bf16: the floor
+            r16 = O.d_plain_forward(x16, cc, clone(sdd), oc, res)
+            ((r16[0] * w0).sum() + (r16[1] * w1).sum()).backward()
+        dev_ours, floor = _rel(xg.grad, xo.grad), _rel(x16.grad, xo.grad)
+        print("D_NET%d input gradient: ours %.3e, bf16-storage floor %.3e" % (res, dev_ours, floor))
+        assert torch.isfinite(xg.grad).all() and dev_ours <= max(2.5 * floor, 3e-2), (res, dev_ours, floor)
 
 
 @pytest.mark.timeout(120, method="thread")
@@ -177,53 +183,18 @@ def test_full_size_step_is_batch_permutation_equivariant():
             assert _rel(a, b[perm]) < 2e-2, (i, _rel(a, b[perm]))
 
 
-# cfg overrides on top of config 4 (cfg/birds_2stg_splitz_cap_ca.realcls.yml) -> the OracleCfg fields they imply
-VARIANTS = {
-    "cat_sum": ({"TRAIN.CAT_Z": "sum"}, dict(CAT_Z="sum")),                         # model.py:500-505, cub:577-582
-    "cat_product": ({"TRAIN.CAT_Z": "product"}, dict(CAT_Z="product")),
-    "exchange_cap": ({"TRAIN.EXCHANGE": True}, dict(EXCHANGE=True)),                # model.py:280-333
-    "scale4_sum": ({"TREE.SCALE": 4, "TRAIN.CAT_Z": "sum"}, dict(SCALE=4, CAT_Z="sum")),   # model.py:406-407, cub:151-154
-}
+# one cfg override each on top of config 4 (text2img_ekl_b200/configs.py VARIANTS, oracle/configs.py);
+# the oracle side of every one is pinned to the REAL reference by tests/golden/step_<variant>_b4_w8.npz
+VARIANTS = ["splitz_cat_sum", "splitz_cat_product", "splitz_scale4_sum", "catz_exchange", "catz_plain"]
 
 
-@pytest.mark.timeout(120, method="thread")
-@pytest.mark.parametrize("variant", list(VARIANTS))
-def test_conditioning_variants_match_oracle(variant, monkeypatch):
-    """the remaining conditioning variants of the split-z generator run through the SAME whole-step
-    parity check as the five BASELINE configs (tests/test_step_parity_gpu.py), with the config-4 yml plus one override:
-    CAT_Z sum / product, the exchange capsule stem, and TREE.SCALE 4 (upsample2 in NEXT_STAGE_G, JOINT_D_NET256 as the
-    second discriminator; only composable with a non-concat CAT_Z in the reference, whose JOINT_D_NET256 ignores CAT_Z).
-    The oracle side of every variant and the state_dict compatibility were dry-run on the CPU."""
-    import dataclasses
+@pytest.mark.timeout(180, method="thread")
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_conditioning_variants_match_oracle(variant):
+    """The remaining conditioning variants run through the SAME whole-step parity check as the five BASELINE configs
+    (tests/test_step_parity_gpu.py): CAT_Z sum / product of the split-z generator (model.py:500-505, cub:577-582),
+    TREE.SCALE 4 (upsample2 in NEXT_STAGE_G, JOINT_D_NET256 as the second discriminator; model.py:406-407, cub:151-154),
+    and COND_G_NET_CATZ (model.py:567-665, two VC_NETs) with the exchange capsule stem (model.py:280-333) and with the
+    Linear stem."""
     import test_step_parity_gpu as P
-    from oracle import configs as ocfg, shapes
-    from oracle.ekl_oracle import OracleTrainer
-    over, oover = VARIANTS[variant]
-
-    def build(name, B):
-        from text2img_ekl_b200 import configs
-        from text2img_ekl_b200.miscc.config import cfg
-        Trainer = configs.setup(name, batch=B)
-        for key, v in over.items():
-            node = cfg
-            *path, leaf = key.split(".")
-            for part in path:
-                node = getattr(node, part)
-            setattr(node, leaf, v)
-        tr = Trainer(None, None, 64)
-        tr.setup()
-        oc = dataclasses.replace(ocfg.oracle_cfg(name, batch=B), **oover)
-        gsh = shapes.g_shapes(oc, cond_dim=ocfg.cond_dim(oc))
-        d_res = [64, 128 if oc.SCALE == 2 else 256, 256][: oc.BRANCH_NUM]
-        dsh = [shapes.d_shapes(oc, r, joint=True, use_cap=oc.D_CAPSULE and r != 256) for r in d_res]
-        sdG = shapes.make_state_dict(gsh, "G")
-        sdDs = [shapes.make_state_dict(s, "D%d" % i) for i, s in enumerate(dsh)]
-        tr.netG.load_state_dict(sdG)
-        for d, sd in zip(tr.netsD, sdDs):
-            d.load_state_dict(sd)
-        clone = lambda sd: {k: v.detach().clone() for k, v in sd.items()}
-        orc16 = OracleTrainer(oc, clone(sdG), [clone(s) for s in sdDs])
-        return tr, oc, OracleTrainer(oc, sdG, sdDs), orc16
-
-    monkeypatch.setattr(P, "build", build)
-    P.test_training_step_matches_oracle("splitz_cap_ca", 4)
+    P.test_training_step_matches_oracle(variant, 4)

@@ -46,11 +46,15 @@ def load_params(net, new_param):
         p.data.copy_(new_p)
 
 
-def build_G(use_cap=None):
-    """The generator train() builds (cub:130-135); evaluate() passes cfg.TEST.G_CAPSULE (cub:787)."""
+def build_G(use_cap=None, g_class=None):
+    """The generator train() builds (cub:130-135); evaluate() passes cfg.TEST.G_CAPSULE (cub:787).  g_class names
+    another split-z assembly of model.py to drive through the same step (COND_G_NET_CATZ, model.py:567)."""
     use_cap = cfg.TRAIN.G_CAPSULE if use_cap is None else use_cap
     shareGs = model.get_shareGs(cfg.GAN.GF_DIM)
-    if USE_CLS and SPLIT_Z:
+    if g_class is not None:
+        netG = getattr(model, g_class)(cfg.TEXT.DIMENSION, cfg.GAN.ENTITY_DIM, shareGs, use_cap=use_cap,
+                                       cat=cfg.TRAIN.CAT_Z, exchange=cfg.TRAIN.EXCHANGE)
+    elif USE_CLS and SPLIT_Z:
         netG = model.COND_G_NET_CATZ_CA(cfg.TEXT.DIMENSION, cfg.GAN.ENTITY_DIM, shareGs, use_cap=use_cap,
                                         cat=cfg.TRAIN.CAT_Z, exchange=cfg.TRAIN.EXCHANGE)            # cub:130
     else:
@@ -126,10 +130,10 @@ def load_snapshots(netG, netsD):
     return count
 
 
-def load_network(gpus, device=None):
+def load_network(gpus, device=None, g_class=None):
     """cub:113-196.  Returns (netG, shareGs, netsD, num_Ds, count)."""
     device = device or (torch.device("cuda", gpus[0]) if gpus else torch.device("cuda"))
-    netG, shareGs = build_G()
+    netG, shareGs = build_G(g_class=g_class)
     netG.apply(weights_init)
     netsD = build_Ds()
     for d in netsD:
@@ -160,6 +164,7 @@ def define_optimizers(netG, netsD=()):
 class condGANTrainer(object):
     KIND = "catz_ca"
     COND = "txt+cls"
+    G_CLASS = None                 # None: the generator cub:130-135 builds
 
     def __init__(self, output_dir, data_loader, imsize):
         if cfg.TRAIN.FLAG and output_dir:
@@ -209,7 +214,7 @@ class condGANTrainer(object):
         self.rank, self.world_size = rank, ws
 
     def setup(self):
-        self.netG, self.shareGs, self.netsD, self.num_Ds, start_count = load_network(self.gpus, self.device)
+        self.netG, self.shareGs, self.netsD, self.num_Ds, start_count = load_network(self.gpus, self.device, self.G_CLASS)
         self._replicate()                    # before the optimisers re-home the parameters into flat buffers
         self.optimizerG, self.optimizersD = define_optimizers(self.netG, self.netsD)
         self.criterion = nn.BCELoss()

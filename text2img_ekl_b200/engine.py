@@ -182,8 +182,11 @@ class StepEngine:
 
     def _generate(self, noise, txt, cls_cond, eps=None, seed=None):
         if self.kind == "catz_ca":
-            (self.hcodes, self.mu1, self.mu2, self.logvar1, self.logvar2, self.std1, self.std2) = \
-                self.netG(noise, txt, cls_cond, eps=eps, seed=seed)
+            if hasattr(self.netG, "vc_net1"):      # COND_G_NET_CATZ (model.py:567): both codes from VC_NETs, two seed draws
+                out = self.netG(noise, txt, cls_cond, seed1=eps, seed2=seed)
+            else:
+                out = self.netG(noise, txt, cls_cond, eps=eps, seed=seed)
+            (self.hcodes, self.mu1, self.mu2, self.logvar1, self.logvar2, self.std1, self.std2) = out
             if self.cat_z == "concat":
                 self.mu = torch.cat((self.mu1, self.mu2), 1)
             elif self.cat_z == "product":
