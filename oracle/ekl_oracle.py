@@ -386,8 +386,11 @@ def onehot(cls, n):
 
 
 def bce(p, target_value):
-    """nn.BCELoss (mean, log clamped at -100) against a constant target (cub:423-431)."""
-    return F.binary_cross_entropy(p, torch.full_like(p, float(target_value)))
+    """nn.BCELoss (mean, log clamped at -100) against a constant target (cub:423-431).  Evaluated in fp32 outside any
+    autocast region (torch refuses BCE on autocast inputs; bench.py's bf16-autocast eager baseline runs this port)."""
+    with torch.autocast(device_type=p.device.type, enabled=False):
+        p = p.float()
+        return F.binary_cross_entropy(p, torch.full_like(p, float(target_value)))
 
 
 def d_loss(real, wrong, fake, real_cp, fake_cp, cfg):

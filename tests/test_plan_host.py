@@ -462,8 +462,6 @@ def test_step_engine_update_paths_run_on_cpu_stand_ins(monkeypatch):
     networks and torch.optim.Adam, so that a Python-level slip in these paths shows up before a GPU run."""
     from text2img_ekl_b200 import configs, ops
     from text2img_ekl_b200.engine import StepEngine
-    for k in ("EKL_WGRAD_STREAM", "EKL_D_PRIO"):
-        monkeypatch.delenv(k, raising=False)
     configs.setup("3stages", batch=4)
     torch.manual_seed(0)
     netG = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.BatchNorm1d(4))
@@ -472,7 +470,6 @@ def test_step_engine_update_paths_run_on_cpu_stand_ins(monkeypatch):
     optsD = [torch.optim.Adam(d.parameters(), lr=1e-2) for d in netsD]
     eng = StepEngine(netG, netsD, optG, optsD, "cond")
     assert eng.redD == [None, None] and eng.redG is None and eng.parallel_d and not ops.GRAD_MARKS
-    assert not ops.WGRAD_STREAM and ops.join_wgrad() is None
     x = torch.randn(6, 4)
     # discriminator update: gradients are views of the flat buffer, _d_update applies them
     w0 = netsD[1].weight.detach().clone()

@@ -204,37 +204,6 @@ def _run_dgrad(spec, c, weight, dy, dx):
     _count(2 if ws is not None else 1)
 
 
-# EKL_WGRAD_STREAM=1 (experiment, off by default): the weight gradient of a layer depends only on that layer's x and dy,
-# not on the data-gradient chain, so parameter wgrad kernels go to a side stream per issuing stream and overlap the rest
-# of backward.  Their operands are kept alive until join_wgrad(), which the step engine calls before it reads the
-# gradient buffer (all-reduce / Adam).  Not used while bench.py's per-kernel event profiling is on.
-WGRAD_STREAM = os.environ.get("EKL_WGRAD_STREAM", "0") == "1"
-_WG_SIDE = {}       # cuda_stream handle of the issuing stream -> (side stream, operands kept alive)
-
-
-def _wgrad_side_launch(c, x, dy, buf):
-    main = torch.cuda.current_stream()
-    ent = _WG_SIDE.get(main.cuda_stream)
-    if ent is None:
-        ent = _WG_SIDE[main.cuda_stream] = (torch.cuda.Stream(), [])
-    side, keep = ent
-    side.wait_stream(main)                    # x and dy are complete on the issuing stream
-    keep.append((x, dy))
-    with torch.cuda.stream(side):
-        L.check(L.lib().ekl_conv_bwd_weight(c, L.ptr(x), L.ptr(dy), L.ptr(buf), L.stream()))
-
-
-def join_wgrad():
-    """The current stream waits for the weight-gradient kernels that were issued from it on its side stream."""
-    if not _WG_SIDE:
-        return
-    main = torch.cuda.current_stream()
-    ent = _WG_SIDE.get(main.cuda_stream)
-    if ent is not None and ent[1]:
-        main.wait_stream(ent[0])
-        ent[1].clear()
-
-
 class _Conv(torch.autograd.Function):
     """y = conv(x) (+ per-tile BatchNorm partial statistics).  Backward: tcgen05 dgrad + wgrad."""
 
@@ -297,11 +266,6 @@ class _Conv(torch.autograd.Function):
                 dy = dy * (1.0 - y.float() ** 2).to(dy.dtype)
         dx = None
         want_w = ctx.needs_input_grad[1] and not ctx.skip_wgrad
-        if want_w and ctx.w_leaf and WGRAD_STREAM:
-            _log("wgrad", fam, spec.mode, *ctx.dims, spec.cin, spec.cout, 0)
-            _wgrad_side_launch(c, x, dy, _grad_buffer(weight))       # ahead of the data gradient, on the side stream
-            _count()
-            want_w = False
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             _log("dgrad", fam, spec.mode, *ctx.dims, spec.cin, spec.cout, 0)
