@@ -53,31 +53,45 @@ typedef struct ekl_conv {
   int x_fmt, y_fmt;  /* SIMT only: EKL_FMT_* of x and y */
   int act;           /* fused epilogue on the conv output: EKL_ACT_NONE | EKL_ACT_LRELU | EKL_ACT_TANH (no BN partials then) */
   int w_layout;      /* master filter / gradient memory: EKL_W_KRSC [Cout][KH][KW][Cin] | EKL_W_KCRS [Cout][Cin][KH][KW] */
+  /* Window of the master filter (all 0 = the whole filter).  The master (and its gradient) has w_cin_total input
+   * channels of which this conv contracts [w_cin_off, w_cin_off + Cin) -- NEXT_STAGE_G.jointConv (model.py:403) whose
+   * first ef channels, the tiled condition code, are folded into ekl_conv_fwd_bias9's bias -- and w_cout_valid real
+   * output channels of the Cout-wide tile -- GET_IMAGE_G (model.py:432: 3 filters in a 16-wide tile; the packed rows
+   * beyond are zero and their weight gradients are not written). */
+  int w_cin_total, w_cin_off, w_cout_valid;
 } ekl_conv;
 
 /* bf16 elements of the packed forward (dgrad=0) / data-gradient (dgrad=1) filter operand */
 int64_t ekl_conv_packed_elems(const ekl_conv* c, int dgrad);
 /* fp32 master filter -> packed bf16 operands (either output may be NULL) */
 int ekl_conv_pack(const ekl_conv* c, const float* w_master, void* w_fwd, void* w_dgrad, void* stream);
-/* rows of the per-tile BatchNorm partial-statistics buffer [rows][2][Cout] ekl_conv_fwd writes (TC impl) */
-int ekl_conv_stats_rows(const ekl_conv* c);
-/* y = conv(x); stats (may be NULL): per-tile per-channel sum / sum-of-squares of y */
-int ekl_conv_fwd(const ekl_conv* c, const void* x, const void* w_fwd, void* y, float* stats, void* stream);
+/* y = conv(x); stats (may be NULL; TC impl): BatchNorm batch statistics of y, double [groups][2][Cout] = per-group,
+ * per-channel sum and sum-of-squares of the bf16 values stored, ACCUMULATED with fp64 atomics by the epilogue (zero the
+ * buffer first); groups = B / group_b.  Consumed directly by ekl_bn_act_fwd: there is no finalize pass. */
+int ekl_conv_fwd(const ekl_conv* c, const void* x, const void* w_fwd, void* y, double* stats, void* stream);
 /* y = conv3x3(x) + bias9[b][border class][Cout]: the spatially constant input channels of a jointConv -- the tiled
  * condition code of NEXT_STAGE_G (model.py:411-414, jointConv :403) -- folded into a per-sample fp32 bias with 9
  * border variants (class = 3*rc + cc; rc / cc = 0 first row / column, 1 interior, 2 last).  EKL_S1, EKL_IMPL_TC. */
-int ekl_conv_fwd_bias9(const ekl_conv* c, const void* x, const void* w_fwd, const float* bias9, void* y, float* stats,
+int ekl_conv_fwd_bias9(const ekl_conv* c, const void* x, const void* w_fwd, const float* bias9, void* y, double* stats,
                        void* stream);
+/* The folded code channels themselves (model.py:403, 411-414).  W: the FULL fp32 master filter [N][3][3][Ctot]
+ * (channels_last storage of [N, Ctot, 3, 3]; the first ef input channels are the tiled code), code [B][ef] fp32:
+ *   ekl_code_bias9_fwd   bias9[b][q][n] = sum_{t valid for class q} sum_{c < ef} code[b][c] * W[n][t][c]
+ *   ekl_border_sums9     S[b][q][n] += sum of dy[b,h,w,n] (bf16 NHWC) over the pixels of border class q -- the gradient of
+ *                        ekl_conv_fwd_bias9's bias9 argument, one pass over dy; S fp32 [B][9][N], ZERO on entry
+ *   ekl_code_bias9_bwd   dcode[b][c] (fp32, ZERO on entry, may be NULL) and dW[n][t][c] += (c < ef; may be NULL) from S */
+int ekl_code_bias9_fwd(const float* code, const float* w, int B, int ef, int Ctot, int N, float* bias9, void* stream);
+int ekl_border_sums9(const void* dy, int B, int H, int W, int N, float* S, void* stream);
+int ekl_code_bias9_bwd(const float* S, const float* code, const float* w, int B, int ef, int Ctot, int N, float* dcode,
+                       float* dw, void* stream);
 /* dx = conv^T(dy) */
 int ekl_conv_bwd_data(const ekl_conv* c, const void* dy, const void* w_dgrad, void* dx, void* stream);
 /* Workspace variants.  Plans with few output tiles and a long contraction (the 4x4 / 8x8 discriminator tails) run
  * split-K: up to 4 work items per tile red-add fp32 partial tiles into `ws`, a finishing pass rounds to bf16 and takes
- * the BatchNorm partial statistics.  ws: ekl_conv_workspace_elems(c, dgrad) floats owned by the caller, ZERO before the
- * first call (every call leaves it zero).  ws == NULL or workspace_elems == 0: identical to the plain calls.  On the
- * split path the statistics buffer has ekl_conv_stats_rows_ws(c) rows. */
+ * the BatchNorm statistics.  ws: ekl_conv_workspace_elems(c, dgrad) floats owned by the caller, ZERO before the
+ * first call (every call leaves it zero).  ws == NULL or workspace_elems == 0: identical to the plain calls. */
 int64_t ekl_conv_workspace_elems(const ekl_conv* c, int dgrad);
-int ekl_conv_stats_rows_ws(const ekl_conv* c);
-int ekl_conv_fwd_ws(const ekl_conv* c, const void* x, const void* w_fwd, void* y, float* stats, float* ws, void* stream);
+int ekl_conv_fwd_ws(const ekl_conv* c, const void* x, const void* w_fwd, void* y, double* stats, float* ws, void* stream);
 int ekl_conv_bwd_data_ws(const ekl_conv* c, const void* dy, const void* w_dgrad, void* dx, float* ws, void* stream);
 /* Data-gradient straight from the FORWARD-packed filter (MN-major tensor-core operand; no transposed copy).  Usable
  * when ekl_conv_dgrad_from_fwd(c) != 0: stride-1 / stride-2 convs with Cin, Cout multiples of 64 on the generic kernel.
@@ -97,25 +111,21 @@ int ekl_conv_plan_dump(const ekl_conv* c, int dgrad, int* out, int cap);
  * replaces nn.BatchNorm2d/1d + GLU (model.py:68-76,91-93) | LeakyReLU(0.2) (:816,826) | ReLU (:177-178) and the
  * ResBlock skip add (:119-123).  y: conv output bf16 [M][C]; rows form `groups` contiguous equal groups with
  * independent batch statistics (the reference's separate real / wrong / fake forwards, cub_trainer...:418-420). */
-int ekl_col_stats_rows(int64_t M, int C, int groups);
-int ekl_col_stats(const void* y, int64_t M, int C, int groups, float* partial /*[rows][2][C]*/, void* stream);
-/* partial [groups*rows_per_group][2][C] -> mean/rstd [groups][C]; running stats (may be NULL) get one momentum
- * update per group, in group order, with the unbiased variance -- exactly one update per reference forward. */
-int ekl_bn_finalize(const float* partial, int rows_per_group, int C, int groups, float count, float eps, float momentum,
-                    float* mean, float* rstd, float* running_mean, float* running_var, void* stream);
-int ekl_bn_act_fwd(const void* y, int64_t M, int Cy, int groups, const float* mean, const float* rstd,
-                   const float* gamma, const float* beta, int act, const void* residual, void* out, void* stream);
-/* small layers (<= 768 rows per group): ekl_bn_finalize + ekl_bn_act_fwd as ONE launch; also writes mean / rstd
- * [groups][Cy].  Returns 0 if it ran, 2000 if the layer does not qualify (use the two-call path), else an error code. */
-int ekl_bn_act_fwd_small(const float* partial, int rows_per_group, float count, float eps, float momentum,
-                         float* running_mean, float* running_var, const void* y, int64_t M, int Cy, int groups,
-                         const float* gamma, const float* beta, int act, const void* residual, void* out, float* mean,
-                         float* rstd, void* stream);
-int ekl_bn_act_bwd_rows(int64_t M, int Cy, int groups, int act);
-/* dy from dout; dgamma/dbeta are accumulated (+=). partial: [ekl_bn_act_bwd_rows][2][Cy], sums: [groups][2][Cy] */
+/* batch statistics of a STORED tensor (layers whose producer is not a conv of this library: the BatchNorm1d of the
+ * generator stem): sums [groups][2][C] doubles, accumulated (zero first) */
+int ekl_col_stats(const void* y, int64_t M, int C, int groups, double* sums, void* stream);
+/* out = act(gamma * (y - mean) * rstd + beta) (+ residual).  Training (sums != NULL): mean / rstd come from the fp64
+ * sums [groups][2][Cy] (count = M / groups rows per group), are WRITTEN to mean / rstd [groups][Cy] for the backward pass,
+ * and running_mean / running_var (may be NULL) get one momentum update per group, in group order, with the unbiased
+ * variance -- exactly one update per reference forward call.  Inference (sums == NULL): mean / rstd are inputs. */
+int ekl_bn_act_fwd(const void* y, int64_t M, int Cy, int groups, const double* sums, float eps, float momentum, float* mean,
+                   float* rstd, float* running_mean, float* running_var, const float* gamma, const float* beta, int act,
+                   const void* residual, void* out, void* stream);
+/* dy from dout; dgamma/dbeta are accumulated (+=).  sums: [groups][2][Cy] doubles of caller scratch, ZERO on entry (the
+ * two backward reductions sum(dz), sum(dz * xhat) are accumulated there between the two passes). */
 int ekl_bn_act_bwd(const void* y, const void* dout, int64_t M, int Cy, int groups, const float* mean, const float* rstd,
-                   const float* gamma, const float* beta, int act, float* partial, float* sums, float* dgamma,
-                   float* dbeta, void* dy, void* stream);
+                   const float* gamma, const float* beta, int act, double* sums, float* dgamma, float* dbeta, void* dy,
+                   void* stream);
 /* LeakyReLU(0.2) backward from the OUTPUT (first discriminator conv has no BN, model.py:835-836) */
 int ekl_lrelu_bwd(const void* out, const void* dout, void* dx, int64_t n, void* stream);
 /* cat(tile(c_code), h) along channels (model.py:411-414, 956-959) and its backward (dcode accumulated) */

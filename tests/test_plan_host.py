@@ -145,15 +145,23 @@ def test_space_to_depth_filter_equals_conv4x4_stride2():
 
 def test_joint_conv_fold_identity():
     """conv3x3(cat(tile(c), h)) == conv3x3(h, Wx) + bias9[b, border class] with bias9 = VALID @ (Wc . c) -- the algebra
-    behind NEXT_STAGE_G._joint / ekl_conv_fwd_bias9, in fp32 on the CPU."""
-    from text2img_ekl_b200 import model
+    behind NEXT_STAGE_G._joint / ekl_code_bias9_fwd / ekl_conv_fwd_bias9, in fp32 on the CPU.  VALID[q, t] = 1 iff tap
+    t = (kh, kw) of a 3x3 / pad-1 conv reads inside the map for a pixel of border class q = 3*rc + cc (the predicate
+    csrc/codefold.cu::tap_valid evaluates)."""
+    valid = torch.zeros(9, 9)
+    ok = lambda cls, k: not ((cls == 0 and k == 0) or (cls == 2 and k == 2))
+    for rc in range(3):
+        for cc in range(3):
+            for kh in range(3):
+                for kw in range(3):
+                    valid[rc * 3 + cc, kh * 3 + kw] = float(ok(rc, kh) and ok(cc, kw))
     torch.manual_seed(0)
     B, Cc, Cx, N, H, W = 2, 5, 4, 6, 7, 5
     c, h = torch.randn(B, Cc), torch.randn(B, Cx, H, W)
     w = torch.randn(N, Cc + Cx, 3, 3)
     ref = F.conv2d(torch.cat((c.view(B, Cc, 1, 1).expand(B, Cc, H, W), h), 1), w, padding=1)
     T = torch.einsum("bc,nckl->bkln", c, w[:, :Cc]).reshape(B, 9, N)
-    bias9 = torch.einsum("qt,btn->bqn", model._border_valid(), T)
+    bias9 = torch.einsum("qt,btn->bqn", valid, T)
     cls_h = torch.tensor([0] + [1] * (H - 2) + [2])
     cls_w = torch.tensor([0] + [1] * (W - 2) + [2])
     q = cls_h.view(H, 1) * 3 + cls_w.view(1, W)                      # [H, W]
@@ -163,21 +171,21 @@ def test_joint_conv_fold_identity():
 
 def test_split_k_and_operand_planning_host_logic():
     """Host-side planning that needs no GPU: which plans get a split-K workspace, which data-gradients can read the
-    forward-packed filter, and the statistics-row count of the workspace path (include/ekl_b200.h)."""
+    forward-packed filter (include/ekl_b200.h)."""
     lib = L.lib()
     mk = lambda mode, B, H, W, Cin, Cout, gb=0: L.EklConv(mode, B, H, W, Cin, Cout, gb, L.IMPL_TC, 0, 0, 0, L.W_KRSC)
     # 4x4 discriminator tail, batch 24: 3 output tiles of 128 rows, contraction 9*2048 -> split
     tail = mk(L.S1, 24, 4, 4, 2048, 1024, 24)
     assert lib.ekl_conv_workspace_elems(tail, 0) == 24 * 16 * 1024
     assert lib.ekl_conv_workspace_elems(tail, 1) == 24 * 16 * 2048
-    assert lib.ekl_conv_stats_rows_ws(tail) != lib.ekl_conv_stats_rows(tail)
+    assert lib.ekl_conv_route(tail, 0) == 2 and lib.ekl_conv_route(tail, 1) == 2          # split-K + finishing pass
     # a layer that fills the machine is never split
     big = mk(L.DOWN2, 72, 64, 64, 128, 256, 24)
     assert lib.ekl_conv_workspace_elems(big, 0) == 0 and lib.ekl_conv_workspace_elems(big, 1) == 0
-    assert lib.ekl_conv_stats_rows_ws(big) == lib.ekl_conv_stats_rows(big)
+    assert lib.ekl_conv_route(big, 0) == 0
     # small-channel 3x3 layers run on the resident-filter kernel: no workspace, transposed operand still packed
     res = mk(L.S1, 24, 128, 128, 32, 64, 24)
-    assert lib.ekl_conv_workspace_elems(res, 0) == 0
+    assert lib.ekl_conv_workspace_elems(res, 0) == 0 and lib.ekl_conv_route(res, 0) == 1
     assert lib.ekl_conv_dgrad_from_fwd(res) == 0
     # stride-1 / stride-2 convs with 64-multiple channels: data-gradient straight from the forward-packed filter
     assert lib.ekl_conv_dgrad_from_fwd(tail) == 1 and lib.ekl_conv_dgrad_from_fwd(big) == 1
@@ -480,7 +488,7 @@ def test_step_engine_update_paths_run_on_cpu_stand_ins(monkeypatch):
     assert not torch.equal(netsD[1].weight.detach(), w0)
     # generator update with a stand-in loss
     g0 = netG[0].weight.detach().clone()
-    monkeypatch.setattr(eng, "g_loss", lambda real_cp: (netsD[0](netG(x)).square().mean(),) + (torch.zeros(()),) * 3)
+    monkeypatch.setattr(eng, "g_loss", lambda real_cp, per_d=None: (netsD[0](netG(x)).square().mean(),) + (torch.zeros(()),) * 3)
     d0 = netsD[0].weight.detach().clone()
     res = eng.g_step(None)
     assert len(res) == 4 and not torch.equal(netG[0].weight.detach(), g0)

@@ -1,0 +1,31 @@
+"""Two-rank run of bench.py under the driver's exact launch command (torchrun, NCCL): needs two GPUs, skipped otherwise.
+Guards round 1's failure: a roofline pass executed by rank 0 only left the other rank in a barrier (rc 124 after 870 s)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.timeout(400, method="thread")
+@pytest.mark.parametrize("comm", ["bf16", "fp32"])
+def test_bench_two_ranks_finishes_with_roofline_and_clean_exit(comm):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, EKL_GRAD_COMM=comm)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "6", "--warmup", "3"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=360, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["value"] > 0 and d["e2e"]["value"] > 0
+    assert d["config"]["grad_comm"] == comm and d["config"]["global_batch"] == 2 * d["config"]["batch_per_gpu"]
+    assert d["roofline"] and d["roofline"].get("frac", 0) > 0, d["roofline"]          # the pass ran on both ranks and returned
+    assert "nccl" in d["roofline"]["families"]

@@ -18,7 +18,8 @@ W_KRSC, W_KCRS = 0, 1
 
 class EklConv(C.Structure):
     _fields_ = [("mode", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
-                ("group_b", C.c_int), ("impl", C.c_int), ("x_fmt", C.c_int), ("y_fmt", C.c_int), ("act", C.c_int), ("w_layout", C.c_int)]
+                ("group_b", C.c_int), ("impl", C.c_int), ("x_fmt", C.c_int), ("y_fmt", C.c_int), ("act", C.c_int), ("w_layout", C.c_int),
+                ("w_cin_total", C.c_int), ("w_cin_off", C.c_int), ("w_cout_valid", C.c_int)]
 
 
 class EklError(RuntimeError):
@@ -36,10 +37,8 @@ SIGNATURES = {
     "ekl_require_sm100": (_i, []),
     "ekl_conv_packed_elems": (_i64, [_cp, _i]),
     "ekl_conv_pack": (_i, [_cp, _vp, _vp, _vp, _vp]),
-    "ekl_conv_stats_rows": (_i, [_cp]),
     "ekl_conv_fwd": (_i, [_cp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_conv_workspace_elems": (_i64, [_cp, _i]),
-    "ekl_conv_stats_rows_ws": (_i, [_cp]),
     "ekl_conv_fwd_ws": (_i, [_cp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_conv_bwd_data_ws": (_i, [_cp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_conv_dgrad_from_fwd": (_i, [_cp]),
@@ -49,13 +48,12 @@ SIGNATURES = {
     "ekl_conv_bwd_data": (_i, [_cp, _vp, _vp, _vp, _vp]),
     "ekl_conv_bwd_weight": (_i, [_cp, _vp, _vp, _vp, _vp]),
     "ekl_conv_plan_dump": (_i, [_cp, _i, C.POINTER(C.c_int), _i]),
-    "ekl_col_stats_rows": (_i, [_i64, _i, _i]),
     "ekl_col_stats": (_i, [_vp, _i64, _i, _i, _vp, _vp]),
-    "ekl_bn_finalize": (_i, [_vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
-    "ekl_bn_act_fwd": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
-    "ekl_bn_act_fwd_small": (_i, [_vp, _i, _f, _f, _f, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
-    "ekl_bn_act_bwd_rows": (_i, [_i64, _i, _i, _i]),
-    "ekl_bn_act_bwd": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ekl_code_bias9_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "ekl_border_sums9": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "ekl_code_bias9_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "ekl_bn_act_fwd": (_i, [_vp, _i64, _i, _i, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "ekl_bn_act_bwd": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "ekl_lrelu_bwd": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "ekl_cat_code": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "ekl_cat_code_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -1,7 +1,10 @@
 // Train-mode BatchNorm + activation family (HBM-bound, vectorised 16-byte accesses, fp32 statistics):
-//   statistics  : per-(group, channel) sum / sum-of-squares partials  (also produced by the conv epilogue)
-//   finalize    : partials -> mean, rstd (+ running_mean/var update, momentum 0.1, unbiased variance)
-//   forward     : z = gamma*(y-mean)*rstd + beta ; out = GLU(z) | LeakyReLU(z, 0.2) | z (+ residual)
+//   statistics  : per-(group, channel) sum / sum-of-squares, accumulated with fp64 red.global.add into ONE [groups][2][C]
+//                 double buffer (zero on entry) by whoever produces the tensor: the conv epilogue, splitk_finish, or
+//                 col_stats for a stored tensor.  No per-tile partial rows and no finalize launch: every consumer block
+//                 derives mean / rstd of its own channels from the two sums.
+//   forward     : z = gamma*(y-mean)*rstd + beta ; out = GLU(z) | LeakyReLU(z, 0.2) | z (+ residual); the blocks of the
+//                 first row chunk also store mean / rstd for the backward pass and update the running statistics
 //   backward    : dz = act'(z)*dout ; partial sums S1 = sum dz, S2 = sum dz*xhat ; dy = gamma*rstd*(dz - S1/n - xhat*S2/n)
 // Activations are bf16 [M rows][C channels] (NHWC flattened); rows are split into `groups` equal contiguous
 // groups with independent batch statistics (real / wrong / fake discriminator passes batched into one tensor;
@@ -27,6 +30,7 @@ struct Tile {
   int oct, rt, RT, CT;    // octet index (8 channels), row-thread id, row-threads / octet-threads per block
   int64_t r0, r1;         // row range of this block
   int g;                  // statistics group
+  int k;                  // row-chunk index inside the group (chunk 0 does the per-group bookkeeping)
   bool active;
 };
 __device__ __forceinline__ Tile make_tile(int64_t M, int noct, int groups) {
@@ -40,6 +44,7 @@ __device__ __forceinline__ Tile make_tile(int64_t M, int noct, int groups) {
   const int chunks_per_group = gridDim.y / groups;
   t.g = blockIdx.y / chunks_per_group;
   const int k = blockIdx.y - t.g * chunks_per_group;
+  t.k = k;
   const int64_t Mg = M / groups;
   const int64_t per = (Mg + chunks_per_group - 1) / chunks_per_group;
   t.r0 = t.g * Mg + k * per;
@@ -48,9 +53,12 @@ __device__ __forceinline__ Tile make_tile(int64_t M, int noct, int groups) {
   return t;
 }
 
+// fp64 accumulation of block-level partial sums into the [groups][2][C] statistics buffer
+__device__ __forceinline__ void stat_add(double* dst, float v) { atomicAdd(dst, (double)v); }
+
 // ---------------------------------------------------------------- statistics of a stored tensor
 __global__ void __launch_bounds__(256) col_stats_kernel(const bf16* __restrict__ y, int64_t M, int C, int groups,
-                                                        float* __restrict__ partial /*[gridDim.y][2][C]*/) {
+                                                        double* __restrict__ sums /*[groups][2][C], accumulated*/) {
   __shared__ float red[256 * 16];
   const Tile t = make_tile(M, C / 8, groups);
   float s1[8], s2[8];
@@ -71,17 +79,17 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const bf16* __restrict__
     for (int k = 1; k < t.RT; ++k)
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s1[i] += red[(threadIdx.x + k * CT) * 16 + i]; s2[i] += red[(threadIdx.x + k * CT) * 16 + 8 + i]; }
-    float* dst = partial + (size_t)blockIdx.y * 2 * C + t.oct * 8;
+    double* dst = sums + (size_t)t.g * 2 * C + t.oct * 8;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { dst[i] = s1[i]; dst[C + i] = s2[i]; }
+    for (int i = 0; i < 8; ++i) { stat_add(dst + i, s1[i]); stat_add(dst + C + i, s2[i]); }
   }
 }
 
 // ---------------------------------------------------------------- split-K finish (conv_tc.cu split plans)
-// fp32 scratch [M][C] (sum of the split work items' partial tiles) -> bf16 y, BatchNorm partial statistics of the
-// ROUNDED values (same contract as the conv epilogue), and the scratch is re-zeroed for its next use.
+// fp32 scratch [M][C] (sum of the split work items' partial tiles) -> bf16 y, BatchNorm statistics of the ROUNDED
+// values (same contract as the conv epilogue), and the scratch is re-zeroed for its next use.
 __global__ void __launch_bounds__(256) splitk_finish_kernel(float* __restrict__ scratch, int64_t M, int C, int groups,
-                                                            bf16* __restrict__ y, float* __restrict__ partial) {
+                                                            bf16* __restrict__ y, double* __restrict__ sums) {
   __shared__ float red[256 * 16];
   const Tile t = make_tile(M, C / 8, groups);
   float s1[8], s2[8];
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(float* __restrict__ 
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s1[i] += f[i]; s2[i] += f[i] * f[i]; }
     }
-  if (partial == nullptr) return;
+  if (sums == nullptr) return;
 #pragma unroll
   for (int i = 0; i < 8; ++i) { red[threadIdx.x * 16 + i] = s1[i]; red[threadIdx.x * 16 + 8 + i] = s2[i]; }
   __syncthreads();
@@ -108,54 +116,23 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(float* __restrict__ 
     for (int k = 1; k < t.RT; ++k)
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s1[i] += red[(threadIdx.x + k * CT) * 16 + i]; s2[i] += red[(threadIdx.x + k * CT) * 16 + 8 + i]; }
-    float* dst = partial + (size_t)blockIdx.y * 2 * C + t.oct * 8;
+    double* dst = sums + (size_t)t.g * 2 * C + t.oct * 8;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { dst[i] = s1[i]; dst[C + i] = s2[i]; }
+    for (int i = 0; i < 8; ++i) { stat_add(dst + i, s1[i]); stat_add(dst + C + i, s2[i]); }
   }
 }
 
-// ---------------------------------------------------------------- finalize
-// partial [rows][2][C]; rows = groups * rows_per_group (group-contiguous). One block (256 thr) per 32 channels.
-__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partial, int rows_per_group, int C,
-                                                           int groups, float count, float eps, float momentum,
-                                                           float* __restrict__ mean, float* __restrict__ rstd,
-                                                           float* running_mean, float* running_var) {
-  __shared__ double sh[2][32][33];
-  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  for (int g = 0; g < groups; ++g) {
-    float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f, a2 = 0.f, b2 = 0.f, a3 = 0.f, b3 = 0.f;
-    if (c < C) {
-      const float* base = partial + (size_t)g * rows_per_group * 2 * C + c;
-      int r = sl;
-      for (; r + 96 < rows_per_group; r += 128) {       // 4 independent row loads in flight
-        const float* p0 = base + (size_t)r * 2 * C;
-        const float* p1 = p0 + (size_t)64 * C;
-        const float* p2 = p1 + (size_t)64 * C;
-        const float* p3 = p2 + (size_t)64 * C;
-        a0 += p0[0]; b0 += p0[C]; a1 += p1[0]; b1 += p1[C]; a2 += p2[0]; b2 += p2[C]; a3 += p3[0]; b3 += p3[C];
-      }
-      for (; r < rows_per_group; r += 32) { const float* p0 = base + (size_t)r * 2 * C; a0 += p0[0]; b0 += p0[C]; }
-    }
-    sh[0][sl][cl] = (double)a0 + (double)a1 + (double)a2 + (double)a3;
-    sh[1][sl][cl] = (double)b0 + (double)b1 + (double)b2 + (double)b3;
-    __syncthreads();
-    if (sl == 0 && c < C) {
-      double a = 0.0, b = 0.0;
-      for (int k = 0; k < 32; ++k) { a += sh[0][k][cl]; b += sh[1][k][cl]; }
-      const double m = a / count;
-      double var = b / count - m * m;
-      if (var < 0.0) var = 0.0;
-      mean[g * C + c] = (float)m;
-      rstd[g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
-      if (running_mean != nullptr) {   // sequential updates, one per group == one per reference forward call
-        const double unb = count > 1.f ? var * count / (count - 1.0) : var;
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
-      }
-    }
-    __syncthreads();
-  }
+// ---------------------------------------------------------------- statistics -> coefficients
+// mean / rstd of channel c of group g from the two fp64 sums (count = rows per group); the subtraction E[y^2] - mean^2
+// is done in fp64, the reciprocal square root in fp32 like torch's batch_norm
+struct BnStat { float mean, rstd, var; };
+__device__ __forceinline__ BnStat bn_stat(const double* __restrict__ sums, int g, int C, int c, double inv_n, float eps) {
+  const double m = sums[((size_t)g * 2 + 0) * C + c] * inv_n;
+  double v = sums[((size_t)g * 2 + 1) * C + c] * inv_n - m * m;
+  v = v < 0.0 ? 0.0 : v;
+  BnStat o;
+  o.mean = (float)m; o.var = (float)v; o.rstd = 1.f / sqrtf((float)v + eps);
+  return o;
 }
 
 // ---------------------------------------------------------------- vector helpers for the streaming passes
@@ -182,9 +159,14 @@ __device__ __forceinline__ Tile make_tile_v(int64_t M, int nvec, int groups) { r
 template <int ACT> struct ActVec { static constexpr int V = ACT == ACT_GLU ? 4 : 8; };
 
 // ---------------------------------------------------------------- forward
+// sums != null (training): statistics from the fp64 sums; mean_io / rstd_io [groups][Cy] are WRITTEN by chunk 0 of each
+// group (saved for the backward pass) and block row 0 applies one running-statistics momentum update per group, in
+// group order (one per reference forward call).  sums == null (inference): mean_io / rstd_io are inputs.
 template <int ACT>
 __global__ void __launch_bounds__(256, 3) bn_act_fwd_kernel(const bf16* __restrict__ y, int64_t M, int Cy, int groups,
-                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            const double* __restrict__ sums, float eps, float momentum,
+                                                            float* mean_io, float* rstd_io, float* running_mean,
+                                                            float* running_var,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const bf16* __restrict__ residual, bf16* __restrict__ out) {
   constexpr int VEC = ActVec<ACT>::V;
@@ -211,15 +193,40 @@ __global__ void __launch_bounds__(256, 3) bn_act_fwd_kernel(const bf16* __restri
   int64_t rb = t.r0 + t.rt;
   load(ca, cb, cq, rb);
   float sc[VEC], sh[VEC], sc2[VEC], sh2[VEC];
+  const double inv_n = 1.0 / (double)(M / groups);
+  constexpr int NHF = ACT == ACT_GLU ? 2 : 1;
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    const float s = gamma[c0 + i] * rstd[t.g * Cy + c0 + i];
-    sc[i] = s; sh[i] = beta[c0 + i] - mean[t.g * Cy + c0 + i] * s;
-    if (ACT == ACT_GLU) {
-      const int c = Co + c0 + i;
-      const float s_ = gamma[c] * rstd[t.g * Cy + c];
-      sc2[i] = s_; sh2[i] = beta[c] - mean[t.g * Cy + c] * s_;
+  for (int h = 0; h < NHF; ++h)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int c = h * Co + c0 + i;
+      float m, r;
+      if (sums != nullptr) {
+        const BnStat st = bn_stat(sums, t.g, Cy, c, inv_n, eps);
+        m = st.mean; r = st.rstd;
+        if (t.k == 0 && t.rt == 0) { mean_io[t.g * Cy + c] = m; rstd_io[t.g * Cy + c] = r; }
+      } else {
+        m = mean_io[t.g * Cy + c]; r = rstd_io[t.g * Cy + c];
+      }
+      const float s = gamma[c] * r;
+      if (h == 0) { sc[i] = s; sh[i] = beta[c] - m * s; } else { sc2[i] = s; sh2[i] = beta[c] - m * s; }
     }
+  if (sums != nullptr && running_mean != nullptr && blockIdx.y == 0 && t.rt == 0) {
+    const float n = (float)(M / groups);
+#pragma unroll
+    for (int h = 0; h < NHF; ++h)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int c = h * Co + c0 + i;
+        float rm = running_mean[c], rv = running_var[c];
+        for (int g = 0; g < groups; ++g) {
+          const BnStat st = bn_stat(sums, g, Cy, c, inv_n, eps);
+          const float unb = n > 1.f ? st.var * n / (n - 1.f) : st.var;
+          rm = (1.f - momentum) * rm + momentum * st.mean;
+          rv = (1.f - momentum) * rv + momentum * unb;
+        }
+        running_mean[c] = rm; running_var[c] = rv;
+      }
   }
   for (; rb < t.r1; rb += (int64_t)U * t.RT) {
     load(na, nb, nq, rb + (int64_t)U * t.RT);
@@ -282,7 +289,7 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_kernel(const bf16* _
                                                                    int64_t M, int Cy, int groups,
                                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                   float* __restrict__ partial /*[gridDim.y][2][Cy]*/) {
+                                                                   double* __restrict__ sums /*[groups][2][Cy], zero on entry*/) {
   constexpr int VEC = ActVec<ACT>::V;
   using IO = VecIO<VEC>;
   __shared__ float red[256 * 2 * VEC];
@@ -362,48 +369,10 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_kernel(const bf16* _
           a[i] += red[(threadIdx.x + k * CT) * 2 * VEC + i];
           b[i] += red[(threadIdx.x + k * CT) * 2 * VEC + VEC + i];
         }
-      float* dst = partial + (size_t)blockIdx.y * 2 * Cy + h * Co + c0;
+      double* dst = sums + (size_t)t.g * 2 * Cy + h * Co + c0;
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) { dst[i] = a[i]; dst[Cy + i] = b[i]; }
+      for (int i = 0; i < VEC; ++i) { stat_add(dst + i, a[i]); stat_add(dst + Cy + i, b[i]); }
     }
-  }
-}
-
-// partial [groups*rows_per_group][2][Cy] -> sums [groups][2][Cy]; dgamma[c] += sum_g S2, dbeta[c] += sum_g S1
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows_per_group, int Cy,
-                                                              int groups, float* __restrict__ sums, float* dgamma, float* dbeta) {
-  __shared__ float sh[2][8][32];
-  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  float tg = 0.f, tb = 0.f;
-  for (int g = 0; g < groups; ++g) {
-    float a = 0.f, b = 0.f, a1 = 0.f, b1 = 0.f;
-    if (c < Cy) {
-      int r = sl;
-      for (; r + 8 < rows_per_group; r += 16) {            // two independent rows in flight
-        const float* p = partial + ((size_t)(g * rows_per_group + r)) * 2 * Cy;
-        const float* q = p + (size_t)16 * Cy;
-        a += p[c]; b += p[Cy + c]; a1 += q[c]; b1 += q[Cy + c];
-      }
-      for (; r < rows_per_group; r += 8) {
-        const float* p = partial + ((size_t)(g * rows_per_group + r)) * 2 * Cy;
-        a += p[c]; b += p[Cy + c];
-      }
-      a += a1; b += b1;
-    }
-    sh[0][sl][cl] = a; sh[1][sl][cl] = b;
-    __syncthreads();
-    if (sl == 0 && c < Cy) {
-      for (int k = 1; k < 8; ++k) { a += sh[0][k][cl]; b += sh[1][k][cl]; }
-      sums[(g * 2 + 0) * Cy + c] = a;
-      sums[(g * 2 + 1) * Cy + c] = b;
-      tb += a; tg += b;
-    }
-    __syncthreads();
-  }
-  if (sl == 0 && c < Cy) {
-    if (dgamma) dgamma[c] += tg;
-    if (dbeta) dbeta[c] += tb;
   }
 }
 
@@ -414,8 +383,8 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_kernel(const bf16* __
                                                                   int64_t M, int Cy, int groups,
                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                  const float* __restrict__ sums /*[groups][2][Cy]*/,
-                                                                  bf16* __restrict__ dy) {
+                                                                  const double* __restrict__ sums /*[groups][2][Cy]*/,
+                                                                  float* dgamma, float* dbeta, bf16* __restrict__ dy) {
   constexpr int VEC = ActVec<ACT>::V;
   using IO = VecIO<VEC>;
   const int Co = ACT == ACT_GLU ? Cy / 2 : Cy;
@@ -445,16 +414,29 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_kernel(const bf16* __
       const int c = c0 + i;
       const float mu = mean[t.g * Cy + c], r = rstd[t.g * Cy + c];
       sc[i] = gamma[c] * r; sh[i] = beta[c] - mu * sc[i];
-      A[i] = -sc[i] * r * sums[(t.g * 2 + 1) * Cy + c] * inv_n;
-      Bc[i] = -sc[i] * sums[(t.g * 2 + 0) * Cy + c] * inv_n - A[i] * mu;
+      A[i] = -sc[i] * r * (float)sums[(t.g * 2 + 1) * Cy + c] * inv_n;
+      Bc[i] = -sc[i] * (float)sums[(t.g * 2 + 0) * Cy + c] * inv_n - A[i] * mu;
     }
     if (ACT == ACT_GLU) {
       const int c = Co + c0 + i;
       const float mu = mean[t.g * Cy + c], r = rstd[t.g * Cy + c];
       sc2[i] = gamma[c] * r; sh2[i] = beta[c] - mu * sc2[i];
-      A2[i] = -sc2[i] * r * sums[(t.g * 2 + 1) * Cy + c] * inv_n;
-      Bc2[i] = -sc2[i] * sums[(t.g * 2 + 0) * Cy + c] * inv_n - A2[i] * mu;
+      A2[i] = -sc2[i] * r * (float)sums[(t.g * 2 + 1) * Cy + c] * inv_n;
+      Bc2[i] = -sc2[i] * (float)sums[(t.g * 2 + 0) * Cy + c] * inv_n - A2[i] * mu;
     }
+  }
+  // parameter gradients (accumulated): dgamma[c] += sum_g S2, dbeta[c] += sum_g S1 -- one thread per channel
+  if (blockIdx.y == 0 && t.rt == 0 && (dgamma != nullptr || dbeta != nullptr)) {
+#pragma unroll
+    for (int h = 0; h < (ACT == ACT_GLU ? 2 : 1); ++h)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int c = h * Co + c0 + i;
+        double tb = 0.0, tg = 0.0;
+        for (int g = 0; g < groups; ++g) { tb += sums[(g * 2 + 0) * Cy + c]; tg += sums[(g * 2 + 1) * Cy + c]; }
+        if (dgamma != nullptr) dgamma[c] += (float)tg;
+        if (dbeta != nullptr) dbeta[c] += (float)tb;
+      }
   }
   for (; rb < t.r1; rb += (int64_t)U * t.RT) {
     load(na, nb, nd, rb + (int64_t)U * t.RT);
@@ -481,13 +463,12 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_kernel(const bf16* __
   }
 }
 
-// ---------------------------------------------------------------- small layers: one launch per direction
+// ---------------------------------------------------------------- small layers: backward in one launch
 // Layers with few rows per statistics group (the 4x4 / 8x8 discriminator tails, the generator stem's BatchNorm1d) are
-// launch-latency bound: three (backward) / two (forward) kernels of a few microseconds each.  Here a block owns a strip
-// of 8 channel vectors of one group for ALL rows, so the batch statistics never leave the block:
-//   backward: rows -> S1, S2 (warp shuffles + shared memory) -> dy (second sweep hits L1/L2) ; dgamma/dbeta by atomics
-//   forward : partial statistics rows -> mean / rstd (+ running statistics) -> activation sweep
-// Block = 256 threads = 8 vector-threads x 32 row-threads.
+// launch-latency bound.  Here a block owns a strip of 8 channel vectors of one group for ALL rows, so the backward sums
+// never leave the block: rows -> S1, S2 (warp shuffles + shared memory) -> dy (second sweep hits L1/L2); dgamma / dbeta
+// by atomics.  Block = 256 threads = 8 vector-threads x 32 row-threads.  (The forward pass needs no such variant: the
+// statistics arrive as two sums per channel, so the streaming kernel is a single launch for every size.)
 constexpr int SM_CT = 8, SM_RT = 32;
 
 // reduce NV per-thread values over the 32 row-threads that share a vector-thread; result valid in every thread
@@ -633,120 +614,6 @@ __global__ void __launch_bounds__(256) bn_act_bwd_small_kernel(const bf16* __res
   }
 }
 
-// forward: finalize (partials -> mean/rstd, running statistics) + normalise + activation in one launch
-template <int ACT>
-__global__ void __launch_bounds__(256) bn_act_fwd_small_kernel(const float* __restrict__ partial, int rows_per_group, float count,
-                                                               float eps, float momentum, float* running_mean, float* running_var,
-                                                               const bf16* __restrict__ y, int64_t Mg, int Cy, int groups,
-                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                               const bf16* __restrict__ residual, bf16* __restrict__ out,
-                                                               float* __restrict__ mean_out, float* __restrict__ rstd_out) {
-  constexpr int VEC = ActVec<ACT>::V;
-  constexpr int NH = ACT == ACT_GLU ? 2 : 1;
-  constexpr int NV = 2 * NH * VEC;
-  using IO = VecIO<VEC>;
-  __shared__ float sh[8 * SM_CT * NV];
-  __shared__ float tot[SM_CT * NV];
-  const int Co = ACT == ACT_GLU ? Cy / 2 : Cy;
-  const int ct = threadIdx.x % SM_CT, rt = threadIdx.x / SM_CT;
-  const int g = blockIdx.y;
-  const int c0 = (blockIdx.x * SM_CT + ct) * VEC;
-  float sc[VEC], shf[VEC], sc2[VEC], sh2[VEC];
-  // Every block reduces its own group's partial statistics; block (strip, 0) reduces ALL groups (their loads are issued
-  // together) so that it can apply the running-statistics momentum updates in group order (one per group == one per
-  // reference forward call).  groups <= 3 on this path.
-  const int ng = g == 0 ? groups : 1;
-  float acc[3][NV];       // per handled group: [sum a | sumsq a | sum b | sumsq b]
-#pragma unroll
-  for (int q = 0; q < 3; ++q)
-#pragma unroll
-    for (int i = 0; i < NV; ++i) acc[q][i] = 0.f;
-#pragma unroll 2
-  for (int r = rt; r < rows_per_group; r += SM_RT) {
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      if (q < ng) {
-        const int gg = g == 0 ? q : g;
-        const float* pr = partial + ((size_t)gg * rows_per_group + r) * 2 * Cy;
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          acc[q][i] += pr[c0 + i]; acc[q][VEC + i] += pr[Cy + c0 + i];
-          if (ACT == ACT_GLU) { acc[q][2 * VEC + i] += pr[Co + c0 + i]; acc[q][3 * VEC + i] += pr[Cy + Co + c0 + i]; }
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    if (q >= ng) break;                  // uniform per block
-    const int gg = g == 0 ? q : g;
-    strip_reduce<NV>(acc[q], sh, tot);
-#pragma unroll
-    for (int h = 0; h < NH; ++h)
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const int c = h * Co + c0 + i;
-        const double md = (double)acc[q][2 * h * VEC + i] / (double)count;
-        double vd = (double)acc[q][(2 * h + 1) * VEC + i] / (double)count - md * md;
-        vd = vd < 0.0 ? 0.0 : vd;
-        const float m = (float)md, var = (float)vd;
-        const float r = (float)(1.0 / sqrt(vd + (double)eps));
-        if (gg == g) {
-          const float s_ = gamma[c] * r;
-          if (h == 0) { sc[i] = s_; shf[i] = beta[c] - m * s_; } else { sc2[i] = s_; sh2[i] = beta[c] - m * s_; }
-          if (rt == 0) { mean_out[g * Cy + c] = m; rstd_out[g * Cy + c] = r; }
-        }
-        if (g == 0 && rt == 0 && running_mean != nullptr) {
-          const float unb = count > 1.f ? var * count / (count - 1.f) : var;
-          running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
-          running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
-        }
-      }
-  }
-  const bf16* yg = y + (int64_t)g * Mg * Cy;
-  const bf16* rg = residual != nullptr ? residual + (int64_t)g * Mg * Co : nullptr;
-  bf16* og = out + (int64_t)g * Mg * Co;
-  constexpr int U = 4;        // rows in flight per thread
-  for (int64_t rb = rt; rb < Mg; rb += (int64_t)U * SM_RT) {
-    typename IO::T ua[U], ub[U], uq[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t r = rb + (int64_t)u * SM_RT;
-      if (r < Mg) {
-        ua[u] = *reinterpret_cast<const typename IO::T*>(yg + r * Cy + c0);
-        if (ACT == ACT_GLU) ub[u] = *reinterpret_cast<const typename IO::T*>(yg + r * Cy + Co + c0);
-        if (rg != nullptr) uq[u] = *reinterpret_cast<const typename IO::T*>(rg + r * Co + c0);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t r = rb + (int64_t)u * SM_RT;
-      if (r >= Mg) break;
-      float a[VEC], o[VEC];
-      IO::unpack(ua[u], a);
-      if (ACT == ACT_GLU) {
-        float b[VEC];
-        IO::unpack(ub[u], b);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) o[i] = (a[i] * sc[i] + shf[i]) * sigmoidf_(b[i] * sc2[i] + sh2[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          const float z = a[i] * sc[i] + shf[i];
-          o[i] = ACT == ACT_LRELU ? (z > 0.f ? z : 0.2f * z) : (ACT == ACT_RELU ? fmaxf(z, 0.f) : z);
-        }
-      }
-      if (rg != nullptr) {
-        float q[VEC];
-        IO::unpack(uq[u], q);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) o[i] += q[i];
-      }
-      *reinterpret_cast<typename IO::T*>(og + r * Co + c0) = IO::pack(o);
-    }
-  }
-}
-
 // ---------------------------------------------------------------- plain LeakyReLU backward / concat helpers
 __global__ void lrelu_bwd_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, bf16* __restrict__ dx, int64_t n8) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
@@ -846,10 +713,11 @@ int grid_rows(int64_t M, int noct, int groups, dim3* grid) {
   const int RT = 256 / CT;
   const int xs = ekl_cdiv(noct, CT);
   const int64_t Mg = M / groups;
-  // enough chunks to fill the machine ~4x, at least 4*RT rows per chunk
-  // ~3 fat blocks per SM: per-block prologue (per-channel parameter loads) is amortised over >= 16 rows per thread
+  // ~3 fat blocks per SM: the per-block prologue (per-channel coefficients) is amortised over >= 16 rows per thread on
+  // large layers; small layers (fewer than 148*3 such chunks) go down to 4 rows per thread to get more blocks in flight
   int64_t chunks = (148 * 3 + xs * groups - 1) / (xs * groups);
-  const int64_t maxc = (Mg + 16 * RT - 1) / (16 * RT);
+  int64_t maxc = (Mg + 16 * RT - 1) / (16 * RT);
+  if (maxc < chunks) maxc = (Mg + 4 * RT - 1) / (4 * RT);
   if (chunks > maxc) chunks = maxc;
   if (chunks < 1) chunks = 1;
   *grid = dim3(xs, (unsigned)(chunks * groups));
@@ -873,40 +741,21 @@ static int finish_grid(int64_t M, int noct, int groups, dim3* grid) {
   return (int)chunks;
 }
 
-// rows of the partial-statistics buffer splitk_finish writes
-int ekl_splitk_finish_rows(int64_t M, int C, int groups) {
-  dim3 grid;
-  return finish_grid(M, C / 8, groups, &grid) * groups;
-}
-
-int ekl_splitk_finish(float* scratch, int64_t M, int C, int groups, void* y, float* partial, cudaStream_t st) {
+int ekl_splitk_finish(float* scratch, int64_t M, int C, int groups, void* y, double* sums, cudaStream_t st) {
   EKL_REQUIRE(C % 8 == 0 && M % groups == 0, "splitk_finish: C %% 8 and M %% groups required (C=%d)", C);
   dim3 grid;
   finish_grid(M, C / 8, groups, &grid);
-  splitk_finish_kernel<<<grid, 256, 0, st>>>(scratch, M, C, groups, (bf16*)y, partial);
+  splitk_finish_kernel<<<grid, 256, 0, st>>>(scratch, M, C, groups, (bf16*)y, sums);
   EKL_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int ekl_col_stats_rows(int64_t M, int C, int groups) {
-  dim3 grid;
-  return grid_rows(M, C / 8, groups, &grid) * groups;
-}
-
-extern "C" int ekl_col_stats(const void* y, int64_t M, int C, int groups, float* partial, void* stream) {
+extern "C" int ekl_col_stats(const void* y, int64_t M, int C, int groups, double* sums, void* stream) {
+  EKL_REQUIRE(y != nullptr && sums != nullptr, "col_stats: null pointer argument");
   EKL_REQUIRE(C % 8 == 0 && M % groups == 0, "col_stats: C %% 8 and M %% groups required (C=%d)", C);
   dim3 grid;
   grid_rows(M, C / 8, groups, &grid);
-  col_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)y, M, C, groups, partial);
-  EKL_LAUNCH_CHECK();
-  return 0;
-}
-
-extern "C" int ekl_bn_finalize(const float* partial, int rows_per_group, int C, int groups, float count, float eps,
-                               float momentum, float* mean, float* rstd, float* running_mean, float* running_var,
-                               void* stream) {
-  bn_finalize_kernel<<<ekl_cdiv(C, 32), 1024, 0, (cudaStream_t)stream>>>(partial, rows_per_group, C, groups, count, eps,
-                                                                        momentum, mean, rstd, running_mean, running_var);
+  col_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)y, M, C, groups, sums);
   EKL_LAUNCH_CHECK();
   return 0;
 }
@@ -920,45 +769,26 @@ extern "C" int ekl_bn_finalize(const float* partial, int rows_per_group, int C, 
     default: return ekl_fail(-1, "bad act %d", act);    \
   }
 
-extern "C" int ekl_bn_act_fwd(const void* y, int64_t M, int Cy, int groups, const float* mean, const float* rstd,
-                              const float* gamma, const float* beta, int act, const void* residual, void* out,
-                              void* stream) {
+extern "C" int ekl_bn_act_fwd(const void* y, int64_t M, int Cy, int groups, const double* sums, float eps, float momentum,
+                              float* mean, float* rstd, float* running_mean, float* running_var, const float* gamma,
+                              const float* beta, int act, const void* residual, void* out, void* stream) {
   const int Co = act == ACT_GLU ? Cy / 2 : Cy;
   EKL_REQUIRE(Co % 8 == 0 && M % groups == 0, "bn_act_fwd: bad shape Cy=%d", Cy);
+  EKL_REQUIRE(y != nullptr && out != nullptr && mean != nullptr && rstd != nullptr, "bn_act_fwd: null pointer argument");
   dim3 grid;
   grid_rows(M, Co / act_vec(act), groups, &grid);
   EKL_ACT_SWITCH(act, (bn_act_fwd_kernel<A><<<grid, 256, 0, (cudaStream_t)stream>>>(
-                          (const bf16*)y, M, Cy, groups, mean, rstd, gamma, beta, (const bf16*)residual, (bf16*)out)));
+                          (const bf16*)y, M, Cy, groups, sums, eps, momentum, mean, rstd, running_mean, running_var, gamma, beta,
+                          (const bf16*)residual, (bf16*)out)));
   EKL_LAUNCH_CHECK();
   return 0;
 }
 
-// finalize + forward in one launch when the layer is small: returns 0 if it ran, 2000 if the layer does not qualify (the
-// caller then uses ekl_bn_finalize + ekl_bn_act_fwd), any other nonzero value is an error
-extern "C" int ekl_bn_act_fwd_small(const float* partial, int rows_per_group, float count, float eps, float momentum,
-                                    float* running_mean, float* running_var, const void* y, int64_t M, int Cy, int groups,
-                                    const float* gamma, const float* beta, int act, const void* residual, void* out,
-                                    float* mean, float* rstd, void* stream) {
-  const int Co = act == ACT_GLU ? Cy / 2 : Cy;
-  if (!(Co % 8 == 0 && M % groups == 0) || !bn_small(M, Co, groups, act) || rows_per_group > 1024 || groups > 3) return 2000;
-  dim3 sg(Co / act_vec(act) / SM_CT, groups);
-  EKL_ACT_SWITCH(act, (bn_act_fwd_small_kernel<A><<<sg, 256, 0, (cudaStream_t)stream>>>(
-                          partial, rows_per_group, count, eps, momentum, running_mean, running_var, (const bf16*)y, M / groups, Cy,
-                          groups, gamma, beta, (const bf16*)residual, (bf16*)out, mean, rstd)));
-  EKL_LAUNCH_CHECK();
-  return 0;
-}
-
-extern "C" int ekl_bn_act_bwd_rows(int64_t M, int Cy, int groups, int act) {
-  const int Co = act == ACT_GLU ? Cy / 2 : Cy;
-  dim3 grid;
-  return grid_rows(M, Co / act_vec(act), groups, &grid) * groups;
-}
-
-// partial: [ekl_bn_act_bwd_rows][2][Cy] scratch; sums: [groups][2][Cy] scratch; dgamma/dbeta accumulated (+=).
+// sums: [groups][2][Cy] doubles of caller scratch, ZERO on entry (unused by single-launch small layers); dgamma/dbeta
+// accumulated (+=).
 extern "C" int ekl_bn_act_bwd(const void* y, const void* dout, int64_t M, int Cy, int groups, const float* mean,
-                              const float* rstd, const float* gamma, const float* beta, int act, float* partial,
-                              float* sums, float* dgamma, float* dbeta, void* dy, void* stream) {
+                              const float* rstd, const float* gamma, const float* beta, int act, double* sums,
+                              float* dgamma, float* dbeta, void* dy, void* stream) {
   const int Co = act == ACT_GLU ? Cy / 2 : Cy;
   EKL_REQUIRE(Co % 8 == 0 && M % groups == 0, "bn_act_bwd: bad shape Cy=%d", Cy);
   cudaStream_t st = (cudaStream_t)stream;
@@ -969,15 +799,14 @@ extern "C" int ekl_bn_act_bwd(const void* y, const void* dout, int64_t M, int Cy
     EKL_LAUNCH_CHECK();
     return 0;
   }
+  EKL_REQUIRE(sums != nullptr, "bn_act_bwd: sums scratch required");
   dim3 grid;
-  const int chunks = grid_rows(M, Co / act_vec(act), groups, &grid);
+  grid_rows(M, Co / act_vec(act), groups, &grid);
   EKL_ACT_SWITCH(act, (bn_act_bwd_reduce_kernel<A><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M, Cy, groups,
-                                                                         mean, rstd, gamma, beta, partial)));
-  EKL_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<ekl_cdiv(Cy, 32), 256, 0, st>>>(partial, chunks, Cy, groups, sums, dgamma, dbeta);
+                                                                         mean, rstd, gamma, beta, sums)));
   EKL_LAUNCH_CHECK();
   EKL_ACT_SWITCH(act, (bn_act_bwd_apply_kernel<A><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M, Cy, groups,
-                                                                        mean, rstd, gamma, beta, sums, (bf16*)dy)));
+                                                                        mean, rstd, gamma, beta, sums, dgamma, dbeta, (bf16*)dy)));
   EKL_LAUNCH_CHECK();
   return 0;
 }

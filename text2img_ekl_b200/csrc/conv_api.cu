@@ -4,16 +4,14 @@
 #include "ekl_common.cuh"
 
 int ekl_tc_supported(const EklGather* g);
-int ekl_tc_stats_rows(const EklGather* g, int group_b);
 void ekl_tc_geometry(const EklGather* g, int group_b, int* tb, int* th, int* tw);
-int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, int group_b, int act, const float* bias9,
+int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, double* stats, int group_b, int act, const float* bias9,
                        float* scratch, int* mtiles_out, cudaStream_t st, int w_is_fwd_packed = 0);
 int ekl_tc_dgrad_from_fwd_ok(const EklGather* g);
 int64_t ekl_tc_split_elems(const EklGather* g, int group_b);
-int ekl_splitk_finish_rows(int64_t M, int C, int groups);
-int ekl_splitk_finish(float* scratch, int64_t M, int C, int groups, void* y, float* partial, cudaStream_t st);
+int ekl_splitk_finish(float* scratch, int64_t M, int C, int groups, void* y, double* sums, cudaStream_t st);
 int ekl_rw_supported(const EklGather* g, int group_b);
-int ekl_conv3x3_rw(const EklGather* g, const void* w_packed, float* stats, int act, const float* bias9, cudaStream_t st);
+int ekl_conv3x3_rw(const EklGather* g, const void* w_packed, double* stats, int act, const float* bias9, cudaStream_t st);
 int ekl_gather_simt(const EklGather* g, const void* w_packed, int act, cudaStream_t st);
 int ekl_wgrad_simt(const EklGather* fwd_plan, float* dw_master, cudaStream_t st);
 int ekl_wgrad_tc_supported(const EklGather* g);
@@ -33,7 +31,7 @@ bool rw_enabled() {
 
 // stride-1 3x3 plans with one K block per tap run on the resident-filter kernel (conv_rw.cu), everything else on the
 // generic gather-GEMM kernel (conv_tc.cu)
-int run_tc(const EklGather* g, const void* w, float* stats, int group_b, int act, const float* bias9, cudaStream_t st) {
+int run_tc(const EklGather* g, const void* w, double* stats, int group_b, int act, const float* bias9, cudaStream_t st) {
   if (rw_enabled() && ekl_rw_supported(g, group_b)) return ekl_conv3x3_rw(g, w, stats, act, bias9, st);
   return ekl_gather_gemm_tc(g, w, stats, group_b, act, bias9, nullptr, nullptr, st);
 }
@@ -48,7 +46,7 @@ int64_t split_elems(const ekl_conv* c, const EklGather* g, int group_b) {
 }
 
 // split-K conv into `ws` (zero on entry, zero on exit) + finish into the bf16 output `out` (+ statistics)
-int run_split(const EklGather* g, const void* w, int group_b, float* ws, void* out, float* stats, cudaStream_t st,
+int run_split(const EklGather* g, const void* w, int group_b, float* ws, void* out, double* stats, cudaStream_t st,
               int w_is_fwd = 0) {
   if (int rc = ekl_gather_gemm_tc(g, w, nullptr, group_b, 0, nullptr, ws, nullptr, st, w_is_fwd)) return rc;
   const int groups = (group_b > 0 && g->mB % group_b == 0) ? g->mB / group_b : 1;
@@ -76,6 +74,10 @@ int check(const ekl_conv* c) {
   EKL_REQUIRE(c->mode >= EKL_S1 && c->mode <= EKL_DOWN2, "bad conv mode %d", c->mode);
   EKL_REQUIRE(c->B > 0 && c->H > 0 && c->W > 0 && c->Cin > 0 && c->Cout > 0, "bad conv extents");
   EKL_REQUIRE(c->mode != EKL_DOWN2 || (c->H % 2 == 0 && c->W % 2 == 0), "DOWN2 needs even H, W");
+  EKL_REQUIRE(c->w_cin_total == 0 || (c->w_cin_off >= 0 && c->w_cin_off + c->Cin <= c->w_cin_total && c->w_layout == EKL_W_KRSC &&
+                                      c->w_cin_off % 4 == 0 && c->w_cin_total % 4 == 0),
+              "bad master-filter channel window (KRSC layout, offsets %% 4)");
+  EKL_REQUIRE(c->w_cout_valid >= 0 && c->w_cout_valid <= c->Cout, "bad w_cout_valid");
   return 0;
 }
 
@@ -86,6 +88,9 @@ int plan(const ekl_conv* c, int dgrad, const void* x, const void* y, EklGather* 
   EklView yv = make_view(y, c->B, Ho, Wo, c->Cout, c->y_fmt);
   int rc = ekl_build_gather(g, c->mode, dgrad, xv, yv, c->Cin, c->Cout);
   g->w_kcrs = c->w_layout == EKL_W_KCRS;
+  g->w_ld = c->w_cin_total > 0 ? c->w_cin_total : c->Cin;
+  g->w_off = c->w_cin_off;
+  g->w_cout = c->w_cout_valid > 0 ? c->w_cout_valid : c->Cout;
   return rc;
 }
 
@@ -112,20 +117,13 @@ extern "C" int ekl_conv_pack(const ekl_conv* c, const float* w_master, void* w_f
   return 0;
 }
 
-extern "C" int ekl_conv_stats_rows(const ekl_conv* c) {
-  if (check(c)) return -1;
-  EklGather g;
-  plan(c, 0, nullptr, nullptr, &g);
-  return ekl_tc_stats_rows(&g, c->group_b);
-}
-
-extern "C" int ekl_conv_fwd(const ekl_conv* c, const void* x, const void* w_fwd, void* y, float* stats, void* stream) {
+extern "C" int ekl_conv_fwd(const ekl_conv* c, const void* x, const void* w_fwd, void* y, double* stats, void* stream) {
   if (int rc = check(c)) return rc;
   EKL_REQUIRE(x != nullptr && w_fwd != nullptr && y != nullptr, "conv_fwd: null pointer argument");
   EklGather g;
   plan(c, 0, x, y, &g);
   if (c->impl == EKL_IMPL_SIMT) {
-    EKL_REQUIRE(stats == nullptr, "SIMT conv does not produce BatchNorm partials (use ekl_col_stats)");
+    EKL_REQUIRE(stats == nullptr, "SIMT conv does not produce BatchNorm statistics (use ekl_col_stats)");
     const int act = c->act == EKL_ACT_LRELU ? 1 : (c->act == EKL_ACT_TANH ? 2 : 0);
     return ekl_gather_simt(&g, w_fwd, act, (cudaStream_t)stream);
   }
@@ -140,7 +138,7 @@ extern "C" int ekl_conv_fwd(const ekl_conv* c, const void* x, const void* w_fwd,
 // of a jointConv (model.py:411-414, 403) folded into a per-sample bias with 9 border variants: class = 3*rc + cc,
 // rc / cc = 0 first row / column, 2 last, 1 interior.  EKL_S1, tcgen05 implementation only.
 extern "C" int ekl_conv_fwd_bias9(const ekl_conv* c, const void* x, const void* w_fwd, const float* bias9, void* y,
-                                  float* stats, void* stream) {
+                                  double* stats, void* stream) {
   if (int rc = check(c)) return rc;
   EKL_REQUIRE(c->mode == EKL_S1 && c->impl == EKL_IMPL_TC && c->x_fmt == 0 && c->y_fmt == 0 && c->act == EKL_ACT_NONE,
               "conv_fwd_bias9: stride-1 3x3, tcgen05, NHWC bf16, no activation");
@@ -162,8 +160,7 @@ extern "C" int ekl_conv_bwd_data(const ekl_conv* c, const void* dy, const void* 
 
 // ---- workspace variants: few-tile / long-contraction plans run split-K through an fp32 workspace the caller owns
 // (ekl_conv_workspace_elems floats, ZERO before the first call; every call leaves it zero again).  With ws == NULL or a
-// plan that does not split they are the plain calls.  The statistics buffer of the split path has
-// ekl_conv_stats_rows_ws rows.
+// plan that does not split they are the plain calls.
 extern "C" int64_t ekl_conv_workspace_elems(const ekl_conv* c, int dgrad) {
   if (check(c)) return -1;
   EklGather g;
@@ -171,16 +168,7 @@ extern "C" int64_t ekl_conv_workspace_elems(const ekl_conv* c, int dgrad) {
   return split_elems(c, &g, dgrad ? 0 : c->group_b);
 }
 
-extern "C" int ekl_conv_stats_rows_ws(const ekl_conv* c) {
-  if (check(c)) return -1;
-  EklGather g;
-  plan(c, 0, nullptr, nullptr, &g);
-  if (split_elems(c, &g, c->group_b) == 0) return ekl_tc_stats_rows(&g, c->group_b);
-  const int groups = (c->group_b > 0 && g.mB % c->group_b == 0) ? g.mB / c->group_b : 1;
-  return ekl_splitk_finish_rows((int64_t)g.mB * g.mH * g.mW, g.N, groups);
-}
-
-extern "C" int ekl_conv_fwd_ws(const ekl_conv* c, const void* x, const void* w_fwd, void* y, float* stats, float* ws,
+extern "C" int ekl_conv_fwd_ws(const ekl_conv* c, const void* x, const void* w_fwd, void* y, double* stats, float* ws,
                                void* stream) {
   if (int rc = check(c)) return rc;
   EklGather g;

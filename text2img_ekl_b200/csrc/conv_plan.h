@@ -34,9 +34,14 @@ struct EklGather {
   int transposed;             // packed weights are [.][Cin_master][t][Cout_master] (data-gradient) instead of [Cout][t][Cin]
   int KH, KW;                 // master filter taps
   int w_kcrs;                 // master filter / gradient memory is [Cout][Cin][KH][KW] instead of [Cout][KH][KW][Cin]
+  // window of the master filter this conv uses: the master has w_ld input channels per (co, tap) of which the conv's
+  // channels are [w_off, w_off + Cin_master) (folded jointConv: the code channels are handled as a bias), and w_cout
+  // real output channels (image head: 3 of a 16-wide tile; packed rows beyond are zero, their gradients are dropped)
+  int w_ld, w_off, w_cout;
 };
 
-// element offset of master-filter entry (co, tap, ci)
+// element offset of master-filter entry (co, tap, ci); Cin = channels per (co, tap) row of the MASTER (EklGather.w_ld),
+// ci already includes the window offset
 #define EKL_WIDX(kcrs, co, tap, ci, KK, Cin) \
   ((kcrs) ? (((int64_t)(co) * (Cin) + (ci)) * (KK) + (tap)) : (((int64_t)(co) * (KK) + (tap)) * (Cin) + (ci)))
 

@@ -31,7 +31,7 @@ namespace {
 struct RwParams {
   CUtensorMap a_map, o_map, w_map;
   EklTap taps[9];
-  float* stats;          // [cta][2][N] or null
+  double* stats;         // [2][N] per-channel sum / sum-of-squares, accumulated with fp64 red.global.add; or null
   const float* bias9;    // [B][9][N] or null
   int N, ntn, H, W, nTh, nTw, tiles, act;
   int halo1;             // experiment: ONE [Cin][10 w][18 h] halo box per tile, taps = row-shifted descriptors
@@ -282,18 +282,18 @@ __global__ void __launch_bounds__(192, 1) conv3x3_rw_kernel(const __grid_constan
           }
           RW_ACC(te_stats);
         }
-      if (p.stats != nullptr) {
+      if (p.stats != nullptr && has_tiles) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         float* my = red + (size_t)slice * 2 * BN;
 #pragma unroll
         for (int i = 0; i < 4; ++i) { my[4 * quad + i] = s1[i]; my[BN + 4 * quad + i] = s2[i]; }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        float* dst = p.stats + (size_t)cta * 2 * p.N + n * BN;
+        double* dst = p.stats + n * BN;
         for (int c = et; c < 2 * BN; c += 128) {
           float acc = 0.f;
 #pragma unroll
           for (int sl = 0; sl < C::SLICES; ++sl) acc += red[(size_t)sl * 2 * BN + c];
-          dst[(c < BN) ? c : (p.N + c - BN)] = acc;
+          atomicAdd(dst + ((c < BN) ? c : (p.N + c - BN)), (double)acc);
         }
       }
     }
@@ -340,7 +340,7 @@ int ekl_rw_supported(const EklGather* g, int group_b) {
   return 1;
 }
 
-int ekl_conv3x3_rw(const EklGather* g, const void* w_packed, float* stats, int act, const float* bias9, cudaStream_t st) {
+int ekl_conv3x3_rw(const EklGather* g, const void* w_packed, double* stats, int act, const float* bias9, cudaStream_t st) {
   EKL_REQUIRE(ekl_rw_supported(g, 0), "conv3x3_rw: unsupported plan");
   RwParams p;
   memset(&p, 0, sizeof(p));
@@ -373,7 +373,7 @@ int ekl_conv3x3_rw(const EklGather* g, const void* w_packed, float* stats, int a
     uint32_t box[2] = {(uint32_t)KC, (uint32_t)BN};
     if (int rc = ekl_make_tmap(&p.w_map, w_packed, 2, dims, strides, box, swz, 2)) return rc;
   }
-  const int grid = ekl_num_sms();      // statistics rows are indexed by the full-machine grid (ekl_tc_stats_rows)
+  const int grid = ekl_num_sms();      // persistent: one CTA per SM
 #define EKL_RW_CASE(bn, kc) if (BN == bn && KC == kc) return launch_rw<bn, kc>(p, grid, st);
   EKL_RW_CASE(64, 64) EKL_RW_CASE(32, 64) EKL_RW_CASE(16, 64)
   EKL_RW_CASE(64, 32) EKL_RW_CASE(32, 32) EKL_RW_CASE(16, 32)

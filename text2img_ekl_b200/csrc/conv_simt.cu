@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(const __grid_const
       const float dy = load_elem(yv, b_, h_, w_, co);
       if (dy != 0.f) acc += dy * load_elem(av, b_, h_ + tap.dh, w_ + tap.dw, ci);
     }
-    for (int s = 0; s < tap.nsrc; ++s) atomicAdd(p.dw + EKL_WIDX(g.w_kcrs, co, tap.src[s], ci, KK, g.Cin), acc);
+    if (co < g.w_cout)
+      for (int s = 0; s < tap.nsrc; ++s) atomicAdd(p.dw + EKL_WIDX(g.w_kcrs, co, tap.src[s], g.w_off + ci, KK, g.w_ld), acc);
   }
 }
 

@@ -22,7 +22,7 @@ struct TcParams {
   CUtensorMap o_maps[EKL_MAX_VAR];
   CUtensorMap w_map;
   EklTap taps[EKL_MAX_VAR][EKL_MAX_TAPS];
-  float* stats;       // [((g*grid + cta)*nvar + v)][2][N] or null
+  double* stats;      // [group][2][N] per-channel sum / sum-of-squares, accumulated with fp64 red.global.add; or null
   int ntaps, ncb;     // taps, Cin/KC
   int Cin, N;
   int tb, th, tw, nTh, nTw;
@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
       int v, n, g;
       round_vng(r, v, n, g);
       float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+      const bool round_has_tiles = first_tile(r) < p.mtg;
       for (int mloc = first_tile(r); mloc < p.mtg; mloc += grid, ++tile) {
         const uint32_t buf = tile & 1u, use = tile >> 1;
         int w0, h0, b0;
@@ -319,20 +320,20 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
           }
         }
       }
-      if (p.stats != nullptr) {
-        // flush this round's partial sums: combine the row slices through smem, one row of the stats array per
-        // (group, cta, variant); channels [n*BN, n*BN+BN)
+      if (p.stats != nullptr && round_has_tiles) {
+        // flush this round's partial sums: combine the row slices through smem, then ONE fp64 red.global.add per channel
+        // sum into the [group][2][N] statistics buffer (all variants of an up-conv land in the same sums)
         asm volatile("bar.sync 1, 128;" ::: "memory");
         float* my = red + (size_t)slice * 2 * BN;
 #pragma unroll
         for (int i = 0; i < 4; ++i) { my[4 * quad + i] = s1[i]; my[BN + 4 * quad + i] = s2[i]; }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        float* dst = p.stats + (((size_t)g * grid + cta) * p.nvar + v) * 2 * p.N + n * BN;
+        double* dst = p.stats + (size_t)g * 2 * p.N + n * BN;
         for (int c = et; c < 2 * BN; c += 128) {
           float acc = 0.f;
 #pragma unroll
           for (int sl = 0; sl < C::SLICES; ++sl) acc += red[(size_t)sl * 2 * BN + c];
-          dst[(c < BN) ? c : (p.N + c - BN)] = acc;
+          atomicAdd(dst + ((c < BN) ? c : (p.N + c - BN)), (double)acc);
         }
       }
     }
@@ -404,13 +405,7 @@ int ekl_num_sms() {
   return n;
 }
 
-// rows of the BatchNorm partial-statistics buffer the kernel writes: groups * grid * nvar
-int ekl_tc_stats_rows(const EklGather* g, int group_b) {
-  const int groups = (group_b > 0 && g->mB % group_b == 0) ? g->mB / group_b : 1;
-  return groups * ekl_num_sms() * g->nvar;
-}
-
-// stats: [((grp*grid + cta)*nvar + v)][2][N] fp32 partials or null.
+// stats: [group][2][N] fp64 sums (accumulated; zero on entry) or null.
 // Split-K plan of a gather-GEMM (0 = not split): few tiles and a long contraction (the 4x4 / 8x8 discriminator tails:
 // M = 384..1152 rows, K up to 18432) leave most SMs idle while each busy SM is bound by its own operand ingest, so the
 // (tap, channel-block) iterations of a tile are spread over up to 4 work items that red-add fp32 partial tiles into a
@@ -460,7 +455,7 @@ int ekl_tc_dgrad_from_fwd_ok(const EklGather* g) {
   return 1;
 }
 
-int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, int group_b, int act, const float* bias9,
+int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, double* stats, int group_b, int act, const float* bias9,
                        float* scratch, int* mtiles_out, cudaStream_t st, int w_is_fwd_packed) {
   EKL_REQUIRE(ekl_tc_supported(g), "gather_gemm_tc: unsupported shape Cin=%d N=%d mH=%d mW=%d", g->Cin, g->N, g->mH, g->mW);
   TcParams p;
@@ -517,8 +512,7 @@ int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, float* stats, i
     int rc = ekl_make_tmap(&p.w_map, w_packed, 2, dims, strides, box, swz, 2);
     if (rc) return rc;
   }
-  // the statistics layout is indexed by the full-machine grid, so the grid is always #SMs
-  const int grid = ekl_num_sms();
+  const int grid = ekl_num_sms();     // persistent: one CTA per SM
 #define EKL_TC_CASE(bn, kc) if (BN == bn && KC == kc) return launch_tc<bn, kc>(g, p, grid, st);
   EKL_TC_CASE(256, 64) EKL_TC_CASE(128, 64) EKL_TC_CASE(64, 64) EKL_TC_CASE(32, 64) EKL_TC_CASE(16, 64)
   EKL_TC_CASE(256, 32) EKL_TC_CASE(128, 32) EKL_TC_CASE(64, 32) EKL_TC_CASE(32, 32) EKL_TC_CASE(16, 32)

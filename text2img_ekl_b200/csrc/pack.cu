@@ -13,6 +13,7 @@ struct PackParams {
   const float* w;
   bf16* out;
   int nvar, ntaps, Cout, Cin, KK, kcrs;
+  int ld, off, cout_valid;   // master row pitch / channel offset / real output channels (EklGather.w_ld, w_off, w_cout)
 };
 
 // non-transposed: one thread per output element, ci fastest (coalesced both sides)
@@ -26,7 +27,8 @@ __global__ void pack_fwd_kernel(const __grid_constant__ PackParams p) {
     const int v = (int)(r / p.Cout);
     const EklTap tap = p.taps[v][t];
     float acc = 0.f;
-    for (int s = 0; s < tap.nsrc; ++s) acc += p.w[EKL_WIDX(p.kcrs, co, tap.src[s], ci, p.KK, p.Cin)];
+    if (co < p.cout_valid)
+      for (int s = 0; s < tap.nsrc; ++s) acc += p.w[EKL_WIDX(p.kcrs, co, tap.src[s], p.off + ci, p.KK, p.ld)];
     p.out[i] = __float2bfloat16(acc);
   }
 }
@@ -43,8 +45,8 @@ __global__ void pack_fwd_vec8_kernel(const __grid_constant__ PackParams p) {
     const int v = (int)(r / p.Cout);
     const EklTap tap = p.taps[v][t];
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int s = 0; s < tap.nsrc; ++s) {
-      const float4* src = reinterpret_cast<const float4*>(p.w + ((int64_t)co * p.KK + tap.src[s]) * p.Cin + ci);
+    for (int s = 0; s < (co < p.cout_valid ? tap.nsrc : 0); ++s) {
+      const float4* src = reinterpret_cast<const float4*>(p.w + ((int64_t)co * p.KK + tap.src[s]) * p.ld + p.off + ci);
       const float4 a = src[0], b = src[1];
       acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
     }
@@ -68,9 +70,9 @@ __global__ void __launch_bounds__(256) pack_dgrad_vec_kernel(const __grid_consta
     const int r = idx >> 4, c4 = (idx & 15) * 4;
     const int co = co0 + r, ci = ci0 + c4;
     acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (co < p.Cout && ci < p.Cin)
+    if (co < p.cout_valid && ci < p.Cin)
       for (int s = 0; s < tap.nsrc; ++s) {
-        const float4 a = *reinterpret_cast<const float4*>(p.w + ((int64_t)co * p.KK + tap.src[s]) * p.Cin + ci);
+        const float4 a = *reinterpret_cast<const float4*>(p.w + ((int64_t)co * p.KK + tap.src[s]) * p.ld + p.off + ci);
         acc[k].x += a.x; acc[k].y += a.y; acc[k].z += a.z; acc[k].w += a.w;
       }
   }
@@ -103,8 +105,8 @@ __global__ void pack_dgrad_kernel(const __grid_constant__ PackParams p) {
   for (int r = threadIdx.y; r < 64; r += 8) {
     const int co = co0 + r, ci = ci0 + threadIdx.x;
     float acc = 0.f;
-    if (co < p.Cout && ci < p.Cin)
-      for (int s = 0; s < tap.nsrc; ++s) acc += p.w[EKL_WIDX(p.kcrs, co, tap.src[s], ci, p.KK, p.Cin)];
+    if (co < p.cout_valid && ci < p.Cin)
+      for (int s = 0; s < tap.nsrc; ++s) acc += p.w[EKL_WIDX(p.kcrs, co, tap.src[s], p.off + ci, p.KK, p.ld)];
     tile[r][threadIdx.x] = acc;
   }
   __syncthreads();
@@ -127,9 +129,10 @@ int ekl_pack_weights(const EklGather* g, const float* w_master, void* out, int C
   memcpy(p.taps, g->taps, sizeof(p.taps));
   p.w = w_master; p.out = (bf16*)out; p.nvar = g->nvar; p.ntaps = g->ntaps; p.Cout = Cout; p.Cin = Cin;
   p.KK = g->KH * g->KW; p.kcrs = g->w_kcrs;
+  p.ld = g->w_ld > 0 ? g->w_ld : Cin; p.off = g->w_off; p.cout_valid = g->w_cout > 0 ? g->w_cout : Cout;
   if (!g->transposed) {
     const int64_t total = (int64_t)p.nvar * Cout * p.ntaps * Cin;
-    if (!p.kcrs && Cin % 8 == 0) {
+    if (!p.kcrs && Cin % 8 == 0 && p.ld % 4 == 0 && p.off % 4 == 0) {
       int blocks = (int)((total / 8 + 255) / 256);
       if (blocks > 148 * 8) blocks = 148 * 8;
       pack_fwd_vec8_kernel<<<blocks, 256, 0, st>>>(p);
@@ -138,7 +141,7 @@ int ekl_pack_weights(const EklGather* g, const float* w_master, void* out, int C
       if (blocks > 148 * 8) blocks = 148 * 8;
       pack_fwd_kernel<<<blocks, 256, 0, st>>>(p);
     }
-  } else if (!p.kcrs && Cin % 4 == 0 && Cout % 8 == 0) {
+  } else if (!p.kcrs && Cin % 4 == 0 && Cout % 8 == 0 && p.ld % 4 == 0 && p.off % 4 == 0) {
     dim3 grid(ekl_cdiv(Cin, 64), ekl_cdiv(Cout, 64), p.nvar * p.ntaps);
     pack_dgrad_vec_kernel<<<grid, 256, 0, st>>>(p);
   } else {

@@ -24,6 +24,7 @@ struct WgParams {
   EklTap taps[EKL_MAX_VAR][EKL_MAX_TAPS];
   float* dw;
   int ntaps, ncb, Cin, Cout, KK, kcrs;
+  int ld, off, cout_valid; // master gradient row pitch / channel offset / real output channels
   int tiles_per_var;       // M tiles per variant
   int tb, th, tw, nTh, nTw, ptiles;   // pixel tiling
   int rows_valid;          // tb*th*tw (<= KP)
@@ -148,8 +149,9 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
             if (c0 + i >= BNW) break;                 // BNW = 16: the TMEM allocation is 32 columns, 16 are live
             const int co = n0 + c0 + i;
             const float val = __uint_as_float(r[i]);
-            for (int s = 0; s < tap.nsrc; ++s)
-              atomicAdd(p.dw + EKL_WIDX(p.kcrs, co, tap.src[s], ci, p.KK, p.Cin), val);
+            if (co < p.cout_valid)
+              for (int s = 0; s < tap.nsrc; ++s)
+                atomicAdd(p.dw + EKL_WIDX(p.kcrs, co, tap.src[s], p.off + ci, p.KK, p.ld), val);
           }
         }
       }
@@ -173,6 +175,7 @@ struct WgCoParams {
   EklTap taps[EKL_MAX_VAR][EKL_MAX_TAPS];
   float* dw;
   int ntaps, ncb, Cin, Cout, KK;
+  int ld, off;             // master gradient row pitch / channel offset
   int tiles_per_var;
   int tb, th, tw, nTh, nTw, ptiles;
   int rows_valid;
@@ -298,8 +301,8 @@ __global__ void __launch_bounds__(192) conv_wgrad_co_kernel(const __grid_constan
 #pragma unroll
         for (int it = 0; it < 8; ++it) val[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * 36 + col);
         for (int s = 0; s < tap.nsrc; ++s) {
-          float* dst = p.dw + ((int64_t)(co0 + q * 32 + rsub) * p.KK + tap.src[s]) * p.Cin + ci;
-          const int64_t rstride = (int64_t)4 * p.KK * p.Cin;
+          float* dst = p.dw + ((int64_t)(co0 + q * 32 + rsub) * p.KK + tap.src[s]) * p.ld + p.off + ci;
+          const int64_t rstride = (int64_t)4 * p.KK * p.ld;
           if (p.exclusive) {
             float4 o[8];
 #pragma unroll
@@ -337,6 +340,7 @@ struct WgHaloParams {
   EklTap taps[9];
   float* dw;
   int Cin, Cout, nTh, nTw, tiles;
+  int ld, off, cout_valid; // master gradient row pitch / channel offset / real output channels
 };
 
 template <int CIN>
@@ -459,9 +463,9 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_halo_kernel(const __grid_co
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int co = q * 32 + it * 4 + rsub;
-            if (in_range && co < p.Cout) {
+            if (in_range && co < p.cout_valid) {
               const float4 v = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * 36 + col);
-              red_add_v4(p.dw + ((int64_t)co * 9 + src) * p.Cin + ci, v.x, v.y, v.z, v.w);
+              red_add_v4(p.dw + ((int64_t)co * 9 + src) * p.ld + p.off + ci, v.x, v.y, v.z, v.w);
             }
           }
         }
@@ -517,6 +521,7 @@ static int wgrad_co(const EklGather* g, float* dw, cudaStream_t st) {
   memset(&p, 0, sizeof(p));
   memcpy(p.taps, g->taps, sizeof(p.taps));
   p.dw = dw; p.ntaps = g->ntaps; p.Cin = g->Cin; p.Cout = g->N; p.KK = g->KH * g->KW;
+  p.ld = g->w_ld; p.off = g->w_off;
   p.ncb = g->Cin / 64;
   p.tiles_per_var = ekl_cdiv(g->ntaps * p.ncb, 4);
   int tw = g->mW < KP ? g->mW : KP;
@@ -586,6 +591,7 @@ static int wgrad_halo(const EklGather* g, float* dw, cudaStream_t st) {
   memset(&p, 0, sizeof(p));
   memcpy(p.taps, g->taps[0], sizeof(p.taps));
   p.dw = dw; p.Cin = g->Cin; p.Cout = g->N;
+  p.ld = g->w_ld; p.off = g->w_off; p.cout_valid = g->w_cout;
   p.nTh = g->mH / 16; p.nTw = g->mW / 8; p.tiles = g->mB * p.nTh * p.nTw;
   {
     const EklView& v = g->a[0];
@@ -617,12 +623,13 @@ int ekl_wgrad_tc(const EklGather* g, float* dw, cudaStream_t st) {
   {
     static int co_on = -1;
     if (co_on < 0) { const char* e = getenv("EKL_DISABLE_WGRAD_CO"); co_on = (e && e[0] == '1') ? 0 : 1; }
-    if (co_on && !g->w_kcrs && g->Cin % 64 == 0 && g->N % 128 == 0) return wgrad_co(g, dw, st);
+    if (co_on && !g->w_kcrs && g->Cin % 64 == 0 && g->N % 128 == 0 && g->w_cout == g->N) return wgrad_co(g, dw, st);
   }
   WgParams p;
   memset(&p, 0, sizeof(p));
   memcpy(p.taps, g->taps, sizeof(p.taps));
   p.dw = dw; p.ntaps = g->ntaps; p.Cin = g->Cin; p.Cout = g->N; p.KK = g->KH * g->KW; p.kcrs = g->w_kcrs;
+  p.ld = g->w_ld; p.off = g->w_off; p.cout_valid = g->w_cout;
   const int CW = g->Cin % 64 == 0 ? 64 : (g->Cin % 32 == 0 ? 32 : 16);
   p.ncb = g->Cin / CW;
   const int BPT = 128 / CW;

@@ -259,10 +259,9 @@ class condGANTrainer(object):
         else:
             self.noise.copy_(noise)
         self.generate(eps, seed)
-        # the discriminator updates are independent: engine.d_steps runs them as parallel stream branches
-        errDs = self.engine.d_steps(self.real_imgs, self.wrong_imgs, self.real_cp, self.fake_cp)
-        errG = self.engine.g_step(self.real_cp)
-        return errDs, errG
+        # the discriminator updates are independent: engine.update runs each as a stream branch that continues into the
+        # generator-loss pass through that discriminator, then the generator update
+        return self.engine.update(self.real_imgs, self.wrong_imgs, self.real_cp, self.fake_cp)
 
     EAGER_STEPS_BEFORE_CAPTURE = 2
 

@@ -155,6 +155,7 @@ class StepEngine:
         # EKL_PARALLEL_D=0 runs the discriminators one after the other on the caller's stream
         self.parallel_d = os.environ.get("EKL_PARALLEL_D", "1") != "0" and len(netsD) > 1
         self.d_streams = None
+        self._pack_sides = []               # (issuing stream, side stream) of operand refreshes still to be joined
         self.d_logits = {}                   # idx -> (real, wrong, fake) x [match p, uncond p, class log-probs]
         self.uncond = float(cfg.TRAIN.COEFF.UNCOND_LOSS)
         self.kl_coeff = float(cfg.TRAIN.COEFF.KL)
@@ -175,10 +176,29 @@ class StepEngine:
         else:
             opt.step()
 
+    def _d_apply(self, idx):
+        """Optimiser step of discriminator idx, then the refresh of its packed filter operands on a side stream (the
+        generator-loss pass through the updated discriminator follows on this branch; it reaches the operands that need
+        packing -- data-gradient filters -- only in its backward)."""
+        self._apply(self.optsD[idx], self.redD[idx])
+        if next(self.netsD[idx].parameters()).is_cuda:
+            side = ops.prepack(self.netsD[idx].parameters(), "D%d" % idx)
+            if side is not None:
+                self._pack_sides.append((torch.cuda.current_stream(), side))
+
     # ---- (1) generate: cub:567-587 / trainer.py:524-528
     def generate(self, noise, txt, cls_cond, eps=None, seed=None):
+        dev = noise.device
+        if dev.type == "cuda":
+            ops.ARENA.reset(dev)             # one memset per step: zeroed scratch of every BatchNorm statistics buffer
+            # the generator's filters changed at the end of the previous step: refresh their packed operands on a side
+            # stream, behind the conditioning nets / stem that open the forward pass
+            side = ops.prepack(self.netG.parameters(), "G")
         with tensor_core_matmul():
-            return self._generate(noise, txt, cls_cond, eps, seed)
+            out = self._generate(noise, txt, cls_cond, eps, seed)
+        if dev.type == "cuda" and side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        return out
 
     def _generate(self, noise, txt, cls_cond, eps=None, seed=None):
         if self.kind == "catz_ca":
@@ -204,7 +224,9 @@ class StepEngine:
     # ---- (2) one discriminator update: cub:404-461
     def d_step(self, idx, real_imgs, wrong_imgs, real_cp, fake_cp):
         with tensor_core_matmul():
-            return self._d_step(idx, real_imgs, wrong_imgs, real_cp, fake_cp)
+            out = self._d_step(idx, real_imgs, wrong_imgs, real_cp, fake_cp)
+        self._join_packs()
+        return out
 
     def _d_step(self, idx, real_imgs, wrong_imgs, real_cp, fake_cp):
         netD, opt, grads = self.netsD[idx], self.optsD[idx], self.gradsD[idx]
@@ -249,7 +271,14 @@ class StepEngine:
         """Gradient average over the ranks (N > 1: the slices still outstanding, see parallel.GradReducer) + Adam step of
         discriminator idx.  The updates of the discriminators are independent (cub:594-596 loops over them) and run as
         parallel stream branches (d_steps), so one discriminator's exchange also overlaps the others' compute."""
-        self._apply(self.optsD[idx], self.redD[idx])
+        self._d_apply(idx)
+
+    def _join_packs(self):
+        """Side-stream operand refreshes rejoin the stream they were forked from (a captured step must end with every
+        stream joined; consumers already ordered themselves individually)."""
+        for main, side in self._pack_sides:
+            main.wait_stream(side)
+        self._pack_sides = []
 
     def _streams(self):
         if self.d_streams is None:
@@ -282,6 +311,38 @@ class StepEngine:
             main.wait_stream(st)
         return errDs
 
+    def update(self, real_imgs, wrong_imgs, real_cp, fake_cp):
+        """Everything after generate(): the discriminator updates (cub:594-596) and the generator update through the
+        updated discriminators (cub:604-608).  With parallel branches each discriminator's stream runs its update AND,
+        right behind it, the generator-loss forward through that same (now updated) discriminator -- the small
+        discriminators' generator-loss passes fill the SMs while the largest one is still updating, instead of all
+        three waiting for a common join.  Returns (errDs, errG)."""
+        n = len(self.netsD)
+        fused = self.parallel_d and self.uncond > 0 and all(hasattr(d, "heads_raw") for d in self.netsD)
+        if not fused:
+            return self.d_steps(real_imgs, wrong_imgs, real_cp, fake_cp), self.g_step(real_cp)
+        errDs, per_d = [None] * n, [None] * n
+        main = torch.cuda.current_stream()
+        streams = self._streams()
+        with tensor_core_matmul():
+            try:
+                for i in reversed(range(n)):              # largest first
+                    streams[i].wait_stream(main)
+                    with torch.cuda.stream(streams[i]):
+                        errDs[i] = self._d_step(i, real_imgs[i], wrong_imgs[i], real_cp, fake_cp)
+                        netD = self.netsD[i]
+                        netD.requires_grad_(False)        # the reference computes and discards these (SURVEY app. A #15)
+                        lm, lu, lc = netD.heads_raw(self.fake_imgs[i], self.mu)
+                        per_d[i] = ops.d_loss(lm, lu, lc, real_cp, None, 1, lm.shape[0], (1,), (1,), (0,), self.uncond)
+                self._join_packs()
+                for st in streams:
+                    main.wait_stream(st)
+                errG = self._g_update(real_cp, per_d)
+            finally:
+                for d in self.netsD:
+                    d.requires_grad_(True)
+        return errDs, errG
+
     def color_consistency(self, fake_imgs):
         """Colour-consistency regulariser between adjacent stages, the StackGAN++ term the reference keeps the statistics
         function and the coefficient for (cub:33-52 compute_mean_covariance, config.py:61 COEFF.COLOR_LOSS) but never
@@ -304,13 +365,18 @@ class StepEngine:
         return total
 
     # ---- (3) generator loss through the UPDATED discriminators: cub:463-490
-    def g_loss(self, real_cp):
+    def g_loss(self, real_cp, per_d=None):
+        """per_d: the discriminators' fused loss tuples when their forward passes already ran (update())."""
         errGs_match = errGs_uncond = errGs_cls = errGs_total_fused = 0
         self.last_g_logits = []
         main = torch.cuda.current_stream()
         par = self.parallel_d and all(hasattr(d, "heads_raw") for d in self.netsD) and self.uncond > 0
-        per_d = []
-        if par:
+        done = per_d is not None
+        if done:
+            par = True
+        else:
+            per_d = []
+        if par and not done:
             # the discriminators judge their own stage's fake independently: one stream each (autograd replays every
             # branch's backward on the stream of its forward), joined before the losses are summed
             for i, netD in enumerate(self.netsD):
@@ -362,15 +428,19 @@ class StepEngine:
             return self._g_step(real_cp)
 
     def _g_step(self, real_cp):
-        self.gradsG.zero()
         for d in self.netsD:
             d.requires_grad_(False)          # the reference computes and discards these
         try:
-            res = self.g_loss(real_cp)
-            res[0].backward()
+            return self._g_update(real_cp)
         finally:
             for d in self.netsD:
                 d.requires_grad_(True)
+
+    def _g_update(self, real_cp, per_d=None):
+        self.gradsG.zero()
+        res = self.g_loss(real_cp, per_d)
+        res[0].backward()
+        self._join_packs()
         if self.redG is not None:
             self.redG.begin()
         self._apply(self.optG, self.redG)
@@ -381,9 +451,7 @@ class StepEngine:
     def step(self, real_imgs, wrong_imgs, txt, cls_cond, real_cp, fake_cp, noise, eps=None, seed=None):
         self.generate(noise, txt, cls_cond, eps, seed)
         # the discriminator updates are independent (cub:594-596): parallel stream branches, the largest issued first
-        errDs = self.d_steps(real_imgs, wrong_imgs, real_cp, fake_cp)
-        errG = self.g_step(real_cp)
-        return errDs, errG
+        return self.update(real_imgs, wrong_imgs, real_cp, fake_cp)
 
 
 class GraphedStep:
@@ -443,8 +511,7 @@ class GraphedStep:
         self.eps.normal_(0, 1)
         self.seed.normal_(0, 1)
         tr.generate(self.eps, self.seed)
-        errDs = tr.engine.d_steps(tr.real_imgs, tr.wrong_imgs, tr.real_cp, tr.fake_cp)
-        errG = tr.engine.g_step(tr.real_cp)
+        errDs, errG = tr.engine.update(tr.real_imgs, tr.wrong_imgs, tr.real_cp, tr.fake_cp)
         return torch.stack([torch.stack([x.detach().float() for x in e]) for e in errDs]), \
             torch.stack([x.detach().float() for x in errG])
 

@@ -298,26 +298,14 @@ class INIT_STAGE_G(_InitStageBase):
         return self._ups(_stem_bn_glu(self.fc[0](in_code), self.fc[1], self.gf_dim))
 
 
-def _border_valid():
-    """VALID[q, t] = 1 iff tap t = (kh, kw) of a 3x3 / pad-1 conv reads inside the map for a pixel of border class
-    q = 3*rc + cc (rc / cc: 0 first row / column, 1 interior, 2 last)."""
-    v = torch.zeros(9, 9)
-    ok = lambda cls, k: not ((cls == 0 and k == 0) or (cls == 2 and k == 2))
-    for rc in range(3):
-        for cc in range(3):
-            for kh in range(3):
-                for kw in range(3):
-                    v[rc * 3 + cc, kh * 3 + kw] = float(ok(rc, kh) and ok(cc, kw))
-    return v
-
-
 class NEXT_STAGE_G(nn.Module):
     """model.py:379-423: cat(tile(c_code), h) -> jointConv -> R_NUM ResBlocks -> upBlock (-> upBlock if SCALE 4).
 
     The tiled code channels are spatially constant, so the jointConv over cat(tile(c), h) is computed as a conv over the
-    h channels only plus a per-sample bias with 9 border variants (bias9[b, q] = sum of the code's tap responses
-    T[b, t] = Wc[:, :, t] c[b] over the taps that fall inside the map for border class q): the [B, ef+ngf, H, W] tensor is
-    never formed and the conv contraction drops from 9*(ef+ngf) to 9*ngf."""
+    h channels only (a window of the master filter's input channels) plus a per-sample bias with 9 border variants
+    (ops.code_bias9: bias9[b, q] = sum of the code's tap responses T[b, t] = Wc[:, :, t] c[b] over the taps that fall
+    inside the map for border class q): the [B, ef+ngf, H, W] tensor is never formed, the conv contraction drops from
+    9*(ef+ngf) to 9*ngf, and the filter gradient lands in place in the two channel ranges of the one master gradient."""
 
     def __init__(self, ngf, num_residual=None):
         super().__init__()
@@ -332,26 +320,21 @@ class NEXT_STAGE_G(nn.Module):
         self.upsample = upBlock(ngf, ngf // 2)
         if cfg.TREE.SCALE == 4:
             self.upsample2 = upBlock(ngf // 2, ngf // 4)
-        self._fold = ngf % 16 == 0 and (2 * ngf) % 32 == 0
-        self._spec_x = ops.ConvSpec(ops.S1, ngf, 2 * ngf, impl=L.IMPL_TC) if self._fold else None
+        self._fold = ngf % 16 == 0 and (2 * ngf) % 32 == 0 and self.ef_dim % 4 == 0 and 2 * ngf <= 512
         if self._fold:
+            # the conv proper contracts the h channels only: a window [ef, ef + ngf) of the master filter's input channels
+            self._spec_x = ops.ConvSpec(ops.S1, ngf, 2 * ngf, impl=L.IMPL_TC, w_cin_total=ngf + self.ef_dim, w_cin_off=self.ef_dim)
             self._spec_x.ref = (ngf + self.ef_dim, 2 * ngf, 9)          # the reference convolves the tiled code channels too
-        self._valid = None
 
     def _joint(self, h_code, c_code):
         x = to_nhwc(h_code)
         c = c_code.view(-1, self.ef_dim)
         conv_mod, bn_mod = self.jointConv[0], self.jointConv[1]
-        if not (self._fold and x.shape[1] >= 2 and x.shape[2] >= 2):
-            return self.jointConv(to_public(ops.cat_code(c, x)))
         w = conv_mod.weight                                              # [2ngf, ef+ngf, 3, 3], code channels first
-        if self._valid is None or self._valid.device != w.device:
-            self._valid = _border_valid().to(w.device)
-        B, N = x.shape[0], w.shape[0]
-        T = torch.einsum("bc,nckl->bkln", c.float(), w[:, :self.ef_dim]).reshape(B, 9, N)
-        bias9 = torch.einsum("qt,btn->bqn", self._valid, T)
-        wx = w[:, self.ef_dim:].contiguous(memory_format=torch.channels_last)
-        y, stats = ops.conv_bias9(x, wx, bias9, self._spec_x, want_stats=bn_mod.training)
+        if not (self._fold and x.shape[1] >= 2 and x.shape[2] >= 2 and w.is_contiguous(memory_format=torch.channels_last)):
+            return self.jointConv(to_public(ops.cat_code(c, x)))
+        bias9 = ops.code_bias9(c.float(), w)                             # [B, 9, 2ngf]: the code channels' contribution
+        y, stats = ops.conv_bias9(x, w, bias9, self._spec_x, want_stats=bn_mod.training)
         return to_public(ops.bn_act(y, stats, bn_mod, 1, ops.ACT_GLU))
 
     def forward(self, h_code, c_code):
@@ -385,7 +368,8 @@ class GET_IMAGE_G(nn.Module):
         self.gf_dim = ngf
         self.img = nn.Sequential(conv3x3(ngf, 3), nn.Tanh())
         if ngf % 16 == 0:
-            self._spec = ops.ConvSpec(ops.S1, ngf, self.PAD, impl=L.IMPL_TC)
+            # 3 real filters in a 16-wide output tile: the packed rows beyond are zero, their gradients are dropped
+            self._spec = ops.ConvSpec(ops.S1, ngf, self.PAD, impl=L.IMPL_TC, w_cout_valid=3)
             self._spec.ref = (ngf, 3, 9)
         else:
             self._spec = ops.ConvSpec(ops.S1, ngf, 3, impl=L.IMPL_SIMT, y_fmt=L.FMT_NCHW_F32, act=ops.ACT_TANH)
@@ -395,8 +379,9 @@ class GET_IMAGE_G(nn.Module):
         if self._spec.impl == L.IMPL_SIMT:
             y, _ = ops.conv(to_nhwc(h_code), w, self._spec)
             return _TanhFromOut.apply(y)
-        w_pad = F.pad(w, (0, 0, 0, 0, 0, 0, 0, self.PAD - 3))
-        y, _ = ops.conv(to_nhwc(h_code), w_pad, self._spec)                   # [B,H,W,16] bf16 pre-activation
+        if not w.is_contiguous(memory_format=torch.channels_last):
+            w = w.contiguous(memory_format=torch.channels_last)
+        y, _ = ops.conv(to_nhwc(h_code), w, self._spec)                       # [B,H,W,16] bf16 pre-activation
         return ops.head_tanh(y)
 
 

@@ -6,6 +6,7 @@ the kernels read and the weight-gradient kernel accumulates into (`.grad` is wri
 accumulation pass).  No op here has a non-CUDA fallback.
 """
 import os
+import weakref
 
 import torch
 
@@ -45,6 +46,47 @@ def grad_mark(x, owner, after):
         cb(after)                  # returns None: the gradient passes through unchanged
     x.register_hook(fire)
     return x
+
+
+class StatsArena:
+    """Zero-initialised fp64 scratch for the BatchNorm statistics of one training step.
+
+    The conv epilogues ACCUMULATE per-channel sums into a [groups][2][C] double buffer (fp64 red.global.add), the
+    normalise pass reads them directly; the backward pass does the same with its two reductions.  Every such buffer must
+    be zero before its producer runs.  Instead of one fill kernel per layer and direction, the step engine calls reset()
+    once per step (one memset for all layers of all networks) and every layer takes the next slice.  Slices are handed
+    out in host program order, which is the same every step, so a captured CUDA graph sees fixed addresses.  Without a
+    reset in the current step (modules used stand-alone) take() falls back to a fresh torch.zeros."""
+
+    def __init__(self):
+        self.buf, self.off, self.want, self.live = None, 0, 0, False
+
+    def reset(self, device):
+        need = max(self.want, 1 << 16)
+        if self.buf is None or self.buf.device != device or self.buf.numel() < need:
+            self.buf = torch.zeros(need + need // 4, dtype=torch.float64, device=device)
+        else:
+            self.buf.zero_()
+        self.off, self.want, self.live = 0, 0, True
+        _count()
+
+    def take(self, n, device):
+        n = (n + 1) // 2 * 2                       # 16-byte aligned slices
+        self.want += n
+        if self.live and self.buf.device == device and self.off + n <= self.buf.numel():
+            v = self.buf[self.off:self.off + n]
+            self.off += n
+            return v
+        self.live = False                          # exhausted: this step finishes on fresh buffers, the next reset() grows
+        return torch.zeros(n, dtype=torch.float64, device=device)
+
+
+def zeros_f32(n, device):
+    """n zero-initialised floats from the step's scratch arena (see StatsArena)."""
+    return ARENA.take((n + 1) // 2, device).view(torch.float32)[:n]
+
+
+ARENA = StatsArena()
 
 
 def _log(*key):
@@ -103,18 +145,22 @@ class ConvSpec:
     """One convolution layer's kernel-side state: packed bf16 filter operands, refreshed when the fp32 master
     parameter changes (optimizer step / load_state_dict)."""
 
-    def __init__(self, mode, cin, cout, impl=L.IMPL_TC, x_fmt=0, y_fmt=0, act=ACT_NONE):
+    def __init__(self, mode, cin, cout, impl=L.IMPL_TC, x_fmt=0, y_fmt=0, act=ACT_NONE, w_cin_total=0, w_cin_off=0,
+                 w_cout_valid=0):
         self.mode, self.cin, self.cout, self.impl = mode, cin, cout, impl
         self.x_fmt, self.y_fmt, self.act = x_fmt, y_fmt, act
+        # window of the master filter (include/ekl_b200.h: ekl_conv.w_cin_total / w_cin_off / w_cout_valid)
+        self.w_cin_total, self.w_cin_off, self.w_cout_valid = w_cin_total, w_cin_off, w_cout_valid
         self.ref = None                  # (cin, cout, taps) of the reference layer when they differ (flop accounting only)
         self._ver, self._dirty = None, False
+        self._weight_ref, self._ready = None, None      # prepack(): the leaf parameter packed from / event of a side-stream pack
         self.w_layout = L.W_KCRS
         self.w_fwd = self.w_dgrad = self._fwd_buf = None
         self._ws = {}
 
     def conv(self, B, H, W, group_b=0):
         return L.EklConv(self.mode, B, H, W, self.cin, self.cout, group_b, self.impl, self.x_fmt, self.y_fmt, self.act,
-                         self.w_layout)
+                         self.w_layout, self.w_cin_total, self.w_cin_off, self.w_cout_valid)
 
     def workspace(self, c, dgrad, device):
         """fp32 split-K workspace of this layer for descriptor c (None when the plan does not split).  Allocated once
@@ -150,9 +196,14 @@ class ConvSpec:
         sh = getattr(weight, "_ekl_shadow", None)
         if sh is None or not weight.is_leaf or self.mode == UP2 or self.w_layout != L.W_KRSC or self.impl != L.IMPL_TC:
             return None
+        if self.w_cin_total or self.w_cout_valid:          # a window of the master is not a plain cast of it
+            return None
         return sh
 
     def packed(self, weight):
+        if self._ready is not None:                # operands were refreshed on a side stream (prepack): order after it
+            torch.cuda.current_stream().wait_event(self._ready)
+            self._ready = None
         key = (weight._version, weight.data_ptr())
         external = key != self._ver or not weight.is_leaf     # derived (e.g. zero-padded) filters are rebuilt every step
         if external or self._dirty:
@@ -161,6 +212,7 @@ class ConvSpec:
                 lst = _SPECS_OF.setdefault(id(weight), [])
                 if self not in lst:
                     lst.append(self)
+                    self._weight_ref = weakref.ref(weight)
             lib = L.lib()
             c = self.conv(1, 4, 4)
             shadow = self._shadow(weight)
@@ -185,6 +237,38 @@ class ConvSpec:
                 _count((w_fwd_arg is not None) + (w_dgrad_arg is not None))
             self._ver, self._dirty = key, False
         return self.w_fwd, self.w_dgrad
+
+
+_PACK_STREAMS = {}
+
+
+def prepack(params, key=0):
+    """Refresh, on a side stream, the packed operands of every convolution whose master filter changed (optimiser step)
+    instead of lazily in front of each convolution's first use: the ~50 small pack kernels of a network leave the
+    critical path and overlap whatever the issuing stream does next.  Consumers order themselves after the side stream
+    at their first use (ConvSpec.packed).  Returns the side stream if anything was issued (the caller joins it before a
+    capture ends), else None."""
+    todo = []
+    for p in params:
+        for spec in _SPECS_OF.get(id(p), ()):
+            w = spec._weight_ref() if spec._weight_ref is not None else None
+            if spec._dirty and w is not None and spec._ready is None:
+                todo.append((spec, w))
+    if not todo:
+        return None
+    main = torch.cuda.current_stream()
+    side = _PACK_STREAMS.get((main.device, key))
+    if side is None:
+        side = _PACK_STREAMS[(main.device, key)] = torch.cuda.Stream()
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        for spec, w in todo:
+            spec.packed(w)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    for spec, _ in todo:
+        spec._ready = ev
+    return side
 
 
 def _run_dgrad(spec, c, weight, dy, dx):
@@ -227,8 +311,8 @@ class _Conv(torch.autograd.Function):
         stats = None
         ws = spec.workspace(c, 0, x.device) if spec.act == ACT_NONE else None
         if want_stats and spec.impl == L.IMPL_TC:
-            rows = lib.ekl_conv_stats_rows_ws(c) if ws is not None else lib.ekl_conv_stats_rows(c)
-            stats = torch.empty(rows, 2, spec.cout, device=x.device, dtype=torch.float32)
+            groups = B // group_b if (group_b > 0 and B % group_b == 0) else 1
+            stats = ARENA.take(groups * 2 * spec.cout, x.device)          # [groups][2][Cout] fp64 sums, zero on entry
         fam = "conv_tc" if spec.impl == L.IMPL_TC else "conv_simt"
         _log("fwd", fam, spec.mode, B, H, W, spec.cin, spec.cout, group_b)
         _acct(_route(spec, c, 0), _conv_flops(spec, B, H, W), x.numel() * x.element_size() + y.numel() * y.element_size())
@@ -290,23 +374,54 @@ def conv(x, weight, spec, group_b=0, want_stats=False, skip_wgrad=False):
 
 
 def border_class_sums(dy):
-    """[B,H,W,N] -> fp32 [B,9,N]: sums of dy over the 9 border classes of ekl_conv_fwd_bias9 (class = 3*rc + cc).
-    The bulk reduction is one pass of the column-statistics kernel with one group per sample; the border rows /
-    columns / corners are small strided slices combined by inclusion-exclusion."""
-    lib = L.lib()
+    """[B,H,W,N] bf16 -> fp32 [B,9,N]: sums of dy over the 9 border classes of ekl_conv_fwd_bias9 (class = 3*rc + cc),
+    i.e. the gradient of its bias9 argument; one pass over dy (include/ekl_b200.h: ekl_border_sums9)."""
     B, H, W, N = dy.shape
-    M = B * H * W
-    rows = lib.ekl_col_stats_rows(M, N, B)
-    part = torch.empty(rows, 2, N, device=dy.device, dtype=torch.float32)
-    L.check(lib.ekl_col_stats(L.ptr(dy), M, N, B, L.ptr(part), L.stream()))
+    S = zeros_f32(B * 9 * N, dy.device).view(B, 9, N)
+    L.check(L.lib().ekl_border_sums9(L.ptr(dy), B, H, W, N, L.ptr(S), L.stream()))
     _count()
-    S = part.view(B, rows // B, 2, N)[:, :, 0].sum(1)
-    f = lambda t: t.float()
-    R0, RL = f(dy[:, 0]).sum(1), f(dy[:, H - 1]).sum(1)
-    C0, CL = f(dy[:, :, 0]).sum(1), f(dy[:, :, W - 1]).sum(1)
-    K00, K0L, KL0, KLL = f(dy[:, 0, 0]), f(dy[:, 0, W - 1]), f(dy[:, H - 1, 0]), f(dy[:, H - 1, W - 1])
-    mid = S - R0 - RL - C0 - CL + K00 + K0L + KL0 + KLL
-    return torch.stack((K00, R0 - K00 - K0L, K0L, C0 - K00 - KL0, mid, CL - K0L - KLL, KL0, RL - KL0 - KLL, KLL), 1)
+    return S
+
+
+class _CodeBias9(torch.autograd.Function):
+    """bias9[b,q,n] = sum over the taps t inside the map for border class q of sum_c code[b,c] * W[n, c, t]: the tiled
+    condition-code channels of a jointConv (model.py:403, 411-414) as a per-sample bias (include/ekl_b200.h:
+    ekl_code_bias9_fwd / _bwd).  weight: the FULL master filter [N, ef + ngf, 3, 3] (channels_last storage), whose first
+    `ef` input channels are the code channels; its gradient over those channels is accumulated in place."""
+
+    @staticmethod
+    def forward(ctx, code, weight):
+        B, ef = code.shape
+        N, Ctot = weight.shape[0], weight.shape[1]
+        assert weight.is_contiguous(memory_format=torch.channels_last) and code.dtype == torch.float32
+        code = code.contiguous()
+        bias9 = torch.empty(B, 9, N, device=code.device, dtype=torch.float32)
+        L.check(L.lib().ekl_code_bias9_fwd(L.ptr(code), L.ptr(weight), B, ef, Ctot, N, L.ptr(bias9), L.stream()))
+        _count()
+        ctx.save_for_backward(code, weight)
+        return bias9
+
+    @staticmethod
+    def backward(ctx, S):
+        code, weight = ctx.saved_tensors
+        B, ef = code.shape
+        N, Ctot = weight.shape[0], weight.shape[1]
+        S = S.contiguous()
+        dcode = zeros_f32(B * ef, code.device).view(B, ef) if ctx.needs_input_grad[0] else None
+        dw = None
+        buf = None
+        if ctx.needs_input_grad[1]:
+            if weight.is_leaf:
+                buf = _grad_buffer(weight)              # accumulated in place (same channels_last memory as the master)
+            else:
+                buf = dw = torch.zeros_like(weight, memory_format=torch.preserve_format)
+        L.check(L.lib().ekl_code_bias9_bwd(L.ptr(S), L.ptr(code), L.ptr(weight), B, ef, Ctot, N, L.ptr(dcode), L.ptr(buf), L.stream()))
+        _count()
+        return dcode, dw
+
+
+def code_bias9(code, weight):
+    return _CodeBias9.apply(code, weight)
 
 
 class _ConvBias9(torch.autograd.Function):
@@ -321,9 +436,7 @@ class _ConvBias9(torch.autograd.Function):
         w_fwd, _ = spec.packed(weight)
         c = spec.conv(B, H, W, 0)
         y = torch.empty(B, H, W, spec.cout, device=x.device, dtype=torch.bfloat16)
-        stats = None
-        if want_stats:
-            stats = torch.empty(lib.ekl_conv_stats_rows(c), 2, spec.cout, device=x.device, dtype=torch.float32)
+        stats = ARENA.take(2 * spec.cout, x.device) if want_stats else None
         bias9 = bias9.float().contiguous()
         _log("fwd", "conv_tc", spec.mode, B, H, W, spec.cin, spec.cout, 0)
         _acct(_route(spec, c, 0), _conv_flops(spec, B, H, W), x.numel() * 2 + y.numel() * 2)
@@ -375,12 +488,10 @@ class _BnAct(torch.autograd.Function):
         M = y.numel() // C
         dev = y.device
         if stats is None:
-            rows = lib.ekl_col_stats_rows(M, C, groups)
-            stats = torch.empty(rows, 2, C, device=dev, dtype=torch.float32)
+            stats = ARENA.take(groups * 2 * C, dev)
             _acct("bn", nbytes=M * C * 2)
             L.check(lib.ekl_col_stats(L.ptr(y), M, C, groups, L.ptr(stats), L.stream()))
             _count()
-        rows_per_group = stats.shape[0] // groups
         _log("bn_fwd", M, C, groups, act, residual is not None)
         mean = torch.empty(groups, C, device=dev, dtype=torch.float32)
         rstd = torch.empty(groups, C, device=dev, dtype=torch.float32)
@@ -388,19 +499,10 @@ class _BnAct(torch.autograd.Function):
         out = torch.empty(*y.shape[:-1], Co, device=dev, dtype=torch.bfloat16)
         # algorithmic bytes (minimal-traffic model): y read once, out written once (+ the residual read)
         _acct("bn", nbytes=M * (C + Co + (Co if residual is not None else 0)) * 2)
-        rc = lib.ekl_bn_act_fwd_small(L.ptr(stats), rows_per_group, float(M // groups), BN_EPS, BN_MOM, L.ptr(running_mean),
-                                          L.ptr(running_var), L.ptr(y), M, C, groups, L.ptr(gamma), L.ptr(beta), act,
-                                          L.ptr(residual), L.ptr(out), L.ptr(mean), L.ptr(rstd), L.stream())
-        if rc == 0:
-            _count(1)
-        elif rc == 2000:       # not a small layer: finalize + streaming pass
-            L.check(lib.ekl_bn_finalize(L.ptr(stats), rows_per_group, C, groups, float(M // groups), BN_EPS, BN_MOM,
-                                        L.ptr(mean), L.ptr(rstd), L.ptr(running_mean), L.ptr(running_var), L.stream()))
-            L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, C, groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), act,
-                                       L.ptr(residual), L.ptr(out), L.stream()))
-            _count(2)
-        else:
-            L.check(rc)
+        L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, C, groups, L.ptr(stats), BN_EPS, BN_MOM, L.ptr(mean), L.ptr(rstd),
+                                   L.ptr(running_mean), L.ptr(running_var), L.ptr(gamma), L.ptr(beta), act, L.ptr(residual),
+                                   L.ptr(out), L.stream()))
+        _count()
         ctx.save_for_backward(y, mean, rstd, gamma, beta)
         ctx.groups, ctx.act, ctx.has_res, ctx.skip_pgrad = groups, act, residual is not None, skip_pgrad
         return out
@@ -412,9 +514,7 @@ class _BnAct(torch.autograd.Function):
         C = y.shape[-1]
         M = y.numel() // C
         dout = dout.contiguous()
-        prow = lib.ekl_bn_act_bwd_rows(M, C, ctx.groups, ctx.act)
-        partial = torch.empty(prow, 2, C, device=y.device, dtype=torch.float32)
-        sums = torch.empty(ctx.groups, 2, C, device=y.device, dtype=torch.float32)
+        sums = ARENA.take(ctx.groups * 2 * C, y.device)            # zero on entry: the two backward reductions land here
         dy = torch.empty_like(y)
         pg = gamma.requires_grad and not ctx.skip_pgrad
         Co = C // 2 if ctx.act == ACT_GLU else C
@@ -422,10 +522,10 @@ class _BnAct(torch.autograd.Function):
         # algorithmic bytes (minimal-traffic model): y and dout read once, dy written once (the kernel makes two passes)
         _acct("bn", nbytes=M * (2 * C + Co) * 2)
         L.check(lib.ekl_bn_act_bwd(L.ptr(y), L.ptr(dout), M, C, ctx.groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma),
-                                   L.ptr(beta), ctx.act, L.ptr(partial), L.ptr(sums),
+                                   L.ptr(beta), ctx.act, L.ptr(sums),
                                    L.ptr(_grad_buffer(gamma)) if pg else None, L.ptr(_grad_buffer(beta)) if pg else None,
                                    L.ptr(dy), L.stream()))
-        _count(3)
+        _count(2)
         return dy, None, None, None, None, None, None, None, (dout if ctx.has_res else None), None
 
 
@@ -440,8 +540,8 @@ def bn_act(y, stats, bn, groups, act, residual=None, skip_pgrad=False):
         rstd = torch.rsqrt(bn.running_var.detach() + bn.eps).view(1, C).contiguous()
         Co = C // 2 if act == ACT_GLU else C
         out = torch.empty(*y.shape[:-1], Co, device=y.device, dtype=torch.bfloat16)
-        L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, C, 1, L.ptr(mean), L.ptr(rstd), L.ptr(bn.weight), L.ptr(bn.bias), act,
-                                   L.ptr(residual), L.ptr(out), L.stream()))
+        L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, C, 1, None, BN_EPS, BN_MOM, L.ptr(mean), L.ptr(rstd), None, None,
+                                   L.ptr(bn.weight), L.ptr(bn.bias), act, L.ptr(residual), L.ptr(out), L.stream()))
         _count()
         return out
     if getattr(bn, "_ekl_counted", False):

@@ -38,7 +38,7 @@ def main():
         y = torch.empty(b, Ho, Wo, Cout, device=dev, dtype=torch.bfloat16)
         dx = torch.empty_like(x)
         dw = torch.zeros(Cout, K, K, Cin, device=dev)
-        stats = torch.empty(lib.ekl_conv_stats_rows(conv), 2, Cout, device=dev)
+        stats = torch.zeros(4, 2, Cout, device=dev, dtype=torch.float64)
         fns = [lambda: lib.ekl_conv_fwd(conv, L.ptr(x), L.ptr(wf), L.ptr(y), L.ptr(stats), L.stream()),
                lambda: lib.ekl_conv_bwd_data(conv, L.ptr(dy), L.ptr(wd), L.ptr(dx), L.stream()),
                lambda: lib.ekl_conv_bwd_weight(conv, L.ptr(x), L.ptr(dy), L.ptr(dw), L.stream())]

@@ -20,7 +20,7 @@ SHAPES = {  # mode -> list of (B, H, W, Cin, Cout)
     1: [(4, 4, 4, 128, 128), (2, 8, 8, 64, 64), (3, 16, 16, 64, 128), (2, 32, 32, 32, 32), (2, 4, 4, 256, 512)],
     2: [(4, 16, 16, 64, 128), (2, 8, 8, 128, 256), (3, 32, 32, 64, 64), (2, 8, 8, 512, 1024), (2, 64, 64, 32, 64)],
 }
-GROUPS = ["tc_fwd", "tc_dgrad", "tc_wgrad", "simt_fwd", "simt_dgrad", "simt_wgrad", "bn", "misc", "heads", "tc_split"]
+GROUPS = ["tc_fwd", "tc_dgrad", "tc_wgrad", "simt_fwd", "simt_dgrad", "simt_wgrad", "bn", "misc", "heads", "tc_split", "fold"]
 
 
 def run_group(group):
@@ -44,6 +44,8 @@ def run_group(group):
         return run_heads(torch, L, lib, dev, rel)
     if group == "tc_split":
         return run_split(torch, L, lib, dev, rel)
+    if group == "fold":
+        return run_fold(torch, L, lib, dev, rel)
     impl = L.IMPL_TC if group.startswith("tc") else L.IMPL_SIMT
     what = group.split("_")[1]
     for mode, shapes in SHAPES.items():
@@ -71,15 +73,14 @@ def run_group(group):
                     y = torch.full((B, Ho, Wo, Cout), float("nan"), device=dev, dtype=torch.bfloat16)
                     stats = None
                     if impl == L.IMPL_TC:
-                        rows = lib.ekl_conv_stats_rows(conv)
-                        stats = torch.full((rows, 2, Cout), float("nan"), device=dev)
+                        stats = torch.zeros(1, 2, Cout, device=dev, dtype=torch.float64)     # fp64 sums, accumulated
                     L.check(lib.ekl_conv_fwd(conv, L.ptr(x), L.ptr(wf), L.ptr(y), L.ptr(stats), L.stream()))
                     torch.cuda.synchronize()
                     e = rel(y.permute(0, 3, 1, 2), yr)
                     msg = "rel %.2e" % e
                     ok = e < 6e-3
                     if stats is not None:
-                        s = stats.sum(0)
+                        s = stats[0].float()
                         yf = y.float().reshape(-1, Cout)
                         e1, e2 = rel(s[0], yf.sum(0)), rel(s[1], (yf * yf).sum(0))
                         msg += " stats %.1e %.1e" % (e1, e2)
@@ -123,31 +124,24 @@ def run_bn(torch, L, lib, dev, rel):
         Co = Cy // 2 if act == L.ACT_GLU else Cy
         res = torch.randn(M, Co, device=dev).bfloat16() if act == L.ACT_NONE else None
         dout = torch.randn(M, Co, device=dev).bfloat16()
-        rows = lib.ekl_col_stats_rows(M, Cy, groups)
-        part = torch.empty(rows, 2, Cy, device=dev)
-        mean = torch.empty(groups, Cy, device=dev)
-        rstd = torch.empty(groups, Cy, device=dev)
+        stats = torch.zeros(groups, 2, Cy, device=dev, dtype=torch.float64)          # fp64 sums, accumulated by col_stats
+        mean = torch.full((groups, Cy), float("nan"), device=dev)
+        rstd = torch.full((groups, Cy), float("nan"), device=dev)
         rm, rv = torch.zeros(Cy, device=dev), torch.ones(Cy, device=dev)
         out = torch.empty(M, Co, device=dev, dtype=torch.bfloat16)
-        L.check(lib.ekl_col_stats(L.ptr(y), M, Cy, groups, L.ptr(part), L.stream()))
-        rc = lib.ekl_bn_act_fwd_small(L.ptr(part), rows // groups, float(M // groups), 1e-5, 0.1, L.ptr(rm), L.ptr(rv), L.ptr(y), M, Cy,
-                                      groups, L.ptr(gamma), L.ptr(beta), act, L.ptr(res), L.ptr(out), L.ptr(mean), L.ptr(rstd),
-                                      L.stream())
-        small = rc == 0
-        if rc == 2000:
-            L.check(lib.ekl_bn_finalize(L.ptr(part), rows // groups, Cy, groups, float(M // groups), 1e-5, 0.1, L.ptr(mean),
-                                        L.ptr(rstd), L.ptr(rm), L.ptr(rv), L.stream()))
-            L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, Cy, groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), act,
-                                       L.ptr(res), L.ptr(out), L.stream()))
-        elif rc != 0:
-            L.check(rc)
-        prow = lib.ekl_bn_act_bwd_rows(M, Cy, groups, act)
-        part2 = torch.empty(prow, 2, Cy, device=dev)
-        sums = torch.empty(groups, 2, Cy, device=dev)
+        L.check(lib.ekl_col_stats(L.ptr(y), M, Cy, groups, L.ptr(stats), L.stream()))
+        L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, Cy, groups, L.ptr(stats), 1e-5, 0.1, L.ptr(mean), L.ptr(rstd), L.ptr(rm), L.ptr(rv),
+                                   L.ptr(gamma), L.ptr(beta), act, L.ptr(res), L.ptr(out), L.stream()))
+        small = M // groups <= 768
+        sums = torch.zeros(groups, 2, Cy, device=dev, dtype=torch.float64)
         dg, db = torch.zeros(Cy, device=dev), torch.zeros(Cy, device=dev)
         dy = torch.empty(M, Cy, device=dev, dtype=torch.bfloat16)
         L.check(lib.ekl_bn_act_bwd(L.ptr(y), L.ptr(dout), M, Cy, groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta),
-                                   act, L.ptr(part2), L.ptr(sums), L.ptr(dg), L.ptr(db), L.ptr(dy), L.stream()))
+                                   act, L.ptr(sums), L.ptr(dg), L.ptr(db), L.ptr(dy), L.stream()))
+        # inference path: the same kernel with mean / rstd given (sums == NULL) must reproduce the training output
+        out_inf = torch.empty(M, Co, device=dev, dtype=torch.bfloat16)
+        L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, Cy, groups, None, 1e-5, 0.1, L.ptr(mean), L.ptr(rstd), None, None,
+                                   L.ptr(gamma), L.ptr(beta), act, L.ptr(res), L.ptr(out_inf), L.stream()))
         torch.cuda.synchronize()
         # reference
         yr = y.float().requires_grad_(True)
@@ -169,7 +163,7 @@ def run_bn(torch, L, lib, dev, rel):
         o = torch.cat(outs)
         o.backward(dout.float())
         errs = dict(out=rel(out, o), dy=rel(dy, yr.grad), dgamma=rel(dg, g_.grad), dbeta=rel(db, b_.grad),
-                    rmean=rel(rm, rm2), rvar=rel(rv, rv2))
+                    rmean=rel(rm, rm2), rvar=rel(rv, rv2), inference=rel(out_inf, out) * 10)
         ok = all(v < 1e-2 for v in errs.values())
         print("%s bn%s M%d C%d g%d act%d %s" % ("PASS" if ok else "FAIL", " (single-launch)" if small else "", M, Cy, groups, act,
                                                " ".join("%s %.1e" % kv for kv in errs.items())), flush=True)
@@ -200,15 +194,14 @@ def run_split(torch, L, lib, dev, rel):
         msg, ok = "ws fwd %d dgrad %d" % (nf, nd), nf > 0
         if nf > 0:
             ws = torch.zeros(nf, device=dev)
-            rows = lib.ekl_conv_stats_rows_ws(conv)
             for rep in range(2):                      # second pass proves the workspace was left zero
                 y = torch.full((B, Ho, Wo, Cout), float("nan"), device=dev, dtype=torch.bfloat16)
-                stats = torch.full((rows, 2, Cout), float("nan"), device=dev)
+                groups = B // gb if gb else 1
+                stats = torch.zeros(groups, 2, Cout, device=dev, dtype=torch.float64)
                 L.check(lib.ekl_conv_fwd_ws(conv, L.ptr(x), L.ptr(wf), L.ptr(y), L.ptr(stats), L.ptr(ws), L.stream()))
                 torch.cuda.synchronize()
                 e = rel(y.permute(0, 3, 1, 2), yr)
-                groups = B // gb if gb else 1
-                sg = stats.view(groups, rows // groups, 2, Cout).sum(1)
+                sg = stats.float()
                 yf = y.float().reshape(groups, -1, Cout)
                 e2 = rel(sg[:, 1], (yf * yf).sum(1))
                 ok = ok and e < 6e-3 and e2 < 1e-3 and float(ws.abs().max()) == 0.0
@@ -361,31 +354,7 @@ def run_misc(torch, L, lib, dev, rel):
         ok = ok and bool((dx == wantd).all())
         print("%s img_s2d G%d B%d %dx%d" % ("PASS" if ok else "FAIL", G, B, H, W), flush=True)
         nfail += 0 if ok else 1
-    from text2img_ekl_b200 import model as M_, ops as O_
-    for (B, H, W, Cc, Cx, N) in [(3, 64, 64, 128, 64, 128), (2, 128, 128, 128, 32, 64), (2, 8, 16, 256, 64, 128)]:
-        # folded jointConv (ekl_conv_fwd_bias9 + border_class_sums) against conv3x3 over cat(tile(c), h) in fp32
-        c = torch.randn(B, Cc, device=dev).requires_grad_(True)
-        x = torch.randn(B, H, W, Cx, device=dev).bfloat16().requires_grad_(True)
-        w = (torch.randn(N, Cc + Cx, 3, 3, device=dev) / (9 * (Cc + Cx)) ** 0.5).bfloat16().float()
-        w = w.contiguous(memory_format=torch.channels_last).requires_grad_(True)
-        spec = O_.ConvSpec(O_.S1, Cx, N, impl=L.IMPL_TC)
-        valid = M_._border_valid().to(dev)
-        T = torch.einsum("bc,nckl->bkln", c, w[:, :Cc]).reshape(B, 9, N)
-        bias9 = torch.einsum("qt,btn->bqn", valid, T)
-        y, _ = O_.conv_bias9(x, w[:, Cc:].contiguous(memory_format=torch.channels_last), bias9, spec)
-        dy = torch.randn_like(y)
-        y.backward(dy)
-        got = [y.permute(0, 3, 1, 2), x.grad.permute(0, 3, 1, 2), w.grad, c.grad]
-        cr, xr, wr = c.detach().clone().requires_grad_(True), x.detach().float().requires_grad_(True), w.detach().clone().requires_grad_(True)
-        xin = torch.cat((cr.view(B, Cc, 1, 1).expand(B, Cc, H, W), xr.permute(0, 3, 1, 2)), 1)
-        torch.backends.cudnn.allow_tf32 = False
-        yr = torch.nn.functional.conv2d(xin, wr, padding=1)
-        yr.backward(dy.float().permute(0, 3, 1, 2))
-        want = [yr, xr.grad.permute(0, 3, 1, 2), wr.grad, cr.grad]
-        errs = [rel(a, b) for a, b in zip(got, want)]
-        ok = errs[0] < 6e-3 and errs[1] < 6e-3 and errs[2] < 2e-3 and errs[3] < 2e-3
-        print("%s conv_bias9 B%d %dx%d Cc%d Cx%d N%d y %.1e dx %.1e dw %.1e dc %.1e" % (("PASS" if ok else "FAIL", B, H, W, Cc, Cx, N) + tuple(errs)), flush=True)
-        nfail += 0 if ok else 1
+    # (the folded jointConv is checked end to end in the `fold` group)
     for (B, H, W, C) in [(2, 64, 64, 16), (3, 16, 32, 8)]:
         y = torch.randn(B, H, W, C, device=dev).bfloat16()
         img = torch.full((B, 3, H, W), float("nan"), device=dev)
@@ -422,6 +391,59 @@ def run_misc(torch, L, lib, dev, rel):
         want = torch.where(o.float() > 0, d.float(), 0.2 * d.float()).bfloat16()
         ok = bool((dx == want).all())
         print("%s lrelu_bwd n%d" % ("PASS" if ok else "FAIL", n), flush=True)
+        nfail += 0 if ok else 1
+    return nfail
+
+
+def run_fold(torch, L, lib, dev, rel):
+    """Folded jointConv (ekl_code_bias9_fwd / ekl_border_sums9 / ekl_code_bias9_bwd + a conv over a channel window of the
+    master filter) and the image head (3 real filters in a 16-wide tile) through the autograd layer, against the
+    reference formulation conv3x3(cat(tile(code), h)) / conv3x3(h) in fp32."""
+    import torch.nn.functional as F
+    from text2img_ekl_b200 import ops
+    nfail = 0
+    for (B, H, W, ngf, ef) in [(3, 16, 16, 64, 128), (2, 32, 32, 32, 128), (4, 16, 8, 64, 256), (2, 64, 64, 64, 128)]:
+        N = 2 * ngf
+        code = torch.randn(B, ef, device=dev).requires_grad_(True)
+        h = torch.randn(B, H, W, ngf, device=dev).bfloat16().requires_grad_(True)
+        wq = (torch.randn(N, ngf + ef, 3, 3, device=dev) / (9 * (ngf + ef)) ** 0.5)
+        wq[:, ef:] = wq[:, ef:].bfloat16().float()                      # the conv part is exact in bf16, the code part stays fp32
+        w = wq.contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        spec = ops.ConvSpec(ops.S1, ngf, N, impl=L.IMPL_TC, w_cin_total=ngf + ef, w_cin_off=ef)
+        bias9 = ops.code_bias9(code, w)
+        y, stats = ops.conv_bias9(h, w, bias9, spec, want_stats=True)
+        dy = torch.randn(B, H, W, N, device=dev).bfloat16()
+        y.backward(dy)
+        torch.cuda.synchronize()
+        cr, hr, wr = code.detach().clone().requires_grad_(True), h.detach().float().requires_grad_(True), wq.clone().requires_grad_(True)
+        xin = torch.cat((cr.view(B, ef, 1, 1).expand(B, ef, H, W), hr.permute(0, 3, 1, 2)), 1)
+        yr = F.conv2d(xin, wr, padding=1)
+        yr.backward(dy.float().permute(0, 3, 1, 2))
+        yf = y.detach().float().reshape(-1, N)
+        errs = dict(y=rel(y.permute(0, 3, 1, 2), yr), dh=rel(h.grad, hr.grad),
+                    dcode=rel(code.grad, cr.grad), dw_code=rel(w.grad[:, :ef], wr.grad[:, :ef]), dw_h=rel(w.grad[:, ef:], wr.grad[:, ef:]),
+                    s1=rel(stats.view(2, N)[0].float(), yf.sum(0)), s2=rel(stats.view(2, N)[1].float(), (yf * yf).sum(0)))
+        tol = dict(y=6e-3, dh=6e-3, dcode=2e-3, dw_code=2e-3, dw_h=2e-3, s1=1e-2, s2=1e-3)
+        ok = all(errs[k] < tol[k] for k in errs)
+        print("%s fold B%d %dx%d ngf%d ef%d %s" % ("PASS" if ok else "FAIL", B, H, W, ngf, ef, " ".join("%s %.1e" % kv for kv in errs.items())), flush=True)
+        nfail += 0 if ok else 1
+    for (B, H, W, ngf) in [(2, 64, 64, 64), (3, 32, 32, 32), (2, 64, 64, 16)]:
+        h = torch.randn(B, H, W, ngf, device=dev).bfloat16().requires_grad_(True)
+        wq = (torch.randn(3, ngf, 3, 3, device=dev) / (9 * ngf) ** 0.5).bfloat16().float()
+        w = wq.contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        spec = ops.ConvSpec(ops.S1, ngf, 16, impl=L.IMPL_TC, w_cout_valid=3)
+        y, _ = ops.conv(h, w, spec)
+        dy = torch.zeros(B, H, W, 16, device=dev, dtype=torch.bfloat16)
+        dy[..., :3] = torch.randn(B, H, W, 3, device=dev).bfloat16()
+        y.backward(dy)
+        torch.cuda.synchronize()
+        hr, wr = h.detach().float().requires_grad_(True), wq.clone().requires_grad_(True)
+        yr = F.conv2d(hr.permute(0, 3, 1, 2), wr, padding=1)
+        yr.backward(dy[..., :3].float().permute(0, 3, 1, 2))
+        errs = dict(y=rel(y[..., :3].permute(0, 3, 1, 2), yr), pad=float(y[..., 3:].float().abs().max()),
+                    dh=rel(h.grad, hr.grad), dw=rel(w.grad, wr.grad))
+        ok = errs["y"] < 6e-3 and errs["pad"] == 0.0 and errs["dh"] < 6e-3 and errs["dw"] < 2e-3
+        print("%s head window B%d %dx%d ngf%d %s" % ("PASS" if ok else "FAIL", B, H, W, ngf, " ".join("%s %.1e" % kv for kv in errs.items())), flush=True)
         nfail += 0 if ok else 1
     return nfail
 

@@ -76,7 +76,7 @@ def main():
             y = torch.empty(b, Ho, Wo, Cout, device=dev, dtype=torch.bfloat16)
             dx = torch.empty_like(x)
             dw = torch.zeros(Cout, K, K, Cin, device=dev)
-            stats = torch.empty(max(lib.ekl_conv_stats_rows(conv), 1), 2, Cout, device=dev)
+            stats = torch.zeros(max(b // group_b if group_b else 1, 1), 2, Cout, device=dev, dtype=torch.float64)
             if kind == "fwd":
                 fn = lambda: L.check(lib.ekl_conv_fwd(conv, L.ptr(x), L.ptr(wf), L.ptr(y), L.ptr(stats), L.stream()))
             elif kind == "dgrad":
@@ -102,18 +102,16 @@ def main():
             mean, rstd = torch.zeros(groups, Cy, device=dev), torch.ones(groups, Cy, device=dev)
             out = torch.empty(M, Co, device=dev, dtype=torch.bfloat16)
             dy = torch.empty_like(y)
-            prow = lib.ekl_bn_act_bwd_rows(M, Cy, groups, act)
-            part2 = torch.empty(prow, 2, Cy, device=dev)
-            sums = torch.empty(groups, 2, Cy, device=dev)
+            sums = torch.zeros(groups, 2, Cy, device=dev, dtype=torch.float64)
             dg, db = torch.zeros(Cy, device=dev), torch.zeros(Cy, device=dev)
             st = L.stream()
             if kind == "bn_fwd":
-                fn = lambda: L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, Cy, groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta),
-                                                        act, L.ptr(res), L.ptr(out), st))
+                fn = lambda: L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, Cy, groups, None, 1e-5, 0.1, L.ptr(mean), L.ptr(rstd), None, None,
+                                                        L.ptr(gamma), L.ptr(beta), act, L.ptr(res), L.ptr(out), st))
                 nbytes = M * (Cy + Co + (Co if has_res else 0)) * 2
             else:
                 fn = lambda: L.check(lib.ekl_bn_act_bwd(L.ptr(y), L.ptr(dout), M, Cy, groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma),
-                                                        L.ptr(beta), act, L.ptr(part2), L.ptr(sums), L.ptr(dg), L.ptr(db), L.ptr(dy), st))
+                                                        L.ptr(beta), act, L.ptr(sums), L.ptr(dg), L.ptr(db), L.ptr(dy), st))
                 nbytes = M * (Cy + Co + Cy) * 2          # minimal traffic: y and dout read once, dy written once
             t = timeit(fn)
             rows.append((t * n, "%-6s M=%8d Cy=%4d g%d act%d res%d" % (kind, M, Cy, groups, act, int(has_res)), n, t,
