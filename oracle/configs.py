@@ -50,7 +50,12 @@ CONFIGS = {
                                     D_CAPSULE=True)),
     "catz_plain": dict(yml="birds_2stg_splitz_cap_ca.realcls.yml", batch=32, over={"TRAIN.G_CAPSULE": False, "TRAIN.D_CAPSULE": False},
                        ocfg=dict(G_KIND="catz", CLS_KIND="index", CAT_Z="concat", Z_DIM=128, G_CAPSULE=False, D_CAPSULE=False)),
+    # config 2's generator + the two-head D_NET64/128/256.  NOT pinned by a golden fixture: the reference's step functions
+    # cannot drive these modules (app. A #14); the modules themselves are pinned (tests/golden/modules.npz dnet*).
+    "3stages_dnet": dict(yml="birds_3stages.yml", batch=24, over={"TRAIN.CAT_Z": "sum"},
+                         ocfg=dict(G_KIND="cond", COND="txt+cls", CLS_KIND="multihot", CAT_Z="sum", Z_DIM=100, BRANCH_NUM=3)),
 }
+NO_REFERENCE_STEP = ("3stages_dnet",)      # configs the reference cannot run: no golden step fixture
 
 BASELINE = ("catcls", "3stages", "onlycapsule", "splitz_cap_ca", "coco")      # the five BASELINE.json configs
 

@@ -64,6 +64,23 @@ class storage:
         STORAGE = self.prev
 
 
+# nn.Module.train() / .eval() of the reference networks: evaluate() builds netG and calls netG.eval() when
+# cfg.TEST.EVAL_MODE (cub:789-793), so BatchNorm normalises with the running statistics and updates nothing.
+TRAINING = True
+
+
+class eval_mode:
+    """with eval_mode(): ... -- the oracle's networks in nn.Module.eval() state (generation path, cub:776-911)."""
+
+    def __enter__(self):
+        global TRAINING
+        self.prev, TRAINING = TRAINING, False
+
+    def __exit__(self, *a):
+        global TRAINING
+        TRAINING = self.prev
+
+
 @dataclass
 class OracleCfg:
     """The subset of miscc/config.py:13-77 the step reads."""
@@ -112,8 +129,10 @@ def glu(x):
     return x[:, :nc] * torch.sigmoid(x[:, nc:])
 
 
-def _bn(x, sd, p, training=True):
-    """nn.BatchNorm{1,2}d in train mode (batch statistics, running stats updated in place)."""
+def _bn(x, sd, p, training=None):
+    """nn.BatchNorm{1,2}d: train mode (batch statistics, running stats updated in place) or, under eval_mode(), the
+    running statistics."""
+    training = TRAINING if training is None else training
     rm, rv = sd.get(p + ".running_mean"), sd.get(p + ".running_var")
     y = F.batch_norm(x, rm, rv, sd[p + ".weight"], sd[p + ".bias"], training, BN_MOM, BN_EPS)
     if training and (p + ".num_batches_tracked") in sd:
@@ -399,7 +418,10 @@ def d_loss(real, wrong, fake, real_cp, fake_cp, cfg):
     if len(real) > 1 and cfg.UNCOND_LOSS > 0:
         u = cfg.UNCOND_LOSS
         e_unc = u * bce(real[1], 1) + u * bce(wrong[1], 1) + u * bce(fake[1], 0)     # wrong -> REAL (cub:430)
-        e_cls = ce_loss(real[2], real_cp) + ce_loss(fake[2], fake_cp)
+        if len(real) > 2:
+            e_cls = ce_loss(real[2], real_cp) + ce_loss(fake[2], fake_cp)
+        else:       # two-head D_NET* (model.py:874-914): no class head; the reference has no loss assembly for these
+            e_cls = torch.zeros((), device=real[0].device)      # (app. A #14) -- match + uncond, trainer.py:408-410
         return e_match + e_unc + e_cls, e_match, e_unc, e_cls
     z = torch.zeros((), device=real[0].device)
     return bce(real[0], 1) + 0.5 * (bce(wrong[0], 0) + bce(fake[0], 0)), e_match, z, z
@@ -500,7 +522,8 @@ class OracleTrainer:
             e_match = e_match + bce(o[0], 1)
             if len(o) > 1 and c.UNCOND_LOSS > 0:
                 e_unc = e_unc + c.UNCOND_LOSS * bce(o[1], 1)
-                e_cls = e_cls + ce_loss(o[2], real_cp)
+                if len(o) > 2:
+                    e_cls = e_cls + ce_loss(o[2], real_cp)
             out["g_logits"].append([t.detach() for t in o])
         kl = [kl_loss(m, l) for m, l in kls]
         errG = e_match + e_unc + e_cls + sum(kl) * c.KL

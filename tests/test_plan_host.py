@@ -430,6 +430,38 @@ def test_reference_yml_plus_overrides_equals_the_shipped_resolved_yml():
     assert configs.setup("catz_exchange").G_CLASS == "COND_G_NET_CATZ" and cfg.TRAIN.EXCHANGE is True
 
 
+def test_async_loss_log_consumes_in_order_and_never_blocks(tmp_path):
+    """miscc.losslog.AsyncLossLog (the sync-free replacement of cub:457-460's per-100-iteration `.item()` scalars):
+    samples are taken only on due iterations, land in the JSONL file with their iteration number, a full ring drops
+    (and counts) instead of waiting, and a tensorboardX-style writer receives add_scalar calls."""
+    import json
+    from text2img_ekl_b200.miscc.losslog import AsyncLossLog
+
+    class W:
+        def __init__(self):
+            self.calls = []
+
+        def add_scalar(self, k, v, step):
+            self.calls.append((k, round(v, 4), step))
+    w = W()
+    path = str(tmp_path / "log" / "scalars.jsonl")
+    log = AsyncLossLog(path, every=100, slots=2, writer=w)
+    assert log.due(0) and log.due(300) and not log.due(150)
+    for count in (0, 100, 200):
+        assert log.push(count, ["D_loss0", "D_loss1", "G_loss"], torch.tensor([1.0, 2.0, 3.0]) + count)
+    assert log.flush() == 1 and log.dropped == 0          # the earlier samples were consumed by the following push's poll
+    rows = [json.loads(ln) for ln in open(path)]
+    assert [r["count"] for r in rows] == [0, 100, 200] and rows[2]["G_loss"] == 203.0
+    assert ("D_loss1", 102.0, 100) in w.calls and len(w.calls) == 9
+    # a ring whose slots are all in flight drops instead of blocking
+    for s in log.slots:
+        s["busy"], s["tag"] = True, (7, ["x"], True)
+        s["ev"] = type("E", (), {"query": lambda self: False, "synchronize": lambda self: None})()
+        s["buf"] = torch.zeros(4)
+    assert log.push(300, ["x"], torch.tensor([1.0])) is False and log.dropped == 1
+    assert log.flush() == 2
+
+
 def test_discriminator_trunk_marks_fire_deepest_first():
     """model._DBase._trunk drops an ops.grad_mark behind its blocks (no-op unless a gradient reducer is registered
     for the network, parallel.GradReducer): with stand-in blocks on the CPU the block order of all three trunk depths is

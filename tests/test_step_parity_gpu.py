@@ -50,15 +50,16 @@ def build(name, B):
     oc = ocfg.oracle_cfg(name, batch=B)
     gsh = shapes.g_shapes(oc, cond_dim=ocfg.cond_dim(oc))
     d_res = [64, 128 if oc.SCALE == 2 else 256, 256][: oc.BRANCH_NUM]                  # cub:144-154
-    dsh = [shapes.d_shapes(oc, r, joint=True, use_cap=oc.D_CAPSULE) for r in d_res]
+    joint = not getattr(Trainer, "PLAIN_D", False)           # False: the two-head D_NET64/128/256
+    dsh = [shapes.d_shapes(oc, r, joint=joint, use_cap=oc.D_CAPSULE) for r in d_res]
     sdG = shapes.make_state_dict(gsh, "G")
     sdDs = [shapes.make_state_dict(s, "D%d" % i) for i, s in enumerate(dsh)]
     tr.netG.load_state_dict(sdG)
     for d, sd in zip(tr.netsD, sdDs):
         d.load_state_dict(sd)
     clone = lambda sd: {k: v.detach().clone() for k, v in sd.items()}
-    orc16 = OracleTrainer(oc, clone(sdG), [clone(s) for s in sdDs])      # evaluated at bf16 storage precision
-    return tr, oc, OracleTrainer(oc, sdG, sdDs), orc16
+    orc16 = OracleTrainer(oc, clone(sdG), [clone(s) for s in sdDs], d_joint=joint)      # evaluated at bf16 storage precision
+    return tr, oc, OracleTrainer(oc, sdG, sdDs, d_joint=joint), orc16
 
 
 # every BASELINE config at batch 4 (fast) AND at the batch BASELINE.json names for it (24 / 24 / 32 / 32 / 64 per GPU)
@@ -174,6 +175,49 @@ def test_eval_mode_generation_is_per_sample():
         assert torch.isfinite(i4).all() and float(i4.abs().max()) <= 1.0
         assert rel(i4[:2], i2) < 2e-3, rel(i4[:2], i2)
     netG.train()
+
+
+@pytest.mark.parametrize("name", ["splitz_cap_ca", "3stages"])
+def test_eval_mode_generation_matches_oracle(name):
+    """evaluate()'s forward (cub:776-911: netG.eval() under cfg.TEST.EVAL_MODE, BatchNorm on the running statistics,
+    model.py:482-527) against the oracle in eval mode on the SAME state_dict -- after one training step, so the running
+    statistics are not their initial values -- with injected noise / eps / seed.  Same image bounds as the training
+    step at batch 4."""
+    from oracle import ekl_oracle as O
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B = 4
+    tr, oc, orc, _ = build(name, B)
+    dev = tr.device
+    b = synth.make_batch(oc, B, "eval0")
+    tr.train_step((b["imgs"], b["wrong_imgs"], b["embedding"], b["cls"], None),
+                  noise=b["noise"].to(dev), eps=b["eps"].to(dev), seed=b["seed"].to(dev))
+    torch.cuda.synchronize()
+    sd = {k: v.detach().float().cpu().clone() if v.is_floating_point() else v.detach().cpu().clone()
+          for k, v in tr.netG.state_dict().items()}
+    b = synth.make_batch(oc, B, "eval1")
+    netG = tr.netG.eval()
+    try:
+        with torch.no_grad(), O.eval_mode():
+            if oc.G_KIND == "catz_ca":
+                cls = O.onehot(b["cls"].long() - 1, oc.ENTITY_DIM)
+                hs = netG(b["noise"].to(dev), b["embedding"].to(dev), cls.to(dev), eps=b["eps"].to(dev), seed=b["seed"].to(dev))[0]
+                hs_o = O.g_forward_catz_ca(sd, oc, b["noise"], b["embedding"], cls, b["eps"], b["seed"])[0]
+            else:
+                cond = torch.cat((b["embedding"], b["cls"].float()), 1) if oc.COND == "txt+cls" else b["embedding"]
+                hs = netG(b["noise"].to(dev), cond.to(dev), seed=b["seed"].to(dev))[0]
+                hs_o = O.g_forward_cond(sd, oc, b["noise"], cond, b["seed"])[0]
+            imgs, imgs_o = netG.image(hs), O.g_images(hs_o, sd)
+        torch.cuda.synchronize()
+        for i, (g, w) in enumerate(zip(imgs, imgs_o)):
+            r = rel(g, w)
+            print("eval-mode %s img%d rel-L2 %.3e" % (name, i, r))
+            assert r <= (TOL_OUT if i == 0 else TOL_DEEP), (name, i, r)
+        # eval mode must not touch the running statistics
+        for k, v in tr.netG.state_dict().items():
+            if "running" in k or "num_batches" in k:
+                assert torch.equal(v.detach().cpu().to(sd[k].dtype), sd[k]), k
+    finally:
+        netG.train()
 
 
 def _graphed(parallel, monkeypatch):

@@ -189,6 +189,17 @@ VARIANTS = ["splitz_cat_sum", "splitz_cat_product", "splitz_scale4_sum", "catz_e
 
 
 @pytest.mark.timeout(180, method="thread")
+def test_two_head_discriminators_whole_step_matches_oracle():
+    """StackGAN++ two-head D_NET64/128/256 (model.py:874-914, 1006-1050, 1154-1202) driven through the whole training
+    step with config 2's generator: match + uncond losses, no class term (the reference has no loss assembly for these
+    modules -- its train_joint_Dnet indexes a third output, SURVEY app. A #14 -- so the oracle step for them is this
+    repo's statement of the StackGAN++ form the reference keeps in comments, trainer.py:408-410; the modules themselves
+    are pinned to the reference by tests/golden/modules.npz)."""
+    import test_step_parity_gpu as P
+    P.test_training_step_matches_oracle("3stages_dnet", 4)
+
+
+@pytest.mark.timeout(180, method="thread")
 @pytest.mark.parametrize("variant", VARIANTS)
 def test_conditioning_variants_match_oracle(variant):
     """The remaining conditioning variants run through the SAME whole-step parity check as the five BASELINE configs

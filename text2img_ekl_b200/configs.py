@@ -34,6 +34,8 @@ VARIANTS = {
     "splitz_scale4_sum": _C4 + ({"TRAIN": {"CAT_Z": "sum"}, "TREE": {"SCALE": 4}}, "cub", None, "index"),   # model.py:406-407
     "catz_exchange": _C4 + ({"TRAIN": {"EXCHANGE": True}}, "cub_catz", None, "index"),                # model.py:280-333,567
     "catz_plain": _C4 + ({"TRAIN": {"G_CAPSULE": False, "D_CAPSULE": False}}, "cub_catz", None, "index"),
+    # config 2's generator with the StackGAN++ two-head D_NET64/128/256 (model.py:874-1202): match + uncond losses only
+    "3stages_dnet": ("birds_3stages.yml", "b200_3stages.yml", {"TRAIN": {"CAT_Z": "sum"}}, "trainer_plain_d", "txt+cls", "multihot"),
 }
 
 
@@ -43,8 +45,9 @@ def yml_path(name, prefer_reference=True):
     ref = os.path.join(REF_ROOT, "cfg", ref_yml)
     if prefer_reference and os.path.isfile(ref):
         return ref, over
-    # the shipped copy of a BASELINE config already contains its overrides; a variant adds its own on top
-    return os.path.join(CFG_DIR, shipped), (over if name in VARIANTS else {})
+    # the shipped copy already contains the BASELINE config's overrides (applying them again changes nothing); a variant
+    # adds its own on top
+    return os.path.join(CFG_DIR, shipped), over
 
 
 def setup(name, batch=None, width=None, prefer_reference=True):
@@ -71,5 +74,6 @@ def setup(name, batch=None, width=None, prefer_reference=True):
     class _Trainer(T.condGANTrainer):
         COND = cond
         CLS_KIND = cls_kind
+        PLAIN_D = flavour == "trainer_plain_d"
     _Trainer.__name__ = "condGANTrainer"
     return _Trainer

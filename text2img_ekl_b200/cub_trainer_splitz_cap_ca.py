@@ -16,6 +16,7 @@ from . import model
 from . import ops
 from .engine import (KL_loss, StepEngine, ce_loss, compute_mean_covariance, onehot)  # noqa: F401  (reference names)
 from .miscc.config import cfg
+from .miscc.losslog import AsyncLossLog
 from .miscc.utils import mkdir_p
 from . import parallel
 
@@ -100,7 +101,11 @@ def image_grid_uint8(images, nrow=10, padding=2):
     return sheet.mul(255).add(0.5).clamp(0, 255).byte().permute(1, 2, 0).contiguous()
 
 
-def build_Ds(allow_three=False):
+def build_Ds(plain=False):
+    """cub:141-157 (JOINT_D_NET*).  plain: the StackGAN++ two-head D_NET64/128/256 (model.py:874-914, 1006-1050,
+    1154-1202) -- in scope as modules; no shipped reference trainer builds them."""
+    if plain:
+        return [D() for D in (model.D_NET64, model.D_NET128, model.D_NET256)[:cfg.TREE.BRANCH_NUM]]
     netsD = []
     if cfg.TREE.BRANCH_NUM > 0:
         netsD.append(model.JOINT_D_NET64(use_cap=cfg.TRAIN.D_CAPSULE))
@@ -130,12 +135,12 @@ def load_snapshots(netG, netsD):
     return count
 
 
-def load_network(gpus, device=None, g_class=None):
+def load_network(gpus, device=None, g_class=None, plain_d=False):
     """cub:113-196.  Returns (netG, shareGs, netsD, num_Ds, count)."""
     device = device or (torch.device("cuda", gpus[0]) if gpus else torch.device("cuda"))
     netG, shareGs = build_G(g_class=g_class)
     netG.apply(weights_init)
-    netsD = build_Ds()
+    netsD = build_Ds(plain_d)
     for d in netsD:
         d.apply(weights_init)
     count = load_snapshots(netG, netsD)
@@ -165,6 +170,7 @@ class condGANTrainer(object):
     KIND = "catz_ca"
     COND = "txt+cls"
     G_CLASS = None                 # None: the generator cub:130-135 builds
+    PLAIN_D = False                # True: the two-head D_NET* instead of JOINT_D_NET*
 
     def __init__(self, output_dir, data_loader, imsize):
         if cfg.TRAIN.FLAG and output_dir:
@@ -214,7 +220,7 @@ class condGANTrainer(object):
         self.rank, self.world_size = rank, ws
 
     def setup(self):
-        self.netG, self.shareGs, self.netsD, self.num_Ds, start_count = load_network(self.gpus, self.device, self.G_CLASS)
+        self.netG, self.shareGs, self.netsD, self.num_Ds, start_count = load_network(self.gpus, self.device, self.G_CLASS, self.PLAIN_D)
         self._replicate()                    # before the optimisers re-home the parameters into flat buffers
         self.optimizerG, self.optimizersD = define_optimizers(self.netG, self.netsD)
         self.criterion = nn.BCELoss()
@@ -292,6 +298,23 @@ class condGANTrainer(object):
             self._train_loop()
         cur.wait_stream(side)
 
+    LOG_EVERY = 100                 # cub:457-460: D_loss scalars every 100 iterations
+
+    def _log_scalars(self, count, errDs, errG):
+        """The reference's per-100-iteration scalars (cub:457-460) without its `.item()` host syncs: an asynchronous
+        device-to-host copy now, consumed when it has landed (miscc.losslog.AsyncLossLog)."""
+        log = getattr(self, "loss_log", None)
+        if log is None:
+            path = os.path.join(self.log_dir, "scalars.jsonl") if hasattr(self, "log_dir") else None
+            log = self.loss_log = AsyncLossLog(path, every=self.LOG_EVERY)
+        if not log.due(count):
+            log.poll()
+            return
+        d = errDs if torch.is_tensor(errDs) else torch.stack([torch.stack([x.detach().float() for x in e]) for e in errDs])
+        g = errG if torch.is_tensor(errG) else torch.stack([x.detach().float() for x in errG])
+        names = ["D_loss%d" % i for i in range(d.shape[0])] + ["G_loss"]
+        log.push(count, names, torch.cat((d[:, 0].reshape(-1), g[:1].reshape(-1))))
+
     def _train_loop(self):
         start_count = self.setup()
         count = start_count
@@ -304,11 +327,13 @@ class condGANTrainer(object):
             while data is not None:
                 nxt = next(it, None)
                 errDs, errG = self._loop_step(data, nxt, count)
+                self._log_scalars(count, errDs, errG)
                 count += 1
                 data = nxt
             if errG is None:
                 break
             end_t = time.time()
+            self.loss_log.flush()
             tot = [sum(e[k] for e in errDs).item() for k in range(4)]
             print("[%d/%d][BN=%d][%d stages] Loss_D_all: %.2f match: %.2f uncond: %.2f cls: %.2f | "
                   "Loss_G_all: %.2f match: %.2f uncond: %.2f cls: %.2f KL: %s Time: %.2fs"

@@ -250,7 +250,10 @@ class StepEngine:
         if len(out) > 1 and self.uncond > 0:
             u = self.uncond
             errD_uncond = u * _bce_const(real[1], 1) + u * _bce_const(wrong[1], 1) + u * _bce_const(fake[1], 0)
-            errD_cls = ce_loss(real[2], real_cp) + ce_loss(fake[2], fake_cp)
+            # two-head discriminators (D_NET64/128/256, model.py:874-914: [cond, uncond], no class head) have no loss
+            # assembly in the reference (its train_joint_Dnet indexes a third output); for them the
+            # same match + uncond sum is taken -- the StackGAN++ form the reference keeps as comments (trainer.py:408-410)
+            errD_cls = (ce_loss(real[2], real_cp) + ce_loss(fake[2], fake_cp)) if len(out) > 2 else torch.zeros((), device=real_imgs.device)
             errD = errD_match + errD_uncond + errD_cls
         else:
             errD_uncond = errD_cls = torch.zeros((), device=real_imgs.device)
@@ -403,7 +406,8 @@ class StepEngine:
             errGs_total_fused = errGs_total_fused + _bce_const(outputs[0], 1)
             errGs_match = errGs_match + _bce_const(outputs[0], 1)
             if len(outputs) > 1 and self.uncond > 0:
-                u_, c_ = self.uncond * _bce_const(outputs[1], 1), ce_loss(outputs[2], real_cp)
+                u_ = self.uncond * _bce_const(outputs[1], 1)
+                c_ = ce_loss(outputs[2], real_cp) if len(outputs) > 2 else torch.zeros((), device=u_.device)
                 errGs_uncond, errGs_cls = errGs_uncond + u_, errGs_cls + c_
                 errGs_total_fused = errGs_total_fused + u_ + c_
             self.last_g_logits.append(outputs)

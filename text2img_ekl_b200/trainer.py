@@ -11,14 +11,14 @@ from .cub_trainer_splitz_cap_ca import (KL_loss, ce_loss, compute_mean_covarianc
 from .miscc.config import cfg
 
 
-def load_network(gpus, device=None, cond="txt+cls"):
+def load_network(gpus, device=None, cond="txt+cls", plain_d=False):
     """trainer.py:107-160 with entity_netG = COND_G_NET(E + 1 + text) (:116) as the generator."""
     device = device or (torch.device("cuda", gpus[0]) if gpus else torch.device("cuda"))
     shareGs = model.get_shareGs(cfg.GAN.GF_DIM)
     cond_dim = cfg.TEXT.DIMENSION + (cfg.GAN.ENTITY_DIM + 1 if cond == "txt+cls" else 0)
     netG = model.COND_G_NET(cond_dim, shareGs, use_cap=cfg.TRAIN.G_CAPSULE)
     netG.apply(weights_init)
-    netsD = _cub.build_Ds()
+    netsD = _cub.build_Ds(plain_d)
     for d in netsD:
         d.apply(weights_init)
     count = _cub.load_snapshots(netG, netsD)           # trainer.py:138-152: cfg.TRAIN.NET_G / NET_D resume
@@ -46,7 +46,7 @@ class condGANTrainer(_cub.condGANTrainer):
         return imgs, real_vimgs, wrong_vimgs, t_embedding.to(dev, non_blocking=True), cls.to(dev, non_blocking=True)
 
     def setup(self):
-        self.netG, self.shareGs, self.netsD, self.num_Ds, start_count = load_network(self.gpus, self.device, self.COND)
+        self.netG, self.shareGs, self.netsD, self.num_Ds, start_count = load_network(self.gpus, self.device, self.COND, self.PLAIN_D)
         self._replicate()
         self.optimizerG, self.optimizersD = define_optimizers(self.netG, self.netsD)
         B = self.batch_size
