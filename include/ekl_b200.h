@@ -141,6 +141,16 @@ int ekl_cat_code_bwd(const void* dcat, int Cc, int Cx, int B, int HW, float* dco
 int ekl_img_s2d(const float* x0, const float* x1, const float* x2, int groups, int B, int H, int W, void* out, void* stream);
 int ekl_img_s2d_bwd(const void* dxs, int B, int H, int W, float* dx, void* stream);
 
+/* ---------------------------------------------------------------- loader image pyramid on the device ----------
+ * datasets.py:43-68 get_imgs: every stage below the last gets a PIL BILINEAR resize (transforms.Scale) of the final-size
+ * uint8 crop; each level is ToTensor()'d and Normalize((0.5,)*3, (0.5,)*3)'d.  One level per call, bit-exact with
+ * PIL's 8-bit resampler (integer weights with 22 fractional bits, horizontal then vertical pass, uint8 intermediate):
+ * src uint8 [B][S][S][3] (HWC), out fp32 [B][3][s][s].  bounds [s][2] = (first source index, count) and kk [s][ksize] are
+ * PIL's coefficient tables of the resize S -> s (device int32, computed on the host: text2img_ekl_b200/datasets.py);
+ * tmp: B*S*s*3 bytes of scratch.  s == S converts without resampling. */
+int ekl_img_pyramid_level(const void* src_u8, int B, int S, int s, const int* bounds, const int* kk, int ksize, void* tmp_u8,
+                          float* out, void* stream);
+
 /* ---------------------------------------------------------------- generator image head ---------------------
  * GET_IMAGE_G (model.py:426-437) = conv3x3(ngf -> 3) + tanh.  The conv runs on ekl_conv_fwd with the 3 filters
  * zero-padded to C (>= 8, multiple of 8) output channels; these passes apply tanh to channels 0..2 of the padded
@@ -192,6 +202,19 @@ int ekl_reparam_kl_fwd(const float* mu, int64_t mu_row_stride, const float* logv
 int ekl_reparam_kl_bwd(const float* mu, int64_t mu_row_stride, const float* logvar, int64_t lv_row_stride,
                        const float* eps, int B, int D, const float* dc, const float* dstd, const float* dkl, float* dmu,
                        float* dlogvar, void* stream);
+
+/* VC_NET's hidden layers (model.py:169-181): h = ReLU(BatchNorm1d(x W^T + b)) on a batch of B <= 64 rows as one kernel
+ * per direction (a warp owns an output column for all rows: the batch statistics stay in registers).  All fp32.
+ * forward: training != 0 -> batch statistics (running_mean / running_var updated, may be NULL), xhat [B][N] and rstd [N]
+ * saved for the backward; training == 0 -> running statistics (xhat / rstd may be NULL).
+ * backward: dW [N][K], dbias, dgamma, dbeta accumulated (+=, each may be NULL); dy [B][N] = gradient of the Linear's
+ * output (the caller forms dx = dy W with one library GEMM where the input needs a gradient). */
+int ekl_linear_bn_relu_fwd(const float* x, const float* W, const float* bias, const float* gamma, const float* beta,
+                           float* running_mean, float* running_var, int B, int K, int N, float eps, float momentum,
+                           int training, float* h, float* xhat, float* rstd, void* stream);
+int ekl_linear_bn_relu_bwd(const float* dh, const float* h, const float* xhat, const float* rstd, const float* gamma,
+                           const float* x, int B, int K, int N, float* dW, float* dbias, float* dgamma, float* dbeta,
+                           float* dy, void* stream);
 
 /* ---------------------------------------------------------------- capsule routing (generator stem) -----------
  * CapsuleLinear of COND_INIT_STAGE_G_withCap (model.py:245-267; third-party `capsule_layer`, un-vendored: parity is

@@ -117,3 +117,31 @@ def test_capsule_reduced_algebra_equals_materialised_priors():
         v = capsule_ref.squash(torch.einsum("olk,bok->bol", w, y))
         vsum = vsum + v
     np.testing.assert_allclose(v.numpy(), ref.numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_pyramid_restatement_equals_pil():
+    """oracle/pil_resample.py restates PIL's 8-bit BILINEAR resize + ToTensor/Normalize (datasets.py:43-68); pinned here
+    against the Pillow / torchvision of this image, bit for bit."""
+    Image = pytest.importorskip("PIL.Image")
+    from oracle import pil_resample as R
+    rng = np.random.default_rng(5)
+    for S, sizes in ((256, (64, 128, 256)), (128, (64, 128)), (76, (64, 76)), (100, (37, 100))):
+        img = rng.integers(0, 256, (S, S, 3), dtype=np.uint8)
+        img[: S // 4, : S // 3] = 255                       # saturated block: exercises the clip
+        img[S // 2:, S // 2:] //= 16
+        levels = R.pyramid(img, sizes)
+        for s, lv in zip(sizes, levels):
+            ref = np.asarray(Image.fromarray(img).resize((s, s), Image.BILINEAR)) if s != S else img
+            want = ((torch.from_numpy(ref.copy()).permute(2, 0, 1).float().div(255) - 0.5) / 0.5).numpy()
+            assert lv.shape == (3, s, s) and lv.dtype == np.float32
+            assert np.array_equal(lv, want), (S, s, np.abs(lv - want).max())
+
+
+def test_pyramid_host_tables_equal_restatement():
+    """the product's host-side coefficient tables (text2img_ekl_b200/datasets.py) are the oracle's, integer for integer."""
+    from oracle import pil_resample as R
+    from text2img_ekl_b200 import datasets as D
+    for a, b in ((256, 128), (256, 64), (128, 64), (76, 64), (100, 37), (64, 128), (299, 64)):
+        bo, ko = R.bilinear_coeffs(a, b)
+        bt, kt = D.pil_bilinear_tables(a, b)
+        assert np.array_equal(bo, bt.numpy()) and np.array_equal(ko, kt.numpy()), (a, b)

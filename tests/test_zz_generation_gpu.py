@@ -209,3 +209,24 @@ def test_conditioning_variants_match_oracle(variant):
     Linear stem."""
     import test_step_parity_gpu as P
     P.test_training_step_matches_oracle(variant, 4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S,sizes,B", [(256, (64, 128, 256), 5), (128, (64, 128), 3), (76, (64, 76), 2), (100, (37, 100), 2)])
+def test_image_pyramid_bit_exact_vs_pil_restatement(S, sizes, B):
+    """datasets.py:43-68: the device pyramid (ekl_img_pyramid_level) equals oracle/pil_resample.py bit for bit
+    (which tests/test_oracle_golden.py pins against PIL itself)."""
+    import numpy as np
+    from oracle import pil_resample as R
+    from text2img_ekl_b200 import datasets as D
+    rng = np.random.default_rng(S)
+    crops = rng.integers(0, 256, (B, S, S, 3), dtype=np.uint8)
+    crops[0, : S // 4, : S // 3] = 255
+    crops[1 % B, S // 2:] //= 16
+    got = D.image_pyramid(torch.from_numpy(crops).cuda(), list(sizes))
+    torch.cuda.synchronize()
+    for b in range(B):
+        want = R.pyramid(crops[b], sizes)
+        for lv, (g, w) in enumerate(zip(got, want)):
+            assert g.shape == (B, 3, sizes[lv], sizes[lv]) and g.dtype == torch.float32
+            assert np.array_equal(g[b].cpu().numpy(), w), (S, sizes[lv], b)

@@ -59,6 +59,7 @@ SIGNATURES = {
     "ekl_cat_code_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "ekl_img_s2d": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "ekl_img_s2d_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "ekl_img_pyramid_level": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "ekl_head_tanh_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "ekl_head_tanh_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "ekl_color_stats_fwd": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
@@ -68,6 +69,8 @@ SIGNATURES = {
     "ekl_dloss_fwd": (_i, [_i, _i, _i, _ip, _ip, _ip, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_reparam_kl_fwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "ekl_reparam_kl_bwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ekl_linear_bn_relu_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp]),
+    "ekl_linear_bn_relu_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_caps_supported": (_i, [_i, _i, _i, _i]),
     "ekl_caps_proj_u": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "ekl_caps_proj_s": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -9,6 +9,8 @@
 // Activations are bf16 [M rows][C channels] (NHWC flattened); rows are split into `groups` equal contiguous
 // groups with independent batch statistics (real / wrong / fake discriminator passes batched into one tensor;
 // reference: three separate netD(...) calls, cub_trainer_splitz_cap_ca.py:418-420).
+#include <stdlib.h>
+
 #include "ekl_common.cuh"
 
 namespace {
@@ -162,8 +164,8 @@ template <int ACT> struct ActVec { static constexpr int V = ACT == ACT_GLU ? 4 :
 // sums != null (training): statistics from the fp64 sums; mean_io / rstd_io [groups][Cy] are WRITTEN by chunk 0 of each
 // group (saved for the backward pass) and block row 0 applies one running-statistics momentum update per group, in
 // group order (one per reference forward call).  sums == null (inference): mean_io / rstd_io are inputs.
-template <int ACT>
-__global__ void __launch_bounds__(256, 3) bn_act_fwd_kernel(const bf16* __restrict__ y, int64_t M, int Cy, int groups,
+template <int ACT, int U>
+__global__ void __launch_bounds__(256, U == 2 ? 3 : 2) bn_act_fwd_kernel(const bf16* __restrict__ y, int64_t M, int Cy, int groups,
                                                             const double* __restrict__ sums, float eps, float momentum,
                                                             float* mean_io, float* rstd_io, float* running_mean,
                                                             float* running_var,
@@ -177,7 +179,6 @@ __global__ void __launch_bounds__(256, 3) bn_act_fwd_kernel(const bf16* __restri
   const int c0 = t.oct * VEC;
   // software pipeline: the loads of the next U rows are in flight while the current U rows are computed; the first
   // batch is issued before the per-channel coefficient loads so the block prologue overlaps the stream
-  constexpr int U = 2;
   typename IO::T ca[U], cb[U], cq[U], na[U], nb[U], nq[U];
   auto load = [&](typename IO::T* a, typename IO::T* b, typename IO::T* q, int64_t rb) {
 #pragma unroll
@@ -284,8 +285,8 @@ __device__ __forceinline__ void act_bwd(const float* ya, const float* yb, const 
 
 // ---------------------------------------------------------------- backward, pass 1: partial sums
 // S1 = sum dz, S2 = sum dz * xhat with xhat = y*rstd - mean*rstd (one FMA; coefficients rs / nmr)
-template <int ACT>
-__global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dout,
+template <int ACT, int U>
+__global__ void __launch_bounds__(256, U == 2 ? 3 : 2) bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dout,
                                                                    int64_t M, int Cy, int groups,
                                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -304,8 +305,7 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_kernel(const bf16* _
 #pragma unroll
     for (int i = 0; i < VEC; ++i) s1[h][i] = s2[h][i] = 0.f;
   if (t.active) {
-    constexpr int U = 2;                   // software pipeline, see bn_act_fwd_kernel
-    typename IO::T ca[U], cb[U], cd[U], na[U], nb[U], nd[U];
+    typename IO::T ca[U], cb[U], cd[U], na[U], nb[U], nd[U];      // software pipeline, see bn_act_fwd_kernel
     auto load = [&](typename IO::T* a, typename IO::T* b, typename IO::T* d, int64_t rb) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -378,8 +378,8 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_kernel(const bf16* _
 
 // ---------------------------------------------------------------- backward, pass 2: dy
 // dy = k*(dz - S1/n - xhat*S2/n), k = gamma*rstd  ==  k*dz + A*y + Bc  with  A = -k*rstd*S2/n,  Bc = -k*S1/n - A*mean
-template <int ACT>
-__global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dout,
+template <int ACT, int U>
+__global__ void __launch_bounds__(256, U == 2 ? 3 : 2) bn_act_bwd_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dout,
                                                                   int64_t M, int Cy, int groups,
                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -392,8 +392,7 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_kernel(const bf16* __
   if (!t.active) return;
   const int c0 = t.oct * VEC;
   const float inv_n = 1.f / (float)(M / groups);
-  constexpr int U = 2;                     // software pipeline, see bn_act_fwd_kernel
-  typename IO::T ca[U], cb[U], cd[U], na[U], nb[U], nd[U];
+  typename IO::T ca[U], cb[U], cd[U], na[U], nb[U], nd[U];        // software pipeline, see bn_act_fwd_kernel
   auto load = [&](typename IO::T* a, typename IO::T* b, typename IO::T* d, int64_t rb) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -760,6 +759,13 @@ extern "C" int ekl_col_stats(const void* y, int64_t M, int C, int groups, double
   return 0;
 }
 
+// rows in flight per thread of the streaming kernels: 2 (3 blocks / SM) or 4 (2 blocks / SM); EKL_BN_U selects (experiments)
+static int bn_u() {
+  static int u = 0;
+  if (u == 0) { const char* e = getenv("EKL_BN_U"); u = (e && e[0] == '4') ? 4 : 2; }
+  return u;
+}
+
 #define EKL_ACT_SWITCH(act, CALL)                       \
   switch (act) {                                        \
     case ACT_NONE: { constexpr int A = ACT_NONE; CALL; } break;   \
@@ -777,9 +783,15 @@ extern "C" int ekl_bn_act_fwd(const void* y, int64_t M, int Cy, int groups, cons
   EKL_REQUIRE(y != nullptr && out != nullptr && mean != nullptr && rstd != nullptr, "bn_act_fwd: null pointer argument");
   dim3 grid;
   grid_rows(M, Co / act_vec(act), groups, &grid);
-  EKL_ACT_SWITCH(act, (bn_act_fwd_kernel<A><<<grid, 256, 0, (cudaStream_t)stream>>>(
-                          (const bf16*)y, M, Cy, groups, sums, eps, momentum, mean, rstd, running_mean, running_var, gamma, beta,
-                          (const bf16*)residual, (bf16*)out)));
+  if (bn_u() == 4) {
+    EKL_ACT_SWITCH(act, (bn_act_fwd_kernel<A, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                            (const bf16*)y, M, Cy, groups, sums, eps, momentum, mean, rstd, running_mean, running_var, gamma, beta,
+                            (const bf16*)residual, (bf16*)out)));
+  } else {
+    EKL_ACT_SWITCH(act, (bn_act_fwd_kernel<A, 2><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                            (const bf16*)y, M, Cy, groups, sums, eps, momentum, mean, rstd, running_mean, running_var, gamma, beta,
+                            (const bf16*)residual, (bf16*)out)));
+  }
   EKL_LAUNCH_CHECK();
   return 0;
 }
@@ -802,11 +814,19 @@ extern "C" int ekl_bn_act_bwd(const void* y, const void* dout, int64_t M, int Cy
   EKL_REQUIRE(sums != nullptr, "bn_act_bwd: sums scratch required");
   dim3 grid;
   grid_rows(M, Co / act_vec(act), groups, &grid);
-  EKL_ACT_SWITCH(act, (bn_act_bwd_reduce_kernel<A><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M, Cy, groups,
-                                                                         mean, rstd, gamma, beta, sums)));
-  EKL_LAUNCH_CHECK();
-  EKL_ACT_SWITCH(act, (bn_act_bwd_apply_kernel<A><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M, Cy, groups,
-                                                                        mean, rstd, gamma, beta, sums, dgamma, dbeta, (bf16*)dy)));
+  if (bn_u() == 4) {
+    EKL_ACT_SWITCH(act, (bn_act_bwd_reduce_kernel<A, 4><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M, Cy, groups,
+                                                                              mean, rstd, gamma, beta, sums)));
+    EKL_LAUNCH_CHECK();
+    EKL_ACT_SWITCH(act, (bn_act_bwd_apply_kernel<A, 4><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M, Cy, groups,
+                                                                             mean, rstd, gamma, beta, sums, dgamma, dbeta, (bf16*)dy)));
+  } else {
+    EKL_ACT_SWITCH(act, (bn_act_bwd_reduce_kernel<A, 2><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M, Cy, groups,
+                                                                              mean, rstd, gamma, beta, sums)));
+    EKL_LAUNCH_CHECK();
+    EKL_ACT_SWITCH(act, (bn_act_bwd_apply_kernel<A, 2><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M, Cy, groups,
+                                                                             mean, rstd, gamma, beta, sums, dgamma, dbeta, (bf16*)dy)));
+  }
   EKL_LAUNCH_CHECK();
   return 0;
 }

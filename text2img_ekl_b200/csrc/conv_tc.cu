@@ -344,6 +344,276 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_tc_kernel(const __grid_const
   if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): the two CTAs of a 2-CTA cluster compute ONE 256-pixel x BN-channel tile.
+// Each CTA loads its own 128-pixel A patch and HALF of the filter tile (BN/2 rows); the leader CTA's MMA thread issues
+// M = 256 instructions that read A and B from both CTAs' shared memory and accumulate into both CTAs' TMEM (128 rows
+// each).  Per CTA and k-iteration that is A + B/2 instead of A + B bytes through the L2->SM port -- the bound of the
+// single-CTA kernel on every layer wider than the ridge (measured ~85-130 GB/s per SM) -- and half the shared-memory
+// reads of B per MMA.  Synchronisation: every TMA of the pair completes on the LEADER's full barrier; the MMA thread's
+// tcgen05.commit multicasts to both CTAs' empty / tmem_full barriers; the 2 x 128 epilogue threads release an
+// accumulator on the leader's tmem_empty barrier.  Everything else (schedule, epilogue variants, statistics, split-K)
+// is the single-CTA kernel's, with "M tile" = pair tile * 2 + CTA rank.
+template <int BN, int KC>
+struct Tc2Cfg {
+  static constexpr int A_BYTES = 128 * KC * 2;
+  static constexpr int B_BYTES = (BN / 2) * KC * 2;            // this CTA's half of the filter tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OUT_BYTES = 128 * BN * 2;
+  static constexpr int STAGES_RAW = (220 * 1024 - OUT_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = PIPE_BYTES + OUT_BYTES + 1024 + 512 + 4096;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr uint32_t LAYOUT = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);
+  static constexpr uint32_t SBO = 8 * KC * 2;
+  static constexpr int OBOX = BN < 64 ? BN : 64;
+  static constexpr int QUADS = BN / 4;
+  static constexpr int SLICES = 128 / QUADS;
+};
+
+template <int BN, int KC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) conv_gemm_tc2_kernel(const __grid_constant__ TcParams p) {
+  using C = Tc2Cfg<BN, KC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_out = smem + C::PIPE_BYTES;
+  uint64_t* full = (uint64_t*)(stage_out + C::OUT_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tmem_full = empty + C::STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]  (the leader's copies are the live ones)
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  float* red = (float*)(stage_out + C::OUT_BYTES + 512);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+  const int n_iters = p.ntaps * p.ncb;
+  const int rounds = p.nvar * p.ntn * p.groups * p.ksplit;
+  const int k_per = (n_iters + p.ksplit - 1) / p.ksplit;
+  const int ptg = (p.mtg + 1) >> 1;             // pair tiles per group
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 256); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                            // both CTAs' barriers are initialised before either is signalled remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto round_vng = [&](int r, int& v, int& n, int& g) { r /= p.ksplit; g = r % p.groups; int q = r / p.groups; n = q % p.ntn; v = q / p.ntn; };
+  auto k_range = [&](int r, int& it0, int& it1) { const int ks = r % p.ksplit; it0 = ks * k_per; it1 = (it0 + k_per) < n_iters ? (it0 + k_per) : n_iters; };
+  auto first_pair = [&](int r) { int rot = (int)(((long long)r * ptg) % npairs); int c = pair - rot; if (c < 0) c += npairs; return c; };
+  // this CTA's M tile of pair tile ploc; an odd tile count leaves the last pair's second CTA without one: it runs the same
+  // protocol on an out-of-range patch (TMA zero fill) and drops its result
+  auto tile_origin = [&](int g, int ploc, int& w0, int& h0, int& b0) {
+    const int mloc = 2 * ploc + rank;
+    if (mloc >= p.mtg) { w0 = 0; h0 = 0; b0 = p.mB + p.tb; return false; }
+    int mt = g * p.mtg + mloc;
+    const int twi = mt % p.nTw; mt /= p.nTw;
+    const int thi = mt % p.nTh; mt /= p.nTh;
+    w0 = twi * p.tw; h0 = thi * p.th; b0 = mt * p.tb;
+    return true;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&p.w_map);
+      const uint32_t tx = (uint32_t)(p.rows_valid * KC * 2 + C::B_BYTES);
+      uint32_t kit = 0;
+      for (int r = 0; r < rounds; ++r) {
+        int v, n, g, it0, it1;
+        round_vng(r, v, n, g);
+        k_range(r, it0, it1);
+        for (int ploc = first_pair(r); ploc < ptg; ploc += npairs) {
+          int w0, h0, b0;
+          tile_origin(g, ploc, w0, h0, b0);
+          for (int it = it0; it < it1; ++it, ++kit) {
+            const int s = kit % C::STAGES;
+            const uint32_t ph = (kit / C::STAGES) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            const int t = it / p.ncb, cb = it - t * p.ncb;
+            const EklTap tap = p.taps[v][t];
+            uint8_t* sa = smem + s * C::STAGE_BYTES;
+            if (rank == 0) mbar_expect_tx(&full[s], 2u * tx);            // both CTAs' bytes land on the leader's barrier
+            tma_load_4d_2sm(&p.a_maps[tap.map], &full[s], sa, cb * KC, w0 + tap.dw, h0 + tap.dh, b0);
+            if (p.b_mn) {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j)
+                tma_load_2d_2sm(&p.w_map, &full[s], sa + C::A_BYTES + j * (KC * 128),
+                                tap.src[0] * p.Nm + n * BN + (rank * (BN / 128) + j) * 64, cb * KC);
+            } else {
+              tma_load_2d_2sm(&p.w_map, &full[s], sa + C::A_BYTES, t * p.Cin + cb * KC, v * p.N + n * BN + rank * (BN / 2));
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+      constexpr uint32_t idesc_mn = umma_idesc_bf16(256, BN, 0, 1);
+      uint32_t kit = 0, tile = 0;
+      for (int r = 0; r < rounds; ++r) {
+        int it0, it1;
+        k_range(r, it0, it1);
+        for (int ploc = first_pair(r); ploc < ptg; ploc += npairs, ++tile) {
+          const uint32_t buf = tile & 1u, use = tile >> 1;
+          mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);        // both CTAs' epilogues have drained this accumulator
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + buf * BN;
+          for (int it = it0; it < it1; ++it, ++kit) {
+            const int s = kit % C::STAGES;
+            const uint32_t ph = (kit / C::STAGES) & 1u;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+              const uint64_t da0 = umma_desc(sa, 16, C::SBO, C::LAYOUT);
+              if (p.b_mn) {
+                const uint64_t db0 = umma_desc(sa + C::A_BYTES, KC * 128, 8 * 128, 2u);
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k)
+                  tc_mma2_bf16(tacc, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(128 * k), idesc_mn, (it != it0 || k != 0) ? 1u : 0u);
+              } else {
+                const uint64_t db0 = umma_desc(sa + C::A_BYTES, 16, C::SBO, C::LAYOUT);
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k)
+                  tc_mma2_bf16(tacc, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, (it != it0 || k != 0) ? 1u : 0u);
+              }
+              tc_commit2(&empty[s]);                             // both CTAs' stage s reusable once these MMAs retire
+              if (it == it1 - 1) tc_commit2(&tmem_full[buf]);    // accumulator complete in both CTAs
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue (warps 2..5 of BOTH CTAs): this CTA's 128 rows of the pair tile
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    const int quad = et % C::QUADS, slice = et / C::QUADS;
+    const uint32_t so = smem_u32(stage_out);
+    uint32_t tile = 0;
+    bool store_pending = false;
+    for (int r = 0; r < rounds; ++r) {
+      int v, n, g;
+      round_vng(r, v, n, g);
+      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+      bool any_valid = false;
+      for (int ploc = first_pair(r); ploc < ptg; ploc += npairs, ++tile) {
+        const uint32_t buf = tile & 1u, use = tile >> 1;
+        int w0, h0, b0;
+        const bool valid = tile_origin(g, ploc, w0, h0, b0);
+        mbar_wait(&tmem_full[buf], use & 1u);
+        tc_fence_after();
+        if (!valid) {                                            // no tile for this CTA: just release the accumulator
+          tc_fence_before();
+          mbar_arrive_leader(&tmem_empty[buf]);
+          continue;
+        }
+        any_valid = true;
+        if (store_pending && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+        const float* brow = nullptr;
+        if (p.bias9 != nullptr) {
+          const int wi = row % p.tw, hi = (row / p.tw) % p.th, bi = row / (p.tw * p.th);
+          const int hh = h0 + hi, ww = w0 + wi;
+          const int cls = (hh == 0 ? 0 : (hh == p.H - 1 ? 2 : 1)) * 3 + (ww == 0 ? 0 : (ww == p.W - 1 ? 2 : 1));
+          brow = p.bias9 + ((size_t)(b0 + bi) * 9 + cls) * p.N + n * BN;
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t rr[32];
+          tmem_ld32(tacc + (uint32_t)c0, rr);
+          tmem_ld_wait();
+          uint32_t pk[16];
+          if (brow != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(brow + c0 + i);
+              rr[i] = __float_as_uint(__uint_as_float(rr[i]) + bv.x); rr[i + 1] = __float_as_uint(__uint_as_float(rr[i + 1]) + bv.y);
+              rr[i + 2] = __float_as_uint(__uint_as_float(rr[i + 2]) + bv.z); rr[i + 3] = __float_as_uint(__uint_as_float(rr[i + 3]) + bv.w);
+            }
+          }
+          if (p.act != 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) rr[i] = __float_as_uint(epi_act(__uint_as_float(rr[i]), p.act));
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1]));
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128(so + stage_off<BN>(row, c0 + 8 * j), make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
+        }
+        tc_fence_before();
+        mbar_arrive_leader(&tmem_empty[buf]);
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+#pragma unroll
+          for (int j = 0; j < BN / C::OBOX; ++j)
+            tma_store_4d(&p.o_maps[v], stage_out + j * (128 * 128), n * BN + j * C::OBOX, w0, h0, b0);
+          tma_store_commit();
+        }
+        store_pending = true;
+        if (p.stats != nullptr) {
+          constexpr int RPS = 128 / C::SLICES;
+          const int r0 = slice * RPS;
+          const int r1 = (r0 + RPS) < p.rows_valid ? (r0 + RPS) : p.rows_valid;
+#pragma unroll 4
+          for (int rr = r0; rr < r1; ++rr) {
+            const uint2 u = lds64(so + stage_off<BN>(rr, 4 * quad));
+            const float x0 = bf16_lo(u.x), x1 = bf16_hi(u.x), x2 = bf16_lo(u.y), x3 = bf16_hi(u.y);
+            s1[0] += x0; s2[0] += x0 * x0; s1[1] += x1; s2[1] += x1 * x1;
+            s1[2] += x2; s2[2] += x2 * x2; s1[3] += x3; s2[3] += x3 * x3;
+          }
+        }
+      }
+      if (p.stats != nullptr && any_valid) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float* my = red + (size_t)slice * 2 * BN;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { my[4 * quad + i] = s1[i]; my[BN + 4 * quad + i] = s2[i]; }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        double* dst = p.stats + (size_t)g * 2 * p.N + n * BN;
+        for (int c = et; c < 2 * BN; c += 128) {
+          float acc = 0.f;
+#pragma unroll
+          for (int sl = 0; sl < C::SLICES; ++sl) acc += red[(size_t)sl * 2 * BN + c];
+          atomicAdd(dst + ((c < BN) ? c : (p.N + c - BN)), (double)acc);
+        }
+      }
+    }
+    if (store_pending && et == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();           // the leader's MMAs read the peer's shared memory: neither CTA leaves before both are done
+  if (warp == 1) tmem_dealloc2<C::TMEM_COLS>(tmem_base);
+}
+
+template <int BN, int KC>
+int launch_tc2(TcParams& p, int grid, cudaStream_t st) {
+  using C = Tc2Cfg<BN, KC>;
+  auto kern = conv_gemm_tc2_kernel<BN, KC>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EKL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  kern<<<grid, 192, C::SMEM_BYTES, st>>>(p);
+  EKL_LAUNCH_CHECK();
+  return 0;
+}
+
 int make_view_map(CUtensorMap* m, const EklView& v, int boxC, int tw, int th, int tb, int swz) {
   uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)v.dW, (uint64_t)v.dH, (uint64_t)v.dB};
   uint64_t strides[3] = {(uint64_t)v.sW * 2, (uint64_t)v.sH * 2, (uint64_t)v.sB * 2};
@@ -487,6 +757,13 @@ int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, double* stats, 
     if (ksplit == 1 && (v == 16 || v == 32 || v == 64 || v == 128 || v == 256) && g->N % v == 0) BN = v;
   }
   p.ntn = g->N / BN;
+  // CTA-pair kernel (conv_gemm_tc2_kernel): layers with enough tiles to keep 74 pairs busy, 64-channel K blocks, N tiles of
+  // >= 128 channels, no split-K.  EKL_TC2 = 0 never, 1 (default) by the rule above, 2 whenever the kernel can run at all.
+  static int tc2_mode = -1;
+  if (tc2_mode < 0) { const char* e = getenv("EKL_TC2"); tc2_mode = e ? atoi(e) : 1; }
+  const int sms = ekl_num_sms();
+  const int64_t work_tiles = (int64_t)mtiles * p.ntn * g->nvar;
+  const bool use2 = tc2_mode > 0 && KC == 64 && ksplit == 1 && BN >= 128 && sms % 2 == 0 && (tc2_mode >= 2 || work_tiles >= 2 * sms);
   for (int i = 0; i < g->n_a; ++i) {
     int rc = make_view_map(&p.a_maps[i], g->a[i], KC, tw, th, tb, swz);
     if (rc) return rc;
@@ -508,11 +785,15 @@ int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, double* stats, 
   } else {
     uint64_t dims[2] = {(uint64_t)g->ntaps * g->Cin, (uint64_t)g->nvar * g->N};
     uint64_t strides[1] = {(uint64_t)g->ntaps * g->Cin * 2};
-    uint32_t box[2] = {(uint32_t)KC, (uint32_t)BN};
+    uint32_t box[2] = {(uint32_t)KC, (uint32_t)(use2 ? BN / 2 : BN)};       // a CTA of a pair loads half of the filter tile
     int rc = ekl_make_tmap(&p.w_map, w_packed, 2, dims, strides, box, swz, 2);
     if (rc) return rc;
   }
-  const int grid = ekl_num_sms();     // persistent: one CTA per SM
+  const int grid = sms;     // persistent: one CTA per SM
+  if (use2) {
+    if (BN == 256) return launch_tc2<256, 64>(p, grid, st);
+    return launch_tc2<128, 64>(p, grid, st);
+  }
 #define EKL_TC_CASE(bn, kc) if (BN == bn && KC == kc) return launch_tc<bn, kc>(g, p, grid, st);
   EKL_TC_CASE(256, 64) EKL_TC_CASE(128, 64) EKL_TC_CASE(64, 64) EKL_TC_CASE(32, 64) EKL_TC_CASE(16, 64)
   EKL_TC_CASE(256, 32) EKL_TC_CASE(128, 32) EKL_TC_CASE(64, 32) EKL_TC_CASE(32, 32) EKL_TC_CASE(16, 32)

@@ -37,6 +37,24 @@ int ekl_make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* 
                   const uint32_t* box, int swizzle, int elem_bytes) {
   PFN_encodeTiled enc = get_encode();
   EKL_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  // The encode call is a DRIVER API call: unlike runtime calls it does not bind the device's primary context to the
+  // calling thread.  A thread whose first CUDA work is this library's (e.g. an autograd worker thread) gets it bound by
+  // one runtime call, once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    typedef CUresult (*PFN_ctxGetCurrent)(CUcontext*);
+    static PFN_ctxGetCurrent get_ctx = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+      void* p = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+        get_ctx = (PFN_ctxGetCurrent)p;
+    });
+    CUcontext cur = nullptr;
+    if (get_ctx == nullptr || get_ctx(&cur) != CUDA_SUCCESS || cur == nullptr) EKL_CHECK_CUDA(cudaFree(nullptr));
+    ctx_bound = true;
+  }
   cuuint64_t gd[5], gs[5];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }

@@ -258,3 +258,112 @@ extern "C" int ekl_img_s2d_bwd(const void* dxs, int B, int H, int W, float* dx, 
   EKL_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------- loader image pyramid (datasets.py:43-68 get_imgs)
+// The reference resizes the final-size uint8 crop to every lower stage size with PIL's BILINEAR resize
+// (transforms.Scale) and normalises each level (ToTensor + Normalize(0.5, 0.5)).  PIL's 8-bit resampler
+// (libImaging/Resample.c) is integer arithmetic: per output pixel a window [xmin, xmin+n) of fixed-point weights with
+// 22 fractional bits, accumulator started at 1 << 21, result clip8(acc >> 22); horizontal pass, then vertical pass on the
+// uint8 intermediate.  The weight tables are computed on the host exactly as PIL does (double arithmetic) and passed in,
+// so the kernels are bit-exact.  Layout: uint8 [B][S][S][3] (PIL's HWC) in, fp32 NCHW [-1, 1] out.
+namespace {
+
+constexpr int PIL_PRECISION_BITS = 22;
+
+// horizontal: src u8 [rows][S][3] -> dst u8 [rows][s][3]; one thread per (row, xx), 3 channels
+__global__ void __launch_bounds__(256) resample_h_kernel(const uint8_t* __restrict__ src, int64_t rows, int S, int s,
+                                                         const int* __restrict__ bounds, const int* __restrict__ kk, int ksize,
+                                                         uint8_t* __restrict__ dst) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < rows * s; i += (int64_t)gridDim.x * 256) {
+    const int64_t r = i / s;
+    const int xx = (int)(i - r * s);
+    const int xmin = bounds[2 * xx], n = bounds[2 * xx + 1];
+    const int* k = kk + (size_t)xx * ksize;
+    int a0 = 1 << (PIL_PRECISION_BITS - 1), a1 = a0, a2 = a0;
+    const uint8_t* p = src + (r * S + xmin) * 3;
+    for (int x = 0; x < n; ++x) {
+      const int w = k[x];
+      a0 += p[3 * x] * w; a1 += p[3 * x + 1] * w; a2 += p[3 * x + 2] * w;
+    }
+    uint8_t* o = dst + i * 3;
+    o[0] = (uint8_t)min(max(a0 >> PIL_PRECISION_BITS, 0), 255);
+    o[1] = (uint8_t)min(max(a1 >> PIL_PRECISION_BITS, 0), 255);
+    o[2] = (uint8_t)min(max(a2 >> PIL_PRECISION_BITS, 0), 255);
+  }
+}
+
+__device__ __forceinline__ float to_norm(int u) {          // ToTensor (u / 255) then Normalize ((x - 0.5) / 0.5), fp32 like torch
+  const float t = __fdiv_rn((float)u, 255.0f);
+  return __fdiv_rn(__fsub_rn(t, 0.5f), 0.5f);
+}
+
+// vertical + normalise: src u8 [B][S][s][3] -> dst fp32 [B][3][s][s]; one thread per (b, yy, xx)
+__global__ void __launch_bounds__(256) resample_v_norm_kernel(const uint8_t* __restrict__ src, int B, int S, int s,
+                                                              const int* __restrict__ bounds, const int* __restrict__ kk, int ksize,
+                                                              float* __restrict__ dst) {
+  const int64_t total = (int64_t)B * s * s;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int xx = (int)(i % s);
+    const int yy = (int)((i / s) % s);
+    const int b = (int)(i / ((int64_t)s * s));
+    const int ymin = bounds[2 * yy], n = bounds[2 * yy + 1];
+    const int* k = kk + (size_t)yy * ksize;
+    int a0 = 1 << (PIL_PRECISION_BITS - 1), a1 = a0, a2 = a0;
+    const uint8_t* p = src + (((int64_t)b * S + ymin) * s + xx) * 3;
+    for (int y = 0; y < n; ++y) {
+      const int w = k[y];
+      a0 += p[(int64_t)y * s * 3] * w; a1 += p[(int64_t)y * s * 3 + 1] * w; a2 += p[(int64_t)y * s * 3 + 2] * w;
+    }
+    const int64_t plane = (int64_t)s * s;
+    float* o = dst + (int64_t)b * 3 * plane + (int64_t)yy * s + xx;
+    o[0] = to_norm(min(max(a0 >> PIL_PRECISION_BITS, 0), 255));
+    o[plane] = to_norm(min(max(a1 >> PIL_PRECISION_BITS, 0), 255));
+    o[2 * plane] = to_norm(min(max(a2 >> PIL_PRECISION_BITS, 0), 255));
+  }
+}
+
+// the final-size level: uint8 HWC -> fp32 NCHW, normalised
+__global__ void __launch_bounds__(256) u8_norm_kernel(const uint8_t* __restrict__ src, int B, int S, float* __restrict__ dst) {
+  const int64_t plane = (int64_t)S * S, total = (int64_t)B * plane;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t b = i / plane, px = i - b * plane;
+    const uint8_t* p = src + i * 3;
+    float* o = dst + b * 3 * plane + px;
+    o[0] = to_norm(p[0]); o[plane] = to_norm(p[1]); o[2 * plane] = to_norm(p[2]);
+  }
+}
+
+}  // namespace
+
+// One pyramid level.  s == S: plain conversion (tmp / tables unused).  Otherwise bounds [s][2] (xmin, n) and kk [s][ksize]
+// are the PIL coefficient tables of the resize S -> s (device int32; the same tables serve both passes of a square
+// resize), tmp is caller scratch of B*S*s*3 bytes.
+extern "C" int ekl_img_pyramid_level(const void* src_u8, int B, int S, int s, const int* bounds, const int* kk, int ksize,
+                                     void* tmp_u8, float* out, void* stream) {
+  EKL_REQUIRE(src_u8 != nullptr && out != nullptr && B > 0 && S > 0 && s > 0, "img_pyramid_level: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s == S) {
+    int64_t total = (int64_t)B * S * S;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    u8_norm_kernel<<<blocks, 256, 0, st>>>((const uint8_t*)src_u8, B, S, out);
+    EKL_LAUNCH_CHECK();
+    return 0;
+  }
+  EKL_REQUIRE(bounds != nullptr && kk != nullptr && tmp_u8 != nullptr && ksize > 0, "img_pyramid_level: coefficient tables / scratch missing");
+  {
+    const int64_t rows = (int64_t)B * S, total = rows * s;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    resample_h_kernel<<<blocks, 256, 0, st>>>((const uint8_t*)src_u8, rows, S, s, bounds, kk, ksize, (uint8_t*)tmp_u8);
+    EKL_LAUNCH_CHECK();
+  }
+  {
+    const int64_t total = (int64_t)B * s * s;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    resample_v_norm_kernel<<<blocks, 256, 0, st>>>((const uint8_t*)tmp_u8, B, S, s, bounds, kk, ksize, out);
+    EKL_LAUNCH_CHECK();
+  }
+  return 0;
+}

@@ -15,6 +15,7 @@ import torch.optim as optim
 from . import model
 from . import ops
 from .engine import (KL_loss, StepEngine, ce_loss, compute_mean_covariance, onehot)  # noqa: F401  (reference names)
+from .datasets import stage_images
 from .miscc.config import cfg
 from .miscc.losslog import AsyncLossLog
 from .miscc.utils import mkdir_p
@@ -198,8 +199,8 @@ class condGANTrainer(object):
         imgs, w_imgs, t_embedding, cls, _ = data
         cls = cls.long() - 1
         dev = self.device
-        real_vimgs = [imgs[i].to(dev, non_blocking=True) for i in range(self.num_Ds)]
-        wrong_vimgs = [w_imgs[i].to(dev, non_blocking=True) for i in range(self.num_Ds)]
+        real_vimgs = stage_images(imgs, self.num_Ds, dev)       # fp32 pyramid as delivered, or uint8 crops -> device pyramid
+        wrong_vimgs = stage_images(w_imgs, self.num_Ds, dev)
         return imgs, real_vimgs, wrong_vimgs, t_embedding.to(dev, non_blocking=True), cls.to(dev, non_blocking=True)
 
     def onehot(self, cls_vec, n):

@@ -176,8 +176,13 @@ class VC_NET(nn.Module):
         self.fc32 = nn.Linear(256, self.manifd_dim)
 
     def encode(self, x):
-        h = F.relu(self.bn_fc1(self.fc1(x)))
-        h = F.relu(self.bn_fc2(self.fc2(h)))
+        if x.is_cuda and x.shape[0] <= 64:
+            # Linear + BatchNorm1d + ReLU as one kernel per layer and direction (ops.linear_bn_relu)
+            h = ops.linear_bn_relu(x, self.fc1, self.bn_fc1)
+            h = ops.linear_bn_relu(h, self.fc2, self.bn_fc2)
+        else:
+            h = F.relu(self.bn_fc1(self.fc1(x)))
+            h = F.relu(self.bn_fc2(self.fc2(h)))
         return self.fc31(h), self.fc32(h)
 
     def reparameterize(self, mu, logvar, seed):

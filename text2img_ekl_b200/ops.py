@@ -817,6 +817,70 @@ def reparam_kl(mu, logvar, eps):
     return _ReparamKL.apply(mu, logvar, eps)
 
 
+class _LinearBnRelu(torch.autograd.Function):
+    """h = ReLU(BatchNorm1d(x W^T + b)) in train mode over a batch of <= 64 rows (VC_NET's hidden layers, model.py:169-181;
+    include/ekl_b200.h: ekl_linear_bn_relu_fwd / _bwd).  Parameter gradients are accumulated in place."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var):
+        B, K = x.shape
+        N = weight.shape[0]
+        x = x.float().contiguous()
+        h = torch.empty(B, N, device=x.device)
+        xhat = torch.empty(B, N, device=x.device)
+        rstd = torch.empty(N, device=x.device)
+        L.check(L.lib().ekl_linear_bn_relu_fwd(L.ptr(x), L.ptr(weight), L.ptr(bias), L.ptr(gamma), L.ptr(beta), L.ptr(running_mean),
+                                               L.ptr(running_var), B, K, N, BN_EPS, BN_MOM, 1, L.ptr(h), L.ptr(xhat), L.ptr(rstd),
+                                               L.stream()))
+        _count()
+        ctx.save_for_backward(x, weight, bias, gamma, beta, h, xhat, rstd)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        x, weight, bias, gamma, beta, h, xhat, rstd = ctx.saved_tensors
+        B, K = x.shape
+        N = weight.shape[0]
+        dh = dh.float().contiguous()
+        dy = torch.empty(B, N, device=x.device)
+
+        def buf(p, need):
+            if not need or p is None:
+                return None, None
+            if p.is_leaf:
+                return _grad_buffer(p), None
+            t = torch.zeros_like(p)
+            return t, t
+        bw, rw = buf(weight, ctx.needs_input_grad[1])
+        bb, rb = buf(bias, ctx.needs_input_grad[2])
+        bg, rg = buf(gamma, ctx.needs_input_grad[3])
+        be, re_ = buf(beta, ctx.needs_input_grad[4])
+        L.check(L.lib().ekl_linear_bn_relu_bwd(L.ptr(dh), L.ptr(h), L.ptr(xhat), L.ptr(rstd), L.ptr(gamma), L.ptr(x), B, K, N, L.ptr(bw),
+                                               L.ptr(bb), L.ptr(bg), L.ptr(be), L.ptr(dy), L.stream()))
+        _count()
+        dx = dy @ weight if ctx.needs_input_grad[0] else None        # one library GEMM, only where the input needs it
+        return dx, rw, rb, rg, re_, None, None
+
+
+def linear_bn_relu(x, linear, bn):
+    """linear: nn.Linear, bn: nn.BatchNorm1d (state_dict-compatible holders of the parameters / running statistics)."""
+    if not bn.training:
+        B, K = x.shape
+        N = linear.weight.shape[0]
+        x = x.float().contiguous()
+        h = torch.empty(B, N, device=x.device)
+        L.check(L.lib().ekl_linear_bn_relu_fwd(L.ptr(x), L.ptr(linear.weight), L.ptr(linear.bias), L.ptr(bn.weight), L.ptr(bn.bias),
+                                               L.ptr(bn.running_mean), L.ptr(bn.running_var), B, K, N, bn.eps, BN_MOM, 0, L.ptr(h), None,
+                                               None, L.stream()))
+        _count()
+        return h
+    if getattr(bn, "_ekl_counted", False):
+        bn._ekl_calls += 1
+    elif bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return _LinearBnRelu.apply(x, linear.weight, linear.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+
+
 class _ColorStats(torch.autograd.Function):
     """Per-image channel mean [B,3,1,1] and covariance [B,3,3] of an fp32 NCHW image batch (cub:33-52
     compute_mean_covariance; include/ekl_b200.h: ekl_color_stats_fwd / _bwd): one read of the images forward, one read +

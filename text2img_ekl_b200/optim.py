@@ -11,8 +11,8 @@ from . import _lib as L
 from . import ops
 
 
-def _pad4(n):
-    return (n + 3) // 4 * 4
+def _pad8(n):
+    return (n + 7) // 8 * 8
 
 
 class FlatAdam(torch.optim.Optimizer):
@@ -21,11 +21,12 @@ class FlatAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self.plist = params
         dev = params[0].device
-        # every parameter starts at a multiple of 4 elements: 16-byte aligned fp32 views, 8-byte aligned bf16 shadows
+        # every parameter starts at a multiple of 8 elements: 32-byte aligned fp32 views and 16-byte aligned bf16 shadows
+        # (a shadow slice is handed to TMA as a packed filter operand: tensor maps need 16-byte aligned bases)
         self.offsets, off = [], 0
         for p in params:
             self.offsets.append(off)
-            off += _pad4(p.numel())
+            off += _pad8(p.numel())
         self.n = off
         self.flat_p = torch.zeros(self.n, device=dev, dtype=torch.float32)
         self.shadow = torch.zeros(self.n, device=dev, dtype=torch.bfloat16)

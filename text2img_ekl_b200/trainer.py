@@ -8,6 +8,7 @@ from . import cub_trainer_splitz_cap_ca as _cub
 from . import model
 from .cub_trainer_splitz_cap_ca import (KL_loss, ce_loss, compute_mean_covariance, copy_G_params, define_optimizers,  # noqa: F401
                                         load_params, weights_init)
+from .datasets import stage_images
 from .miscc.config import cfg
 
 
@@ -41,8 +42,8 @@ class condGANTrainer(_cub.condGANTrainer):
         if self.CLS_KIND == "index":
             cls = cls.long() - 1
         dev = self.device
-        real_vimgs = [imgs[i].to(dev, non_blocking=True) for i in range(self.num_Ds)]
-        wrong_vimgs = [w_imgs[i].to(dev, non_blocking=True) for i in range(self.num_Ds)]
+        real_vimgs = stage_images(imgs, self.num_Ds, dev)       # fp32 pyramid as delivered, or uint8 crops -> device pyramid
+        wrong_vimgs = stage_images(w_imgs, self.num_Ds, dev)
         return imgs, real_vimgs, wrong_vimgs, t_embedding.to(dev, non_blocking=True), cls.to(dev, non_blocking=True)
 
     def setup(self):

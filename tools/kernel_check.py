@@ -20,7 +20,7 @@ SHAPES = {  # mode -> list of (B, H, W, Cin, Cout)
     1: [(4, 4, 4, 128, 128), (2, 8, 8, 64, 64), (3, 16, 16, 64, 128), (2, 32, 32, 32, 32), (2, 4, 4, 256, 512)],
     2: [(4, 16, 16, 64, 128), (2, 8, 8, 128, 256), (3, 32, 32, 64, 64), (2, 8, 8, 512, 1024), (2, 64, 64, 32, 64)],
 }
-GROUPS = ["tc_fwd", "tc_dgrad", "tc_wgrad", "simt_fwd", "simt_dgrad", "simt_wgrad", "bn", "misc", "heads", "tc_split", "fold"]
+GROUPS = ["tc_fwd", "tc_dgrad", "tc_wgrad", "simt_fwd", "simt_dgrad", "simt_wgrad", "bn", "misc", "heads", "tc_split", "fold", "vc"]
 
 
 def run_group(group):
@@ -46,6 +46,8 @@ def run_group(group):
         return run_split(torch, L, lib, dev, rel)
     if group == "fold":
         return run_fold(torch, L, lib, dev, rel)
+    if group == "vc":
+        return run_vc(torch, L, lib, dev, rel)
     impl = L.IMPL_TC if group.startswith("tc") else L.IMPL_SIMT
     what = group.split("_")[1]
     for mode, shapes in SHAPES.items():
@@ -391,6 +393,41 @@ def run_misc(torch, L, lib, dev, rel):
         want = torch.where(o.float() > 0, d.float(), 0.2 * d.float()).bfloat16()
         ok = bool((dx == want).all())
         print("%s lrelu_bwd n%d" % ("PASS" if ok else "FAIL", n), flush=True)
+        nfail += 0 if ok else 1
+    return nfail
+
+
+def run_vc(torch, L, lib, dev, rel):
+    """ekl_linear_bn_relu_fwd / _bwd (VC_NET hidden layers) against F.linear + batch_norm + relu in fp32, train and eval."""
+    import torch.nn.functional as F
+    from text2img_ekl_b200 import ops
+    nfail = 0
+    for (B, K, N) in [(24, 1325, 512), (24, 512, 256), (32, 228, 512), (64, 1215, 512), (64, 512, 256), (4, 300, 512), (33, 100, 64)]:
+        lin, bn = torch.nn.Linear(K, N).to(dev), torch.nn.BatchNorm1d(N).to(dev)
+        with torch.no_grad():
+            bn.weight.normal_(1.0, 0.1); bn.bias.normal_(0, 0.1)
+        lin_r, bn_r = torch.nn.Linear(K, N).to(dev), torch.nn.BatchNorm1d(N).to(dev)
+        lin_r.load_state_dict(lin.state_dict()); bn_r.load_state_dict(bn.state_dict())
+        x = torch.randn(B, K, device=dev, requires_grad=True)
+        xr = x.detach().clone().requires_grad_(True)
+        dh = torch.randn(B, N, device=dev)
+        h = ops.linear_bn_relu(x, lin, bn)
+        h.backward(dh)
+        saved = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        hr = F.relu(bn_r(lin_r(xr)))
+        hr.backward(dh)
+        torch.backends.cuda.matmul.allow_tf32 = saved
+        bn.eval(); bn_r.eval()
+        with torch.no_grad():
+            he, her = ops.linear_bn_relu(x.detach(), lin, bn), F.relu(bn_r(lin_r(xr.detach())))
+        torch.cuda.synchronize()
+        errs = dict(h=rel(h, hr), dx=rel(x.grad, xr.grad), dW=rel(lin.weight.grad, lin_r.weight.grad),
+                    dgamma=rel(bn.weight.grad, bn_r.weight.grad), dbeta=rel(bn.bias.grad, bn_r.bias.grad),
+                    rmean=rel(bn.running_mean, bn_r.running_mean), rvar=rel(bn.running_var, bn_r.running_var), eval=rel(he, her),
+                    count=abs(int(bn.num_batches_tracked) - int(bn_r.num_batches_tracked)))
+        ok = all(v < 2e-4 for v in errs.values())
+        print("%s linear_bn_relu B%d K%d N%d %s" % ("PASS" if ok else "FAIL", B, K, N, " ".join("%s %.1e" % kv for kv in errs.items())), flush=True)
         nfail += 0 if ok else 1
     return nfail
 

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--only", default="")
+    ap.add_argument("--json", default="")
     a = ap.parse_args()
     import torch
     from bench import DEFAULT_BATCH
@@ -119,6 +120,9 @@ def main():
             del y, dout, res, out, dy
     rows.sort(key=lambda r: -r[0])
     tot = sum(r[0] for r in rows)
+    if a.json:
+        import json
+        json.dump([[name, n, t] for tt, name, n, t, rate in rows], open(a.json, "w"))
     print("config %s B=%d: isolated kernel time weighted by calls/step = %.2f ms" % (a.config, B, tot / 1e3))
     print("%-44s %3s %9s %9s  %s" % ("call", "n", "us each", "us/step", "rate"))
     for tt, name, n, t, rate in rows:
