@@ -235,6 +235,18 @@ int ekl_caps_agree_fwd(const float* x, const float* u, int B, int I, int O, int 
 int ekl_caps_agree_bwd(const float* x, const float* u, const float* M, const float* Z, const float* gy, int B, int I, int O,
                        int K, float* gu, float* gx, void* stream);
 
+/* ---------------------------------------------------------------- capsule routing (discriminator class head) --
+ * CapsuleLinear of JOINT_D_NET64/128.fc_ac_cap (model.py:943,967-971,1082: 201 out-capsules of length 16 on the 16
+ * positions x 512 channels of the trunk output; parity against oracle/capsule_ref.py like the generator stem).
+ * prior [B][I=16][O][L=16] fp32 = x[B*16, 512] W^T (one library GEMM; it IS small here) -> three routing iterations in
+ * one kernel: v [B][O][16] (nullable) and norms [B][O] = |v| (nullable; model.py:969-970 takes .norm(dim=-1)).
+ * The backward recomputes the routing on chip: g_v [B][O][16] and / or g_norm [B][O] -> g_prior (same layout as prior).
+ * Supported: I == 16, L == 16, iters == 3, O <= 224 (ekl_caps_route_supported). */
+int ekl_caps_route_supported(int I, int O, int L, int iters);
+int ekl_caps_route_fwd(const float* prior, int B, int I, int O, int L, int iters, float* v, float* norms, void* stream);
+int ekl_caps_route_bwd(const float* prior, const float* g_v, const float* g_norm, int B, int I, int O, int L, int iters,
+                       float* g_prior, void* stream);
+
 /* ---------------------------------------------------------------- optimiser ---------------------------------
  * torch.optim.Adam as define_optimizers configures it (cub_trainer_splitz_cap_ca.py:199-215: lr 2e-4, betas (0.5, 0.999),
  * eps 1e-8, no weight decay) over a network's flat fp32 parameter / gradient / moment buffers (n % 4 == 0, 16-byte
@@ -249,6 +261,13 @@ int ekl_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf1
 int ekl_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 int ekl_adam_step_g16(float* p, const void* g_bf16, float* m, float* v, void* shadow_bf16, int64_t n, float* state, float lr,
                       float beta1, float beta2, float eps, void* stream);
+/* The same update in pieces, so that the optimiser step overlaps the backward pass (the deepest layers' gradients are
+ * final first and hold most of a discriminator's parameters): ekl_adam_tick advances the step count and the bias
+ * corrections once, ekl_adam_apply then updates any 16-byte aligned slice of the flat buffers, n % 4 == 0, without touching
+ * the count.  g_is_bf16: the gradient slice is bf16 (8-byte aligned). */
+int ekl_adam_tick(float* state, float beta1, float beta2, void* stream);
+int ekl_adam_apply(float* p, const void* g, int g_is_bf16, float* m, float* v, void* shadow_bf16, int64_t n, const float* state,
+                   float lr, float beta1, float beta2, float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -230,3 +230,35 @@ def test_image_pyramid_bit_exact_vs_pil_restatement(S, sizes, B):
         for lv, (g, w) in enumerate(zip(got, want)):
             assert g.shape == (B, 3, sizes[lv], sizes[lv]) and g.dtype == torch.float32
             assert np.array_equal(g[b].cpu().numpy(), w), (S, sizes[lv], b)
+
+
+@pytest.mark.gpu
+def test_adam_in_pieces_is_bit_identical_to_one_step():
+    """optim.FlatAdam.tick + apply_slice over any partition of the flat buffer == step() (engine.TailUpdate relies on it),
+    for fp32 and bf16 gradient buffers; the step count advances once."""
+    from text2img_ekl_b200.optim import FlatAdam
+    torch.manual_seed(3)
+    shapes = [(64, 3, 4, 4), (128, 64, 4, 4), (128,), (201, 16, 512), (7,), (512, 640, 3, 3)]
+
+    def make():
+        torch.manual_seed(4)
+        ps = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+        opt = FlatAdam(ps, lr=2e-4, betas=(0.5, 0.999))
+        opt.make_flat_grads()
+        return ps, opt
+
+    (pa, oa), (pb, ob) = make(), make()
+    for it in range(3):
+        g = torch.randn(oa.n, device="cuda") * 0.1
+        oa.flat_g.copy_(g); ob.flat_g.copy_(g)
+        g16 = g.bfloat16() if it == 2 else None
+        oa.step(grads_bf16=g16)
+        ob.tick()
+        cuts = [0, ob.offsets[2], ob.offsets[4], ob.n]
+        for lo, hi in reversed(list(zip(cuts[:-1], cuts[1:]))):       # tail first, as the backward pass delivers them
+            ob.apply_slice(lo, hi, g16)
+        ob.finish_step()
+    torch.cuda.synchronize()
+    assert float(oa.state_dev[0]) == float(ob.state_dev[0]) == 3.0
+    for name in ("flat_p", "exp_avg", "exp_avg_sq", "shadow"):
+        assert torch.equal(getattr(oa, name), getattr(ob, name)), name

@@ -78,8 +78,13 @@ SIGNATURES = {
     "ekl_caps_outer": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "ekl_caps_agree_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ekl_caps_agree_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "ekl_caps_route_supported": (_i, [_i, _i, _i, _i]),
+    "ekl_caps_route_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "ekl_caps_route_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "ekl_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _vp]),
     "ekl_adam_step_g16": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _vp]),
+    "ekl_adam_tick": (_i, [_vp, _f, _f, _vp]),
+    "ekl_adam_apply": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _vp]),
     "ekl_cast_bf16": (_i, [_vp, _vp, _i64, _vp]),
     "ekl_dloss_bwd": (_i, [_i, _i, _i, _ip, _ip, _ip, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

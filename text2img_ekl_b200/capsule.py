@@ -8,8 +8,10 @@ Shared-weight mode only (what the reference uses): weight [out_capsules, out_len
 
 The [B, O, I, L] prior tensor (201 MB at B=32 for the generator stem) is never formed.  On the GPU the
 small-in_length case (the generator stem, in_length 8) runs on the capsule kernels of csrc/capsule.cu (agreement
-logits / softmax over out-capsules kept on chip); the wide case (the discriminator class head, in_length 512) runs the
-same reduced algebra as cuBLAS GEMMs through torch.einsum.  Because
+logits / softmax over out-capsules kept on chip).  The wide case (the discriminator class head: in_length 512, 16
+in-capsules, 201 out-capsules of length 16) is the opposite regime -- there the prior is small (206 KB per sample) -- so
+it is one library GEMM for the prior and ONE routing kernel per direction (csrc/capsule_route.cu); other shapes run the
+reduced algebra below as GEMMs through torch.einsum.  Because
 prior[b,o,i,:] = W[o] x[b,i], every routing quantity lives in in_length space:
     logit[b,o,i] = <x[b,i], u[b,o]>,  u[b,o] = W[o]^T (sum of earlier v[b,o])
     s[b,o]       = W[o] y[b,o],       y[b,o] = sum_i softmax_o(logit)[b,o,i] x[b,i]
@@ -128,6 +130,50 @@ class _Agree(torch.autograd.Function):
         return gx, gu
 
 
+class _Route(torch.autograd.Function):
+    """prior [B,I,O,L] -> (v [B,O,L], |v| [B,O]): the whole routing in one kernel per direction (csrc/capsule_route.cu;
+    the discriminator class head, where in_length is wide and the prior small)."""
+
+    @staticmethod
+    def forward(ctx, prior, iters):
+        L, lib = _k()
+        B, I, O, Lh = prior.shape
+        prior = prior.contiguous()
+        v = torch.empty(B, O, Lh, device=prior.device)
+        n = torch.empty(B, O, device=prior.device)
+        L.check(lib.ekl_caps_route_fwd(L.ptr(prior), B, I, O, Lh, iters, L.ptr(v), L.ptr(n), L.stream()))
+        _count()
+        ctx.save_for_backward(prior)
+        ctx.iters = iters
+        return v, n
+
+    @staticmethod
+    def backward(ctx, gv, gn):
+        L, lib = _k()
+        prior, = ctx.saved_tensors
+        B, I, O, Lh = prior.shape
+        gp = torch.empty_like(prior)
+        gv = gv.contiguous() if gv is not None else None
+        gn = gn.contiguous() if gn is not None else None
+        L.check(lib.ekl_caps_route_bwd(L.ptr(prior), L.ptr(gv) if gv is not None else None, L.ptr(gn) if gn is not None else None,
+                                       B, I, O, Lh, ctx.iters, L.ptr(gp), L.stream()))
+        _count()
+        return gp, None
+
+
+def _route_wide(x, weight, num_iterations):
+    """(v, |v|) through the materialised-prior kernels, or None when the shape is outside their regime."""
+    if not (x.is_cuda and weight.dtype == torch.float32):
+        return None
+    B, I, K = x.shape
+    O, Lh = weight.shape[0], weight.shape[1]
+    L, lib = _k()
+    if K < 64 or not lib.ekl_caps_route_supported(I, O, Lh, num_iterations):
+        return None
+    prior = torch.matmul(x.reshape(B * I, K), weight.reshape(O * Lh, K).t()).view(B, I, O, Lh)
+    return _Route.apply(prior, num_iterations)
+
+
 def _dynamic_routing_cuda(x, weight, num_iterations):
     B, I, K = x.shape
     O = weight.shape[0]
@@ -147,6 +193,9 @@ def capsule_linear(x, weight, routing_type="dynamic", num_iterations=3):
         L, lib = _k()
         if lib.ekl_caps_supported(x.shape[1], x.shape[2], O, weight.shape[1]):
             return _dynamic_routing_cuda(x, weight, num_iterations)
+        routed = _route_wide(x, weight, num_iterations)
+        if routed is not None:
+            return routed[0]
     if routing_type == "dynamic":
         vsum = x.new_zeros(B, O, weight.shape[1])
         v = None
@@ -189,6 +238,14 @@ class CapsuleLinear(nn.Module):
 
     def forward(self, input):
         return capsule_linear(input, self.weight, self.routing_type, self.num_iterations)
+
+    def forward_norm(self, input):
+        """forward(input).norm(dim=-1) (model.py:969-970), the norm fused into the routing kernel where that runs."""
+        if self.routing_type == "dynamic" and input.is_cuda:
+            routed = _route_wide(input.float(), self.weight, self.num_iterations)
+            if routed is not None:
+                return routed[1]
+        return self.forward(input).norm(dim=-1)
 
     def extra_repr(self):
         return "out_capsules=%d, in_length=%d, out_length=%d, routing=%s x%d" % (

@@ -54,10 +54,14 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict
 }
 
 int adam_launch(float* p, const void* g, int g_bf16, float* m, float* v, void* shadow_bf16, int64_t n, float* state, float lr,
-                float beta1, float beta2, float eps, cudaStream_t st) {
+                float beta1, float beta2, float eps, cudaStream_t st, bool tick) {
   EKL_REQUIRE(n % 4 == 0 && n > 0, "adam_step: n %% 4");
-  adam_tick_kernel<<<1, 1, 0, st>>>(state, beta1, beta2);
-  EKL_LAUNCH_CHECK();
+  EKL_REQUIRE((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v) & 15) == 0 && ((uintptr_t)g & (g_bf16 ? 7 : 15)) == 0 &&
+                  ((uintptr_t)shadow_bf16 & 7) == 0, "adam_step: buffers must be 16-byte aligned (bf16 buffers: 8)");
+  if (tick) {
+    adam_tick_kernel<<<1, 1, 0, st>>>(state, beta1, beta2);
+    EKL_LAUNCH_CHECK();
+  }
   int64_t blocks = (n / 4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (g_bf16)
@@ -76,14 +80,29 @@ int adam_launch(float* p, const void* g, int g_bf16, float* m, float* v, void* s
 // zero-initialised by the caller; every call advances the step (device side, so the call is CUDA-graph capturable).
 extern "C" int ekl_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float* state,
                              float lr, float beta1, float beta2, float eps, void* stream) {
-  return adam_launch(p, g, 0, m, v, shadow_bf16, n, state, lr, beta1, beta2, eps, (cudaStream_t)stream);
+  return adam_launch(p, g, 0, m, v, shadow_bf16, n, state, lr, beta1, beta2, eps, (cudaStream_t)stream, true);
 }
 
 // Same update with the gradient read from a bf16 buffer: the data-parallel path all-reduces gradients as bf16 (half the
 // NVLink bytes of the reference's fp32 DataParallel reduce) and the optimiser consumes that staging buffer directly.
 extern "C" int ekl_adam_step_g16(float* p, const void* g_bf16, float* m, float* v, void* shadow_bf16, int64_t n, float* state,
                                  float lr, float beta1, float beta2, float eps, void* stream) {
-  return adam_launch(p, g_bf16, 1, m, v, shadow_bf16, n, state, lr, beta1, beta2, eps, (cudaStream_t)stream);
+  return adam_launch(p, g_bf16, 1, m, v, shadow_bf16, n, state, lr, beta1, beta2, eps, (cudaStream_t)stream, true);
+}
+
+// The same update in pieces, for an optimiser step that overlaps the backward pass: ekl_adam_tick advances the step count
+// (and both bias corrections) ONCE, then ekl_adam_apply updates any slice [p, p + n) of the flat buffers -- as soon as that
+// slice's gradients are final -- without touching the count.  g_is_bf16: the gradient slice is bf16 (all-reduce staging).
+extern "C" int ekl_adam_tick(float* state, float beta1, float beta2, void* stream) {
+  EKL_REQUIRE(state != nullptr, "adam_tick: null state");
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, beta1, beta2);
+  EKL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ekl_adam_apply(float* p, const void* g, int g_is_bf16, float* m, float* v, void* shadow_bf16, int64_t n,
+                              const float* state, float lr, float beta1, float beta2, float eps, void* stream) {
+  return adam_launch(p, g, g_is_bf16, m, v, shadow_bf16, n, const_cast<float*>(state), lr, beta1, beta2, eps, (cudaStream_t)stream, false);
 }
 
 // dst[i] = bf16(src[i]), n % 4 == 0, both 16 / 8-byte aligned: gradient slice -> NVLink payload

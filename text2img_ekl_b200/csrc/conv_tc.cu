@@ -757,13 +757,14 @@ int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, double* stats, 
     if (ksplit == 1 && (v == 16 || v == 32 || v == 64 || v == 128 || v == 256) && g->N % v == 0) BN = v;
   }
   p.ntn = g->N / BN;
-  // CTA-pair kernel (conv_gemm_tc2_kernel): layers with enough tiles to keep 74 pairs busy, 64-channel K blocks, N tiles of
-  // >= 128 channels, no split-K.  EKL_TC2 = 0 never, 1 (default) by the rule above, 2 whenever the kernel can run at all.
+  // CTA-pair kernel (conv_gemm_tc2_kernel): 64-channel K blocks, N tiles of >= 128 channels, no split-K, and at least 12
+  // M tiles per (group, variant).  The threshold is measured (profiles/r02_summary.md, per-layer A/B on config 2): layers
+  // with >= 12 M tiles gain 6-14 %, the weight-dominated layers below it (3-9 M tiles) lose 40-70 %.
+  // EKL_TC2 = 0 never, 1 (default) by the rule above, 2 whenever the kernel can run at all.
   static int tc2_mode = -1;
   if (tc2_mode < 0) { const char* e = getenv("EKL_TC2"); tc2_mode = e ? atoi(e) : 1; }
   const int sms = ekl_num_sms();
-  const int64_t work_tiles = (int64_t)mtiles * p.ntn * g->nvar;
-  const bool use2 = tc2_mode > 0 && KC == 64 && ksplit == 1 && BN >= 128 && sms % 2 == 0 && (tc2_mode >= 2 || work_tiles >= 2 * sms);
+  const bool use2 = tc2_mode > 0 && KC == 64 && ksplit == 1 && BN >= 128 && sms % 2 == 0 && (tc2_mode >= 2 || p.mtg >= 12);
   for (int i = 0; i < g->n_a; ++i) {
     int rc = make_view_map(&p.a_maps[i], g->a[i], KC, tw, th, tb, swz);
     if (rc) return rc;

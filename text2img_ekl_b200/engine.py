@@ -101,6 +101,71 @@ class FlatGrads:
         self.flat.zero_()
 
 
+class TailUpdate:
+    """Optimiser step of ONE discriminator overlapped with its own backward pass.
+
+    The parameters sit in the flat buffers in registration = forward order, so the deepest layers -- whose gradients
+    backward produces first and which hold most of the weights (JOINT_D_NET256: the 1024->2048 4x4 and 2048->1024 3x3
+    filters are 52 M of 73 M parameters) -- form the tail.  The network's forward marks block boundaries
+    (ops.grad_mark); when the gradient of a marked activation arrives every parameter registered after that block is
+    final (and the backward no longer reads those filters), so the Adam update of that slice runs on a side stream while
+    the main stream continues the backward through the high-resolution layers.  finish() updates the remaining head slice
+    and joins.  Adam is element-wise: the pieces give bit-identical results to one full step.
+
+    With several ranks the slices are the gradient reducer's (parallel.GradReducer): each slice is updated on the
+    reducer's side stream right behind its all-reduce."""
+
+    MIN_ELEMS = 1 << 20
+
+    def __init__(self, opt, net, grads, reducer=None):
+        self.opt, self.red, self.total = opt, reducer, opt.n
+        self.side = torch.cuda.Stream() if reducer is None else None
+        self.end_of = {}
+        end_of_param = {id(p): o + (p.numel() + 7) // 8 * 8 for p, o in zip(grads.params, grads.offsets)}
+        for m in net.modules():
+            ends = [end_of_param[id(p)] for p in m.parameters() if id(p) in end_of_param]
+            if ends:
+                self.end_of[id(m)] = min(max(ends), self.total)
+        self.active, self.lo = False, self.total
+        if reducer is not None:
+            reducer.after_slice = self._after_reduced
+
+    def begin(self):
+        """Right before backward of the discriminator's own update (marks fired at any other time are ignored)."""
+        self.opt.tick()
+        self.active, self.lo, self.forked = True, self.total, False
+        if self.red is not None:
+            self.red.begin()
+
+    def _after_reduced(self, lo, hi):
+        # on the reducer's side stream, behind the all-reduce of [lo, hi)
+        self.opt.apply_slice(lo, hi, self.red.stage)
+
+    def on_mark(self, after_module):
+        if not self.active:
+            return
+        if self.red is not None:
+            return self.red.on_mark(after_module)
+        lo = self.end_of.get(id(after_module))
+        if lo is None or self.lo - lo < self.MIN_ELEMS:
+            return
+        self.side.wait_stream(torch.cuda.current_stream())      # the slice's gradients are complete on the issuing stream
+        with torch.cuda.stream(self.side):
+            self.opt.apply_slice(lo, self.lo)
+        self.lo, self.forked = lo, True
+
+    def finish(self):
+        self.active = False
+        if self.red is not None:
+            self.red.finish()               # sends the head slice (updated behind its all-reduce) and joins the side stream
+        else:
+            self.opt.apply_slice(0, self.lo)
+            if self.forked:
+                torch.cuda.current_stream().wait_stream(self.side)
+            self.lo = 0
+        self.opt.finish_step()
+
+
 class BnCounters:
     """nn.BatchNorm's num_batches_tracked bookkeeping (one += per forward call in the reference) for a whole network
     as ONE kernel per step: every counter becomes a 0-dim view into one int64 tensor (state_dict keys / values are
@@ -148,8 +213,13 @@ class StepEngine:
         dp = parallel.world()[1] > 1 if data_parallel is None else data_parallel
         self.redG = parallel.make_reducer(self.gradsG.flat) if dp else None
         self.redD = [parallel.make_reducer(g.flat, d, g.params, g.offsets) if dp else None for d, g in zip(netsD, self.gradsD)]
-        for d, r in zip(netsD, self.redD):
-            if r is not None:
+        # the discriminators' optimiser steps overlap their backward passes (EKL_TAIL_ADAM=0: one Adam launch after it)
+        tail = os.environ.get("EKL_TAIL_ADAM", "1") != "0" and all(hasattr(o, "apply_slice") and o.flat_p.is_cuda for o in optimizersD)
+        self.tailD = [TailUpdate(o, d, g, r) if tail else None for o, d, g, r in zip(optimizersD, netsD, self.gradsD, self.redD)]
+        for d, r, t in zip(netsD, self.redD, self.tailD):
+            if t is not None:
+                ops.GRAD_MARKS[id(d)] = t.on_mark
+            elif r is not None:
                 ops.GRAD_MARKS[id(d)] = r.on_mark
         self.bn_counters = BnCounters([netG] + list(netsD))
         # EKL_PARALLEL_D=0 runs the discriminators one after the other on the caller's stream
@@ -176,11 +246,21 @@ class StepEngine:
         else:
             opt.step()
 
+    def _d_begin(self, idx):
+        """Arms the overlap machinery of discriminator idx right before its backward."""
+        if self.tailD[idx] is not None:
+            self.tailD[idx].begin()
+        elif self.redD[idx] is not None:
+            self.redD[idx].begin()
+
     def _d_apply(self, idx):
         """Optimiser step of discriminator idx, then the refresh of its packed filter operands on a side stream (the
         generator-loss pass through the updated discriminator follows on this branch; it reaches the operands that need
         packing -- data-gradient filters -- only in its backward)."""
-        self._apply(self.optsD[idx], self.redD[idx])
+        if self.tailD[idx] is not None:
+            self.tailD[idx].finish()
+        else:
+            self._apply(self.optsD[idx], self.redD[idx])
         if next(self.netsD[idx].parameters()).is_cuda:
             side = ops.prepack(self.netsD[idx].parameters(), "D%d" % idx)
             if side is not None:
@@ -236,8 +316,7 @@ class StepEngine:
             # fused path: raw logits of the stacked real / wrong / fake pass -> one loss kernel (cub:423-448)
             lm, lu, lc = netD.heads_raw((real_imgs, wrong_imgs, self.fake_imgs[idx].detach()), self.mu.detach(), groups=3)
             losses, pm, pu, logp = ops.d_loss(lm, lu, lc, real_cp, fake_cp, 3, B, (1, 0, 0), (1, 1, 0), (0, -1, 1), self.uncond)
-            if self.redD[idx] is not None:
-                self.redD[idx].begin()
+            self._d_begin(idx)
             losses[0].backward()
             self._d_update(idx)
             self.d_logits[idx] = tuple([pm[i * B:(i + 1) * B], pu[i * B:(i + 1) * B], logp[i * B:(i + 1) * B]] for i in range(3))
@@ -258,8 +337,7 @@ class StepEngine:
         else:
             errD_uncond = errD_cls = torch.zeros((), device=real_imgs.device)
             errD = _bce_const(real[0], 1) + 0.5 * (_bce_const(wrong[0], 0) + _bce_const(fake[0], 0))
-        if self.redD[idx] is not None:
-            self.redD[idx].begin()
+        self._d_begin(idx)
         errD.backward()
         self._d_update(idx)
         self.d_logits[idx] = (real, wrong, fake)

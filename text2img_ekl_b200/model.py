@@ -706,8 +706,8 @@ class _JointD(_DBase):
                                 self.logits[0].weight, self.logits[0].bias)
         B = x_code.shape[0]
         if self.use_cap:
-            out = self.fc_ac_cap(x_code.reshape(B, 16, self.df_dim * 8).float())     # == permute(0,2,3,1).view (:967-968)
-            cls = out.norm(dim=-1)
+            cls = self.fc_ac_cap[0].forward_norm(x_code.reshape(B, 16, self.df_dim * 8).float())   # == permute(0,2,3,1).view
+            #                                                                  (:967-968), then .norm(dim=-1) (:969-970)
         else:
             flat = x_code.permute(0, 3, 1, 2).reshape(B, -1).float()                 # NCHW flatten order (:974)
             cls = self.fc_ac(flat)

@@ -104,17 +104,37 @@ class FlatAdam(torch.optim.Optimizer):
             for p, g in zip(self.plist, old):
                 if g is not None:
                     p.grad.copy_(g)
+        self.tick()
+        self.apply_slice(0, self.n, grads_bf16)
+        self.finish_step()
+
+    # ---- the same step in pieces (engine.TailUpdate: the optimiser overlaps the backward pass)
+    @torch.no_grad()
+    def tick(self):
+        """Advance the step count / bias corrections once (device side, capturable); apply_slice() calls follow."""
+        grp = self.param_groups[0]
+        b1, b2 = grp["betas"]
+        L.check(L.lib().ekl_adam_tick(L.ptr(self.state_dev), float(b1), float(b2), L.stream()))
+        ops._count()
+
+    @torch.no_grad()
+    def apply_slice(self, lo, hi, grads_bf16=None):
+        """Adam update of the flat slice [lo, hi) (multiples of 4) from the fp32 flat gradients, or from `grads_bf16`, a
+        bf16 buffer in the flat layout (the rank-averaged staging buffer of parallel.GradReducer)."""
+        if hi <= lo:
+            return
         grp = self.param_groups[0]
         b1, b2 = grp["betas"]
         if grads_bf16 is not None:
             assert grads_bf16.dtype == torch.bfloat16 and grads_bf16.numel() == self.n
-            L.check(L.lib().ekl_adam_step_g16(L.ptr(self.flat_p), L.ptr(grads_bf16), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
-                                              L.ptr(self.shadow), self.n, L.ptr(self.state_dev), float(grp["lr"]), float(b1),
-                                              float(b2), float(grp["eps"]), L.stream()))
+            g, g16 = grads_bf16, 1
         else:
-            L.check(L.lib().ekl_adam_step(L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
-                                          L.ptr(self.shadow), self.n, L.ptr(self.state_dev), float(grp["lr"]), float(b1),
-                                          float(b2), float(grp["eps"]), L.stream()))
-        ops._count(2)
-        ops._acct("adam", nbytes=30.0 * self.n)          # 16 B read (p, g, m, v) + 14 B written (p, m, v, bf16 shadow) per parameter
+            g, g16 = self.flat_g, 0
+        L.check(L.lib().ekl_adam_apply(L.ptr(self.flat_p[lo:hi]), L.ptr(g[lo:hi]), g16, L.ptr(self.exp_avg[lo:hi]),
+                                       L.ptr(self.exp_avg_sq[lo:hi]), L.ptr(self.shadow[lo:hi]), hi - lo, L.ptr(self.state_dev),
+                                       float(grp["lr"]), float(b1), float(b2), float(grp["eps"]), L.stream()))
+        ops._count()
+        ops._acct("adam", nbytes=30.0 * (hi - lo))       # 16 B read (p, g, m, v) + 14 B written (p, m, v, bf16 shadow) per parameter
+
+    def finish_step(self):
         ops.mark_dirty(self.plist)          # the packed data-gradient filter operands are stale now

@@ -102,6 +102,7 @@ class GradReducer:
                     self.end_of[id(m)] = (max(ends) + 3) // 4 * 4 if max(ends) < self.total else self.total
         self.side = torch.cuda.Stream() if flat.is_cuda else None
         self.active, self.lo, self.slices = False, self.total, []
+        self.after_slice = None          # optional callback(lo, hi), run on the side stream behind the slice's all-reduce
 
     def begin(self):
         """Call right before backward of this network's own update (marks fired at any other time are ignored)."""
@@ -138,11 +139,15 @@ class GradReducer:
         self.slices.append((lo, hi))
         if self.side is None:
             self._reduce(lo, hi)
+            if self.after_slice is not None:
+                self.after_slice(lo, hi)
             return
         cur = torch.cuda.current_stream()
         self.side.wait_stream(cur)              # the slice's gradients are complete on the issuing stream
         with torch.cuda.stream(self.side):
             self._reduce(lo, hi)
+            if self.after_slice is not None:
+                self.after_slice(lo, hi)        # e.g. the optimiser update of the slice (engine.TailUpdate)
 
     def finish(self):
         """Reduce what is left (the head of the buffer), wait for every slice; returns (gradient buffer, is_bf16): the

@@ -20,7 +20,7 @@ SHAPES = {  # mode -> list of (B, H, W, Cin, Cout)
     1: [(4, 4, 4, 128, 128), (2, 8, 8, 64, 64), (3, 16, 16, 64, 128), (2, 32, 32, 32, 32), (2, 4, 4, 256, 512)],
     2: [(4, 16, 16, 64, 128), (2, 8, 8, 128, 256), (3, 32, 32, 64, 64), (2, 8, 8, 512, 1024), (2, 64, 64, 32, 64)],
 }
-GROUPS = ["tc_fwd", "tc_dgrad", "tc_wgrad", "simt_fwd", "simt_dgrad", "simt_wgrad", "bn", "misc", "heads", "tc_split", "fold", "vc"]
+GROUPS = ["tc_fwd", "tc_dgrad", "tc_wgrad", "simt_fwd", "simt_dgrad", "simt_wgrad", "bn", "misc", "heads", "tc_split", "fold", "vc", "route"]
 
 
 def run_group(group):
@@ -48,6 +48,8 @@ def run_group(group):
         return run_fold(torch, L, lib, dev, rel)
     if group == "vc":
         return run_vc(torch, L, lib, dev, rel)
+    if group == "route":
+        return run_route(torch, L, lib, dev, rel)
     impl = L.IMPL_TC if group.startswith("tc") else L.IMPL_SIMT
     what = group.split("_")[1]
     for mode, shapes in SHAPES.items():
@@ -430,6 +432,53 @@ def run_vc(torch, L, lib, dev, rel):
         print("%s linear_bn_relu B%d K%d N%d %s" % ("PASS" if ok else "FAIL", B, K, N, " ".join("%s %.1e" % kv for kv in errs.items())), flush=True)
         nfail += 0 if ok else 1
     return nfail
+
+
+def run_route(torch, L, lib, dev, rel):
+    """ekl_caps_route_fwd / _bwd (discriminator capsule class head) against the materialised-prior restatement
+    oracle/capsule_ref.py in fp32 (autograd for the gradients), through capsule.CapsuleLinear.forward / forward_norm."""
+    from oracle import capsule_ref as R
+    from text2img_ekl_b200 import capsule
+    nfail = 0
+    saved = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for (B, O, K, scale) in [(32, 201, 512, 1.0), (96, 201, 512, 1.0), (4, 201, 512, 3.0), (5, 37, 64, 2.0), (3, 224, 128, 1.0), (2, 20, 64, 1.0),
+                             (3, 100, 256, 0.3)]:
+        mod = capsule.CapsuleLinear(out_capsules=O, in_length=K, out_length=16).to(dev)
+        x = (torch.randn(B, 16, K, device=dev) * scale).requires_grad_(True)
+        xr = x.detach().clone().requires_grad_(True)
+        wr = mod.weight.detach().clone().requires_grad_(True)
+        assert lib.ekl_caps_route_supported(16, O, 16, 3)
+        launches0 = ops_count()
+        n = mod.forward_norm(x)
+        used = ops_count() - launches0
+        gn = torch.randn_like(n)
+        n.backward(gn)
+        nr = R.capsule_linear(xr, wr).norm(dim=-1)
+        nr.backward(gn)
+        e = dict(norm=rel(n, nr), dx=rel(x.grad, xr.grad), dW=rel(mod.weight.grad, wr.grad))
+        # the vector output (forward()) with its own gradient
+        mod.weight.grad = None
+        x2 = x.detach().clone().requires_grad_(True)
+        v = mod(x2)
+        gv = torch.randn_like(v)
+        v.backward(gv)
+        xr2, wr2 = x.detach().clone().requires_grad_(True), mod.weight.detach().clone().requires_grad_(True)
+        vr = R.capsule_linear(xr2, wr2)
+        vr.backward(gv)
+        torch.cuda.synchronize()
+        e.update(v=rel(v, vr), dx_v=rel(x2.grad, xr2.grad), dW_v=rel(mod.weight.grad, wr2.grad))
+        ok = all(val < 2e-4 for val in e.values()) and used == 1          # forward: one routing launch
+        print("%s caps_route B%d O%d K%d x%.1f launches %d %s" % ("PASS" if ok else "FAIL", B, O, K, scale, used,
+                                                                 " ".join("%s %.1e" % kv for kv in e.items())), flush=True)
+        nfail += 0 if ok else 1
+    torch.backends.cuda.matmul.allow_tf32 = saved
+    return nfail
+
+
+def ops_count():
+    from text2img_ekl_b200 import ops
+    return ops.LAUNCHES[0]
 
 
 def run_fold(torch, L, lib, dev, rel):
