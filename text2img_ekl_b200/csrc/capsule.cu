@@ -135,17 +135,19 @@ __device__ __forceinline__ float half_sum(float v) {
 }
 
 constexpr int NCH = 4;                 // in-capsule chunks of 16 (I <= 64)
+constexpr int AGT = 512;               // threads per block of the agreement kernels
+constexpr int AGH = AGT / 16;          // half-warps per block
 
-// Thread mapping of the agreement kernels: one block (256 threads = 16 half-warps) per sample.  Lane j of a half-warp
-// owns in-capsules i = 16*ch + j (their x rows live in registers), half-warp h walks out-capsules o = h, h+16, ...
+// Thread mapping of the agreement kernels: one block (512 threads = 32 half-warps) per sample.  Lane j of a half-warp
+// owns in-capsules i = 16*ch + j (their x rows live in registers), half-warp h walks out-capsules o = h, h+32, ...
 // (u_o / gy_o are broadcast loads).  Softmax statistics over the O axis are therefore lane-local running max / sums,
-// combined across the 16 half-warps through shared memory; sums over i are 16-lane shuffles.
+// combined across the half-warps through shared memory; sums over i are 16-lane shuffles.
 
 // ---- agreement step: y[b,o] = sum_i softmax_o(<x[b,i], u[b,o]>) x[b,i];  saves the softmax statistics M, Z [B][I]
 template <int K>
-__global__ void __launch_bounds__(256) caps_agree_fwd_kernel(const float* __restrict__ x, const float* __restrict__ u, int I, int O,
+__global__ void __launch_bounds__(AGT) caps_agree_fwd_kernel(const float* __restrict__ x, const float* __restrict__ u, int I, int O,
                                                              float* __restrict__ y, float* __restrict__ Ms, float* __restrict__ Zs) {
-  __shared__ float red[16][NCH * 16];
+  __shared__ float red[AGH][NCH * 16];
   __shared__ float Mi[NCH * 16], Zi[NCH * 16];
   const int b = blockIdx.x;
   const int h = threadIdx.x >> 4, j = threadIdx.x & 15;
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(256) caps_agree_fwd_kernel(const float* __rest
   float m[NCH];
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) m[ch] = -INFINITY;
-  for (int o = h; o < O; o += 16) {
+  for (int o = h; o < O; o += AGH) {
     float uo[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) uo[k] = ub[(int64_t)o * K + k];
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(256) caps_agree_fwd_kernel(const float* __rest
   __syncthreads();
   if (threadIdx.x < NCH * 16) {
     float r = red[0][threadIdx.x];
-    for (int q = 1; q < 16; ++q) r = fmaxf(r, red[q][threadIdx.x]);
+    for (int q = 1; q < AGH; ++q) r = fmaxf(r, red[q][threadIdx.x]);
     Mi[threadIdx.x] = r;
   }
   __syncthreads();
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(256) caps_agree_fwd_kernel(const float* __rest
   float z[NCH];
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) z[ch] = 0.f;
-  for (int o = h; o < O; o += 16) {
+  for (int o = h; o < O; o += AGH) {
     float uo[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) uo[k] = ub[(int64_t)o * K + k];
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(256) caps_agree_fwd_kernel(const float* __rest
   __syncthreads();
   if (threadIdx.x < NCH * 16) {
     float r = 0.f;
-    for (int q = 0; q < 16; ++q) r += red[q][threadIdx.x];
+    for (int q = 0; q < AGH; ++q) r += red[q][threadIdx.x];
     Zi[threadIdx.x] = r;
     if ((int)threadIdx.x < I) { Ms[(int64_t)b * I + threadIdx.x] = Mi[threadIdx.x]; Zs[(int64_t)b * I + threadIdx.x] = r; }
   }
@@ -213,9 +215,9 @@ __global__ void __launch_bounds__(256) caps_agree_fwd_kernel(const float* __rest
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) rz[ch] = ch < nch ? 1.f / Zi[ch * 16 + j] : 0.f;
   // pass 3: y_o = sum_i c[o,i] x_i
-  const int n_o = (O + 15) / 16;
+  const int n_o = (O + AGH - 1) / AGH;
   for (int it = 0; it < n_o; ++it) {
-    const int o = h + it * 16;
+    const int o = h + it * AGH;
     const bool live = o < O;
     float uo[K], yo[K];
 #pragma unroll
@@ -238,11 +240,11 @@ __global__ void __launch_bounds__(256) caps_agree_fwd_kernel(const float* __rest
 // ---- backward of the agreement step.  gc[o,i] = <gy_o, x_i>;  D_i = sum_o c gc;  ga = c (gc - D_i);
 //      gu_o = sum_i ga x_i;  gx_i = sum_o (c gy_o + ga u_o)
 template <int K>
-__global__ void __launch_bounds__(256) caps_agree_bwd_kernel(const float* __restrict__ x, const float* __restrict__ u,
+__global__ void __launch_bounds__(AGT) caps_agree_bwd_kernel(const float* __restrict__ x, const float* __restrict__ u,
                                                              const float* __restrict__ Ms, const float* __restrict__ Zs,
                                                              const float* __restrict__ gy, int I, int O, float* __restrict__ gu,
                                                              float* __restrict__ gx) {
-  __shared__ float red[16][NCH * 16];
+  __shared__ float red[AGH][NCH * 16];
   __shared__ float Di[NCH * 16];
   __shared__ float gxs[NCH * 16 * K];
   const int b = blockIdx.x;
@@ -257,14 +259,14 @@ __global__ void __launch_bounds__(256) caps_agree_bwd_kernel(const float* __rest
     m[ch] = on ? Ms[(int64_t)b * I + ch * 16 + j] : 0.f;
     rz[ch] = on ? 1.f / Zs[(int64_t)b * I + ch * 16 + j] : 0.f;
   }
-  for (int i = threadIdx.x; i < NCH * 16 * K; i += 256) gxs[i] = 0.f;
+  for (int i = threadIdx.x; i < NCH * 16 * K; i += AGT) gxs[i] = 0.f;
   const float* ub = u + (int64_t)b * O * K;
   const float* gyb = gy + (int64_t)b * O * K;
   // pass 1: D_i = sum_o c[o,i] * gc[o,i]
   float d[NCH];
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) d[ch] = 0.f;
-  for (int o = h; o < O; o += 16) {
+  for (int o = h; o < O; o += AGH) {
     float uo[K], go[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) { uo[k] = ub[(int64_t)o * K + k]; go[k] = gyb[(int64_t)o * K + k]; }
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(256) caps_agree_bwd_kernel(const float* __rest
   __syncthreads();
   if (threadIdx.x < NCH * 16) {
     float r = 0.f;
-    for (int q = 0; q < 16; ++q) r += red[q][threadIdx.x];
+    for (int q = 0; q < AGH; ++q) r += red[q][threadIdx.x];
     Di[threadIdx.x] = r;
   }
   __syncthreads();
@@ -293,9 +295,9 @@ __global__ void __launch_bounds__(256) caps_agree_bwd_kernel(const float* __rest
   for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
     for (int k = 0; k < K; ++k) gxi[ch][k] = 0.f;
-  const int n_o = (O + 15) / 16;
+  const int n_o = (O + AGH - 1) / AGH;
   for (int it = 0; it < n_o; ++it) {
-    const int o = h + it * 16;
+    const int o = h + it * AGH;
     const bool live = o < O;
     float uo[K], go[K], guo[K];
 #pragma unroll
@@ -318,13 +320,13 @@ __global__ void __launch_bounds__(256) caps_agree_bwd_kernel(const float* __rest
     for (int k = 0; k < K; ++k) guo[k] = half_sum(guo[k]);
     if (live && j < K) gu[((int64_t)b * O + o) * K + j] = guo[j < K ? j : 0];
   }
-  // combine the 16 half-warps' gx partials
+  // combine the half-warps' gx partials
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
     for (int k = 0; k < K; ++k) atomicAdd(&gxs[(ch * 16 + j) * K + k], gxi[ch][k]);
   __syncthreads();
-  for (int i = threadIdx.x; i < I * K; i += 256) gx[(int64_t)b * I * K + i] = gxs[i];
+  for (int i = threadIdx.x; i < I * K; i += AGT) gx[(int64_t)b * I * K + i] = gxs[i];
 }
 
 }  // namespace
@@ -372,7 +374,7 @@ extern "C" int ekl_caps_outer(const float* A, const float* Bm, int B, int O, int
 extern "C" int ekl_caps_agree_fwd(const float* x, const float* u, int B, int I, int O, int K, float* y, float* M, float* Z,
                                   void* stream) {
   EKL_REQUIRE(ekl_caps_supported(I, K, O, 1), "caps_agree: unsupported shape I=%d K=%d", I, K);
-  EKL_CAPS_K(K, (caps_agree_fwd_kernel<KK><<<B, 256, 0, (cudaStream_t)stream>>>(x, u, I, O, y, M, Z)));
+  EKL_CAPS_K(K, (caps_agree_fwd_kernel<KK><<<B, AGT, 0, (cudaStream_t)stream>>>(x, u, I, O, y, M, Z)));
   EKL_LAUNCH_CHECK();
   return 0;
 }
@@ -380,7 +382,7 @@ extern "C" int ekl_caps_agree_fwd(const float* x, const float* u, int B, int I, 
 extern "C" int ekl_caps_agree_bwd(const float* x, const float* u, const float* M, const float* Z, const float* gy, int B,
                                   int I, int O, int K, float* gu, float* gx, void* stream) {
   EKL_REQUIRE(ekl_caps_supported(I, K, O, 1), "caps_agree: unsupported shape I=%d K=%d", I, K);
-  EKL_CAPS_K(K, (caps_agree_bwd_kernel<KK><<<B, 256, 0, (cudaStream_t)stream>>>(x, u, M, Z, gy, I, O, gu, gx)));
+  EKL_CAPS_K(K, (caps_agree_bwd_kernel<KK><<<B, AGT, 0, (cudaStream_t)stream>>>(x, u, M, Z, gy, I, O, gu, gx)));
   EKL_LAUNCH_CHECK();
   return 0;
 }

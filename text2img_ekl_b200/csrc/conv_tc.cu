@@ -701,8 +701,17 @@ static void tc_tile_plan(const EklGather* g, int group_b, bool allow_split, int*
       if (ks > 4) ks = 4;
       if (ks < 1) ks = 1;
     }
-    // bytes the busiest CTA fetches (per-SM operand ingest is the bound: ~85 GB/s measured whether 48 or 148 SMs run)
-    const double cost = (double)((tiles * ks + sms - 1) / sms) * (128 + bn) / ks;
+    // bytes the busiest CTA fetches (per-SM operand ingest is the bound: ~85 GB/s measured whether 48 or 148 SMs run), but
+    // never less than the plan's TOTAL operand traffic divided by rho SM-equivalents of L2 fabric.  The second term makes
+    // few-tile layers (the 4x4 / 8x8 tails) take wider N tiles = fewer work items.  Measured (profiles/r02_summary.md):
+    // timed alone those layers are a wash (+-10 % either way, +1.8 % in sum), but inside the step, where the
+    // discriminator branches run concurrently and a persistent conv CTA owns its SM, fewer busy SMs per kernel let the
+    // other branches' kernels in: config 2 8.43 -> 8.19 ms/step for any rho in 20..60, configs 1 / 4 +2 % / +1 %, coco
+    // unchanged.  EKL_TC_RHO=0 restores the per-CTA term alone.
+    static double rho = -1.0;
+    if (rho < 0) { const char* e = getenv("EKL_TC_RHO"); rho = e ? atof(e) : 45.0; }
+    double cost = (double)((tiles * ks + sms - 1) / sms) * (128 + bn) / ks;
+    if (rho > 0) { const double total = (double)tiles * (128 + bn) / rho; if (total > cost) cost = total; }
     if (best < 0 || cost < best) { best = cost; BN = bn; KS = ks; }
   }
   *BN_out = BN; *ks_out = KS;
