@@ -29,3 +29,21 @@ def test_bench_two_ranks_finishes_with_roofline_and_clean_exit(comm):
     assert d["config"]["grad_comm"] == comm and d["config"]["global_batch"] == 2 * d["config"]["batch_per_gpu"]
     assert d["roofline"] and d["roofline"].get("frac", 0) > 0, d["roofline"]          # the pass ran on both ranks and returned
     assert "nccl" in d["roofline"]["families"]
+
+
+@pytest.mark.timeout(400, method="thread")
+@pytest.mark.parametrize("comm,graph", [("bf16", 0), ("fp32", 0), ("bf16", 1)])
+def test_replicas_stay_bit_identical(comm, graph):
+    """Different batches and different initial seeds per rank: after three steps every rank holds the same parameters,
+    moments and shadows, bit for bit (tail-first reducer + optimiser slices behind their all-reduce, eager and captured)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, EKL_GRAD_COMM=comm)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29543", os.path.join(ROOT, "tools", "dp_sync_check.py"), "--graph", str(graph)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=360, env=env, cwd=ROOT)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    err = [ln for ln in r.stderr.splitlines() if "Error" in ln or "error" in ln or "File \"/root" in ln or "repo/" in ln]
+    assert r.returncode == 0 and len(lines) == 1, (r.stdout[-800:], "\n".join(err[:30]))
+    d = json.loads(lines[0])
+    assert d["diverged_buffers"] == 0 and d["updated"] and d["world"] == 2, d
