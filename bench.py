@@ -417,12 +417,13 @@ def run_ours(a):
 # ------------------------------------------------------------------------------------------------ roofline
 # kernel-name pattern -> family (first match wins).  Names are the demangled CUPTI kernel names.
 FAMILIES = [
-    ("conv_gemm_tc", r"conv_gemm_tc_kernel"),
+    ("conv_gemm_tc", r"conv_gemm_tc2?_kernel"),          # single-CTA and CTA-pair variants of the same tile program
     ("conv3x3_rw", r"conv3x3_rw_kernel"),
     ("conv_wgrad", r"conv_wgrad_"),
     ("splitk_finish", r"splitk_finish"),
+    ("ekl_small", r"linear_bn_relu"),          # VC_NET's fused layers: not the feature-map BatchNorm passes accounted as "bn"
     ("batchnorm", r"bn_|col_stats"),
-    ("adam", r"adam_step"),
+    ("adam", r"adam_step|adam_tick"),
     ("pack_weights", r"pack_"),
     ("capsule", r"caps_|dcaps_"),
     ("nccl", r"nccl"),
@@ -499,7 +500,8 @@ def kernel_roofline(tr, gs, batch, pk, replays=3):
         out[k] = {"us_per_step": round(d["us"], 1), "share": round(d["us"] / total, 4), "launches_per_step": round(d["launches"], 1),
                   "tflops_reference_count": round(w["ref"] / sec / 1e12, 1) if w.get("ref") else None,
                   "tflops_executed": round(w["exe"] / sec / 1e12, 1) if w.get("exe") else None,
-                  "gbs_algorithmic": round(w["bytes"] / sec / 1e9, 1) if w.get("bytes") and not w.get("ref") else None}
+                  "gbs_algorithmic": round(w["bytes"] / sec / 1e9, 1) if w.get("bytes") and not w.get("ref") else None,
+                  "calls_accounted": w.get("calls")}
     tensor = [k for k in fam if work.get(k, {}).get("ref")]
     if not tensor:
         return {"families": out, "kernel_us_per_step": round(total, 1)}
@@ -518,6 +520,9 @@ def kernel_roofline(tr, gs, batch, pk, replays=3):
             "flop_counting": "reference dense-conv count (upsampled grid for up-convs, tiled code channels included)",
             "achieved_executed": w["exe"] / (d["us"] * 1e-6) / 1e12,
             "avg_launch_us": d["us"] / max(d["launches"], 1), "launches_per_step": d["launches"],
+            # every accounted library call of this family is exactly one launch of it: a mismatch means the flops and the
+            # device time describe different sets of launches (a kernel variant the family pattern misses)
+            "calls_accounted": w["calls"], "launches_match_calls": abs(d["launches"] - w["calls"]) < 0.5,
             "all_conv_kernels": {"us_per_step": round(conv_us, 1), "tflops_reference_count": round(conv_ref / conv_us / 1e6, 1),
                                  "tflops_executed": round(conv_exe / conv_us / 1e6, 1),
                                  "frac_reference_count": conv_ref / conv_us / 1e6 / pk["bf16_sustained"]},
