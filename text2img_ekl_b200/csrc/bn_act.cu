@@ -35,8 +35,12 @@ struct Tile {
   int k;                  // row-chunk index inside the group (chunk 0 does the per-group bookkeeping)
   bool active;
 };
-__device__ __forceinline__ Tile make_tile(int64_t M, int noct, int groups) {
+// rev: row chunks are walked from the END of the tensor (blockIdx.y = 0 takes the last chunk).  CTAs are dispatched in
+// blockIdx order, so a reversed pass starts on the rows its producer / the previous pass touched LAST -- the ones still
+// resident in the 126 MB L2.
+__device__ __forceinline__ Tile make_tile(int64_t M, int noct, int groups, bool rev = false) {
   Tile t;
+  const int by = rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const int CT = noct < 256 ? noct : 256;
   t.RT = 256 / CT;
   t.CT = CT;
@@ -44,8 +48,8 @@ __device__ __forceinline__ Tile make_tile(int64_t M, int noct, int groups) {
   t.rt = threadIdx.x / CT;
   t.oct = blockIdx.x * CT + ct;
   const int chunks_per_group = gridDim.y / groups;
-  t.g = blockIdx.y / chunks_per_group;
-  const int k = blockIdx.y - t.g * chunks_per_group;
+  t.g = by / chunks_per_group;
+  const int k = by - t.g * chunks_per_group;
   t.k = k;
   const int64_t Mg = M / groups;
   const int64_t per = (Mg + chunks_per_group - 1) / chunks_per_group;
@@ -170,11 +174,11 @@ __global__ void __launch_bounds__(256, U == 2 ? 3 : 2) bn_act_fwd_kernel(const b
                                                             float* mean_io, float* rstd_io, float* running_mean,
                                                             float* running_var,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                            const bf16* __restrict__ residual, bf16* __restrict__ out) {
+                                                            const bf16* __restrict__ residual, bf16* __restrict__ out, int rev) {
   constexpr int VEC = ActVec<ACT>::V;
   using IO = VecIO<VEC>;
   const int Co = ACT == ACT_GLU ? Cy / 2 : Cy;
-  const Tile t = make_tile(M, Co / VEC, groups);
+  const Tile t = make_tile(M, Co / VEC, groups, rev != 0);
   if (!t.active) return;
   const int c0 = t.oct * VEC;
   // software pipeline: the loads of the next U rows are in flight while the current U rows are computed; the first
@@ -290,12 +294,12 @@ __global__ void __launch_bounds__(256, U == 2 ? 3 : 2) bn_act_bwd_reduce_kernel(
                                                                    int64_t M, int Cy, int groups,
                                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                   double* __restrict__ sums /*[groups][2][Cy], zero on entry*/) {
+                                                                   double* __restrict__ sums /*[groups][2][Cy], zero on entry*/, int rev) {
   constexpr int VEC = ActVec<ACT>::V;
   using IO = VecIO<VEC>;
   __shared__ float red[256 * 2 * VEC];
   const int Co = ACT == ACT_GLU ? Cy / 2 : Cy;
-  const Tile t = make_tile(M, Co / VEC, groups);
+  const Tile t = make_tile(M, Co / VEC, groups, rev != 0);
   const int c0 = t.oct * VEC;
   constexpr int NH = ACT == ACT_GLU ? 2 : 1;
   float sc[VEC], sh[VEC], sc2[VEC], sh2[VEC], rs[VEC], nmr[VEC], rs2[VEC], nmr2[VEC];
@@ -384,11 +388,11 @@ __global__ void __launch_bounds__(256, U == 2 ? 3 : 2) bn_act_bwd_apply_kernel(c
                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   const double* __restrict__ sums /*[groups][2][Cy]*/,
-                                                                  float* dgamma, float* dbeta, bf16* __restrict__ dy) {
+                                                                  float* dgamma, float* dbeta, bf16* __restrict__ dy, int rev) {
   constexpr int VEC = ActVec<ACT>::V;
   using IO = VecIO<VEC>;
   const int Co = ACT == ACT_GLU ? Cy / 2 : Cy;
-  const Tile t = make_tile(M, Co / VEC, groups);
+  const Tile t = make_tile(M, Co / VEC, groups, rev != 0);
   if (!t.active) return;
   const int c0 = t.oct * VEC;
   const float inv_n = 1.f / (float)(M / groups);
@@ -766,6 +770,14 @@ static int bn_u() {
   return u;
 }
 
+// traversal direction of the streaming passes (bit 0 forward pass, bit 1 backward reduce, bit 2 backward apply run from the
+// end of the tensor); EKL_BN_REV selects (experiments)
+static int bn_rev() {
+  static int r = -1;
+  if (r < 0) { const char* e = getenv("EKL_BN_REV"); r = e ? atoi(e) : 0; }
+  return r;
+}
+
 #define EKL_ACT_SWITCH(act, CALL)                       \
   switch (act) {                                        \
     case ACT_NONE: { constexpr int A = ACT_NONE; CALL; } break;   \
@@ -786,11 +798,11 @@ extern "C" int ekl_bn_act_fwd(const void* y, int64_t M, int Cy, int groups, cons
   if (bn_u() == 4) {
     EKL_ACT_SWITCH(act, (bn_act_fwd_kernel<A, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(
                             (const bf16*)y, M, Cy, groups, sums, eps, momentum, mean, rstd, running_mean, running_var, gamma, beta,
-                            (const bf16*)residual, (bf16*)out)));
+                            (const bf16*)residual, (bf16*)out, bn_rev() & 1)));
   } else {
     EKL_ACT_SWITCH(act, (bn_act_fwd_kernel<A, 2><<<grid, 256, 0, (cudaStream_t)stream>>>(
                             (const bf16*)y, M, Cy, groups, sums, eps, momentum, mean, rstd, running_mean, running_var, gamma, beta,
-                            (const bf16*)residual, (bf16*)out)));
+                            (const bf16*)residual, (bf16*)out, bn_rev() & 1)));
   }
   EKL_LAUNCH_CHECK();
   return 0;
@@ -816,16 +828,16 @@ extern "C" int ekl_bn_act_bwd(const void* y, const void* dout, int64_t M, int Cy
   grid_rows(M, Co / act_vec(act), groups, &grid);
   if (bn_u() == 4) {
     EKL_ACT_SWITCH(act, (bn_act_bwd_reduce_kernel<A, 4><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M, Cy, groups,
-                                                                              mean, rstd, gamma, beta, sums)));
+                                                                              mean, rstd, gamma, beta, sums, bn_rev() & 2)));
     EKL_LAUNCH_CHECK();
     EKL_ACT_SWITCH(act, (bn_act_bwd_apply_kernel<A, 4><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M, Cy, groups,
-                                                                             mean, rstd, gamma, beta, sums, dgamma, dbeta, (bf16*)dy)));
+                                                                             mean, rstd, gamma, beta, sums, dgamma, dbeta, (bf16*)dy, bn_rev() & 4)));
   } else {
     EKL_ACT_SWITCH(act, (bn_act_bwd_reduce_kernel<A, 2><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M, Cy, groups,
-                                                                              mean, rstd, gamma, beta, sums)));
+                                                                              mean, rstd, gamma, beta, sums, bn_rev() & 2)));
     EKL_LAUNCH_CHECK();
     EKL_ACT_SWITCH(act, (bn_act_bwd_apply_kernel<A, 2><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M, Cy, groups,
-                                                                             mean, rstd, gamma, beta, sums, dgamma, dbeta, (bf16*)dy)));
+                                                                             mean, rstd, gamma, beta, sums, dgamma, dbeta, (bf16*)dy, bn_rev() & 4)));
   }
   EKL_LAUNCH_CHECK();
   return 0;

@@ -18,6 +18,7 @@ namespace {
 
 constexpr int KC = 128;      // K chunk staged in shared memory
 constexpr int WARPS = 8;     // columns per block
+constexpr int KSPLIT = 256;  // backward: K range of one block row (multiple of KC)
 
 template <int BMAX>
 __global__ void __launch_bounds__(32 * WARPS) linear_bn_relu_fwd_kernel(
@@ -114,16 +115,19 @@ __global__ void __launch_bounds__(32 * WARPS) linear_bn_relu_bwd_kernel(
       if (b < B) {
         dy[b] = k * (dz[b] - sb * inv - xh[b] * sg * inv);
         sdy += dy[b];
-        if ((b & 31) == lane) dy_out[(size_t)b * N + n] = dy[b];
+        if ((b & 31) == lane && blockIdx.y == 0) dy_out[(size_t)b * N + n] = dy[b];
       }
-    if (lane == 0) {
+    if (lane == 0 && blockIdx.y == 0) {
       if (dgamma != nullptr) dgamma[n] += sg;
       if (dbeta != nullptr) dbeta[n] += sb;
       if (dbias != nullptr) dbias[n] += sdy;
     }
   }
   if (dW == nullptr) return;
-  for (int k0 = 0; k0 < K; k0 += KC) {
+  // the K range of this block row: the weight gradient is split along K over gridDim.y block rows (each dW element has
+  // exactly one owner, so no atomics); the short prologue above is repeated per row, its outputs written by row 0
+  const int kbeg = blockIdx.y * KSPLIT, kend = kbeg + KSPLIT < K ? kbeg + KSPLIT : K;
+  for (int k0 = kbeg; k0 < kend; k0 += KC) {
     __syncthreads();
     for (int i = threadIdx.x; i < B * KC; i += 32 * WARPS) {
       const int b = i / KC, kk = i - b * KC;
@@ -171,7 +175,7 @@ extern "C" int ekl_linear_bn_relu_bwd(const float* dh, const float* h, const flo
   EKL_REQUIRE(dh != nullptr && h != nullptr && xhat != nullptr && rstd != nullptr && gamma != nullptr && x != nullptr && dy != nullptr,
               "linear_bn_relu_bwd: null pointer argument");
   EKL_REQUIRE(B >= 1 && B <= 64 && K > 0 && N > 0, "linear_bn_relu_bwd: batch 1..64 (got %d)", B);
-  const int grid = ekl_cdiv(N, WARPS);
+  const dim3 grid(ekl_cdiv(N, WARPS), dW != nullptr ? ekl_cdiv(K, KSPLIT) : 1);
   if (B <= 32)
     linear_bn_relu_bwd_kernel<32><<<grid, 32 * WARPS, 0, (cudaStream_t)stream>>>(dh, h, xhat, rstd, gamma, x, B, K, N, dW, dbias, dgamma, dbeta, dy);
   else

@@ -211,11 +211,19 @@ class StepEngine:
         # discriminator's reducer starts from the tail of its flat buffer while its backward is still running.
         from . import parallel
         dp = parallel.world()[1] > 1 if data_parallel is None else data_parallel
-        self.redG = parallel.make_reducer(self.gradsG.flat) if dp else None
+        self.redG = parallel.make_reducer(self.gradsG.flat, netG, self.gradsG.params, self.gradsG.offsets) if dp else None
         self.redD = [parallel.make_reducer(g.flat, d, g.params, g.offsets) if dp else None for d, g in zip(netsD, self.gradsD)]
         # the discriminators' optimiser steps overlap their backward passes (EKL_TAIL_ADAM=0: one Adam launch after it)
         tail = os.environ.get("EKL_TAIL_ADAM", "1") != "0" and all(hasattr(o, "apply_slice") and o.flat_p.is_cuda for o in optimizersD)
         self.tailD = [TailUpdate(o, d, g, r) if tail else None for o, d, g, r in zip(optimizersD, netsD, self.gradsD, self.redD)]
+        # the generator's tail: everything but its conditioning nets (and, one mark earlier, everything but the stem Linear) is
+        # final before backward reaches them (model._GBase)
+        self.tailG = TailUpdate(optimizerG, netG, self.gradsG, self.redG) if (
+            tail and hasattr(optimizerG, "apply_slice") and optimizerG.flat_p.is_cuda) else None
+        if self.tailG is not None:
+            ops.GRAD_MARKS[id(netG)] = self.tailG.on_mark
+            if hasattr(netG, "h_net1"):
+                ops.GRAD_MARKS[id(netG.h_net1)] = self.tailG.on_mark
         for d, r, t in zip(netsD, self.redD, self.tailD):
             if t is not None:
                 ops.GRAD_MARKS[id(d)] = t.on_mark
@@ -521,11 +529,16 @@ class StepEngine:
     def _g_update(self, real_cp, per_d=None):
         self.gradsG.zero()
         res = self.g_loss(real_cp, per_d)
+        if self.tailG is not None:
+            self.tailG.begin()
         res[0].backward()
         self._join_packs()
-        if self.redG is not None:
-            self.redG.begin()
-        self._apply(self.optG, self.redG)
+        if self.tailG is not None:
+            self.tailG.finish()
+        else:
+            if self.redG is not None:
+                self.redG.begin()
+            self._apply(self.optG, self.redG)
         self.bn_counters.flush()
         return res
 

@@ -238,7 +238,8 @@ class COND_INIT_STAGE_G(_InitStageBase):
         self._make_ups(ngf)
 
     def forward(self, ac_x):
-        return self._ups(_stem_bn_glu(self.fc[0](ac_x), self.fc[1], self.gf_dim))
+        x = _stem_bn_glu(self.fc[0](ac_x), self.fc[1], self.gf_dim)
+        return self._ups(ops.grad_mark(x, self, self.fc))          # everything after the stem Linear is final past this point
 
 
 class COND_INIT_STAGE_G_withCap(_InitStageBase):
@@ -259,7 +260,8 @@ class COND_INIT_STAGE_G_withCap(_InitStageBase):
         if noise is not None:
             z = torch.cat((z, noise), 1)
         caps = self.fc_cap[1](z.view(z.shape[0], -1, 8))
-        return self._ups(_stem_bn_glu(caps.reshape(z.shape[0], -1), self.fc_cap[3], self.gf_dim))
+        x = _stem_bn_glu(caps.reshape(z.shape[0], -1), self.fc_cap[3], self.gf_dim)
+        return self._ups(ops.grad_mark(x, self, self.fc_cap))
 
 
 class COND_INIT_STAGE_G_Exchange_Cap(_InitStageBase):
@@ -402,6 +404,12 @@ def get_shareGs(gf_dim):            # model.py:439-451
 
 
 class _GBase(nn.Module):
+    """Registration order = forward order: conditioning nets (registered by the subclass BEFORE _build_stages), then the
+    stages.  The subclasses mark the condition code (ops.grad_mark, a no-op unless the step engine registered a callback):
+    when ITS gradient arrives -- after the backward of every stage, the code feeds them all -- every parameter registered
+    after the conditioning nets is final, so their optimiser update / gradient exchange overlaps the conditioning nets'
+    backward (engine.TailUpdate).  The stem marks its Linear / capsule output the same way."""
+
     def _build_stages(self, share_Gs, h_net1):
         if cfg.TREE.BRANCH_NUM > 0:
             self.h_net1 = h_net1
@@ -460,6 +468,7 @@ class COND_G_NET_CATZ_CA(_GBase):
             c_code = c_code1 * c_code2
         else:
             c_code = c_code1 + c_code2
+        c_code = ops.grad_mark(c_code, self, self.vc_net2)        # see _GBase._build_stages
         if isinstance(self.h_net1, COND_INIT_STAGE_G_withCap):
             h_code1 = self.h_net1(c_code, noise)          # model.py:512
         else:
@@ -491,6 +500,7 @@ class COND_G_NET_CATZ(_GBase):
             c_code = c_code1 * c_code2
         else:
             c_code = c_code1 + c_code2
+        c_code = ops.grad_mark(c_code, self, self.vc_net2)
         return self._later_stages(self.h_net1(c_code), c_code), mu1, mu2, logvar1, logvar2, std1, std2
 
 
@@ -506,6 +516,7 @@ class COND_G_NET(_GBase):
 
     def forward(self, noise, cond, seed=None):
         c_code, mu, logvar, std = self.vc_net(noise, cond, seed)
+        c_code = ops.grad_mark(c_code, self, self.vc_net)
         return self._later_stages(self.h_net1(c_code), c_code), mu, logvar, std
 
 

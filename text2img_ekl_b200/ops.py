@@ -153,7 +153,9 @@ class ConvSpec:
         self.w_cin_total, self.w_cin_off, self.w_cout_valid = w_cin_total, w_cin_off, w_cout_valid
         self.ref = None                  # (cin, cout, taps) of the reference layer when they differ (flop accounting only)
         self._ver, self._dirty = None, False
-        self._weight_ref, self._ready = None, None      # prepack(): the leaf parameter packed from / event of a side-stream pack
+        self._weight_ref = None                         # prepack(): the leaf parameter packed from
+        self._ready_f = self._ready_d = None            # events of a side-stream refresh of the forward / data-gradient operand
+        self._stale = 0                                 # operands to repack: bit 0 forward, bit 1 data-gradient
         self.w_layout = L.W_KCRS
         self.w_fwd = self.w_dgrad = self._fwd_buf = None
         self._ws = {}
@@ -200,12 +202,19 @@ class ConvSpec:
             return None
         return sh
 
-    def packed(self, weight):
-        if self._ready is not None:                # operands were refreshed on a side stream (prepack): order after it
-            torch.cuda.current_stream().wait_event(self._ready)
-            self._ready = None
+    def packed(self, weight, need=3):
+        """(forward operand, data-gradient operand) of `weight`, refreshed if the master changed.  need: bit 0 = the
+        caller reads the forward operand, bit 1 = the data-gradient operand; only what is needed is (re)packed / waited
+        for, so a forward pass never waits for the transposed packs of a side-stream refresh (prepack)."""
+        if (need & 1) and self._ready_f is not None:        # refreshed on a side stream (prepack): order after it
+            torch.cuda.current_stream().wait_event(self._ready_f)
+            self._ready_f = None
+        if (need & 2) and self._ready_d is not None:
+            torch.cuda.current_stream().wait_event(self._ready_d)
+            self._ready_d = None
         key = (weight._version, weight.data_ptr())
         external = key != self._ver or not weight.is_leaf     # derived (e.g. zero-padded) filters are rebuilt every step
+        lib = L.lib()
         if external or self._dirty:
             self.bind(weight)
             if weight.is_leaf:
@@ -213,29 +222,34 @@ class ConvSpec:
                 if self not in lst:
                     lst.append(self)
                     self._weight_ref = weakref.ref(weight)
-            lib = L.lib()
             c = self.conv(1, 4, 4)
             shadow = self._shadow(weight)
+            self._stale = 3
             if shadow is not None:
                 if external:                       # parameter changed outside the fused optimiser (init / load_state_dict)
                     shadow.copy_(weight.detach().permute(0, 2, 3, 1).reshape(-1))
                 self.w_fwd = shadow
+                self._stale &= ~1                  # the optimiser's bf16 shadow IS the forward operand
             else:
                 if self._fwd_buf is None:
                     self._fwd_buf = torch.empty(lib.ekl_conv_packed_elems(c, 0), device=weight.device, dtype=torch.bfloat16)
                 self.w_fwd = self._fwd_buf
-            need_dgrad = not self.dgrad_from_fwd()
-            if need_dgrad and self.w_dgrad is None:
+            if self.dgrad_from_fwd():
+                self._stale &= ~2                  # the data-gradient kernel reads the forward operand
+            elif self.w_dgrad is None:
                 self.w_dgrad = torch.empty(lib.ekl_conv_packed_elems(c, 1), device=weight.device, dtype=torch.bfloat16)
-            w_fwd_arg = None if shadow is not None else self.w_fwd
-            w_dgrad_arg = self.w_dgrad if need_dgrad else None
-            if w_fwd_arg is not None or w_dgrad_arg is not None:
-                nb = weight.numel() * 4 + ((w_fwd_arg.numel() if w_fwd_arg is not None else 0) +
-                                           (w_dgrad_arg.numel() if w_dgrad_arg is not None else 0)) * 2
-                _acct("pack_weights", nbytes=nb)
-                L.check(lib.ekl_conv_pack(c, L.ptr(weight), L.ptr(w_fwd_arg), L.ptr(w_dgrad_arg), L.stream()))
-                _count((w_fwd_arg is not None) + (w_dgrad_arg is not None))
             self._ver, self._dirty = key, False
+        do = self._stale & need
+        if do:
+            c = self.conv(1, 4, 4)
+            w_fwd_arg = self.w_fwd if do & 1 else None
+            w_dgrad_arg = self.w_dgrad if do & 2 else None
+            nb = weight.numel() * 4 + ((w_fwd_arg.numel() if w_fwd_arg is not None else 0) +
+                                       (w_dgrad_arg.numel() if w_dgrad_arg is not None else 0)) * 2
+            _acct("pack_weights", nbytes=nb)
+            L.check(lib.ekl_conv_pack(c, L.ptr(weight), L.ptr(w_fwd_arg), L.ptr(w_dgrad_arg), L.stream()))
+            _count((w_fwd_arg is not None) + (w_dgrad_arg is not None))
+            self._stale &= ~do
         return self.w_fwd, self.w_dgrad
 
 
@@ -252,7 +266,7 @@ def prepack(params, key=0):
     for p in params:
         for spec in _SPECS_OF.get(id(p), ()):
             w = spec._weight_ref() if spec._weight_ref is not None else None
-            if spec._dirty and w is not None and spec._ready is None:
+            if spec._dirty and w is not None and spec._ready_f is None and spec._ready_d is None:
                 todo.append((spec, w))
     if not todo:
         return None
@@ -262,12 +276,18 @@ def prepack(params, key=0):
         side = _PACK_STREAMS[(main.device, key)] = torch.cuda.Stream()
     side.wait_stream(main)
     with torch.cuda.stream(side):
+        # forward operands first (few: up-convs and filter windows; the rest read the optimiser's shadow), with their own
+        # event: the network's next FORWARD pass waits for these only, its backward for the transposed operands
         for spec, w in todo:
-            spec.packed(w)
-        ev = torch.cuda.Event()
-        ev.record(side)
+            spec.packed(w, 1)
+        ev_f = torch.cuda.Event()
+        ev_f.record(side)
+        for spec, w in todo:
+            spec.packed(w, 2)
+        ev_d = torch.cuda.Event()
+        ev_d.record(side)
     for spec, _ in todo:
-        spec._ready = ev
+        spec._ready_f, spec._ready_d = ev_f, ev_d
     return side
 
 
@@ -277,10 +297,10 @@ def _run_dgrad(spec, c, weight, dy, dx):
     lib = L.lib()
     ws = spec.workspace(c, 1, dx.device)
     if spec.dgrad_from_fwd():
-        w_fwd, _ = spec.packed(weight)
+        w_fwd, _ = spec.packed(weight, 1)
         L.check(lib.ekl_conv_bwd_data_fw(c, L.ptr(dy), L.ptr(w_fwd), L.ptr(dx), L.ptr(ws), L.stream()))
     else:
-        _, w_dgrad = spec.packed(weight)
+        _, w_dgrad = spec.packed(weight, 2)
         if ws is not None:
             L.check(lib.ekl_conv_bwd_data_ws(c, L.ptr(dy), L.ptr(w_dgrad), L.ptr(dx), L.ptr(ws), L.stream()))
         else:
@@ -302,7 +322,7 @@ class _Conv(torch.autograd.Function):
             B, H, W, _ = x.shape
             assert x.dtype == torch.bfloat16 and x.is_contiguous()
         Ho, Wo = spec.out_hw(H, W)
-        w_fwd, _ = spec.packed(weight)
+        w_fwd, _ = spec.packed(weight, 1)
         c = spec.conv(B, H, W, group_b)
         if spec.y_fmt == L.FMT_NCHW_F32:
             y = torch.empty(B, spec.cout, Ho, Wo, device=x.device, dtype=torch.float32)
@@ -433,7 +453,7 @@ class _ConvBias9(torch.autograd.Function):
         lib = L.lib()
         B, H, W, _ = x.shape
         assert x.dtype == torch.bfloat16 and x.is_contiguous() and spec.mode == S1 and spec.impl == L.IMPL_TC
-        w_fwd, _ = spec.packed(weight)
+        w_fwd, _ = spec.packed(weight, 1)
         c = spec.conv(B, H, W, 0)
         y = torch.empty(B, H, W, spec.cout, device=x.device, dtype=torch.bfloat16)
         stats = ARENA.take(2 * spec.cout, x.device) if want_stats else None
