@@ -10,6 +10,8 @@ Tensor conventions at this boundary
 RNG injection (SURVEY 8b extension): CA_NET / VC_NET / the G nets take optional eps / seed tensors; by default
 they draw as the reference does (CA eps on the device, VC seed on the host).
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -678,6 +680,9 @@ def _logit_head(ndf):
     return nn.Sequential(nn.Conv2d(ndf * 8, 1, kernel_size=4, stride=4), nn.Sigmoid())
 
 
+_FC_TRANSPOSED = os.environ.get("EKL_FC_T", "1") != "0"
+
+
 class _JointD(_DBase):
     """model.py:918-977 / 1054-1121 / 1206-1257 JOINT_D_NET{64,128,256}: returns [match[B], real[B], cp[B,E+1]].
     `groups` > 1 = several equally-sized batches stacked along dim 0 with independent BatchNorm statistics (the
@@ -721,7 +726,13 @@ class _JointD(_DBase):
             #                                                                  (:967-968), then .norm(dim=-1) (:969-970)
         else:
             flat = x_code.permute(0, 3, 1, 2).reshape(B, -1).float()                 # NCHW flatten order (:974)
-            cls = self.fc_ac(flat)
+            if flat.is_cuda and _FC_TRANSPOSED:
+                # the same Linear as W x^T: its [E+1, B] result and both gradient GEMMs have 16-byte aligned leading
+                # dimensions, whereas [B, 201] (ld 201) sends cuBLAS to its unaligned 64x64 kernel -- 43-89 us per call on
+                # the discriminator branch's critical path
+                cls = torch.addmm(self.fc_ac.bias.unsqueeze(1), self.fc_ac.weight, flat.t()).t()
+            else:
+                cls = self.fc_ac(flat)
         return lm, lu, cls
 
     def forward(self, x_var, c_code, groups=1):
