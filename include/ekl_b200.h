@@ -121,8 +121,12 @@ int ekl_col_stats(const void* y, int64_t M, int C, int groups, double* sums, voi
 int ekl_bn_act_fwd(const void* y, int64_t M, int Cy, int groups, const double* sums, float eps, float momentum, float* mean,
                    float* rstd, float* running_mean, float* running_var, const float* gamma, const float* beta, int act,
                    const void* residual, void* out, void* stream);
-/* dy from dout; dgamma/dbeta are accumulated (+=).  sums: [groups][2][Cy] doubles of caller scratch, ZERO on entry (the
- * two backward reductions sum(dz), sum(dz * xhat) are accumulated there between the two passes). */
+/* dy from dout; dgamma/dbeta are accumulated (+=).  sums: ekl_bn_bwd_scratch_doubles(M, Cy, groups, act) doubles of
+ * caller scratch, ZERO on entry: the two backward reductions sum(dz), sum(dz * xhat) are accumulated there between the two
+ * passes, one sum per 128-byte line ([groups][2][Cy] entries EKL_BN_BWD_SPREAD doubles apart) so that the fp64 reds of a
+ * block spread over the L2 slices.  Layers with few rows per group run as one launch and need no scratch (0 doubles). */
+#define EKL_BN_BWD_SPREAD 16
+int64_t ekl_bn_bwd_scratch_doubles(int64_t M, int Cy, int groups, int act);
 int ekl_bn_act_bwd(const void* y, const void* dout, int64_t M, int Cy, int groups, const float* mean, const float* rstd,
                    const float* gamma, const float* beta, int act, double* sums, float* dgamma, float* dbeta, void* dy,
                    void* stream);

@@ -53,6 +53,7 @@ SIGNATURES = {
     "ekl_border_sums9": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "ekl_code_bias9_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "ekl_bn_act_fwd": (_i, [_vp, _i64, _i, _i, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "ekl_bn_bwd_scratch_doubles": (_i64, [_i64, _i, _i, _i]),
     "ekl_bn_act_bwd": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "ekl_lrelu_bwd": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "ekl_cat_code": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp]),

@@ -24,7 +24,6 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 // Common thread mapping: block = 256 threads = RT row-threads x CT octet-threads; blockIdx.x = octet strip,
 // blockIdx.y = row chunk (chunks never straddle a statistics group).
@@ -159,310 +158,483 @@ template <> struct VecIO<4> {
   static __device__ __forceinline__ T pack(const float* f) { return make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3])); }
 };
 
-template <int VEC>
-__device__ __forceinline__ Tile make_tile_v(int64_t M, int nvec, int groups) { return make_tile(M, nvec, groups); }
-
 template <int ACT> struct ActVec { static constexpr int V = ACT == ACT_GLU ? 4 : 8; };
+
+// ---------------------------------------------------------------- streaming passes: common structure
+// Grid = (channel strips, row chunks per group, groups); block = 256 threads = RT row-threads x CT vector-threads; a
+// thread owns VEC consecutive channels (of EACH half for GLU) of the rows rt, rt + RT, ...
+//
+// Data path (round 2, after the ncu captures in profiles/r02_bn_summary.md): the rows of a block's chunk stream through a
+// ring of RING_S shared-memory stages filled by 1-D bulk async copies (cp.async.bulk ... mbarrier::complete_tx; thread 0
+// issues them, one copy per tensor and tile when the block spans all channels -- the usual case -- else one per row
+// segment).  The bytes in flight per SM are then RING_S tiles of every resident block (~48-64 KB per block) instead of
+// what fits in registers next to the coefficients and partial sums (two rows per thread, ~37 KB per SM: the previous
+// register-pipelined versions ran at 1.8-3.5 TB/s and spilled in the hot loop when widened).  Also from those captures:
+//   * geometry is 32-bit and comes from the host (rows per group / per chunk, CT); groups are the grid's z dimension --
+//     a third of the old kernels' executed instructions were 64-bit divisions, an fp64 reciprocal and the fp64
+//     statistics of 8 channels recomputed by EVERY row-thread;
+//   * per-channel coefficients are computed ONCE per block into shared memory (one thread per channel) while the first
+//     tiles are in flight, and each thread then takes its 4..8 channels from there;
+//   * GLU's gate is rcp(1 + ex2(b * sc' + sh')) with -log2(e) folded into sc' / sh' (FFMA, MUFU.EX2, FADD, MUFU.RCP);
+//   * the backward sums live one per 128-byte line (EKL_BN_BWD_SPREAD doubles apart), so the fp64 reds of a block land
+//     on as many L2 slices as it has channels (444 blocks x 256 reds onto 16 lines used to drain for ~8 us after the last
+//     block had finished), and the block-level reduction issues ONE red per (channel, sum) from CT * NV threads.
+constexpr int BWD_SPREAD = 16;                  // == EKL_BN_BWD_SPREAD (include/ekl_b200.h)
+constexpr float NEG_LOG2E = -1.4426950408889634f;
+constexpr int RING_S = 4;                       // stages of the shared-memory ring
+constexpr int RPT = 2;                          // rows per thread and tile (a tile is RT * RPT rows)
+
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// sigmoid of the pre-scaled gate argument t = -log2(e) * z:  1 / (1 + 2^t)   (t -> +inf gives 0, t -> -inf gives 1)
+__device__ __forceinline__ float gate_sigmoid(float t) { return rcp_approx(1.f + ex2_approx(t)); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+template <int VEC> struct SmemIO;
+template <> struct SmemIO<8> { static __device__ __forceinline__ void load(uint32_t a, float* f) { unpack8(lds128(a), f); } };
+template <> struct SmemIO<4> {
+  static __device__ __forceinline__ void load(uint32_t a, float* f) {
+    const uint2 u = lds64(a);
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  }
+};
+
+// Producer side of the ring (thread 0 of a block, once per tile): see struct Ring below for the stage layout.
+template <int VEC, int NH>
+__device__ __noinline__ void ring_issue(int j, int Mg, int per, int CT, int Cy, int has1, const bf16* t0, const bf16* t1,
+                                        uint32_t sbase, uint32_t bars, int stage_bytes, int RT, int nrows, int g, int k,
+                                        int strip0, int segv) {
+  const int Co = NH == 2 ? Cy / 2 : Cy;
+  const int seg = CT * VEC, TR = RT * RPT;
+  const int s = j % RING_S;
+  const uint32_t st = sbase + (uint32_t)s * stage_bytes, fb = bars + 8 * s;
+  const int first = j * TR;
+  const int rows = nrows - first < TR ? nrows - first : TR;
+  const int64_t grow = (int64_t)g * Mg + k * per + first;
+  const uint32_t y_bytes = (uint32_t)TR * NH * seg * 2;
+  if (gridDim.x == 1) {
+    const uint32_t b0 = (uint32_t)rows * Cy * 2, b1 = has1 ? (uint32_t)rows * Co * 2 : 0u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(b0 + b1) : "memory");
+    bulk_g2s(st, t0 + grow * Cy, b0, fb);
+    if (has1) bulk_g2s(st + y_bytes, t1 + grow * Co, b1, fb);
+  } else {
+    const uint32_t sb = (uint32_t)segv * 2;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)rows * sb * (NH + has1)) : "memory");
+#pragma unroll 1
+    for (int r = 0; r < rows; ++r) {
+      bulk_g2s(st + (uint32_t)(r * NH * seg * 2), t0 + (grow + r) * Cy + strip0, sb, fb);
+      if (NH == 2) bulk_g2s(st + (uint32_t)((r * NH + 1) * seg * 2), t0 + (grow + r) * Cy + Co + strip0, sb, fb);
+      if (has1) bulk_g2s(st + y_bytes + (uint32_t)(r * seg * 2), t1 + (grow + r) * Co + strip0, sb, fb);
+    }
+  }
+}
+
+// One block's view of a streaming pass.  Up to two tensors stream through the ring: tensor 0 is y ([rows][Cy], NH halves
+// of the block's channel strip per row), tensor 1 (optional) has Co channels per row (dout / residual).  A stage holds
+// TR = RT * RPT rows: [TR][NH][seg] of y, then [TR][seg] of tensor 1 (seg = CT * VEC channels; with one strip seg == Co
+// and a row is laid out exactly as in global memory, so a tile is ONE contiguous copy per tensor).
+// The struct keeps only what the consumer loop needs; the producer (thread 0, once per tile) re-derives its geometry.
+template <int VEC, int NH>
+struct Ring {
+  uint32_t sbase, bars;           // shared-window addresses: stage 0 / full[0] (empty[s] = bars + 8 * (RING_S + s))
+  uint32_t off_a, step_a;         // byte offset of this thread's y vector in row rt of a stage / stride of RT rows
+  uint32_t off_1, step_1;         // the same for tensor 1
+  uint32_t seg2;                  // bytes between the two halves of a row (GLU gate half)
+  int stage_bytes;
+  int rt, RT, nrows, ntiles;
+  int g, k, ct, strip0, segv;     // statistics group, chunk, vector-thread; strip origin / valid width (channels, per half)
+  bool active;
+
+  __device__ __forceinline__ void init(int Mg, int per, int CT, int Cy, bool rev, bool has1, uint8_t* smem_ring) {
+    const int Co = NH == 2 ? Cy / 2 : Cy;
+    RT = 256 / CT;
+    rt = (int)threadIdx.x / CT;
+    ct = (int)threadIdx.x - rt * CT;
+    k = rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+    g = rev ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+    const int seg = CT * VEC;
+    strip0 = (int)blockIdx.x * seg;
+    segv = Co - strip0 < seg ? Co - strip0 : seg;
+    active = ct * VEC < segv && rt < RT;
+    const int r0 = k * per;
+    const int r1 = r0 + per < Mg ? r0 + per : Mg;
+    nrows = r1 > r0 ? r1 - r0 : 0;
+    const int TR = RT * RPT;
+    ntiles = (nrows + TR - 1) / TR;
+    bars = smem_u32(smem_ring);
+    sbase = bars + 128;
+    const int y_bytes = TR * NH * seg * 2;
+    stage_bytes = y_bytes + (has1 ? TR * seg * 2 : 0);
+    seg2 = (uint32_t)seg * 2;
+    off_a = (uint32_t)((rt * NH * seg + ct * VEC) * 2);
+    step_a = (uint32_t)(RT * NH * seg * 2);
+    off_1 = (uint32_t)(y_bytes + (rt * seg + ct * VEC) * 2);
+    step_1 = (uint32_t)(RT * seg * 2);
+  }
+  static __device__ __forceinline__ void bar_init(uint32_t a, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+  }
+  __device__ __forceinline__ void barriers() {
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < RING_S; ++s) { bar_init(bars + 8 * s, 1); bar_init(bars + 8 * (RING_S + s), 8); }
+      fence_barrier_init();
+    }
+    __syncthreads();
+  }
+  // thread 0: start the copies of tile j into stage j % RING_S (an out-of-line call: the producer's address arithmetic must
+  // not hold registers across the consumer loop of all 256 threads)
+  __device__ __forceinline__ void issue(int j, int Mg, int per, int CT, int Cy, bool has1, const bf16* t0, const bf16* t1) const {
+    ring_issue<VEC, NH>(j, Mg, per, CT, Cy, has1 ? 1 : 0, t0, t1, sbase, bars, stage_bytes, RT, nrows, g, k, strip0, segv);
+  }
+  static __device__ __forceinline__ void wait_bar(uint32_t a, uint32_t parity) {
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                   : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+      if (!ok && clock64() - t0 > 8000000000LL) __trap();      // a protocol bug must trap, not hang the GPU box
+    }
+  }
+  __device__ __forceinline__ void wait_tile(int j) const { wait_bar(bars + 8 * (j % RING_S), (uint32_t)(j / RING_S) & 1u); }
+  // every warp releases the stage; thread 0 refills it with tile j + RING_S once all 8 warps have
+  __device__ __forceinline__ void release(int j, int Mg, int per, int CT, int Cy, bool has1, const bf16* t0, const bf16* t1) const {
+    __syncwarp();
+    const uint32_t eb = bars + 8 * (RING_S + j % RING_S);
+    if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(eb) : "memory");
+    if (threadIdx.x == 0 && j + RING_S < ntiles) {
+      wait_bar(eb, (uint32_t)(j / RING_S) & 1u);
+      issue(j + RING_S, Mg, per, CT, Cy, has1, t0, t1);
+    }
+  }
+  __device__ __forceinline__ uint32_t stage(int j) const { return sbase + (uint32_t)(j % RING_S) * stage_bytes; }
+};
 
 // ---------------------------------------------------------------- forward
 // sums != null (training): statistics from the fp64 sums; mean_io / rstd_io [groups][Cy] are WRITTEN by chunk 0 of each
-// group (saved for the backward pass) and block row 0 applies one running-statistics momentum update per group, in
-// group order (one per reference forward call).  sums == null (inference): mean_io / rstd_io are inputs.
-template <int ACT, int U>
-__global__ void __launch_bounds__(256, U == 2 ? 3 : 2) bn_act_fwd_kernel(const bf16* __restrict__ y, int64_t M, int Cy, int groups,
-                                                            const double* __restrict__ sums, float eps, float momentum,
+// group (saved for the backward pass) and the first block of every strip applies one running-statistics momentum update
+// per group, in group order (one per reference forward call).  sums == null (inference): mean_io / rstd_io are inputs.
+// Dynamic shared memory: [NH * CT * VEC] float2 (scale, shift; GLU gate half pre-multiplied by -log2 e) | ring.
+template <int ACT>
+__global__ void __launch_bounds__(256, 3) bn_act_fwd_kernel(const bf16* __restrict__ y, int Mg, int per, int CT, int Cy,
+                                                            const double* __restrict__ sums, double inv_n, float eps, float momentum,
                                                             float* mean_io, float* rstd_io, float* running_mean,
                                                             float* running_var,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                            const bf16* __restrict__ residual, bf16* __restrict__ out, int rev) {
+                                                            const bf16* __restrict__ residual, bf16* __restrict__ out, int rev,
+                                                            int coef_bytes) {
   constexpr int VEC = ActVec<ACT>::V;
+  constexpr int NH = ACT == ACT_GLU ? 2 : 1;
   using IO = VecIO<VEC>;
-  const int Co = ACT == ACT_GLU ? Cy / 2 : Cy;
-  const Tile t = make_tile(M, Co / VEC, groups, rev != 0);
-  if (!t.active) return;
-  const int c0 = t.oct * VEC;
-  // software pipeline: the loads of the next U rows are in flight while the current U rows are computed; the first
-  // batch is issued before the per-channel coefficient loads so the block prologue overlaps the stream
-  typename IO::T ca[U], cb[U], cq[U], na[U], nb[U], nq[U];
-  auto load = [&](typename IO::T* a, typename IO::T* b, typename IO::T* q, int64_t rb) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t r = rb + (int64_t)u * t.RT;
-      if (r < t.r1) {
-        a[u] = *reinterpret_cast<const typename IO::T*>(y + r * Cy + c0);
-        if (ACT == ACT_GLU) b[u] = *reinterpret_cast<const typename IO::T*>(y + r * Cy + Co + c0);
-        if (residual != nullptr) q[u] = *reinterpret_cast<const typename IO::T*>(residual + r * Co + c0);
-      }
-    }
-  };
-  int64_t rb = t.r0 + t.rt;
-  load(ca, cb, cq, rb);
-  float sc[VEC], sh[VEC], sc2[VEC], sh2[VEC];
-  const double inv_n = 1.0 / (double)(M / groups);
-  constexpr int NHF = ACT == ACT_GLU ? 2 : 1;
-#pragma unroll
-  for (int h = 0; h < NHF; ++h)
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const int c = h * Co + c0 + i;
-      float m, r;
-      if (sums != nullptr) {
-        const BnStat st = bn_stat(sums, t.g, Cy, c, inv_n, eps);
-        m = st.mean; r = st.rstd;
-        if (t.k == 0 && t.rt == 0) { mean_io[t.g * Cy + c] = m; rstd_io[t.g * Cy + c] = r; }
-      } else {
-        m = mean_io[t.g * Cy + c]; r = rstd_io[t.g * Cy + c];
-      }
-      const float s = gamma[c] * r;
-      if (h == 0) { sc[i] = s; sh[i] = beta[c] - m * s; } else { sc2[i] = s; sh2[i] = beta[c] - m * s; }
-    }
-  if (sums != nullptr && running_mean != nullptr && blockIdx.y == 0 && t.rt == 0) {
-    const float n = (float)(M / groups);
-#pragma unroll
-    for (int h = 0; h < NHF; ++h)
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const int c = h * Co + c0 + i;
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  float2* coef = reinterpret_cast<float2*>(smem_dyn);
+  Ring<VEC, NH> R;
+  const bool has1 = residual != nullptr;
+  R.init(Mg, per, CT, Cy, rev != 0, has1, smem_dyn + coef_bytes);
+  R.barriers();
+  if (threadIdx.x == 0)
+    for (int j = 0; j < RING_S && j < R.ntiles; ++j) R.issue(j, Mg, per, CT, Cy, has1, y, residual);
+  const int Co = ACT == ACT_GLU ? Cy / 2 : Cy, groups = (int)gridDim.z, nstrip = CT * VEC;
+  for (int j = threadIdx.x; j < NH * nstrip; j += 256) {
+    const int h = j >= nstrip ? 1 : 0;
+    const int cc = R.strip0 + j - h * nstrip;
+    if (cc >= Co) continue;
+    const int c = h * Co + cc;
+    float m, r;
+    if (sums != nullptr) {
+      const BnStat st = bn_stat(sums, R.g, Cy, c, inv_n, eps);
+      m = st.mean; r = st.rstd;
+      if (R.k == 0) { mean_io[R.g * Cy + c] = m; rstd_io[R.g * Cy + c] = r; }
+      if (running_mean != nullptr && blockIdx.y == 0 && blockIdx.z == 0) {
+        const float n = (float)Mg;
         float rm = running_mean[c], rv = running_var[c];
         for (int g = 0; g < groups; ++g) {
-          const BnStat st = bn_stat(sums, g, Cy, c, inv_n, eps);
-          const float unb = n > 1.f ? st.var * n / (n - 1.f) : st.var;
-          rm = (1.f - momentum) * rm + momentum * st.mean;
+          const BnStat sg = bn_stat(sums, g, Cy, c, inv_n, eps);
+          const float unb = n > 1.f ? sg.var * n / (n - 1.f) : sg.var;
+          rm = (1.f - momentum) * rm + momentum * sg.mean;
           rv = (1.f - momentum) * rv + momentum * unb;
         }
         running_mean[c] = rm; running_var[c] = rv;
       }
-  }
-  for (; rb < t.r1; rb += (int64_t)U * t.RT) {
-    load(na, nb, nq, rb + (int64_t)U * t.RT);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t r = rb + (int64_t)u * t.RT;
-      if (r >= t.r1) break;
-      float a[VEC], o[VEC];
-      IO::unpack(ca[u], a);
-      if (ACT == ACT_GLU) {
-        float b[VEC];
-        IO::unpack(cb[u], b);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) o[i] = (a[i] * sc[i] + sh[i]) * sigmoidf_(b[i] * sc2[i] + sh2[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          const float z = a[i] * sc[i] + sh[i];
-          o[i] = ACT == ACT_LRELU ? (z > 0.f ? z : 0.2f * z) : (ACT == ACT_RELU ? fmaxf(z, 0.f) : z);
-        }
-      }
-      if (residual != nullptr) {
-        float q[VEC];
-        IO::unpack(cq[u], q);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) o[i] += q[i];
-      }
-      *reinterpret_cast<typename IO::T*>(out + r * Co + c0) = IO::pack(o);
+    } else {
+      m = mean_io[R.g * Cy + c]; r = rstd_io[R.g * Cy + c];
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) { ca[u] = na[u]; cb[u] = nb[u]; cq[u] = nq[u]; }
+    float s = gamma[c] * r, b = beta[c] - m * s;
+    if (ACT == ACT_GLU && h == 1) { s *= NEG_LOG2E; b *= NEG_LOG2E; }
+    coef[j] = make_float2(s, b);
   }
-}
-
-// dz (pre-activation gradient) for the VEC (GLU: VEC+VEC) channels a thread owns
-template <int ACT, int VEC>
-__device__ __forceinline__ void act_bwd(const float* ya, const float* yb, const float* d, const float* sc, const float* sh,
-                                        const float* sc2, const float* sh2, float* dza, float* dzb) {
+  __syncthreads();
+  float sc[VEC], sh[VEC], sc2[VEC], sh2[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    const float z = ya[i] * sc[i] + sh[i];
-    if (ACT == ACT_GLU) {
-      const float s = sigmoidf_(yb[i] * sc2[i] + sh2[i]);
-      dza[i] = d[i] * s;
-      dzb[i] = d[i] * z * s * (1.f - s);
-    } else if (ACT == ACT_LRELU) {
-      dza[i] = z > 0.f ? d[i] : 0.2f * d[i];
-    } else if (ACT == ACT_RELU) {
-      dza[i] = z > 0.f ? d[i] : 0.f;
-    } else {
-      dza[i] = d[i];
+    const float2 v = coef[R.ct * VEC + i];
+    sc[i] = v.x; sh[i] = v.y;
+    if (ACT == ACT_GLU) { const float2 w = coef[nstrip + R.ct * VEC + i]; sc2[i] = w.x; sh2[i] = w.y; }
+  }
+  bf16* po = out + ((int64_t)R.g * Mg + R.k * per + R.rt) * Co + R.strip0 + R.ct * VEC;
+  const int64_t stepO = (int64_t)R.RT * Co;
+  int left = R.active ? R.nrows - R.rt : 0;          // rows of this thread's residue class still to come (> 0: row valid)
+  for (int j = 0; j < R.ntiles; ++j) {
+    R.wait_tile(j);
+    const uint32_t st = R.stage(j);
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+      if (left - u * R.RT > 0) {
+        const uint32_t p = st + R.off_a + u * R.step_a;
+        float a[VEC], o[VEC];
+        SmemIO<VEC>::load(p, a);
+        if (ACT == ACT_GLU) {
+          float b[VEC];
+          SmemIO<VEC>::load(p + R.seg2, b);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) o[i] = fmaf(a[i], sc[i], sh[i]) * gate_sigmoid(fmaf(b[i], sc2[i], sh2[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            const float z = fmaf(a[i], sc[i], sh[i]);
+            o[i] = ACT == ACT_LRELU ? (z > 0.f ? z : 0.2f * z) : (ACT == ACT_RELU ? fmaxf(z, 0.f) : z);
+          }
+        }
+        if (has1) {
+          float q[VEC];
+          SmemIO<VEC>::load(st + R.off_1 + u * R.step_1, q);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) o[i] += q[i];
+        }
+        *reinterpret_cast<typename IO::T*>(po + u * stepO) = IO::pack(o);
+      }
     }
+    po += RPT * stepO;
+    left -= RPT * R.RT;
+    R.release(j, Mg, per, CT, Cy, has1, y, residual);
   }
 }
 
 // ---------------------------------------------------------------- backward, pass 1: partial sums
-// S1 = sum dz, S2 = sum dz * xhat with xhat = y*rstd - mean*rstd (one FMA; coefficients rs / nmr)
-template <int ACT, int U>
-__global__ void __launch_bounds__(256, U == 2 ? 3 : 2) bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dout,
-                                                                   int64_t M, int Cy, int groups,
+// S1 = sum dz, S2 = sum dz * xhat with xhat = y*rstd - mean*rstd (one FMA; coefficients rs / nmr), accumulated into
+// sums[((g*2 + which) * Cy + c) * BWD_SPREAD] (fp64 reds, one 128-byte line per sum).
+// Dynamic shared memory: [NH * CT * VEC] float4 (scale, shift, rstd, -mean*rstd) | ring (re-used for the block reduction).
+template <int ACT>
+__global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dout,
+                                                                   int Mg, int per, int CT, int Cy,
                                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                   double* __restrict__ sums /*[groups][2][Cy], zero on entry*/, int rev) {
+                                                                   double* __restrict__ sums, int rev, int coef_bytes) {
   constexpr int VEC = ActVec<ACT>::V;
-  using IO = VecIO<VEC>;
-  __shared__ float red[256 * 2 * VEC];
-  const int Co = ACT == ACT_GLU ? Cy / 2 : Cy;
-  const Tile t = make_tile(M, Co / VEC, groups, rev != 0);
-  const int c0 = t.oct * VEC;
   constexpr int NH = ACT == ACT_GLU ? 2 : 1;
-  float sc[VEC], sh[VEC], sc2[VEC], sh2[VEC], rs[VEC], nmr[VEC], rs2[VEC], nmr2[VEC];
-  float s1[NH][VEC], s2[NH][VEC];
-#pragma unroll
-  for (int h = 0; h < NH; ++h)
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) s1[h][i] = s2[h][i] = 0.f;
-  if (t.active) {
-    typename IO::T ca[U], cb[U], cd[U], na[U], nb[U], nd[U];      // software pipeline, see bn_act_fwd_kernel
-    auto load = [&](typename IO::T* a, typename IO::T* b, typename IO::T* d, int64_t rb) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t r = rb + (int64_t)u * t.RT;
-        if (r < t.r1) {
-          a[u] = *reinterpret_cast<const typename IO::T*>(y + r * Cy + c0);
-          if (ACT == ACT_GLU) b[u] = *reinterpret_cast<const typename IO::T*>(y + r * Cy + Co + c0);
-          d[u] = *reinterpret_cast<const typename IO::T*>(dout + r * Co + c0);
-        }
-      }
-    };
-    int64_t rb = t.r0 + t.rt;
-    load(ca, cb, cd, rb);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const float mu = mean[t.g * Cy + c0 + i];
-      rs[i] = rstd[t.g * Cy + c0 + i]; nmr[i] = -mu * rs[i];
-      sc[i] = gamma[c0 + i] * rs[i]; sh[i] = beta[c0 + i] - mu * sc[i];
-      if (ACT == ACT_GLU) {
-        const int c = Co + c0 + i;
-        const float mu_ = mean[t.g * Cy + c];
-        rs2[i] = rstd[t.g * Cy + c]; nmr2[i] = -mu_ * rs2[i];
-        sc2[i] = gamma[c] * rs2[i]; sh2[i] = beta[c] - mu_ * sc2[i];
-      }
-    }
-    for (; rb < t.r1; rb += (int64_t)U * t.RT) {
-      load(na, nb, nd, rb + (int64_t)U * t.RT);
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t r = rb + (int64_t)u * t.RT;
-        if (r >= t.r1) break;
-        float ya[VEC], yb[VEC], d[VEC], dza[VEC], dzb[VEC];
-        IO::unpack(ca[u], ya);
-        if (ACT == ACT_GLU) IO::unpack(cb[u], yb);
-        IO::unpack(cd[u], d);
-        act_bwd<ACT, VEC>(ya, yb, d, sc, sh, sc2, sh2, dza, dzb);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          s1[0][i] += dza[i]; s2[0][i] += dza[i] * (ya[i] * rs[i] + nmr[i]);
-          if (ACT == ACT_GLU) { s1[NH - 1][i] += dzb[i]; s2[NH - 1][i] += dzb[i] * (yb[i] * rs2[i] + nmr2[i]); }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) { ca[u] = na[u]; cb[u] = nb[u]; cd[u] = nd[u]; }
-    }
+  constexpr int NV = 2 * NH * VEC;                 // sums a thread carries: [S1 a | S2 a | S1 b | S2 b]
+  using IO = VecIO<VEC>;
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  float4* coef = reinterpret_cast<float4*>(smem_dyn);
+  Ring<VEC, NH> R;
+  R.init(Mg, per, CT, Cy, rev != 0, true, smem_dyn + coef_bytes);
+  R.barriers();
+  if (threadIdx.x == 0)
+    for (int j = 0; j < RING_S && j < R.ntiles; ++j) R.issue(j, Mg, per, CT, Cy, true, y, dout);
+  const int Co = ACT == ACT_GLU ? Cy / 2 : Cy, nstrip = CT * VEC;
+  for (int j = threadIdx.x; j < NH * nstrip; j += 256) {
+    const int h = j >= nstrip ? 1 : 0;
+    const int cc = R.strip0 + j - h * nstrip;
+    if (cc >= Co) continue;
+    const int c = h * Co + cc;
+    const float mu = mean[R.g * Cy + c], r = rstd[R.g * Cy + c];
+    float s = gamma[c] * r, b = beta[c] - mu * s;
+    if (ACT == ACT_GLU && h == 1) { s *= NEG_LOG2E; b *= NEG_LOG2E; }
+    coef[j] = make_float4(s, b, r, -mu * r);
   }
-  const int CT = t.CT;
+  __syncthreads();
+  float sc[VEC], sh[VEC], sc2[VEC], sh2[VEC], rs[VEC], nmr[VEC], rs2[VEC], nmr2[VEC];
 #pragma unroll
-  for (int h = 0; h < NH; ++h) {
-    __syncthreads();
+  for (int i = 0; i < VEC; ++i) {
+    const float4 v = coef[R.ct * VEC + i];
+    sc[i] = v.x; sh[i] = v.y; rs[i] = v.z; nmr[i] = v.w;
+    if (ACT == ACT_GLU) { const float4 w = coef[nstrip + R.ct * VEC + i]; sc2[i] = w.x; sh2[i] = w.y; rs2[i] = w.z; nmr2[i] = w.w; }
+  }
+  float acc[NV];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { red[threadIdx.x * 2 * VEC + i] = s1[h][i]; red[threadIdx.x * 2 * VEC + VEC + i] = s2[h][i]; }
-    __syncthreads();
-    if (t.active && t.rt == 0) {
-      float a[VEC], b[VEC];
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+  int left = R.active ? R.nrows - R.rt : 0;
+  for (int j = 0; j < R.ntiles; ++j) {
+    R.wait_tile(j);
+    const uint32_t st = R.stage(j);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) { a[i] = s1[h][i]; b[i] = s2[h][i]; }
-      for (int k = 1; k < t.RT; ++k)
+    for (int u = 0; u < RPT; ++u) {
+      if (left - u * R.RT > 0) {
+        const uint32_t p = st + R.off_a + u * R.step_a;
+        float ya[VEC], yb[VEC], d[VEC];
+        SmemIO<VEC>::load(p, ya);
+        if (ACT == ACT_GLU) SmemIO<VEC>::load(p + R.seg2, yb);
+        SmemIO<VEC>::load(st + R.off_1 + u * R.step_1, d);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-          a[i] += red[(threadIdx.x + k * CT) * 2 * VEC + i];
-          b[i] += red[(threadIdx.x + k * CT) * 2 * VEC + VEC + i];
+          const float z = fmaf(ya[i], sc[i], sh[i]);
+          float dza;
+          if (ACT == ACT_GLU) {
+            const float s = gate_sigmoid(fmaf(yb[i], sc2[i], sh2[i]));
+            dza = d[i] * s;
+            const float dzb = dza * z * (1.f - s);
+            acc[2 * VEC + i] += dzb;
+            acc[3 * VEC + i] = fmaf(dzb, fmaf(yb[i], rs2[i], nmr2[i]), acc[3 * VEC + i]);
+          } else if (ACT == ACT_LRELU) {
+            dza = z > 0.f ? d[i] : 0.2f * d[i];
+          } else if (ACT == ACT_RELU) {
+            dza = z > 0.f ? d[i] : 0.f;
+          } else {
+            dza = d[i];
+          }
+          acc[i] += dza;
+          acc[VEC + i] = fmaf(dza, fmaf(ya[i], rs[i], nmr[i]), acc[VEC + i]);
         }
-      double* dst = sums + (size_t)t.g * 2 * Cy + h * Co + c0;
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) { stat_add(dst + i, a[i]); stat_add(dst + Cy + i, b[i]); }
+      }
     }
+    left -= RPT * R.RT;
+    R.release(j, Mg, per, CT, Cy, true, y, dout);
+  }
+  // block reduction over the row-threads (the ring is drained: its memory holds the partials): thread (rt, ct) parks its
+  // NV sums, then thread j = ct * NV + v adds the RT partials of ONE (vector-thread, sum) pair and issues one fp64 red
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(smem_dyn + coef_bytes + 128);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) red[threadIdx.x * NV + v] = acc[v];
+  __syncthreads();
+  for (int j = threadIdx.x; j < CT * NV; j += 256) {
+    const int ct = j / NV, v = j - ct * NV;
+    if (ct * VEC >= R.segv) continue;
+    float a = 0.f;
+    for (int k = 0; k < R.RT; ++k) a += red[(k * CT + ct) * NV + v];
+    const int h = v / (2 * VEC), which = (v / VEC) & 1, i = v % VEC;
+    const int c = h * Co + R.strip0 + ct * VEC + i;
+    stat_add(sums + ((size_t)(R.g * 2 + which) * Cy + c) * BWD_SPREAD, a);
   }
 }
 
 // ---------------------------------------------------------------- backward, pass 2: dy
 // dy = k*(dz - S1/n - xhat*S2/n), k = gamma*rstd  ==  k*dz + A*y + Bc  with  A = -k*rstd*S2/n,  Bc = -k*S1/n - A*mean
-template <int ACT, int U>
-__global__ void __launch_bounds__(256, U == 2 ? 3 : 2) bn_act_bwd_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dout,
-                                                                  int64_t M, int Cy, int groups,
+// Dynamic shared memory: [NH * CT * VEC] float4 (scale, shift, A, Bc) | ring.
+template <int ACT>
+__global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dout,
+                                                                  int Mg, int per, int CT, int Cy, float inv_n,
                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                  const double* __restrict__ sums /*[groups][2][Cy]*/,
-                                                                  float* dgamma, float* dbeta, bf16* __restrict__ dy, int rev) {
+                                                                  const double* __restrict__ sums,
+                                                                  float* dgamma, float* dbeta, bf16* __restrict__ dy, int rev,
+                                                                  int coef_bytes) {
   constexpr int VEC = ActVec<ACT>::V;
+  constexpr int NH = ACT == ACT_GLU ? 2 : 1;
   using IO = VecIO<VEC>;
-  const int Co = ACT == ACT_GLU ? Cy / 2 : Cy;
-  const Tile t = make_tile(M, Co / VEC, groups, rev != 0);
-  if (!t.active) return;
-  const int c0 = t.oct * VEC;
-  const float inv_n = 1.f / (float)(M / groups);
-  typename IO::T ca[U], cb[U], cd[U], na[U], nb[U], nd[U];        // software pipeline, see bn_act_fwd_kernel
-  auto load = [&](typename IO::T* a, typename IO::T* b, typename IO::T* d, int64_t rb) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t r = rb + (int64_t)u * t.RT;
-      if (r < t.r1) {
-        a[u] = *reinterpret_cast<const typename IO::T*>(y + r * Cy + c0);
-        if (ACT == ACT_GLU) b[u] = *reinterpret_cast<const typename IO::T*>(y + r * Cy + Co + c0);
-        d[u] = *reinterpret_cast<const typename IO::T*>(dout + r * Co + c0);
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  float4* coef = reinterpret_cast<float4*>(smem_dyn);
+  Ring<VEC, NH> R;
+  R.init(Mg, per, CT, Cy, rev != 0, true, smem_dyn + coef_bytes);
+  R.barriers();
+  if (threadIdx.x == 0)
+    for (int j = 0; j < RING_S && j < R.ntiles; ++j) R.issue(j, Mg, per, CT, Cy, true, y, dout);
+  const int Co = ACT == ACT_GLU ? Cy / 2 : Cy, groups = (int)gridDim.z, nstrip = CT * VEC;
+  for (int j = threadIdx.x; j < NH * nstrip; j += 256) {
+    const int h = j >= nstrip ? 1 : 0;
+    const int cc = R.strip0 + j - h * nstrip;
+    if (cc >= Co) continue;
+    const int c = h * Co + cc;
+    const float mu = mean[R.g * Cy + c], r = rstd[R.g * Cy + c];
+    const float s = gamma[c] * r, b = beta[c] - mu * s;
+    const float S1 = (float)sums[((size_t)(R.g * 2 + 0) * Cy + c) * BWD_SPREAD];
+    const float S2 = (float)sums[((size_t)(R.g * 2 + 1) * Cy + c) * BWD_SPREAD];
+    const float A = -s * r * S2 * inv_n;
+    const float Bc = -s * S1 * inv_n - A * mu;
+    const bool gate = ACT == ACT_GLU && h == 1;
+    coef[j] = make_float4(gate ? s * NEG_LOG2E : s, gate ? b * NEG_LOG2E : b, A, Bc);
+    // parameter gradients (accumulated): dgamma[c] += sum_g S2, dbeta[c] += sum_g S1 -- one thread per channel
+    if (blockIdx.y == 0 && blockIdx.z == 0 && (dgamma != nullptr || dbeta != nullptr)) {
+      double tb = 0.0, tg = 0.0;
+      for (int g = 0; g < groups; ++g) {
+        tb += sums[((size_t)(g * 2 + 0) * Cy + c) * BWD_SPREAD];
+        tg += sums[((size_t)(g * 2 + 1) * Cy + c) * BWD_SPREAD];
       }
+      if (dgamma != nullptr) dgamma[c] += (float)tg;
+      if (dbeta != nullptr) dbeta[c] += (float)tb;
     }
-  };
-  int64_t rb = t.r0 + t.rt;
-  load(ca, cb, cd, rb);
-  float sc[VEC], sh[VEC], sc2[VEC], sh2[VEC], A[VEC], Bc[VEC], A2[VEC], Bc2[VEC];
+  }
+  __syncthreads();
+  // k2: the true gamma*rstd of the gate half (its stored scale carries the -log2 e factor)
+  float sc[VEC], sh[VEC], sc2[VEC], sh2[VEC], A[VEC], Bc[VEC], A2[VEC], Bc2[VEC], k2[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    {
-      const int c = c0 + i;
-      const float mu = mean[t.g * Cy + c], r = rstd[t.g * Cy + c];
-      sc[i] = gamma[c] * r; sh[i] = beta[c] - mu * sc[i];
-      A[i] = -sc[i] * r * (float)sums[(t.g * 2 + 1) * Cy + c] * inv_n;
-      Bc[i] = -sc[i] * (float)sums[(t.g * 2 + 0) * Cy + c] * inv_n - A[i] * mu;
-    }
+    const float4 v = coef[R.ct * VEC + i];
+    sc[i] = v.x; sh[i] = v.y; A[i] = v.z; Bc[i] = v.w;
     if (ACT == ACT_GLU) {
-      const int c = Co + c0 + i;
-      const float mu = mean[t.g * Cy + c], r = rstd[t.g * Cy + c];
-      sc2[i] = gamma[c] * r; sh2[i] = beta[c] - mu * sc2[i];
-      A2[i] = -sc2[i] * r * (float)sums[(t.g * 2 + 1) * Cy + c] * inv_n;
-      Bc2[i] = -sc2[i] * (float)sums[(t.g * 2 + 0) * Cy + c] * inv_n - A2[i] * mu;
+      const float4 w = coef[nstrip + R.ct * VEC + i];
+      sc2[i] = w.x; sh2[i] = w.y; A2[i] = w.z; Bc2[i] = w.w; k2[i] = w.x * (1.f / NEG_LOG2E);
     }
   }
-  // parameter gradients (accumulated): dgamma[c] += sum_g S2, dbeta[c] += sum_g S1 -- one thread per channel
-  if (blockIdx.y == 0 && t.rt == 0 && (dgamma != nullptr || dbeta != nullptr)) {
+  bf16* po = dy + ((int64_t)R.g * Mg + R.k * per + R.rt) * Cy + R.strip0 + R.ct * VEC;
+  const int64_t stepY = (int64_t)R.RT * Cy;
+  int left = R.active ? R.nrows - R.rt : 0;
+  for (int j = 0; j < R.ntiles; ++j) {
+    R.wait_tile(j);
+    const uint32_t st = R.stage(j);
 #pragma unroll
-    for (int h = 0; h < (ACT == ACT_GLU ? 2 : 1); ++h)
+    for (int u = 0; u < RPT; ++u) {
+      if (left - u * R.RT > 0) {
+        const uint32_t p = st + R.off_a + u * R.step_a;
+        float ya[VEC], yb[VEC], d[VEC], oa[VEC], ob[VEC];
+        SmemIO<VEC>::load(p, ya);
+        if (ACT == ACT_GLU) SmemIO<VEC>::load(p + R.seg2, yb);
+        SmemIO<VEC>::load(st + R.off_1 + u * R.step_1, d);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const int c = h * Co + c0 + i;
-        double tb = 0.0, tg = 0.0;
-        for (int g = 0; g < groups; ++g) { tb += sums[(g * 2 + 0) * Cy + c]; tg += sums[(g * 2 + 1) * Cy + c]; }
-        if (dgamma != nullptr) dgamma[c] += (float)tg;
-        if (dbeta != nullptr) dbeta[c] += (float)tb;
-      }
-  }
-  for (; rb < t.r1; rb += (int64_t)U * t.RT) {
-    load(na, nb, nd, rb + (int64_t)U * t.RT);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t r = rb + (int64_t)u * t.RT;
-      if (r >= t.r1) break;
-      float ya[VEC], yb[VEC], d[VEC], dza[VEC], dzb[VEC], o[VEC];
-      IO::unpack(ca[u], ya);
-      if (ACT == ACT_GLU) IO::unpack(cb[u], yb);
-      IO::unpack(cd[u], d);
-      act_bwd<ACT, VEC>(ya, yb, d, sc, sh, sc2, sh2, dza, dzb);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) o[i] = sc[i] * dza[i] + (A[i] * ya[i] + Bc[i]);
-      *reinterpret_cast<typename IO::T*>(dy + r * Cy + c0) = IO::pack(o);
-      if (ACT == ACT_GLU) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) o[i] = sc2[i] * dzb[i] + (A2[i] * yb[i] + Bc2[i]);
-        *reinterpret_cast<typename IO::T*>(dy + r * Cy + Co + c0) = IO::pack(o);
+        for (int i = 0; i < VEC; ++i) {
+          const float z = fmaf(ya[i], sc[i], sh[i]);
+          float dza;
+          if (ACT == ACT_GLU) {
+            const float s = gate_sigmoid(fmaf(yb[i], sc2[i], sh2[i]));
+            dza = d[i] * s;
+            const float dzb = dza * z * (1.f - s);
+            ob[i] = fmaf(k2[i], dzb, fmaf(A2[i], yb[i], Bc2[i]));
+          } else if (ACT == ACT_LRELU) {
+            dza = z > 0.f ? d[i] : 0.2f * d[i];
+          } else if (ACT == ACT_RELU) {
+            dza = z > 0.f ? d[i] : 0.f;
+          } else {
+            dza = d[i];
+          }
+          oa[i] = fmaf(sc[i], dza, fmaf(A[i], ya[i], Bc[i]));
+        }
+        *reinterpret_cast<typename IO::T*>(po + u * stepY) = IO::pack(oa);
+        if (ACT == ACT_GLU) *reinterpret_cast<typename IO::T*>(po + u * stepY + Co) = IO::pack(ob);
       }
     }
+    po += RPT * stepY;
+    left -= RPT * R.RT;
+    R.release(j, Mg, per, CT, Cy, true, y, dout);
+  }
+}
+
+// dz (pre-activation gradient) for the VEC (GLU: VEC+VEC) channels a thread owns; sc2 / sh2 are the gate half's
+// coefficients pre-multiplied by -log2(e) (see gate_sigmoid).  Used by the single-launch small-layer kernel.
+template <int ACT, int VEC>
+__device__ __forceinline__ void act_bwd(const float* ya, const float* yb, const float* d, const float* sc, const float* sh,
+                                        const float* sc2, const float* sh2, float* dza, float* dzb) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) { ca[u] = na[u]; cb[u] = nb[u]; cd[u] = nd[u]; }
+  for (int i = 0; i < VEC; ++i) {
+    if (ACT == ACT_GLU) {
+      const float z = fmaf(ya[i], sc[i], sh[i]);
+      const float s = gate_sigmoid(fmaf(yb[i], sc2[i], sh2[i]));
+      dza[i] = d[i] * s;
+      dzb[i] = dza[i] * z * (1.f - s);
+    } else if (ACT == ACT_LRELU) {
+      dza[i] = fmaf(ya[i], sc[i], sh[i]) > 0.f ? d[i] : 0.2f * d[i];
+    } else if (ACT == ACT_RELU) {
+      dza[i] = fmaf(ya[i], sc[i], sh[i]) > 0.f ? d[i] : 0.f;
+    } else {
+      dza[i] = d[i];
+    }
   }
 }
 
@@ -519,7 +691,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_small_kernel(const bf16* __res
   const bf16* yg = y + (int64_t)g * Mg * Cy;
   const bf16* dg = dout + (int64_t)g * Mg * Co;
   bf16* dyg = dy + (int64_t)g * Mg * Cy;
-  float sc[VEC], shf[VEC], sc2[VEC], sh2[VEC], rs[VEC], nmr[VEC], rs2[VEC], nmr2[VEC];
+  float sc[VEC], shf[VEC], sc2[VEC], sh2[VEC], g2s[VEC], g2h[VEC], rs[VEC], nmr[VEC], rs2[VEC], nmr2[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     const float mu = mean[g * Cy + c0 + i];
@@ -530,6 +702,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_small_kernel(const bf16* __res
       const float mu_ = mean[g * Cy + c];
       rs2[i] = rstd[g * Cy + c]; nmr2[i] = -mu_ * rs2[i];
       sc2[i] = gamma[c] * rs2[i]; sh2[i] = beta[c] - mu_ * sc2[i];
+      g2s[i] = sc2[i] * NEG_LOG2E; g2h[i] = sh2[i] * NEG_LOG2E;       // gate argument pre-scaled for gate_sigmoid
     }
   }
   float acc[NV];       // [S1 a | S2 a | S1 b | S2 b]
@@ -554,7 +727,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_small_kernel(const bf16* __res
       IO::unpack(ua[u], ya);
       if (ACT == ACT_GLU) IO::unpack(ub[u], yb);
       IO::unpack(ud[u], d);
-      act_bwd<ACT, VEC>(ya, yb, d, sc, shf, sc2, sh2, dza, dzb);
+      act_bwd<ACT, VEC>(ya, yb, d, sc, shf, g2s, g2h, dza, dzb);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         acc[i] += dza[i]; acc[VEC + i] += dza[i] * (ya[i] * rs[i] + nmr[i]);
@@ -604,7 +777,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_small_kernel(const bf16* __res
       IO::unpack(ua[u], ya);
       if (ACT == ACT_GLU) IO::unpack(ub[u], yb);
       IO::unpack(ud[u], d);
-      act_bwd<ACT, VEC>(ya, yb, d, sc, shf, sc2, sh2, dza, dzb);
+      act_bwd<ACT, VEC>(ya, yb, d, sc, shf, g2s, g2h, dza, dzb);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) o[i] = sc[i] * dza[i] + (A[i] * ya[i] + Bc[i]);
       *reinterpret_cast<typename IO::T*>(dyg + r * Cy + c0) = IO::pack(o);
@@ -763,13 +936,6 @@ extern "C" int ekl_col_stats(const void* y, int64_t M, int C, int groups, double
   return 0;
 }
 
-// rows in flight per thread of the streaming kernels: 2 (3 blocks / SM) or 4 (2 blocks / SM); EKL_BN_U selects (experiments)
-static int bn_u() {
-  static int u = 0;
-  if (u == 0) { const char* e = getenv("EKL_BN_U"); u = (e && e[0] == '4') ? 4 : 2; }
-  return u;
-}
-
 // traversal direction of the streaming passes (bit 0 forward pass, bit 1 backward reduce, bit 2 backward apply run from the
 // end of the tensor); EKL_BN_REV selects (experiments)
 static int bn_rev() {
@@ -787,34 +953,75 @@ static int bn_rev() {
     default: return ekl_fail(-1, "bad act %d", act);    \
   }
 
+// Launch geometry of a streaming pass: grid (channel strips, row chunks per group, groups), rows per chunk, vector
+// threads per block; dynamic shared memory = `ncoef` floats per channel of the block's strip + the tile ring
+// (RING_S stages of RT * RPT rows of y [+ the second tensor]).
+struct StreamGeom { dim3 grid; int Mg, per, CT, coef_bytes; size_t smem; };
+static int stream_geom(int64_t M, int Co, int groups, int act, int ncoef, bool second, StreamGeom* o) {
+  const int VEC = act_vec(act), NH = act == ACT_GLU ? 2 : 1;
+  const int nvec = Co / VEC;
+  EKL_REQUIRE(M / groups < (int64_t)1 << 31, "bn_act: more than 2^31 rows per group");
+  EKL_REQUIRE(groups <= 65535, "bn_act: too many statistics groups");
+  dim3 g2;
+  const int chunks = grid_rows(M, nvec, groups, &g2);
+  o->Mg = (int)(M / groups);
+  o->per = (o->Mg + chunks - 1) / chunks;
+  o->CT = nvec < 256 ? nvec : 256;
+  o->grid = dim3(g2.x, (unsigned)chunks, (unsigned)groups);
+  const int RT = 256 / o->CT;
+  const size_t seg = (size_t)o->CT * VEC;
+  o->coef_bytes = (int)((NH * seg * ncoef * sizeof(float) + 127) / 128 * 128);
+  const size_t stage = (size_t)RT * RPT * seg * 2 * (NH + (second ? 1 : 0));
+  o->smem = o->coef_bytes + 128 + RING_S * stage;
+  return 0;
+}
+
+// dynamic shared memory above 48 KB needs an opt-in per kernel; done once per instantiation
+template <typename K>
+static int allow_smem(K kern, size_t bytes) {
+  EKL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  (void)bytes;
+  return 0;
+}
+#define EKL_BN_LAUNCH(KERN, SG, ST, ...)                                          \
+  do {                                                                            \
+    static bool attr_done = false;                                                \
+    if (!attr_done) { if (int rc = allow_smem(KERN, (SG).smem)) return rc; attr_done = true; } \
+    KERN<<<(SG).grid, 256, (SG).smem, ST>>>(__VA_ARGS__);                         \
+  } while (0)
+
 extern "C" int ekl_bn_act_fwd(const void* y, int64_t M, int Cy, int groups, const double* sums, float eps, float momentum,
                               float* mean, float* rstd, float* running_mean, float* running_var, const float* gamma,
                               const float* beta, int act, const void* residual, void* out, void* stream) {
   const int Co = act == ACT_GLU ? Cy / 2 : Cy;
-  EKL_REQUIRE(Co % 8 == 0 && M % groups == 0, "bn_act_fwd: bad shape Cy=%d", Cy);
+  EKL_REQUIRE(groups > 0 && Co % 8 == 0 && M % groups == 0, "bn_act_fwd: bad shape Cy=%d", Cy);
   EKL_REQUIRE(y != nullptr && out != nullptr && mean != nullptr && rstd != nullptr, "bn_act_fwd: null pointer argument");
-  dim3 grid;
-  grid_rows(M, Co / act_vec(act), groups, &grid);
-  if (bn_u() == 4) {
-    EKL_ACT_SWITCH(act, (bn_act_fwd_kernel<A, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(
-                            (const bf16*)y, M, Cy, groups, sums, eps, momentum, mean, rstd, running_mean, running_var, gamma, beta,
-                            (const bf16*)residual, (bf16*)out, bn_rev() & 1)));
-  } else {
-    EKL_ACT_SWITCH(act, (bn_act_fwd_kernel<A, 2><<<grid, 256, 0, (cudaStream_t)stream>>>(
-                            (const bf16*)y, M, Cy, groups, sums, eps, momentum, mean, rstd, running_mean, running_var, gamma, beta,
-                            (const bf16*)residual, (bf16*)out, bn_rev() & 1)));
-  }
+  StreamGeom sg;
+  if (int rc = stream_geom(M, Co, groups, act, 2, residual != nullptr, &sg)) return rc;
+  const double inv_n = 1.0 / (double)sg.Mg;
+  cudaStream_t st = (cudaStream_t)stream;
+  EKL_ACT_SWITCH(act, EKL_BN_LAUNCH(bn_act_fwd_kernel<A>, sg, st, (const bf16*)y, sg.Mg, sg.per, sg.CT, Cy, sums, inv_n, eps, momentum,
+                                    mean, rstd, running_mean, running_var, gamma, beta, (const bf16*)residual, (bf16*)out,
+                                    bn_rev() & 1, sg.coef_bytes));
   EKL_LAUNCH_CHECK();
   return 0;
 }
 
-// sums: [groups][2][Cy] doubles of caller scratch, ZERO on entry (unused by single-launch small layers); dgamma/dbeta
-// accumulated (+=).
+// doubles of zeroed scratch ekl_bn_act_bwd needs for its two reductions (0: the layer runs the single-launch kernel)
+extern "C" int64_t ekl_bn_bwd_scratch_doubles(int64_t M, int Cy, int groups, int act) {
+  if (groups <= 0 || Cy <= 0 || M <= 0 || M % groups != 0) return -1;
+  const int Co = act == ACT_GLU ? Cy / 2 : Cy;
+  if (bn_small(M, Co, groups, act)) return 0;
+  return (int64_t)groups * 2 * Cy * BWD_SPREAD;
+}
+
+// sums: ekl_bn_bwd_scratch_doubles(...) doubles of caller scratch, ZERO on entry (unused by single-launch small layers);
+// dgamma/dbeta accumulated (+=).
 extern "C" int ekl_bn_act_bwd(const void* y, const void* dout, int64_t M, int Cy, int groups, const float* mean,
                               const float* rstd, const float* gamma, const float* beta, int act, double* sums,
                               float* dgamma, float* dbeta, void* dy, void* stream) {
   const int Co = act == ACT_GLU ? Cy / 2 : Cy;
-  EKL_REQUIRE(Co % 8 == 0 && M % groups == 0, "bn_act_bwd: bad shape Cy=%d", Cy);
+  EKL_REQUIRE(groups > 0 && Co % 8 == 0 && M % groups == 0, "bn_act_bwd: bad shape Cy=%d", Cy);
   cudaStream_t st = (cudaStream_t)stream;
   if (bn_small(M, Co, groups, act)) {
     dim3 sg(Co / act_vec(act) / SM_CT, groups);
@@ -824,21 +1031,14 @@ extern "C" int ekl_bn_act_bwd(const void* y, const void* dout, int64_t M, int Cy
     return 0;
   }
   EKL_REQUIRE(sums != nullptr, "bn_act_bwd: sums scratch required");
-  dim3 grid;
-  grid_rows(M, Co / act_vec(act), groups, &grid);
-  if (bn_u() == 4) {
-    EKL_ACT_SWITCH(act, (bn_act_bwd_reduce_kernel<A, 4><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M, Cy, groups,
-                                                                              mean, rstd, gamma, beta, sums, bn_rev() & 2)));
-    EKL_LAUNCH_CHECK();
-    EKL_ACT_SWITCH(act, (bn_act_bwd_apply_kernel<A, 4><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M, Cy, groups,
-                                                                             mean, rstd, gamma, beta, sums, dgamma, dbeta, (bf16*)dy, bn_rev() & 4)));
-  } else {
-    EKL_ACT_SWITCH(act, (bn_act_bwd_reduce_kernel<A, 2><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M, Cy, groups,
-                                                                              mean, rstd, gamma, beta, sums, bn_rev() & 2)));
-    EKL_LAUNCH_CHECK();
-    EKL_ACT_SWITCH(act, (bn_act_bwd_apply_kernel<A, 2><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)dout, M, Cy, groups,
-                                                                             mean, rstd, gamma, beta, sums, dgamma, dbeta, (bf16*)dy, bn_rev() & 4)));
-  }
+  StreamGeom sg;
+  if (int rc = stream_geom(M, Co, groups, act, 4, true, &sg)) return rc;
+  const float inv_n = 1.f / (float)sg.Mg;
+  EKL_ACT_SWITCH(act, EKL_BN_LAUNCH(bn_act_bwd_reduce_kernel<A>, sg, st, (const bf16*)y, (const bf16*)dout, sg.Mg, sg.per, sg.CT, Cy,
+                                    mean, rstd, gamma, beta, sums, bn_rev() & 2, sg.coef_bytes));
+  EKL_LAUNCH_CHECK();
+  EKL_ACT_SWITCH(act, EKL_BN_LAUNCH(bn_act_bwd_apply_kernel<A>, sg, st, (const bf16*)y, (const bf16*)dout, sg.Mg, sg.per, sg.CT, Cy,
+                                    inv_n, mean, rstd, gamma, beta, sums, dgamma, dbeta, (bf16*)dy, bn_rev() & 4, sg.coef_bytes));
   EKL_LAUNCH_CHECK();
   return 0;
 }

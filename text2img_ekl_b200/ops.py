@@ -534,7 +534,8 @@ class _BnAct(torch.autograd.Function):
         C = y.shape[-1]
         M = y.numel() // C
         dout = dout.contiguous()
-        sums = ARENA.take(ctx.groups * 2 * C, y.device)            # zero on entry: the two backward reductions land here
+        nsum = lib.ekl_bn_bwd_scratch_doubles(M, C, ctx.groups, ctx.act)
+        sums = ARENA.take(nsum, y.device) if nsum > 0 else None    # zero on entry: the two backward reductions land here
         dy = torch.empty_like(y)
         pg = gamma.requires_grad and not ctx.skip_pgrad
         Co = C // 2 if ctx.act == ACT_GLU else C

@@ -137,7 +137,7 @@ def run_bn(torch, L, lib, dev, rel):
         L.check(lib.ekl_bn_act_fwd(L.ptr(y), M, Cy, groups, L.ptr(stats), 1e-5, 0.1, L.ptr(mean), L.ptr(rstd), L.ptr(rm), L.ptr(rv),
                                    L.ptr(gamma), L.ptr(beta), act, L.ptr(res), L.ptr(out), L.stream()))
         small = M // groups <= 768
-        sums = torch.zeros(groups, 2, Cy, device=dev, dtype=torch.float64)
+        sums = torch.zeros(max(int(lib.ekl_bn_bwd_scratch_doubles(M, Cy, groups, act)), 2), device=dev, dtype=torch.float64)
         dg, db = torch.zeros(Cy, device=dev), torch.zeros(Cy, device=dev)
         dy = torch.empty(M, Cy, device=dev, dtype=torch.bfloat16)
         L.check(lib.ekl_bn_act_bwd(L.ptr(y), L.ptr(dout), M, Cy, groups, L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta),

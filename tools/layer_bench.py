@@ -103,7 +103,7 @@ def main():
             mean, rstd = torch.zeros(groups, Cy, device=dev), torch.ones(groups, Cy, device=dev)
             out = torch.empty(M, Co, device=dev, dtype=torch.bfloat16)
             dy = torch.empty_like(y)
-            sums = torch.zeros(groups, 2, Cy, device=dev, dtype=torch.float64)
+            sums = torch.zeros(max(int(lib.ekl_bn_bwd_scratch_doubles(M, Cy, groups, act)), 2), device=dev, dtype=torch.float64)
             dg, db = torch.zeros(Cy, device=dev), torch.zeros(Cy, device=dev)
             st = L.stream()
             if kind == "bn_fwd":

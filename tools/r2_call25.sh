@@ -1,0 +1,16 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+timeout 300 python tools/kernel_check.py --group bn > gpurun_out/c25_kc_bn.log 2>&1
+echo "group bn: $(grep -c '^PASS' gpurun_out/c25_kc_bn.log) pass, $(grep -c '^FAIL' gpurun_out/c25_kc_bn.log) fail"; grep '^FAIL' gpurun_out/c25_kc_bn.log | head
+for u in 2; do
+echo "EKL_BN_U=$u"
+EKL_BN_U=$u timeout 120 python tools/bn_bench.py 5 393216,64,1,1 98304,128,1,1 1572864,32,1,1 294912,128,3,2 393216,32,1,0 73728,256,3,2 2>&1 | grep -v Warn | tail -6
+done
+for rep in 1 2; do
+for u in 2; do
+EKL_BN_U=$u timeout 150 python bench.py --steps 40 --warmup 5 --no-cpu --no-extra --no-profile 2>/dev/null | grep '^{' | python -c "
+import sys, json
+d = json.loads(sys.stdin.read()); print('rep $rep EKL_BN_U=$u 3stages', round(d['value']), 'img/s', round(d['ms_per_step'], 3), 'ms')"
+done
+done

@@ -47,16 +47,18 @@ def capture(a):
     ev = []
     for e in json.load(open(tmp))["traceEvents"]:
         if e.get("ph") == "X" and e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset"):
-            ev.append((short(e["name"]), int(e.get("args", {}).get("stream", 0)), float(e["ts"]), float(e["dur"])))
+            ar = e.get("args", {})
+            ev.append((short(e["name"]), int(ar.get("stream", 0)), float(e["ts"]), float(e["dur"]), list(ar.get("grid", []))))
     os.remove(tmp)
     ev.sort(key=lambda x: x[2])
     t0 = ev[0][2]
-    ev = [(n, s, round(ts - t0, 3), round(d, 3)) for n, s, ts, d in ev]
+    ev = [(n, s, round(ts - t0, 3), round(d, 3), g) for n, s, ts, d, g in ev]
     json.dump({"config": a.config, "batch": B, "events": ev}, open(a.json, "w"))
     return ev
 
 
 def summarize(ev, top=12):
+    ev = [tuple(e[:4]) for e in ev]          # (name, stream, start us, duration us[, grid])
     end = max(ts + d for _, _, ts, d in ev)
     streams = collections.OrderedDict()
     for n, s, ts, d in ev:
