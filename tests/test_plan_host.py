@@ -190,6 +190,18 @@ def test_split_k_and_operand_planning_host_logic():
     # stride-1 / stride-2 convs with 64-multiple channels: data-gradient straight from the forward-packed filter
     assert lib.ekl_conv_dgrad_from_fwd(tail) == 1 and lib.ekl_conv_dgrad_from_fwd(big) == 1
     assert lib.ekl_conv_dgrad_from_fwd(mk(L.UP2, 24, 8, 8, 512, 512)) == 0          # pre-summed taps need their own pack
+    # sub-pixel plans with a short contraction and a few tiles per SM run on the resident-filter kernel as well: the
+    # data-gradient of the 64 -> 128 discriminator conv (contraction 128) and the small-channel up-convs of the generator
+    d1 = mk(L.DOWN2, 72, 128, 128, 64, 128, 24)
+    assert lib.ekl_conv_route(d1, 1) == 1 and lib.ekl_conv_dgrad_from_fwd(d1) == 0 and lib.ekl_conv_route(d1, 0) == 0
+    assert lib.ekl_conv_route(mk(L.UP2, 24, 128, 128, 32, 32, 24), 0) == 1
+    assert lib.ekl_conv_route(mk(L.UP2, 24, 64, 64, 64, 64, 24), 0) == 1
+    assert lib.ekl_conv_route(mk(L.UP2, 24, 32, 32, 128, 128, 24), 0) == 0          # 192 tiles: stays on the CTA-pair kernel
+    assert lib.ekl_conv_route(mk(L.DOWN2, 72, 32, 32, 64, 128, 24), 1) == 0        # too few tiles per SM
+    from text2img_ekl_b200 import ops
+    s1, s2 = ops.ConvSpec(L.DOWN2, 64, 128), ops.ConvSpec(L.DOWN2, 128, 256)
+    s1.w_layout = s2.w_layout = L.W_KRSC
+    assert not s1.dgrad_from_fwd() and s2.dgrad_from_fwd()        # the host keeps a transposed operand for the former
 
 
 def test_bn_counters_single_vector_add():

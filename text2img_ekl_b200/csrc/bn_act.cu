@@ -181,8 +181,8 @@ template <int ACT> struct ActVec { static constexpr int V = ACT == ACT_GLU ? 4 :
 //     block had finished), and the block-level reduction issues ONE red per (channel, sum) from CT * NV threads.
 constexpr int BWD_SPREAD = 16;                  // == EKL_BN_BWD_SPREAD (include/ekl_b200.h)
 constexpr float NEG_LOG2E = -1.4426950408889634f;
-constexpr int RING_S = 4;                       // stages of the shared-memory ring
-constexpr int RPT = 2;                          // rows per thread and tile (a tile is RT * RPT rows)
+// RING_S stages of the shared-memory ring, RPT rows per thread and tile (a tile is RT * RPT rows): template parameters
+// <RING_S, RPT> of the kernels below; measured choice in ring_cfg().
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -209,7 +209,7 @@ template <> struct SmemIO<4> {
 };
 
 // Producer side of the ring (thread 0 of a block, once per tile): see struct Ring below for the stage layout.
-template <int VEC, int NH>
+template <int VEC, int NH, int RING_S, int RPT>
 __device__ __noinline__ void ring_issue(int j, int Mg, int per, int CT, int Cy, int has1, const bf16* t0, const bf16* t1,
                                         uint32_t sbase, uint32_t bars, int stage_bytes, int RT, int nrows, int g, int k,
                                         int strip0, int segv) {
@@ -243,7 +243,7 @@ __device__ __noinline__ void ring_issue(int j, int Mg, int per, int CT, int Cy, 
 // TR = RT * RPT rows: [TR][NH][seg] of y, then [TR][seg] of tensor 1 (seg = CT * VEC channels; with one strip seg == Co
 // and a row is laid out exactly as in global memory, so a tile is ONE contiguous copy per tensor).
 // The struct keeps only what the consumer loop needs; the producer (thread 0, once per tile) re-derives its geometry.
-template <int VEC, int NH>
+template <int VEC, int NH, int RING_S, int RPT>
 struct Ring {
   uint32_t sbase, bars;           // shared-window addresses: stage 0 / full[0] (empty[s] = bars + 8 * (RING_S + s))
   uint32_t off_a, step_a;         // byte offset of this thread's y vector in row rt of a stage / stride of RT rows
@@ -293,7 +293,7 @@ struct Ring {
   // thread 0: start the copies of tile j into stage j % RING_S (an out-of-line call: the producer's address arithmetic must
   // not hold registers across the consumer loop of all 256 threads)
   __device__ __forceinline__ void issue(int j, int Mg, int per, int CT, int Cy, bool has1, const bf16* t0, const bf16* t1) const {
-    ring_issue<VEC, NH>(j, Mg, per, CT, Cy, has1 ? 1 : 0, t0, t1, sbase, bars, stage_bytes, RT, nrows, g, k, strip0, segv);
+    ring_issue<VEC, NH, RING_S, RPT>(j, Mg, per, CT, Cy, has1 ? 1 : 0, t0, t1, sbase, bars, stage_bytes, RT, nrows, g, k, strip0, segv);
   }
   static __device__ __forceinline__ void wait_bar(uint32_t a, uint32_t parity) {
     uint32_t ok = 0;
@@ -323,7 +323,7 @@ struct Ring {
 // group (saved for the backward pass) and the first block of every strip applies one running-statistics momentum update
 // per group, in group order (one per reference forward call).  sums == null (inference): mean_io / rstd_io are inputs.
 // Dynamic shared memory: [NH * CT * VEC] float2 (scale, shift; GLU gate half pre-multiplied by -log2 e) | ring.
-template <int ACT>
+template <int ACT, int RING_S, int RPT>
 __global__ void __launch_bounds__(256, 3) bn_act_fwd_kernel(const bf16* __restrict__ y, int Mg, int per, int CT, int Cy,
                                                             const double* __restrict__ sums, double inv_n, float eps, float momentum,
                                                             float* mean_io, float* rstd_io, float* running_mean,
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(256, 3) bn_act_fwd_kernel(const bf16* __restri
   using IO = VecIO<VEC>;
   extern __shared__ __align__(128) uint8_t smem_dyn[];
   float2* coef = reinterpret_cast<float2*>(smem_dyn);
-  Ring<VEC, NH> R;
+  Ring<VEC, NH, RING_S, RPT> R;
   const bool has1 = residual != nullptr;
   R.init(Mg, per, CT, Cy, rev != 0, has1, smem_dyn + coef_bytes);
   R.barriers();
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(256, 3) bn_act_fwd_kernel(const bf16* __restri
 // S1 = sum dz, S2 = sum dz * xhat with xhat = y*rstd - mean*rstd (one FMA; coefficients rs / nmr), accumulated into
 // sums[((g*2 + which) * Cy + c) * BWD_SPREAD] (fp64 reds, one 128-byte line per sum).
 // Dynamic shared memory: [NH * CT * VEC] float4 (scale, shift, rstd, -mean*rstd) | ring (re-used for the block reduction).
-template <int ACT>
+template <int ACT, int RING_S, int RPT>
 __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dout,
                                                                    int Mg, int per, int CT, int Cy,
                                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_kernel(const bf16* _
   using IO = VecIO<VEC>;
   extern __shared__ __align__(128) uint8_t smem_dyn[];
   float4* coef = reinterpret_cast<float4*>(smem_dyn);
-  Ring<VEC, NH> R;
+  Ring<VEC, NH, RING_S, RPT> R;
   R.init(Mg, per, CT, Cy, rev != 0, true, smem_dyn + coef_bytes);
   R.barriers();
   if (threadIdx.x == 0)
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_kernel(const bf16* _
 // ---------------------------------------------------------------- backward, pass 2: dy
 // dy = k*(dz - S1/n - xhat*S2/n), k = gamma*rstd  ==  k*dz + A*y + Bc  with  A = -k*rstd*S2/n,  Bc = -k*S1/n - A*mean
 // Dynamic shared memory: [NH * CT * VEC] float4 (scale, shift, A, Bc) | ring.
-template <int ACT>
+template <int ACT, int RING_S, int RPT>
 __global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dout,
                                                                   int Mg, int per, int CT, int Cy, float inv_n,
                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_kernel(const bf16* __
   using IO = VecIO<VEC>;
   extern __shared__ __align__(128) uint8_t smem_dyn[];
   float4* coef = reinterpret_cast<float4*>(smem_dyn);
-  Ring<VEC, NH> R;
+  Ring<VEC, NH, RING_S, RPT> R;
   R.init(Mg, per, CT, Cy, rev != 0, true, smem_dyn + coef_bytes);
   R.barriers();
   if (threadIdx.x == 0)
@@ -956,8 +956,13 @@ static int bn_rev() {
 // Launch geometry of a streaming pass: grid (channel strips, row chunks per group, groups), rows per chunk, vector
 // threads per block; dynamic shared memory = `ncoef` floats per channel of the block's strip + the tile ring
 // (RING_S stages of RT * RPT rows of y [+ the second tensor]).
+// ring shape <stages, rows per thread and tile>: measured on config 2 (profiles/r02_bn_summary.md) <4, 2> 7.73-7.85 ms/step,
+// <3, 4> 7.88, <6, 2> 7.95, <8, 1> 7.87-7.98
+constexpr int BN_RING_S = 4, BN_RPT = 2;
+
 struct StreamGeom { dim3 grid; int Mg, per, CT, coef_bytes; size_t smem; };
 static int stream_geom(int64_t M, int Co, int groups, int act, int ncoef, bool second, StreamGeom* o) {
+  const int RING_S = BN_RING_S, RPT = BN_RPT;
   const int VEC = act_vec(act), NH = act == ACT_GLU ? 2 : 1;
   const int nvec = Co / VEC;
   EKL_REQUIRE(M / groups < (int64_t)1 << 31, "bn_act: more than 2^31 rows per group");
@@ -986,8 +991,9 @@ static int allow_smem(K kern, size_t bytes) {
 #define EKL_BN_LAUNCH(KERN, SG, ST, ...)                                          \
   do {                                                                            \
     static bool attr_done = false;                                                \
-    if (!attr_done) { if (int rc = allow_smem(KERN, (SG).smem)) return rc; attr_done = true; } \
-    KERN<<<(SG).grid, 256, (SG).smem, ST>>>(__VA_ARGS__);                         \
+    auto kern_ = KERN<A, BN_RING_S, BN_RPT>;                                      \
+    if (!attr_done) { if (int rc = allow_smem(kern_, (SG).smem)) return rc; attr_done = true; } \
+    kern_<<<(SG).grid, 256, (SG).smem, ST>>>(__VA_ARGS__);                        \
   } while (0)
 
 extern "C" int ekl_bn_act_fwd(const void* y, int64_t M, int Cy, int groups, const double* sums, float eps, float momentum,
@@ -1000,7 +1006,7 @@ extern "C" int ekl_bn_act_fwd(const void* y, int64_t M, int Cy, int groups, cons
   if (int rc = stream_geom(M, Co, groups, act, 2, residual != nullptr, &sg)) return rc;
   const double inv_n = 1.0 / (double)sg.Mg;
   cudaStream_t st = (cudaStream_t)stream;
-  EKL_ACT_SWITCH(act, EKL_BN_LAUNCH(bn_act_fwd_kernel<A>, sg, st, (const bf16*)y, sg.Mg, sg.per, sg.CT, Cy, sums, inv_n, eps, momentum,
+  EKL_ACT_SWITCH(act, EKL_BN_LAUNCH(bn_act_fwd_kernel, sg, st, (const bf16*)y, sg.Mg, sg.per, sg.CT, Cy, sums, inv_n, eps, momentum,
                                     mean, rstd, running_mean, running_var, gamma, beta, (const bf16*)residual, (bf16*)out,
                                     bn_rev() & 1, sg.coef_bytes));
   EKL_LAUNCH_CHECK();
@@ -1034,10 +1040,10 @@ extern "C" int ekl_bn_act_bwd(const void* y, const void* dout, int64_t M, int Cy
   StreamGeom sg;
   if (int rc = stream_geom(M, Co, groups, act, 4, true, &sg)) return rc;
   const float inv_n = 1.f / (float)sg.Mg;
-  EKL_ACT_SWITCH(act, EKL_BN_LAUNCH(bn_act_bwd_reduce_kernel<A>, sg, st, (const bf16*)y, (const bf16*)dout, sg.Mg, sg.per, sg.CT, Cy,
+  EKL_ACT_SWITCH(act, EKL_BN_LAUNCH(bn_act_bwd_reduce_kernel, sg, st, (const bf16*)y, (const bf16*)dout, sg.Mg, sg.per, sg.CT, Cy,
                                     mean, rstd, gamma, beta, sums, bn_rev() & 2, sg.coef_bytes));
   EKL_LAUNCH_CHECK();
-  EKL_ACT_SWITCH(act, EKL_BN_LAUNCH(bn_act_bwd_apply_kernel<A>, sg, st, (const bf16*)y, (const bf16*)dout, sg.Mg, sg.per, sg.CT, Cy,
+  EKL_ACT_SWITCH(act, EKL_BN_LAUNCH(bn_act_bwd_apply_kernel, sg, st, (const bf16*)y, (const bf16*)dout, sg.Mg, sg.per, sg.CT, Cy,
                                     inv_n, mean, rstd, gamma, beta, sums, dgamma, dbeta, (bf16*)dy, bn_rev() & 4, sg.coef_bytes));
   EKL_LAUNCH_CHECK();
   return 0;

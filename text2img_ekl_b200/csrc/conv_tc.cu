@@ -695,7 +695,9 @@ static void tc_tile_plan(const EklGather* g, int group_b, bool allow_split, int*
     if (g->N % bn != 0) continue;
     const int64_t tiles = (int64_t)mtiles * (g->N / bn) * g->nvar;
     int ks = 1;
-    if (allow_split && g->nvar == 1 && KC == 64 && tiles * 3 <= sms && n_iters >= 64) {
+    static int split_min = -1;          // a plan splits when split_min x its work items fit the SMs (EKL_TC_SPLIT_MIN, default 3)
+    if (split_min < 0) { const char* e = getenv("EKL_TC_SPLIT_MIN"); split_min = e ? atoi(e) : 3; if (split_min < 2) split_min = 2; }
+    if (allow_split && g->nvar == 1 && KC == 64 && tiles * split_min <= sms && n_iters >= 64) {
       ks = (int)(sms / tiles);
       if (ks > n_iters / 16) ks = n_iters / 16;
       if (ks > 4) ks = 4;

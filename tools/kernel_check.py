@@ -17,8 +17,13 @@ SHAPES = {  # mode -> list of (B, H, W, Cin, Cout)
         (8, 4, 4, 192, 512), (2, 8, 8, 320, 128), (3, 32, 32, 16, 64), (2, 32, 32, 32, 16), (2, 64, 64, 16, 16),
         # resident-filter kernel (conv_rw.cu): two N tiles, one tile per image, more tiles than SMs
         (2, 16, 16, 64, 128), (5, 16, 8, 64, 64), (6, 64, 64, 64, 64), (3, 32, 64, 32, 32)],
-    1: [(4, 4, 4, 128, 128), (2, 8, 8, 64, 64), (3, 16, 16, 64, 128), (2, 32, 32, 32, 32), (2, 4, 4, 256, 512)],
-    2: [(4, 16, 16, 64, 128), (2, 8, 8, 128, 256), (3, 32, 32, 64, 64), (2, 8, 8, 512, 1024), (2, 64, 64, 32, 64)],
+    1: [(4, 4, 4, 128, 128), (2, 8, 8, 64, 64), (3, 16, 16, 64, 128), (2, 32, 32, 32, 32), (2, 4, 4, 256, 512),
+        # sub-pixel plans on the resident-filter kernel (>= 2 x 148 tiles of 16x8 low-resolution pixels): one / two channel
+        # blocks, SW128 / SW64 / SW32 rows, two N tiles
+        (10, 64, 64, 64, 64), (5, 128, 128, 32, 32), (20, 32, 64, 128, 64), (3, 128, 128, 16, 16), (10, 64, 64, 64, 128)],
+    2: [(4, 16, 16, 64, 128), (2, 8, 8, 128, 256), (3, 32, 32, 64, 64), (2, 8, 8, 512, 1024), (2, 64, 64, 32, 64),
+        # data-gradients of these are sub-pixel plans on the resident-filter kernel (contraction 128 = two channel blocks / 64)
+        (10, 128, 128, 64, 128), (6, 128, 128, 16, 64), (10, 128, 128, 128, 64)],
 }
 GROUPS = ["tc_fwd", "tc_dgrad", "tc_wgrad", "simt_fwd", "simt_dgrad", "simt_wgrad", "bn", "misc", "heads", "tc_split", "fold", "vc", "route"]
 
