@@ -1,7 +1,7 @@
 // tcgen05 convolution with the filter RESIDENT in shared memory and the input fetched once per tile as a row-halo patch:
 // the small-contraction layers (Cin <= 128) whose taps all lie in the 3x3 neighbourhood of the output pixel --
-//   * 3x3 / stride-1 forward and data-gradient, Cin in {16, 32, 64} (model.py:107-123 ResBlock, :426-437 GET_IMAGE_G, the
-//     folded jointConv, the discriminator stem);
+//   * 3x3 / stride-1 forward and data-gradient, Cin in {16, 32, 64, 128} (model.py:107-123 ResBlock, :426-437 GET_IMAGE_G,
+//     the folded jointConv, the discriminator stem);
 //   * the sub-pixel plans with 4 output-parity variants x 2x2 taps: nearest-up-x2 + 3x3 forward (model.py:87-94) and the
 //     data-gradient of conv4x4/s2 (model.py:816-830), Cin in {16, 32, 64, 128}.
 //
@@ -328,8 +328,28 @@ int launch_rw(RwParams& p, int grid, cudaStream_t st) {
   return 0;
 }
 
-int rw_bn(const EklGather* g) { return g->N % 64 == 0 ? 64 : (g->N % 32 == 0 ? 32 : 16); }
 int rw_kc(const EklGather* g) { return g->Cin % 64 == 0 ? 64 : g->Cin; }
+
+// input-pipeline stages that fit next to the resident filter (same arithmetic as rw_smem_plan)
+int rw_fit(int ntaps, int nkb, int KC, int BN, int halo1) {
+  const int rowb = KC * 2;
+  const int wt = (BN * rowb + 1023) / 1024 * 1024;
+  const int box = ((halo1 ? 180 : 144) * rowb + 1023) / 1024 * 1024;
+  const int stage = nkb * (halo1 ? 1 : 3) * box;
+  const int fixed = ntaps * nkb * wt + 128 * BN * 2 + 512 + 4096 + 1024;
+  return (214 * 1024 - fixed) / stage;
+}
+
+int rw_halo1(const EklGather* g);
+
+// N-tile width: the widest of 64 / 32 / 16 that divides N and leaves room for two input stages (0: none does).  A 3x3 conv
+// over 128 channels keeps 18 filter blocks resident: 32-wide tiles there (generator ResBlock data-gradients).
+int rw_bn(const EklGather* g) {
+  const int KC = rw_kc(g), nkb = g->Cin / KC, halo1 = rw_halo1(g);
+  for (int bn = 64; bn >= 16; bn >>= 1)
+    if (g->N % bn == 0 && rw_fit(g->ntaps, nkb, KC, bn, halo1) >= 2) return bn;
+  return 0;
+}
 
 // single-halo-box mode: forced for the plans that only exist in that form (several channel blocks, parity variants),
 // opt-in for the classic 3x3 layers (EKL_RW_HALO=1; measured a wash there: those are not load bound)
@@ -351,13 +371,13 @@ bool rw_subpixel_enabled() {
 
 // The resident-filter kernel applies to: one A view, one statistics group, every tap inside the 3x3 neighbourhood,
 // (1 variant x 9 taps) or (4 parity variants x 4 taps), Cin in {16, 32, 64, 128}, N % 16 == 0, H % 16 == 0, W % 8 == 0,
-// and a filter (taps x Cin x N-tile) that leaves room for a two-stage input pipeline.
+// and a filter (taps x Cin x N-tile) that leaves room for a two-stage input pipeline (rw_bn picks the N-tile width).
 int ekl_rw_supported(const EklGather* g, int group_b) {
   if (g->n_a != 1) return 0;
   const bool classic = g->nvar == 1 && g->ntaps == 9, sub = g->nvar == 4 && g->ntaps == 4;
   if (!classic && !sub) return 0;
   if (sub && !rw_subpixel_enabled()) return 0;
-  if (!(g->Cin == 16 || g->Cin == 32 || g->Cin == 64 || (g->Cin == 128 && sub))) return 0;
+  if (!(g->Cin == 16 || g->Cin == 32 || g->Cin == 64 || g->Cin == 128)) return 0;
   if (g->N % 16 != 0 || g->mH % 16 != 0 || g->mW % 8 != 0) return 0;
   if (group_b > 0 && group_b != g->mB) return 0;
   if (g->a[0].f32 || g->a[0].sC != 1) return 0;
@@ -370,14 +390,10 @@ int ekl_rw_supported(const EklGather* g, int group_b) {
   // sub-pixel plans reload the resident filter once per (variant, N tile) round: worth it only when a round has a few
   // tiles per CTA (the generator's 32x32 -> 64x64 up-conv, 192 tiles, stays on the CTA-pair kernel)
   if (sub && (int64_t)g->mB * (g->mH / 16) * (g->mW / 8) < 2 * (int64_t)ekl_num_sms()) return 0;
-  // shared-memory plan (same arithmetic as rw_smem_plan): filter blocks + staging + >= 2 input stages
-  const int KC = rw_kc(g), BN = rw_bn(g), nkb = g->Cin / KC, halo1 = rw_halo1(g);
-  const int rowb = KC * 2;
-  const int wt = (BN * rowb + 1023) / 1024 * 1024;
-  const int box = ((halo1 ? 180 : 144) * rowb + 1023) / 1024 * 1024;
-  const int stage = nkb * (halo1 ? 1 : 3) * box;
-  const int fixed = g->ntaps * nkb * wt + 128 * BN * 2 + 512 + 4096 + 1024;
-  if ((214 * 1024 - fixed) / stage < 2) return 0;
+  // shared-memory plan: filter blocks + staging + >= 2 input stages for some N-tile width
+  if (rw_bn(g) == 0) return 0;
+  // a 3x3 conv over 128 channels runs 32-wide N tiles and re-reads the input once per tile: only for one or two of them
+  if (classic && g->Cin == 128 && g->N / rw_bn(g) > 2) return 0;
   return 1;
 }
 
@@ -421,7 +437,7 @@ int ekl_conv3x3_rw(const EklGather* g, const void* w_packed, double* stats, int 
   if (BN == bn && KC == kc && p.nkb == NKB_ && p.ntaps == NT_) return launch_rw<bn, kc, NKB_, NT_>(p, grid, st);
 #define EKL_RW_BN(kc, NKB_, NT_) EKL_RW_CASE(64, kc, NKB_, NT_) EKL_RW_CASE(32, kc, NKB_, NT_) EKL_RW_CASE(16, kc, NKB_, NT_)
   EKL_RW_BN(64, 1, 9) EKL_RW_BN(32, 1, 9) EKL_RW_BN(16, 1, 9)
-  EKL_RW_BN(64, 1, 4) EKL_RW_BN(32, 1, 4) EKL_RW_BN(16, 1, 4) EKL_RW_BN(64, 2, 4)
+  EKL_RW_BN(64, 1, 4) EKL_RW_BN(32, 1, 4) EKL_RW_BN(16, 1, 4) EKL_RW_BN(64, 2, 4) EKL_RW_BN(64, 2, 9)
 #undef EKL_RW_BN
 #undef EKL_RW_CASE
   return ekl_fail(-1, "conv3x3_rw: no kernel for BN=%d KC=%d", BN, KC);

@@ -188,11 +188,10 @@ class ConvSpec:
     def dgrad_from_fwd(self):
         """The data-gradient kernel can read the forward-packed filter as an MN-major operand (no transposed pack):
         stride-1 / stride-2 convs with 64-multiple channel counts that never take the resident-filter path (its
-        data-gradient contraction is Cout: <= 64 for a 3x3 conv, <= 128 for the sub-pixel plan of a 4x4 / stride-2 conv;
-        conv_rw.cu: ekl_rw_supported)."""
+        data-gradient contraction is Cout <= 128; conv_rw.cu: ekl_rw_supported).  Shape-independent on purpose: the
+        operand a layer keeps packed must not depend on the batch it happens to see."""
         return (self.impl == L.IMPL_TC and self.mode != UP2 and self.w_layout == L.W_KRSC and self.cin % 64 == 0
-                and self.cout % 64 == 0 and self.cout > (128 if self.mode == DOWN2 else 64)
-                and self.x_fmt == 0 and self.y_fmt == 0)
+                and self.cout % 64 == 0 and self.cout > 128 and self.x_fmt == 0 and self.y_fmt == 0)
 
     def _shadow(self, weight):
         """bf16 shadow slice maintained by optim.FlatAdam, usable as the packed forward operand when that operand is a

@@ -16,7 +16,9 @@ SHAPES = {  # mode -> list of (B, H, W, Cin, Cout)
     0: [(4, 8, 8, 64, 128), (2, 16, 16, 128, 64), (3, 4, 4, 64, 256), (2, 32, 32, 32, 64), (2, 64, 64, 16, 32),
         (8, 4, 4, 192, 512), (2, 8, 8, 320, 128), (3, 32, 32, 16, 64), (2, 32, 32, 32, 16), (2, 64, 64, 16, 16),
         # resident-filter kernel (conv_rw.cu): two N tiles, one tile per image, more tiles than SMs
-        (2, 16, 16, 64, 128), (5, 16, 8, 64, 64), (6, 64, 64, 64, 64), (3, 32, 64, 32, 32)],
+        (2, 16, 16, 64, 128), (5, 16, 8, 64, 64), (6, 64, 64, 64, 64), (3, 32, 64, 32, 32),
+        # 128-channel contraction on the resident-filter kernel (two channel blocks, 32-wide N tiles): forward / data-gradient
+        (3, 32, 64, 128, 64), (4, 64, 64, 64, 128)],
     1: [(4, 4, 4, 128, 128), (2, 8, 8, 64, 64), (3, 16, 16, 64, 128), (2, 32, 32, 32, 32), (2, 4, 4, 256, 512),
         # sub-pixel plans on the resident-filter kernel (>= 2 x 148 tiles of 16x8 low-resolution pixels): one / two channel
         # blocks, SW128 / SW64 / SW32 rows, two N tiles
