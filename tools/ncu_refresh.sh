@@ -15,12 +15,12 @@ CMD="python bench.py --steps 1 --warmup 1 --no-graph --no-cpu --no-profile"
 mkdir -p gpurun_out
 timeout 120 $CMD > gpurun_out/${TAG}_plain.log 2>&1 || { echo "plain command failed"; tail -5 gpurun_out/${TAG}_plain.log; exit 1; }
 if [ "$MODE" = list ]; then
-timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv \
+timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 1800 --csv \
     --log-file gpurun_out/${TAG}_launches_3stages.csv $CMD > gpurun_out/${TAG}_ncu_list.log 2>&1
 echo "launch list rc=$? lines=$(wc -l < gpurun_out/${TAG}_launches_3stages.csv)"
 else
 timeout 400 ncu --set full --clock-control none --import-source on \
-    -k regex:'conv_gemm_tc2?_kernel|conv3x3_rw_kernel|conv_wgrad_co_kernel|conv_wgrad_halo_kernel|bn_act_bwd_reduce_kernel' \
-    --launch-skip 60 -c 16 -f -o gpurun_out/${TAG}_conv_full $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
+    -k regex:'conv_gemm_tc2?_kernel|conv3x3_rw_kernel|conv_wgrad_co_kernel|conv_wgrad_halo_kernel|bn_act_(fwd|bwd_reduce|bwd_apply)_kernel' \
+    --launch-skip 40 -c 40 -f -o gpurun_out/${TAG}_conv_full $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "full set rc=$?"; ls -la gpurun_out/${TAG}_conv_full.ncu-rep
 fi
