@@ -380,6 +380,16 @@ class condGANTrainer(object):
         for o in [self.optimizerG] + list(self.optimizersD):
             if hasattr(o, "refresh_shadow"):
                 o.refresh_shadow()
+        # packed filter operands that are not the optimiser's bf16 shadow (transposed data-gradient operands, up-conv tap
+        # sums, filter windows) are refreshed by the step itself only AFTER each network's optimiser update: repack them
+        # now, so that the first (possibly graph-replayed) step after a restore reads the restored filters everywhere
+        if next(self.netG.parameters()).is_cuda:
+            for net in [self.netG] + list(self.netsD):
+                ops.mark_dirty(net.parameters())
+                side = ops.prepack(net.parameters(), "restore")
+                if side is not None:
+                    torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
         return int(ck["count"])
 
     # ------------------------------------------------------------------ generation path (cub:720-911)
