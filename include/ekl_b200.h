@@ -98,6 +98,17 @@ int ekl_conv_bwd_data_ws(const ekl_conv* c, const void* dy, const void* w_dgrad,
  * ws: split-K workspace as for ekl_conv_bwd_data_ws (may be NULL). */
 int ekl_conv_dgrad_from_fwd(const ekl_conv* c);
 int ekl_conv_bwd_data_fw(const ekl_conv* c, const void* dy, const void* w_fwd, void* dx, float* ws, void* stream);
+/* Split-K convolution + train-mode BatchNorm + activation (model.py:816-830 downBlock / Block3x3_leakRelu on the 4x4 / 8x8
+ * discriminator tails) as two launches: the split conv into ws, then ONE kernel that finishes y (bf16, kept for the
+ * backward pass), takes the per-group batch statistics (mean / rstd [groups][Cout] written), applies one running-statistics
+ * update per group in group order, and writes out = act(BN(y)) with bn_act in {EKL_ACT_NONE, EKL_ACT_LRELU, EKL_ACT_RELU}.
+ * Available when ekl_conv_split_bn_fusable(c, bn_act) != 0 (the plan splits, Cout % 32 == 0, <= 768 pixels per group).
+ * aux: ekl_conv_split_bn_aux_floats(c) ZEROED floats of caller scratch (left zero). */
+int ekl_conv_split_bn_fusable(const ekl_conv* c, int bn_act);
+int64_t ekl_conv_split_bn_aux_floats(const ekl_conv* c);
+int ekl_conv_fwd_split_bn_act(const ekl_conv* c, const void* x, const void* w_fwd, float* ws, void* y, float eps, float momentum,
+                              float* mean, float* rstd, float* running_mean, float* running_var, const float* gamma,
+                              const float* beta, int bn_act, void* out, void* aux, void* stream);
 /* accounting only: the kernel family a call runs on -- 0 generic gather-GEMM kernel, 1 resident-filter 3x3 kernel,
  * 2 generic kernel with split-K + finishing pass (-1: not a tcgen05 plan) */
 int ekl_conv_route(const ekl_conv* c, int dgrad);

@@ -46,6 +46,9 @@ SIGNATURES = {
     "ekl_conv_bwd_data_fw": (_i, [_cp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_conv_fwd_bias9": (_i, [_cp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ekl_conv_bwd_data": (_i, [_cp, _vp, _vp, _vp, _vp]),
+    "ekl_conv_split_bn_fusable": (_i, [_cp, _i]),
+    "ekl_conv_split_bn_aux_floats": (_i64, [_cp]),
+    "ekl_conv_fwd_split_bn_act": (_i, [_cp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "ekl_conv_bwd_weight": (_i, [_cp, _vp, _vp, _vp, _vp]),
     "ekl_conv_plan_dump": (_i, [_cp, _i, C.POINTER(C.c_int), _i]),
     "ekl_col_stats": (_i, [_vp, _i64, _i, _i, _vp, _vp]),

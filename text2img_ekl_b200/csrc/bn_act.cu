@@ -790,6 +790,114 @@ __global__ void __launch_bounds__(256) bn_act_bwd_small_kernel(const bf16* __res
   }
 }
 
+// ---------------------------------------------------------------- split-K finish + BatchNorm forward in one launch
+// The split-K convolutions of the step (4x4 / 8x8 discriminator tails) are all followed by train-mode BatchNorm +
+// LeakyReLU on a few hundred rows per group: finish (fp32 scratch -> bf16 y + statistics), then the normalise pass, were
+// two launch-latency-bound kernels per layer (8-17 us + 7-19 us on the discriminator branch's critical path).  Here a block
+// owns a strip of 32 channels of ONE group for all its rows: sweep 1 rounds the scratch to bf16 y, re-zeroes it and
+// takes the statistics of the rounded values (same contract as the conv epilogue / splitk_finish); sweep 2 re-reads y
+// (L1 / L2) and writes out = act(gamma * (y - mean) * rstd + beta).  mean / rstd are stored for the backward pass.  The
+// running statistics need one momentum update per group IN GROUP ORDER: each block leaves its (mean, var) in global
+// memory and takes a ticket per strip; the last block of a strip applies the updates of all groups.
+// aux: [strips] tickets (uint32, ZERO on entry, left zero) then [groups][C] floats of variances.
+// Block = 256 threads = 8 vector-threads (4 channels, 16-byte fp32 reads) x 32 row-threads; grid = (C / 32, groups).
+template <int ACT>
+__global__ void __launch_bounds__(256) splitk_bn_act_fwd_kernel(float* __restrict__ scratch, int Mg, int C, float eps, float momentum,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                                float* running_mean, float* running_var, unsigned int* aux,
+                                                                bf16* __restrict__ y, bf16* __restrict__ out) {
+  constexpr int NV = 8;                      // [sum x 4 | sum of squares x 4]
+  __shared__ float sh[8 * SM_CT * NV];
+  __shared__ float tot[SM_CT * NV];
+  __shared__ int last_block;
+  const int ct = threadIdx.x % SM_CT, rt = threadIdx.x / SM_CT;
+  const int g = blockIdx.y, groups = (int)gridDim.y;
+  const int c0 = ((int)blockIdx.x * SM_CT + ct) * 4;
+  float* sg = scratch + (int64_t)g * Mg * C;
+  bf16* yg = y + (int64_t)g * Mg * C;
+  bf16* og = out + (int64_t)g * Mg * C;
+  float acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+  constexpr int U = 4;
+  for (int rb = rt; rb < Mg; rb += U * 32) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = rb + u * 32;
+      if (r < Mg) v[u] = *reinterpret_cast<const float4*>(sg + (int64_t)r * C + c0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = rb + u * 32;
+      if (r >= Mg) break;
+      *reinterpret_cast<float4*>(sg + (int64_t)r * C + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+      const uint2 o = make_uint2(pack_bf16x2(v[u].x, v[u].y), pack_bf16x2(v[u].z, v[u].w));
+      *reinterpret_cast<uint2*>(yg + (int64_t)r * C + c0) = o;
+      const float f0 = bf16_lo(o.x), f1 = bf16_hi(o.x), f2 = bf16_lo(o.y), f3 = bf16_hi(o.y);
+      acc[0] += f0; acc[1] += f1; acc[2] += f2; acc[3] += f3;
+      acc[4] += f0 * f0; acc[5] += f1 * f1; acc[6] += f2 * f2; acc[7] += f3 * f3;
+    }
+  }
+  strip_reduce<NV>(acc, sh, tot);
+  const double inv_n = 1.0 / (double)Mg;
+  float sc[4], sf[4];
+  float* var_buf = reinterpret_cast<float*>(aux + gridDim.x);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double m = (double)acc[i] * inv_n;
+    double v = (double)acc[4 + i] * inv_n - m * m;
+    v = v < 0.0 ? 0.0 : v;
+    const float mean = (float)m, rstd = 1.f / sqrtf((float)v + eps);
+    const int c = c0 + i;
+    if (rt == 0) { mean_out[g * C + c] = mean; rstd_out[g * C + c] = rstd; var_buf[g * C + c] = (float)v; }
+    sc[i] = gamma[c] * rstd; sf[i] = beta[c] - mean * sc[i];
+  }
+  if (running_mean != nullptr) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last_block = atomicAdd(aux + blockIdx.x, 1u) == (unsigned)(groups - 1);
+    __syncthreads();
+    if (last_block) {
+      __threadfence();
+      if (threadIdx.x < SM_CT * 4) {
+        const int c = (int)blockIdx.x * SM_CT * 4 + threadIdx.x;
+        const float n = (float)Mg;
+        float rm = running_mean[c], rv = running_var[c];
+        for (int gg = 0; gg < groups; ++gg) {
+          const float m = __ldcg(mean_out + gg * C + c), v = __ldcg(var_buf + gg * C + c);
+          const float unb = n > 1.f ? v * n / (n - 1.f) : v;
+          rm = (1.f - momentum) * rm + momentum * m;
+          rv = (1.f - momentum) * rv + momentum * unb;
+        }
+        running_mean[c] = rm; running_var[c] = rv;
+      }
+      if (threadIdx.x == 0) aux[blockIdx.x] = 0u;        // tickets are left zero for the next use of the arena slice
+    }
+  }
+  for (int rb = rt; rb < Mg; rb += U * 32) {
+    uint2 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = rb + u * 32;
+      if (r < Mg) v[u] = *reinterpret_cast<const uint2*>(yg + (int64_t)r * C + c0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = rb + u * 32;
+      if (r >= Mg) break;
+      float z[4] = {bf16_lo(v[u].x), bf16_hi(v[u].x), bf16_lo(v[u].y), bf16_hi(v[u].y)};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        z[i] = fmaf(z[i], sc[i], sf[i]);
+        z[i] = ACT == ACT_LRELU ? (z[i] > 0.f ? z[i] : 0.2f * z[i]) : (ACT == ACT_RELU ? fmaxf(z[i], 0.f) : z[i]);
+      }
+      *reinterpret_cast<uint2*>(og + (int64_t)r * C + c0) = make_uint2(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]));
+    }
+  }
+}
+
 // ---------------------------------------------------------------- plain LeakyReLU backward / concat helpers
 __global__ void lrelu_bwd_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, bf16* __restrict__ dx, int64_t n8) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
@@ -922,6 +1030,39 @@ int ekl_splitk_finish(float* scratch, int64_t M, int C, int groups, void* y, dou
   dim3 grid;
   finish_grid(M, C / 8, groups, &grid);
   splitk_finish_kernel<<<grid, 256, 0, st>>>(scratch, M, C, groups, (bf16*)y, sums);
+  EKL_LAUNCH_CHECK();
+  return 0;
+}
+
+// eligibility of the fused finish + BatchNorm forward for an [M][C] split-K output with `groups` statistics groups
+int ekl_splitk_bn_fusable(int64_t M, int C, int groups, int act) {
+  if (groups <= 0 || M % groups != 0 || C % (SM_CT * 4) != 0) return 0;
+  if (!(act == ACT_NONE || act == ACT_LRELU || act == ACT_RELU)) return 0;
+  return M / groups <= 768;
+}
+
+// aux: C / 32 uint32 tickets + groups * C floats, ZERO on entry (see splitk_bn_act_fwd_kernel)
+int ekl_splitk_bn_act_fwd(float* scratch, int64_t M, int C, int groups, float eps, float momentum, float* mean, float* rstd,
+                          float* running_mean, float* running_var, const float* gamma, const float* beta, int act, void* y,
+                          void* out, void* aux, cudaStream_t st) {
+  EKL_REQUIRE(ekl_splitk_bn_fusable(M, C, groups, act), "splitk_bn_act_fwd: unsupported shape M=%lld C=%d groups=%d act=%d",
+              (long long)M, C, groups, act);
+  EKL_REQUIRE(scratch && mean && rstd && gamma && beta && y && out && aux, "splitk_bn_act_fwd: null pointer argument");
+  const dim3 grid(C / (SM_CT * 4), groups);
+  const int Mg = (int)(M / groups);
+  switch (act) {
+    case ACT_LRELU:
+      splitk_bn_act_fwd_kernel<ACT_LRELU><<<grid, 256, 0, st>>>(scratch, Mg, C, eps, momentum, gamma, beta, mean, rstd, running_mean,
+                                                                running_var, (unsigned int*)aux, (bf16*)y, (bf16*)out);
+      break;
+    case ACT_RELU:
+      splitk_bn_act_fwd_kernel<ACT_RELU><<<grid, 256, 0, st>>>(scratch, Mg, C, eps, momentum, gamma, beta, mean, rstd, running_mean,
+                                                               running_var, (unsigned int*)aux, (bf16*)y, (bf16*)out);
+      break;
+    default:
+      splitk_bn_act_fwd_kernel<ACT_NONE><<<grid, 256, 0, st>>>(scratch, Mg, C, eps, momentum, gamma, beta, mean, rstd, running_mean,
+                                                               running_var, (unsigned int*)aux, (bf16*)y, (bf16*)out);
+  }
   EKL_LAUNCH_CHECK();
   return 0;
 }

@@ -10,6 +10,10 @@ int ekl_gather_gemm_tc(const EklGather* g, const void* w_packed, double* stats, 
 int ekl_tc_dgrad_from_fwd_ok(const EklGather* g);
 int64_t ekl_tc_split_elems(const EklGather* g, int group_b);
 int ekl_splitk_finish(float* scratch, int64_t M, int C, int groups, void* y, double* sums, cudaStream_t st);
+int ekl_splitk_bn_fusable(int64_t M, int C, int groups, int act);
+int ekl_splitk_bn_act_fwd(float* scratch, int64_t M, int C, int groups, float eps, float momentum, float* mean, float* rstd,
+                          float* running_mean, float* running_var, const float* gamma, const float* beta, int act, void* y,
+                          void* out, void* aux, cudaStream_t st);
 int ekl_rw_supported(const EklGather* g, int group_b);
 int ekl_conv3x3_rw(const EklGather* g, const void* w_packed, double* stats, int act, const float* bias9, cudaStream_t st);
 int ekl_gather_simt(const EklGather* g, const void* w_packed, int act, cudaStream_t st);
@@ -175,6 +179,40 @@ extern "C" int ekl_conv_fwd_ws(const ekl_conv* c, const void* x, const void* w_f
   plan(c, 0, x, y, &g);
   if (ws == nullptr || split_elems(c, &g, c->group_b) == 0) return ekl_conv_fwd(c, x, w_fwd, y, stats, stream);
   return run_split(&g, w_fwd, c->group_b, ws, y, stats, (cudaStream_t)stream);
+}
+
+// Split-K convolution followed by train-mode BatchNorm + activation as TWO launches instead of three: the conv's work
+// items red-add into ws, then one kernel finishes y (bf16, kept for the backward pass), takes the batch statistics,
+// updates the running statistics and writes out = act(BN(y)).  ekl_conv_split_bn_fusable(c, act) != 0 says when: the
+// plan splits (ekl_conv_workspace_elems > 0), act is none / LeakyReLU / ReLU, Cout % 32 == 0 and a statistics group
+// has <= 768 pixels.  aux: ekl_conv_split_bn_aux_floats(c) zeroed floats of caller scratch (left zero).
+extern "C" int ekl_conv_split_bn_fusable(const ekl_conv* c, int bn_act) {
+  if (check(c) || c->mode == EKL_UP2) return 0;
+  EklGather g;
+  plan(c, 0, nullptr, nullptr, &g);
+  if (split_elems(c, &g, c->group_b) == 0) return 0;
+  const int groups = (c->group_b > 0 && c->B % c->group_b == 0) ? c->B / c->group_b : 1;
+  return ekl_splitk_bn_fusable((int64_t)g.mB * g.mH * g.mW, g.N, groups, bn_act);
+}
+
+extern "C" int64_t ekl_conv_split_bn_aux_floats(const ekl_conv* c) {
+  if (check(c)) return -1;
+  const int groups = (c->group_b > 0 && c->B % c->group_b == 0) ? c->B / c->group_b : 1;
+  return (int64_t)c->Cout / 32 + (int64_t)groups * c->Cout;
+}
+
+extern "C" int ekl_conv_fwd_split_bn_act(const ekl_conv* c, const void* x, const void* w_fwd, float* ws, void* y, float eps,
+                                         float momentum, float* mean, float* rstd, float* running_mean, float* running_var,
+                                         const float* gamma, const float* beta, int bn_act, void* out, void* aux, void* stream) {
+  if (int rc = check(c)) return rc;
+  EKL_REQUIRE(x != nullptr && w_fwd != nullptr && ws != nullptr && y != nullptr, "conv_fwd_split_bn_act: null pointer argument");
+  EKL_REQUIRE(ekl_conv_split_bn_fusable(c, bn_act), "conv_fwd_split_bn_act: this layer / shape does not take the fused path");
+  EklGather g;
+  plan(c, 0, x, y, &g);
+  if (int rc = ekl_gather_gemm_tc(&g, w_fwd, nullptr, c->group_b, 0, nullptr, ws, nullptr, (cudaStream_t)stream)) return rc;
+  const int groups = (c->group_b > 0 && c->B % c->group_b == 0) ? c->B / c->group_b : 1;
+  return ekl_splitk_bn_act_fwd(ws, (int64_t)g.mB * g.mH * g.mW, g.N, groups, eps, momentum, mean, rstd, running_mean, running_var,
+                               gamma, beta, bn_act, y, out, aux, (cudaStream_t)stream);
 }
 
 extern "C" int ekl_conv_bwd_data_ws(const ekl_conv* c, const void* dy, const void* w_dgrad, void* dx, float* ws, void* stream) {

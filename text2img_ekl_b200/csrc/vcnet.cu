@@ -20,32 +20,42 @@ constexpr int KC = 128;      // K chunk staged in shared memory
 constexpr int WARPS = 8;     // columns per block
 constexpr int KSPLIT = 256;  // backward: K range of one block row (multiple of KC)
 
+// Forward K chunk: KCF columns of x for all B rows live in (dynamic) shared memory at a time.  The chunk loop is a latency
+// chain (stage x -> barrier -> read W -> multiply), so chunks are large (3 for K = 1225 instead of 10 of 128) and the
+// warp's W values of a chunk are requested BEFORE the staging barrier: both global round trips of a chunk overlap.
+constexpr int KCF = 512;
+
 template <int BMAX>
 __global__ void __launch_bounds__(32 * WARPS) linear_bn_relu_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ gamma,
     const float* __restrict__ beta, float* running_mean, float* running_var, int B, int K, int N, float eps, float momentum,
     int training, float* __restrict__ h, float* __restrict__ xhat, float* __restrict__ rstd_out) {
-  __shared__ float xs[BMAX * KC];
+  extern __shared__ float xs[];          // [B][KCF]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * WARPS + warp;
   float acc[BMAX];
 #pragma unroll
   for (int b = 0; b < BMAX; ++b) acc[b] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += KC) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < B * KC; i += 32 * WARPS) {
-      const int b = i / KC, k = i - b * KC;
-      xs[b * KC + k] = (k0 + k) < K ? x[(size_t)b * K + k0 + k] : 0.f;
+  for (int k0 = 0; k0 < K; k0 += KCF) {
+    float w[KCF / 32];
+#pragma unroll
+    for (int j = 0; j < KCF / 32; ++j) {
+      const int k = k0 + j * 32 + lane;
+      w[j] = (n < N && k < K) ? W[(size_t)n * K + k] : 0.f;
+    }
+    __syncthreads();                      // the previous chunk has been consumed
+    for (int i = threadIdx.x; i < B * KCF; i += 32 * WARPS) {
+      const int b = i / KCF, k = i - b * KCF;
+      xs[i] = (k0 + k) < K ? x[(size_t)b * K + k0 + k] : 0.f;
     }
     __syncthreads();
     if (n < N) {
 #pragma unroll
-      for (int j = 0; j < KC / 32; ++j) {
+      for (int j = 0; j < KCF / 32; ++j) {
         const int k = j * 32 + lane;
-        const float w = (k0 + k) < K ? W[(size_t)n * K + k0 + k] : 0.f;
 #pragma unroll
         for (int b = 0; b < BMAX; ++b)
-          if (b < B) acc[b] += xs[b * KC + k] * w;
+          if (b < B) acc[b] = fmaf(xs[b * KCF + k], w[j], acc[b]);
       }
     }
   }
@@ -159,12 +169,19 @@ extern "C" int ekl_linear_bn_relu_fwd(const float* x, const float* W, const floa
   EKL_REQUIRE(B >= 1 && B <= 64 && K > 0 && N > 0, "linear_bn_relu_fwd: batch 1..64 (got %d)", B);
   EKL_REQUIRE(training || (running_mean != nullptr && running_var != nullptr), "linear_bn_relu_fwd: inference needs running statistics");
   const int grid = ekl_cdiv(N, WARPS);
+  const size_t smem = (size_t)B * KCF * sizeof(float);           // <= 128 KB at B = 64
+  static bool attr_done = false;
+  if (!attr_done) {
+    EKL_CHECK_CUDA(cudaFuncSetAttribute(linear_bn_relu_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * KCF * 4));
+    EKL_CHECK_CUDA(cudaFuncSetAttribute(linear_bn_relu_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * KCF * 4));
+    attr_done = true;
+  }
   if (B <= 32)
-    linear_bn_relu_fwd_kernel<32><<<grid, 32 * WARPS, 0, (cudaStream_t)stream>>>(x, W, bias, gamma, beta, running_mean, running_var, B, K,
-                                                                                N, eps, momentum, training, h, xhat, rstd);
+    linear_bn_relu_fwd_kernel<32><<<grid, 32 * WARPS, smem, (cudaStream_t)stream>>>(x, W, bias, gamma, beta, running_mean, running_var, B,
+                                                                                   K, N, eps, momentum, training, h, xhat, rstd);
   else
-    linear_bn_relu_fwd_kernel<64><<<grid, 32 * WARPS, 0, (cudaStream_t)stream>>>(x, W, bias, gamma, beta, running_mean, running_var, B, K,
-                                                                                N, eps, momentum, training, h, xhat, rstd);
+    linear_bn_relu_fwd_kernel<64><<<grid, 32 * WARPS, smem, (cudaStream_t)stream>>>(x, W, bias, gamma, beta, running_mean, running_var, B,
+                                                                                   K, N, eps, momentum, training, h, xhat, rstd);
   EKL_LAUNCH_CHECK();
   return 0;
 }

@@ -44,9 +44,7 @@ def _spec(mode, cin, cout, **kw):
 
 
 def _conv_bn_act(x, conv_mod, bn_mod, spec, act, groups=1, residual=None):
-    B = x.shape[0]
-    y, stats = ops.conv(x, conv_mod.weight, spec, group_b=B // groups, want_stats=bn_mod.training)
-    return ops.bn_act(y, stats, bn_mod, groups, act, residual)
+    return ops.conv_bn_act(x, conv_mod.weight, spec, bn_mod, groups, act, residual)
 
 
 class Reshape(nn.Module):          # model.py:50-56

@@ -314,7 +314,10 @@ class _Conv(torch.autograd.Function):
     """y = conv(x) (+ per-tile BatchNorm partial statistics).  Backward: tcgen05 dgrad + wgrad."""
 
     @staticmethod
-    def forward(ctx, x, weight, spec, group_b, want_stats, skip_wgrad):
+    def forward(ctx, x, weight, spec, group_b, want_stats, skip_wgrad, fuse_bn=None):
+        """fuse_bn = (bn module, groups, act) or None: when the plan splits along K and the layer is followed by train-mode
+        BatchNorm + activation, the finishing pass and the normalise pass are ONE kernel (ekl_conv_fwd_split_bn_act); the
+        extra outputs (out, mean, rstd) are handed to _BnAct, which then launches nothing in its forward."""
         ctx.set_materialize_grads(False)      # no zero-filled "gradient" of the statistics output
         lib = L.lib()
         if spec.x_fmt == L.FMT_NCHW_F32:
@@ -338,24 +341,39 @@ class _Conv(torch.autograd.Function):
         fam = "conv_tc" if spec.impl == L.IMPL_TC else "conv_simt"
         _log("fwd", fam, spec.mode, B, H, W, spec.cin, spec.cout, group_b)
         _acct(_route(spec, c, 0), _conv_flops(spec, B, H, W), x.numel() * x.element_size() + y.numel() * y.element_size())
-        if ws is not None:
+        pre = (None, None, None)
+        if ws is not None and fuse_bn is not None and lib.ekl_conv_split_bn_fusable(c, fuse_bn[2]):
+            bn, groups, act = fuse_bn
+            C = spec.cout
+            mean = torch.empty(groups, C, device=x.device, dtype=torch.float32)
+            rstd = torch.empty(groups, C, device=x.device, dtype=torch.float32)
+            out = torch.empty_like(y)
+            aux = zeros_f32(int(lib.ekl_conv_split_bn_aux_floats(c)), x.device)
+            _acct("bn", nbytes=y.numel() * 4)
+            L.check(lib.ekl_conv_fwd_split_bn_act(c, L.ptr(x), L.ptr(w_fwd), L.ptr(ws), L.ptr(y), BN_EPS, BN_MOM, L.ptr(mean),
+                                                  L.ptr(rstd), L.ptr(bn.running_mean), L.ptr(bn.running_var), L.ptr(bn.weight),
+                                                  L.ptr(bn.bias), act, L.ptr(out), L.ptr(aux), L.stream()))
+            _count(2)
+            pre, stats = (out, mean, rstd), None
+        elif ws is not None:
             L.check(lib.ekl_conv_fwd_ws(c, L.ptr(x), L.ptr(w_fwd), L.ptr(y), L.ptr(stats), L.ptr(ws), L.stream()))
+            _count(2)
         else:
             L.check(lib.ekl_conv_fwd(c, L.ptr(x), L.ptr(w_fwd), L.ptr(y), L.ptr(stats), L.stream()))
-        _count(2 if ws is not None else 1)
+            _count(1)
         ctx.dims = (B, H, W)
         if spec.act != ACT_NONE and spec.impl == L.IMPL_TC:
             ctx.save_for_backward(x, weight, y)        # fused epilogue activation: its derivative needs the output
         else:
             ctx.save_for_backward(x, weight)
         ctx.spec, ctx.c, ctx.skip_wgrad, ctx.w_leaf = spec, c, skip_wgrad, weight.is_leaf
-        ctx.mark_non_differentiable(*([stats] if stats is not None else []))
-        return y, stats
+        ctx.mark_non_differentiable(*[t for t in (stats,) + pre if t is not None])
+        return (y, stats) + pre
 
     @staticmethod
-    def backward(ctx, dy, _dstats):
+    def backward(ctx, dy, _dstats, _dout=None, _dmean=None, _drstd=None):
         if dy is None:
-            return None, None, None, None, None, None
+            return None, None, None, None, None, None, None
         lib = L.lib()
         x, weight = ctx.saved_tensors[:2]
         spec, c = ctx.spec, ctx.c
@@ -388,11 +406,23 @@ class _Conv(torch.autograd.Function):
                   x.numel() * x.element_size() + dy.numel() * dy.element_size())
             L.check(lib.ekl_conv_bwd_weight(c, L.ptr(x), L.ptr(dy), L.ptr(buf), L.stream()))
             _count()
-        return dx, dw, None, None, None, None
+        return dx, dw, None, None, None, None, None
 
 
 def conv(x, weight, spec, group_b=0, want_stats=False, skip_wgrad=False):
-    return _Conv.apply(x, weight, spec, group_b, want_stats, skip_wgrad)
+    return _Conv.apply(x, weight, spec, group_b, want_stats, skip_wgrad)[:2]
+
+
+_SPLIT_BN = os.environ.get("EKL_SPLIT_BN", "1") != "0"      # fused finishing + BatchNorm forward kernel after split-K convs
+
+
+def conv_bn_act(x, weight, spec, bn, groups, act, residual=None):
+    """conv -> train-mode BatchNorm -> activation (+ residual).  Layers whose conv plan splits along K run the finishing
+    pass and the normalise pass as one kernel (see _Conv.forward); everything else is conv() + bn_act()."""
+    B = x.shape[0]
+    fuse = (bn, groups, act) if (_SPLIT_BN and bn.training and residual is None and spec.impl == L.IMPL_TC and x.is_cuda) else None
+    y, stats, out, mean, rstd = _Conv.apply(x, weight, spec, B // groups, bn.training, False, fuse)
+    return bn_act(y, stats, bn, groups, act, residual, pre=(out, mean, rstd) if out is not None else None)
 
 
 def border_class_sums(dy):
@@ -504,11 +534,18 @@ class _BnAct(torch.autograd.Function):
     """Train-mode BatchNorm (per-group batch statistics) + GLU / LeakyReLU / ReLU / identity (+ residual)."""
 
     @staticmethod
-    def forward(ctx, y, stats, gamma, beta, running_mean, running_var, groups, act, residual, skip_pgrad):
+    def forward(ctx, y, stats, gamma, beta, running_mean, running_var, groups, act, residual, skip_pgrad, pre=None):
         lib = L.lib()
         C = y.shape[-1]
         M = y.numel() // C
         dev = y.device
+        if pre is not None:
+            # out / mean / rstd (and the running-statistics update) were produced by the conv's fused finishing kernel
+            out, mean, rstd = pre
+            _log("bn_fwd", M, C, groups, act, False)
+            ctx.save_for_backward(y, mean, rstd, gamma, beta)
+            ctx.groups, ctx.act, ctx.has_res, ctx.skip_pgrad = groups, act, False, skip_pgrad
+            return out.view_as(out)
         if stats is None:
             stats = ARENA.take(groups * 2 * C, dev)
             _acct("bn", nbytes=M * C * 2)
@@ -549,10 +586,10 @@ class _BnAct(torch.autograd.Function):
                                    L.ptr(_grad_buffer(gamma)) if pg else None, L.ptr(_grad_buffer(beta)) if pg else None,
                                    L.ptr(dy), L.stream()))
         _count(2)
-        return dy, None, None, None, None, None, None, None, (dout if ctx.has_res else None), None
+        return dy, None, None, None, None, None, None, None, (dout if ctx.has_res else None), None, None
 
 
-def bn_act(y, stats, bn, groups, act, residual=None, skip_pgrad=False):
+def bn_act(y, stats, bn, groups, act, residual=None, skip_pgrad=False, pre=None):
     """bn: an nn.BatchNorm{1,2}d module holding weight/bias/running stats (state_dict-compatible)."""
     if not bn.training:
         # inference: normalise with the running statistics (no autograd; the evaluate() path)
@@ -571,7 +608,7 @@ def bn_act(y, stats, bn, groups, act, residual=None, skip_pgrad=False):
         bn._ekl_calls += groups          # flushed once per step for the whole network (engine.BnCounters)
     elif bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(groups)
-    return _BnAct.apply(y, stats, bn.weight, bn.bias, bn.running_mean, bn.running_var, groups, act, residual, skip_pgrad)
+    return _BnAct.apply(y, stats, bn.weight, bn.bias, bn.running_mean, bn.running_var, groups, act, residual, skip_pgrad, pre)
 
 
 class _LReluFromOut(torch.autograd.Function):

@@ -217,6 +217,37 @@ def run_split(torch, L, lib, dev, rel):
                 e2 = rel(sg[:, 1], (yf * yf).sum(1))
                 ok = ok and e < 6e-3 and e2 < 1e-3 and float(ws.abs().max()) == 0.0
                 msg += " | y %.1e stats %.1e" % (e, e2)
+            # the same conv with the finishing pass fused with train-mode BatchNorm + LeakyReLU (one kernel) against the
+            # unfused sequence ekl_conv_fwd_ws -> ekl_bn_act_fwd on the same inputs: y bit-identical, the rest to rounding
+            if lib.ekl_conv_split_bn_fusable(conv, L.ACT_LRELU):
+                groups = B // gb if gb else 1
+                gamma, beta = 1 + 0.1 * torch.randn(Cout, device=dev), 0.1 * torch.randn(Cout, device=dev)
+                ref = {}
+                for fused in (0, 1):
+                    yv = torch.full((B, Ho, Wo, Cout), float("nan"), device=dev, dtype=torch.bfloat16)
+                    out = torch.full((B, Ho, Wo, Cout), float("nan"), device=dev, dtype=torch.bfloat16)
+                    mean, rstd = torch.empty(groups, Cout, device=dev), torch.empty(groups, Cout, device=dev)
+                    rm, rv = torch.zeros(Cout, device=dev), torch.ones(Cout, device=dev)
+                    if fused:
+                        aux = torch.zeros(int(lib.ekl_conv_split_bn_aux_floats(conv)), device=dev)
+                        L.check(lib.ekl_conv_fwd_split_bn_act(conv, L.ptr(x), L.ptr(wf), L.ptr(ws), L.ptr(yv), 1e-5, 0.1, L.ptr(mean),
+                                                              L.ptr(rstd), L.ptr(rm), L.ptr(rv), L.ptr(gamma), L.ptr(beta), L.ACT_LRELU,
+                                                              L.ptr(out), L.ptr(aux), L.stream()))
+                    else:
+                        stats = torch.zeros(groups, 2, Cout, device=dev, dtype=torch.float64)
+                        L.check(lib.ekl_conv_fwd_ws(conv, L.ptr(x), L.ptr(wf), L.ptr(yv), L.ptr(stats), L.ptr(ws), L.stream()))
+                        L.check(lib.ekl_bn_act_fwd(L.ptr(yv), B * Ho * Wo, Cout, groups, L.ptr(stats), 1e-5, 0.1, L.ptr(mean),
+                                                   L.ptr(rstd), L.ptr(rm), L.ptr(rv), L.ptr(gamma), L.ptr(beta), L.ACT_LRELU, None,
+                                                   L.ptr(out), L.stream()))
+                    torch.cuda.synchronize()
+                    if fused:
+                        same_y = bool(torch.equal(yv, ref["y"]))
+                        errs = [rel(out, ref["out"]), rel(mean, ref["mean"]), rel(rstd, ref["rstd"]), rel(rm, ref["rm"]), rel(rv, ref["rv"])]
+                        zero = float(ws.abs().max()) == 0.0 and float(aux[:Cout // 32].abs().max()) == 0.0
+                        ok = ok and same_y and zero and errs[0] < 6e-3 and max(errs[1:]) < 1e-4
+                        msg += " | fused-bn y==%s out %.1e mean %.1e rstd %.1e run %.1e %.1e" % ((same_y,) + tuple(errs))
+                    else:
+                        ref = dict(y=yv, out=out, mean=mean, rstd=rstd, rm=rm, rv=rv)
         if nd > 0:
             ws = torch.zeros(nd, device=dev)
             dx = torch.full((B, H, W, Cin), float("nan"), device=dev, dtype=torch.bfloat16)
