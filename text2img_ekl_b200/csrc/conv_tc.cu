@@ -695,8 +695,11 @@ static void tc_tile_plan(const EklGather* g, int group_b, bool allow_split, int*
     if (g->N % bn != 0) continue;
     const int64_t tiles = (int64_t)mtiles * (g->N / bn) * g->nvar;
     int ks = 1;
-    static int split_min = -1;          // a plan splits when split_min x its work items fit the SMs (EKL_TC_SPLIT_MIN, default 3)
-    if (split_min < 0) { const char* e = getenv("EKL_TC_SPLIT_MIN"); split_min = e ? atoi(e) : 3; if (split_min < 2) split_min = 2; }
+    // a plan splits when split_min x its work items fit the SMs (EKL_TC_SPLIT_MIN).  2 since the finishing pass is fused
+    // with the BatchNorm that follows: config 2, four A/B pairs, 7.642-7.652 ms/step at 3 vs 7.605-7.617 at 2 (the
+    // 1024 -> 2048 discriminator conv at 72 images, 72 work items, now runs as 144 half-length ones)
+    static int split_min = -1;
+    if (split_min < 0) { const char* e = getenv("EKL_TC_SPLIT_MIN"); split_min = e ? atoi(e) : 2; if (split_min < 2) split_min = 2; }
     if (allow_split && g->nvar == 1 && KC == 64 && tiles * split_min <= sms && n_iters >= 64) {
       ks = (int)(sms / tiles);
       if (ks > n_iters / 16) ks = n_iters / 16;

@@ -1,7 +1,7 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-for rep in 1 2 3; do
+for rep in 1 2 3 4; do
 for m in 3 2; do
 EKL_TC_SPLIT_MIN=$m timeout 150 python bench.py --steps 40 --warmup 5 --no-cpu --no-extra --no-profile 2>/dev/null | grep '^{' | python -c "
 import sys, json
