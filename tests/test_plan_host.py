@@ -204,6 +204,27 @@ def test_split_k_and_operand_planning_host_logic():
     assert not s1.dgrad_from_fwd() and s2.dgrad_from_fwd()        # the host keeps a transposed operand for the former
 
 
+def test_batchnorm_scratch_and_fused_finishing_eligibility_on_host():
+    """Host-side answers of the round-2 BatchNorm entry points (no kernel launch): the backward scratch is one sum per
+    128-byte line for the streaming passes and empty for the single-launch small layers; the fused split-K finishing +
+    BatchNorm kernel is offered exactly for split plans with <= 768 pixels per group and Cout % 32 == 0."""
+    lib = L.lib()
+    spread = 16
+    assert lib.ekl_bn_bwd_scratch_doubles(24 * 64 * 64, 128, 1, L.ACT_GLU) == 1 * 2 * 128 * spread
+    assert lib.ekl_bn_bwd_scratch_doubles(72 * 64 * 64, 128, 3, L.ACT_LRELU) == 3 * 2 * 128 * spread
+    assert lib.ekl_bn_bwd_scratch_doubles(72 * 16, 1024, 3, L.ACT_LRELU) == 0            # 384 rows per group: one launch
+    assert lib.ekl_bn_bwd_scratch_doubles(10, 128, 3, L.ACT_LRELU) == -1                  # rows do not divide into groups
+    mk = lambda mode, B, H, W, Cin, Cout, gb=0: L.EklConv(mode, B, H, W, Cin, Cout, gb, L.IMPL_TC, 0, 0, 0, L.W_KRSC)
+    tail = mk(L.S1, 72, 4, 4, 2048, 1024, 24)                                              # split, 3 groups of 384 pixels
+    assert lib.ekl_conv_workspace_elems(tail, 0) > 0
+    assert lib.ekl_conv_split_bn_fusable(tail, L.ACT_LRELU) == 1 and lib.ekl_conv_split_bn_fusable(tail, L.ACT_GLU) == 0
+    assert lib.ekl_conv_split_bn_aux_floats(tail) == 1024 // 32 + 3 * 1024
+    big = mk(L.DOWN2, 72, 64, 64, 128, 256, 24)                                            # fills the machine: never split
+    assert lib.ekl_conv_split_bn_fusable(big, L.ACT_LRELU) == 0
+    up = mk(L.UP2, 24, 4, 4, 1024, 1024, 24)                                               # 4 variants: not a split plan
+    assert lib.ekl_conv_split_bn_fusable(up, L.ACT_GLU) == 0
+
+
 def test_bn_counters_single_vector_add():
     """engine.BnCounters: every num_batches_tracked becomes a view into one int64 tensor, the per-call increments are
     tallied on the host and added once; state_dict keys / values stay those of nn.BatchNorm."""

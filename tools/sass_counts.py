@@ -10,7 +10,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "text2img_ekl_b200", "libekl_b200.so")
-PAT = collections.OrderedDict([("UTCHMMA", "UTCHMMA"), ("UTMALDG", "UTMALDG"), ("UTMASTG", "UTMASTG"), ("LDTM", "LDTM"),
+PAT = collections.OrderedDict([("UTCHMMA", "UTCHMMA"), ("UTMALDG", "UTMALDG"), ("UTMASTG", "UTMASTG"), ("UBLKCP", "UBLKCP"), ("LDTM", "LDTM"),
                                ("UTCBAR", "UTCBAR"), ("SYNCS", "SYNCS"), ("RED", " RED."), ("REDG", " REDG."), ("ATOM", " ATOM")])
 
 
@@ -34,7 +34,7 @@ def main():
     dem = subprocess.run(["c++filt"] + names, capture_output=True, text=True).stdout.splitlines()
     print("# SASS mnemonic counts per kernel of `libekl_b200.so`\n")
     print("`cuobjdump -sass text2img_ekl_b200/libekl_b200.so`, counted per `Function :` block by `tools/sass_counts.py`. "
-          "UTCHMMA = `tcgen05.mma` (bf16), UTMALDG / UTMASTG = TMA tensor load / store, LDTM = `tcgen05.ld`, UTCBAR = "
+          "UTCHMMA = `tcgen05.mma` (bf16), UTMALDG / UTMASTG = TMA tensor load / store, UBLKCP = `cp.async.bulk` (1-D bulk copy), LDTM = `tcgen05.ld`, UTCBAR = "
           "`tcgen05.commit`, SYNCS = mbarrier operations, RED/REDG = `red.global.add`.\n")
     keys = ["instr"] + list(PAT)
     print("| kernel | " + " | ".join(keys) + " |\n|---|" + "---:|" * len(keys))
