@@ -1,4 +1,4 @@
-// Train-mode BatchNorm + activation family (HBM-bound, vectorised 16-byte accesses, fp32 statistics):
+// Train-mode BatchNorm + activation family (HBM-bound; fp32 arithmetic, fp64 sums):
 //   statistics  : per-(group, channel) sum / sum-of-squares, accumulated with fp64 red.global.add into ONE [groups][2][C]
 //                 double buffer (zero on entry) by whoever produces the tensor: the conv epilogue, splitk_finish, or
 //                 col_stats for a stored tensor.  No per-tile partial rows and no finalize launch: every consumer block
@@ -6,6 +6,9 @@
 //   forward     : z = gamma*(y-mean)*rstd + beta ; out = GLU(z) | LeakyReLU(z, 0.2) | z (+ residual); the blocks of the
 //                 first row chunk also store mean / rstd for the backward pass and update the running statistics
 //   backward    : dz = act'(z)*dout ; partial sums S1 = sum dz, S2 = sum dz*xhat ; dy = gamma*rstd*(dz - S1/n - xhat*S2/n)
+//   data path   : the three streaming passes read their rows through a shared-memory ring of bulk async copies (struct
+//                 Ring); layers with few rows per group run the backward as one launch (bn_act_bwd_small_kernel) and,
+//                 after a split-K conv, the finishing pass and the forward as one launch (splitk_bn_act_fwd_kernel)
 // Activations are bf16 [M rows][C channels] (NHWC flattened); rows are split into `groups` equal contiguous
 // groups with independent batch statistics (real / wrong / fake discriminator passes batched into one tensor;
 // reference: three separate netD(...) calls, cub_trainer_splitz_cap_ca.py:418-420).
